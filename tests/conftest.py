@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+GOLDEN_CASES = ["small_r3_odd", "basic_r4", "levels3_r4"]
+
+
+@pytest.fixture(params=GOLDEN_CASES)
+def golden(request):
+    import numpy as np
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"corr_{request.param}.npz"))
+    return {k: g[k] for k in g.files}
