@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py -- headline metric of BASELINE.json: RAFT correlation build + 12 lookups, frame-pairs/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic input: CorrBlock build (volume +
+4-level pyramid) followed by `--iters` (12) lookups with fresh coordinates, for B=8 frame pairs of
+436x1024 (padded 440x1024 -> 55x128 feature maps, D=256, r=4: BASELINE.json configs[1] shape) per GPU.
+Work is sharded by frame pair across ranks with no collective on the data path (weak scaling:
+every rank processes its own B pairs).  Prints ONE JSON line (rank 0).
+
+`value`      : pairs/s with inputs already resident in HBM (CUDA events on the launch stream).
+`e2e`        : the same step through the public API from pinned HOST buffers: H2D of both feature
+               maps and all coordinate sets + D2H of the last lookup's features, inside the timing.
+`roofline`   : the dominant kernel (largest share of the step), algorithmic bytes / measured time
+               against MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle's torch-CPU port of the reference CorrBlock (same ATen ops the reference
+               calls) on this box's host cores, bounded sample (B=1).
+`--impl reference` times that CPU port alone (the reference's Python cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "RAFT corr build+12-iter lookup frame-pairs/s @436x1024"
+UNIT = "frame-pairs/s"
+SHAPE = dict(B=8, D=256, H=55, W=128, L=4, r=4)  # per GPU
+
+
+def algorithmic_bytes(D, H, W, L, r):
+    """SURVEY.md section 8(d) / BASELINE.md section 2, per frame pair."""
+    N = H * W
+    K = 2 * r + 1
+    sizes, h, w = [], H, W
+    for _ in range(L):
+        sizes.append(h * w)
+        h, w = h // 2, w // 2
+    build = 2 * N * D * 4 + 4 * N * sum(sizes)
+    lookup = N * (L * (K + 1) ** 2 * 4 + L * K * K * 4 + 8)
+    flops = 2 * N * N * D
+    return build, lookup, flops
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 0.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_port_run(steps, warmup, iters, shape, seed=1234):
+    """Times the oracle's torch-CPU port of the reference CorrBlock: one step = one frame pair (B=1)."""
+    import torch
+
+    from oracle.torch_cpu_port import CpuCorrBlock
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    D, H, W, L, r = shape["D"], shape["H"], shape["W"], shape["L"], shape["r"]
+    g = torch.Generator().manual_seed(seed)
+    f1 = torch.randn((1, D, H, W), generator=g)
+    f2 = torch.randn((1, D, H, W), generator=g)
+    ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    grid = torch.stack([xs, ys]).float()[None]
+    coords = [grid + 4.0 * torch.randn((1, 2, H, W), generator=g)]
+    for _ in range(iters - 1):
+        coords.append(coords[-1] + 0.5 * torch.randn((1, 2, H, W), generator=g))
+    times = []
+    with torch.no_grad():
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            blk = CpuCorrBlock(f1, f2, L, r)
+            for c in coords:
+                out = blk(c)
+            dt = time.perf_counter() - t0
+            if s >= warmup:
+                times.append(dt)
+    _ = float(out.sum())
+    total = sum(times)
+    return {"pairs_per_s": len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": torch.get_num_threads(),
+            "sample": f"B=1 frame pair x {len(times)} steps (build + {iters} lookups, D={D}, {H}x{W}, r={r}), torch {torch.__version__} CPU ops"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = cpu_port_run(args.steps, max(args.warmup, 1), args.iters, SHAPE)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["pairs_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"RAFT-basic CorrBlock build + {args.iters} lookups, 436x1024 (fmap 55x128, D=256, r=4, L=4), "
+                               "1 frame pair per step on host cores", "iters": args.iters},
+        "cpu_baseline": {"value": r["pairs_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["pairs_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import optical_flow_dnn_b200 as rc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, D, H, W, L, r = (SHAPE[k] for k in "BDHWLr")
+    B = args.batch or B
+    iters = args.iters
+    K = 2 * r + 1
+    mode = args.mode
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    f1 = torch.randn((B, D, H, W), generator=g, device=dev)
+    f2 = torch.randn((B, D, H, W), generator=g, device=dev)
+    ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+    grid = torch.stack([xs, ys]).float()[None].expand(B, 2, H, W)
+    # "realistic" flow: sigma 4 px at 1/8 res smoothed by a 5x5 box filter, fresh coords per iteration
+    flow = 4.0 * torch.randn((B, 2, H, W), generator=g, device=dev)
+    flow = torch.nn.functional.avg_pool2d(flow, 5, stride=1, padding=2, count_include_pad=False) * 5.0
+    coords = [(grid + flow).contiguous()]
+    for _ in range(iters - 1):
+        coords.append((coords[-1] + 0.5 * torch.randn((B, 2, H, W), generator=g, device=dev)).contiguous())
+
+    def step():
+        blk = rc.CorrBlock(f1, f2, num_levels=L, radius=r, build_mode=mode)
+        out = None
+        for c in coords:
+            out = blk(c)
+        return blk, out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            blk, out = step()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            blk, out = step()
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        # per-kernel shares, measured live with events on the launch stream (same inputs)
+        del blk, out
+        kb0, kb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kl0, kl1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        build_ms, look_ms = [], []
+        for _ in range(max(3, min(args.steps, 10))):
+            kb0.record()
+            blk = rc.CorrBlock(f1, f2, num_levels=L, radius=r, build_mode=mode)
+            kb1.record()
+            kl0.record()
+            for c in coords:
+                out = blk(c)
+            kl1.record()
+            torch.cuda.synchronize(dev)
+            build_ms.append(kb0.elapsed_time(kb1))
+            look_ms.append(kl0.elapsed_time(kl1) / iters)
+            del blk
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---- e2e: public API from pinned host buffers, copies inside the timed region
+        hf1, hf2 = f1.cpu().pin_memory(), f2.cpu().pin_memory()
+        hco = torch.stack([c.cpu() for c in coords]).pin_memory()
+        hout = torch.empty((B, L * K * K, H, W), dtype=torch.float32).pin_memory()
+        h2d = (hf1.numel() + hf2.numel() + hco.numel()) * 4
+        d2h = hout.numel() * 4
+
+        def e2e_step():
+            d1 = hf1.to(dev, non_blocking=True)
+            d2 = hf2.to(dev, non_blocking=True)
+            dc = hco.to(dev, non_blocking=True)
+            b_ = rc.CorrBlock(d1, d2, num_levels=L, radius=r, build_mode=mode)
+            o = None
+            for i in range(iters):
+                o = b_(dc[i])
+            hout.copy_(o, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        x1.record()
+        barrier()
+        e2e_ms = x0.elapsed_time(x1)
+
+    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        hbm, bf16, peak_src = peaks()
+        bb, lb, flops = algorithmic_bytes(D, H, W, L, r)
+        b_ms = sorted(build_ms)[len(build_ms) // 2]
+        l_ms = sorted(look_ms)[len(look_ms) // 2]
+        build_share = b_ms / (b_ms + iters * l_ms)
+        kern = {
+            "build": {"ms_per_launch_group": b_ms, "achieved_gbs": B * bb / (b_ms * 1e-3) / 1e9,
+                      "achieved_tflops": B * flops / (b_ms * 1e-3) / 1e12, "share_of_step": build_share},
+            "lookup": {"ms_per_launch": l_ms, "achieved_gbs": B * lb / (l_ms * 1e-3) / 1e9,
+                       "share_of_step": 1.0 - build_share},
+        }
+        if build_share >= 0.5:
+            dom, ach, alg = "corr_build (" + mode + ")", kern["build"]["achieved_gbs"], B * bb
+        else:
+            dom, ach, alg = "lookup_fwd_kernel<4,4>", kern["lookup"]["achieved_gbs"], B * lb
+        launches_per_step = (3 if mode == "tf32" else 1 + (L - 1)) + iters
+        cpu = cpu_port_run(3, 1, iters, SHAPE) if world == 1 and not args.no_cpu_baseline else None
+        line = {
+            "metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if mode == "tf32" else "f32",
+            "data": "synthetic",
+            "config": {"workload": f"RAFT-basic CorrBlock build + {iters} lookups @436x1024 (fmap {H}x{W}, D={D}, r={r}, L={L}), "
+                                   f"B={B} frame pairs per GPU (BASELINE.json configs[1] shape)",
+                       "pairs_per_gpu": B, "iters": iters, "build_mode": mode, "parallelism": f"pair-sharded x{world}, no collective",
+                       "l2": f"pyramid {B * 4 * H * W * (H * W) * 1.33 / 1e9:.2f} GB per GPU >> 126 MB L2 (inputs larger than L2)"},
+            "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "result": "last lookup's [B,324,H,W] features copied to pinned host memory"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                         "traffic": None, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+            "kernels": kern,
+        }
+        if cpu:
+            line["cpu_baseline"] = {"value": cpu["pairs_per_s"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
+                                    "sample": cpu["sample"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--iters", type=int, default=12, help="lookups per build (metric: 12)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("RAFTCORR_BUILD_MODE", "tf32"), choices=["tf32", "fp32"])
+    ap.add_argument("--batch", type=int, default=0, help="frame pairs per GPU (default 8)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,141 @@
+/*
+ * raftcorr.h -- C ABI of the B200-native RAFT correlation hot path (libraftcorr_b200.so).
+ *
+ * Drop-in boundary for andrei-iosif/optical-flow-dnn's correlation subsystem.  Every entry point
+ * names the reference interface it replaces (paths relative to the reference root):
+ *
+ *   raft/core/corr.py:18-43      CorrBlock.__init__  (volume + pyramid)      -> raftcorr_build_fwd
+ *   raft/core/corr.py:45-91      CorrBlock.__call__  (lookup)                -> raftcorr_lookup_fwd
+ *   autograd of corr.py:81       grid_sampler_2d_backward x L x iters        -> raftcorr_lookup_bwd
+ *   autograd of corr.py:31-43    avg_pool2d_backward, mul, 2 x matmul bwd    -> raftcorr_build_bwd
+ *   raft/alt_cuda_corr/correlation.cpp:23-33  alt_cuda_corr.forward          -> raftcorr_alt_forward
+ *   raft/alt_cuda_corr/correlation.cpp:36-49  alt_cuda_corr.backward         -> raftcorr_alt_backward
+ *   raft/core/corr.py:124-140    AlternateCorrBlock.__init__ (feature pyramid)-> raftcorr_alt_pyramid
+ *   raft/core/corr.py:142-167    AlternateCorrBlock.__call__ (all levels)    -> raftcorr_alt_lookup_fwd / _bwd
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless stated otherwise;
+ *   - every compute call takes the CUDA device ordinal and the stream to launch on and is
+ *     asynchronous with respect to the host; no call allocates or frees device memory
+ *     (work space is queried with *_workspace_bytes and supplied by the caller);
+ *   - return value 0 = success, anything else = error; raftcorr_last_error() returns a
+ *     thread-local, human-readable description of the last failure on the calling thread;
+ *   - the library keeps no mutable global state and is re-entrant: it may be called from one
+ *     host thread per device concurrently (nn.DataParallel's threading model, raft/train.py:71);
+ *   - all tensors are fp32.  Feature maps are NCHW [B,D,H,W] as produced by the reference's
+ *     encoders (raft/core/raft.py:110-115) unless the name says nhwc;
+ *   - coords are [B,2,H,W], channel 0 = x, channel 1 = y, in level-0 pixels (corr.py:57).
+ */
+#ifndef RAFTCORR_H_
+#define RAFTCORR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAFTCORR_ABI_VERSION 1
+#define RAFTCORR_MAX_LEVELS 8
+
+/* Opaque here: the caller passes its cudaStream_t (or 0 for the legacy default stream). */
+typedef void* raftcorr_stream_t;
+
+/* Where each pyramid level lives inside ONE flat device buffer.
+ * Level l is a dense array [B][N][h[l]][pitch[l]] of fp32, N = H*W source pixels, starting
+ * offset[l] floats from the buffer base.  (h[l], w[l]) = cascaded floor halving of (H, W)
+ * (F.avg_pool2d(2, stride=2), corr.py:42); pitch[l] >= w[l] is the row pitch in floats
+ * (multiple of 8 so every row starts on a 32-byte sector and satisfies TMA's 16-byte stride
+ * rule).  The reference's corr_pyramid[l] ([B*N,1,h,w], corr.py:35-43) is the strided view
+ * base+offset[l] with strides (h*pitch, -, pitch, 1). */
+typedef struct raftcorr_pyramid_layout {
+    int32_t B, H, W, L;
+    int32_t h[RAFTCORR_MAX_LEVELS];
+    int32_t w[RAFTCORR_MAX_LEVELS];
+    int32_t pitch[RAFTCORR_MAX_LEVELS];
+    int64_t offset[RAFTCORR_MAX_LEVELS];
+    int64_t total_floats;
+} raftcorr_pyramid_layout;
+
+/* Build precision modes for raftcorr_build_fwd. */
+enum {
+    RAFTCORR_BUILD_FP32_SIMT = 0, /* exact fp32 FFMA accumulation (CUDA cores) */
+    RAFTCORR_BUILD_TF32_TC = 1    /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM, TMA fed,
+                                     pooling fused into the epilogue */
+};
+
+int raftcorr_abi_version(void);
+const char* raftcorr_last_error(void);
+
+/* Host-only helper: fill *layout for a [B,D,H,W] pair of feature maps and L levels.
+ * Fails if L < 1, L > RAFTCORR_MAX_LEVELS or a level would collapse below 2x2 (the reference
+ * divides by (W_l - 1), utils.py:74-75, and yields NaN there). */
+int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* layout, int B, int H, int W, int L);
+
+/* CorrBlock.__init__ (corr.py:18-43): pyramid <- all-pairs <f1,f2>/sqrt(D) + L-1 poolings. */
+size_t raftcorr_build_fwd_workspace_bytes(int B, int D, int H, int W, int mode);
+int raftcorr_build_fwd(const float* fmap1, const float* fmap2, int D, float* pyramid,
+                       const raftcorr_pyramid_layout* layout, int mode, void* workspace,
+                       size_t workspace_bytes, int device, raftcorr_stream_t stream);
+
+/* CorrBlock.__call__ (corr.py:45-91): out[B, L*(2r+1)^2, H, W]. */
+int raftcorr_lookup_fwd(const float* pyramid, const raftcorr_pyramid_layout* layout, const float* coords,
+                        int radius, float* out, int device, raftcorr_stream_t stream);
+
+/* Adjoint of the lookup: dpyramid (same layout, ACCUMULATED into -- zero it once, then call once
+ * per refinement iteration) += scatter of grad_out[B, L*(2r+1)^2, H, W].
+ * dcoords [B,2,H,W] is optional (NULL to skip); when given, pyramid must be the forward pyramid. */
+int raftcorr_lookup_bwd(const float* grad_out, const float* coords, const float* pyramid, float* dpyramid,
+                        const raftcorr_pyramid_layout* layout, int radius, float* dcoords, int device,
+                        raftcorr_stream_t stream);
+
+/* Adjoint of the build.  dpyramid is CONSUMED (pooled-level gradients are folded into level 0
+ * in place); dfmap1/dfmap2 [B,D,H,W] are overwritten. */
+int raftcorr_build_bwd(float* dpyramid, const raftcorr_pyramid_layout* layout, const float* fmap1,
+                       const float* fmap2, int D, float* dfmap1, float* dfmap2, int device,
+                       raftcorr_stream_t stream);
+
+/* alt_cuda_corr.forward (correlation.cpp:23-33, correlation_kernel.cu:260-286), same tensors:
+ * fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C] (NHWC), coords [B,N,H1,W1,2] (x,y interleaved),
+ * corr [B,N,(2r+1)^2,H1,W1] is OVERWRITTEN (the reference allocates zeros and accumulates). */
+int raftcorr_alt_forward(const float* fmap1_nhwc, const float* fmap2_nhwc, const float* coords, int B, int N,
+                         int H1, int W1, int H2, int W2, int C, int radius, float* corr, int device,
+                         raftcorr_stream_t stream);
+
+/* alt_cuda_corr.backward (correlation.cpp:36-49, correlation_kernel.cu:288-324).
+ * fmap1_grad [B,H1,W1,C], fmap2_grad [B,H2,W2,C] and coords_grad [B,N,H1,W1,2] must be
+ * zero-initialised by the caller (the reference's launcher does torch::zeros, :305-307) and are
+ * accumulated into; coords_grad stays zero as in the reference (:307) and may be NULL. */
+int raftcorr_alt_backward(const float* fmap1_nhwc, const float* fmap2_nhwc, const float* coords,
+                          const float* corr_grad, int B, int N, int H1, int W1, int H2, int W2, int C,
+                          int radius, float* fmap1_grad, float* fmap2_grad, float* coords_grad, int device,
+                          raftcorr_stream_t stream);
+
+/* AlternateCorrBlock.__init__ (corr.py:124-140), done once instead of per call (corr.py:158-159):
+ * f1_nhwc [B,H,W,D] <- transpose(fmap1); f2_pyramid_nhwc <- levels l<L of avg-pooled fmap2, NHWC,
+ * level l at float offset raftcorr_alt_level_offset(B,D,H,W,l), dense [B][H_l][W_l][D]. */
+int64_t raftcorr_alt_level_offset(int B, int D, int H, int W, int level);
+int raftcorr_alt_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int L,
+                         float* f1_nhwc, float* f2_pyramid_nhwc, int device, raftcorr_stream_t stream);
+
+/* AlternateCorrBlock.__call__ (corr.py:142-167) fused over all L levels, incl. the 1/sqrt(D). */
+int raftcorr_alt_lookup_fwd(const float* f1_nhwc, const float* f2_pyramid_nhwc, const float* coords, int B,
+                            int D, int H, int W, int L, int radius, float* out, int device,
+                            raftcorr_stream_t stream);
+
+/* Gradient of raftcorr_alt_lookup_fwd w.r.t. the NHWC feature tensors (accumulated into
+ * df1_nhwc [B,H,W,D] and df2_pyramid_nhwc, same layout as the forward pyramid; zero them first). */
+int raftcorr_alt_lookup_bwd(const float* f1_nhwc, const float* f2_pyramid_nhwc, const float* coords,
+                            const float* grad_out, int B, int D, int H, int W, int L, int radius,
+                            float* df1_nhwc, float* df2_pyramid_nhwc, int device, raftcorr_stream_t stream);
+
+/* Fold the pooled-level gradients of df2_pyramid_nhwc down to level 0 (adjoint of corr.py:138-139,
+ * in place) and transpose both gradients back to NCHW [B,D,H,W] (overwritten). */
+int raftcorr_alt_grad_finish(const float* df1_nhwc, float* df2_pyramid_nhwc, int B, int D, int H, int W, int L,
+                             float* dfmap1, float* dfmap2, int device, raftcorr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAFTCORR_H_ */

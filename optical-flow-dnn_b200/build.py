@@ -1,0 +1,85 @@
+"""Builds libraftcorr_b200.so (hand-written sm_100a CUDA + the C ABI in include/raftcorr.h) in-tree.
+
+nvcc cross-compiles without a GPU, so this runs in the CPU-only build container; the resulting
+.so travels to the B200 box with the repo snapshot.  No JIT, no torch extension machinery:
+the library has no torch (or Python) dependency at all.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+OBJ = os.path.join(PKG, "build")
+LIB = os.path.join(PKG, "libraftcorr_b200.so")
+SOURCES = ["api.cu", "prep.cu", "lookup.cu", "build_simt.cu", "build_tc.cu", "build_bwd.cu", "altcorr.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+    "-Xcompiler", "-fPIC", "--use_fast_math=false", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
+]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: cannot build libraftcorr_b200.so")
+    return exe
+
+
+def _digest(paths):
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu for sm_100a and link the shared library.  Returns its path."""
+    os.makedirs(OBJ, exist_ok=True)
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(ROOT, "include", "raftcorr.h"))
+    hdr_digest = _digest(headers)
+    nvcc = _nvcc()
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+
+    def compile_one(src):
+        obj = os.path.join(OBJ, os.path.basename(src) + ".o")
+        stamp = obj + ".sha"
+        want = _digest([src]) + hdr_digest
+        if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == want:
+            return obj, False
+        cmd = [nvcc, *flags, "-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            sys.stderr.write(r.stderr)
+        with open(stamp, "w") as f:
+            f.write(want)
+        return obj, True
+
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(compile_one, srcs))
+    objs = [o for o, _ in results]
+    if force or any(c for _, c in results) or not os.path.exists(LIB):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB, *objs, "-lcudart_static",
+               "-ldl", "-lrt", "-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

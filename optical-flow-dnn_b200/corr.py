@@ -1,0 +1,346 @@
+"""Host-side mirror of the reference's ``raft/core/corr.py``: same classes, constructor and call
+signatures, attributes and autograd behaviour -- all arithmetic in libraftcorr_b200 (sm_100a).
+
+    CorrBlock(fmap1, fmap2, num_levels=4, radius=4)        raft/core/corr.py:18
+    CorrBlock.__call__(coords) -> [B, L*(2r+1)^2, H, W]    raft/core/corr.py:45
+    CorrBlock.corr(fmap1, fmap2) -> [B, H, W, 1, H, W]     raft/core/corr.py:93
+    AlternateCorrBlock(...) / __call__                      raft/core/corr.py:124,142
+
+PyTorch is used for device memory (caching allocator), streams and autograd bookkeeping only.
+CPU tensors are rejected: there is no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+
+import torch
+
+from . import _lib
+from ._lib import RaftCorrError, check
+
+_MODES = {"fp32": _lib.BUILD_FP32_SIMT, "tf32": _lib.BUILD_TF32_TC}
+_default_mode = os.environ.get("RAFTCORR_BUILD_MODE", "tf32")
+
+
+def set_default_build_mode(mode: str) -> None:
+    """``"tf32"``: tcgen05 tensor-core build (TF32 operands, fp32 accumulate; <=1e-3 of max|V|).
+    ``"fp32"``: exact fp32 FFMA build on CUDA cores."""
+    global _default_mode
+    if mode not in _MODES:
+        raise ValueError(f"unknown build mode {mode!r} (expected one of {sorted(_MODES)})")
+    _default_mode = mode
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_fmaps(fmap1, fmap2, who):
+    for name, t in (("fmap1", fmap1), ("fmap2", fmap2)):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{who}: {name} must be a torch.Tensor")
+        if not t.is_cuda:
+            # same contract as the reference extension's CHECK_CUDA (raft/alt_cuda_corr/correlation.cpp:19)
+            raise RuntimeError(f"{who}: {name} must be a CUDA tensor (this package has no CPU path)")
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"{who}: {name} must be float32 (RAFT casts with .float(), raft/core/raft.py:114-115)")
+        if t.dim() != 4:
+            raise RuntimeError(f"{who}: {name} must be [B, C, H, W]")
+    if fmap1.shape != fmap2.shape or fmap1.device != fmap2.device:
+        raise RuntimeError(f"{who}: fmap1 and fmap2 must have the same shape and device")
+
+
+def _check_coords(coords, B, H, W, device, who):
+    if not (isinstance(coords, torch.Tensor) and coords.is_cuda and coords.dtype == torch.float32):
+        raise RuntimeError(f"{who}: coords must be a float32 CUDA tensor")
+    if tuple(coords.shape) != (B, 2, H, W):
+        raise RuntimeError(f"{who}: coords must be [B, 2, H, W] = {(B, 2, H, W)}, got {tuple(coords.shape)}")
+    if coords.device != device:
+        raise RuntimeError(f"{who}: coords is on {coords.device}, the correlation block on {device}")
+
+
+# ----------------------------------------------------------------------------------------------
+# all-pairs volume
+# ----------------------------------------------------------------------------------------------
+class _BuildFn(torch.autograd.Function):
+    """fmaps -> flat pyramid buffer (raft/core/corr.py:31-43)."""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, block):
+        ctx.block = block
+        ctx.save_for_backward(fmap1, fmap2)
+        return block._build(fmap1, fmap2)
+
+    @staticmethod
+    def backward(ctx, dpyr):
+        fmap1, fmap2 = ctx.saved_tensors
+        block = ctx.block
+        acc = block._grad_acc
+        block._grad_acc = None  # a second backward pass (retain_graph) starts a fresh accumulator
+        if dpyr is None:
+            return None, None, None
+        if acc is None or dpyr.data_ptr() != acc.data_ptr():
+            dpyr = dpyr.contiguous().clone()  # build_bwd folds levels in place: never clobber foreign grads
+        lay = block._layout
+        df1 = torch.empty_like(fmap1)
+        df2 = torch.empty_like(fmap2)
+        dev = fmap1.device
+        check(_lib.lib().raftcorr_build_bwd(_ptr(dpyr), ctypes.byref(lay), _ptr(fmap1), _ptr(fmap2), block._D,
+                                            _ptr(df1), _ptr(df2), dev.index, _stream(dev)), "raftcorr_build_bwd")
+        return df1, df2, None
+
+
+class _LookupFn(torch.autograd.Function):
+    """(pyramid, coords) -> motion features (raft/core/corr.py:45-91)."""
+
+    @staticmethod
+    def forward(ctx, pyr, coords, block):
+        ctx.block = block
+        ctx.need_dcoords = coords.requires_grad
+        ctx.save_for_backward(coords, pyr if coords.requires_grad else None)
+        return block._lookup(pyr, coords)
+
+    @staticmethod
+    def backward(ctx, gout):
+        coords, pyr = ctx.saved_tensors
+        block = ctx.block
+        lay = block._layout
+        dev = coords.device
+        dpyr_ret = None
+        if ctx.needs_input_grad[0]:
+            # One persistent gradient pyramid for ALL refinement iterations: every lookup backward
+            # scatter-adds into it; it is handed to autograd exactly once (by the first lookup whose
+            # backward runs) and the build backward -- which depends on every lookup -- only runs after
+            # the last one has added its share.  The reference instead materialises iters x L dense,
+            # zero-filled level-sized tensors (grid_sampler_2d_backward) and sums them.
+            first = block._grad_acc is None
+            if first:
+                block._grad_acc = torch.zeros(lay.total_floats, dtype=torch.float32, device=dev)
+                dpyr_ret = block._grad_acc
+            acc = block._grad_acc
+        else:
+            acc = None
+        dcoords = torch.empty_like(coords) if ctx.need_dcoords and ctx.needs_input_grad[1] else None
+        if acc is None and dcoords is None:
+            return None, None, None
+        if acc is None:  # coords gradient only: scatter into a scratch pyramid
+            acc = torch.zeros(lay.total_floats, dtype=torch.float32, device=dev)
+        check(_lib.lib().raftcorr_lookup_bwd(_ptr(gout.contiguous()), _ptr(coords), _ptr(pyr), _ptr(acc),
+                                             ctypes.byref(lay), block.radius, _ptr(dcoords), dev.index, _stream(dev)),
+              "raftcorr_lookup_bwd")
+        return dpyr_ret, dcoords, None
+
+
+class CorrBlock:
+    """All-pairs correlation volume + pyramid + lookup; drop-in for raft/core/corr.py:13-116.
+
+    ``build_mode`` (extension; RAFT never passes it): ``"tf32"`` | ``"fp32"``, default from
+    :func:`set_default_build_mode` / ``RAFTCORR_BUILD_MODE``.
+    """
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, build_mode=None):
+        _check_fmaps(fmap1, fmap2, "CorrBlock")
+        self.num_levels = int(num_levels)
+        self.radius = int(radius)
+        if not 1 <= self.radius <= 4:
+            raise RaftCorrError(f"CorrBlock: radius must be in [1, 4] (got {radius})")
+        mode = build_mode or _default_mode
+        if mode not in _MODES:
+            raise ValueError(f"unknown build mode {mode!r}")
+        self._mode = _MODES[mode]
+        B, D, H, W = fmap1.shape
+        self._B, self._D, self._H, self._W = B, D, H, W
+        self._device = fmap1.device
+        self._layout = _lib.make_layout(B, H, W, self.num_levels)
+        self._grad_acc = None
+        fmap1 = fmap1.contiguous()
+        fmap2 = fmap2.contiguous()
+        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+            self._pyr = _BuildFn.apply(fmap1, fmap2, self)
+        else:
+            self._pyr = self._build(fmap1, fmap2)
+
+    # -- kernels ------------------------------------------------------------------------------
+    def _build(self, fmap1, fmap2):
+        lay, dev = self._layout, self._device
+        L = _lib.lib()
+        pyr = torch.empty(lay.total_floats, dtype=torch.float32, device=dev)
+        ws_bytes = L.raftcorr_build_fwd_workspace_bytes(self._B, self._D, self._H, self._W, self._mode)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+        check(L.raftcorr_build_fwd(_ptr(fmap1), _ptr(fmap2), self._D, _ptr(pyr), ctypes.byref(lay), self._mode,
+                                   _ptr(ws), ws_bytes, dev.index, _stream(dev)), "raftcorr_build_fwd")
+        return pyr
+
+    def _lookup(self, pyr, coords):
+        lay, dev = self._layout, self._device
+        K = 2 * self.radius + 1
+        out = torch.empty((self._B, self.num_levels * K * K, self._H, self._W), dtype=torch.float32, device=dev)
+        check(_lib.lib().raftcorr_lookup_fwd(_ptr(pyr), ctypes.byref(lay), _ptr(coords), self.radius, _ptr(out),
+                                             dev.index, _stream(dev)), "raftcorr_lookup_fwd")
+        return out
+
+    # -- reference surface ----------------------------------------------------------------------
+    def __call__(self, coords):
+        _check_coords(coords, self._B, self._H, self._W, self._device, "CorrBlock.__call__")
+        coords = coords.contiguous()
+        if torch.is_grad_enabled() and (self._pyr.requires_grad or coords.requires_grad):
+            return _LookupFn.apply(self._pyr, coords, self)
+        return self._lookup(self._pyr, coords)
+
+    @property
+    def corr_pyramid(self):
+        """The reference's list of ``[B*H*W, 1, H_l, W_l]`` tensors (corr.py:35-43), as strided views
+        into the single pyramid buffer (rows are padded to a multiple of 8 floats)."""
+        lay = self._layout
+        N = self._H * self._W
+        out = []
+        for l in range(self.num_levels):
+            h, w, p = lay.h[l], lay.w[l], lay.pitch[l]
+            flat = self._pyr[lay.offset[l]: lay.offset[l] + self._B * N * h * p]
+            out.append(flat.view(self._B * N, 1, h, p)[..., :w])
+        return out
+
+    @staticmethod
+    def corr(fmap1, fmap2, build_mode=None):
+        """Level-0 volume ``[B, H, W, 1, H, W]`` = <f1, f2> / sqrt(D)  (raft/core/corr.py:93-116)."""
+        blk = CorrBlock(fmap1, fmap2, num_levels=1, radius=1, build_mode=build_mode)
+        B, H, W = blk._B, blk._H, blk._W
+        return blk.corr_pyramid[0].reshape(B, H, W, 1, H, W)
+
+
+# ----------------------------------------------------------------------------------------------
+# on-the-fly variant
+# ----------------------------------------------------------------------------------------------
+def _alt_sizes(B, D, H, W, L):
+    total = _lib.lib().raftcorr_alt_level_offset(B, D, H, W, L)
+    return int(total)
+
+
+class _AltPrepFn(torch.autograd.Function):
+    """NCHW fmaps -> (fmap1 NHWC, pooled fmap2 pyramid NHWC)   (raft/core/corr.py:136-140,158-159)."""
+
+    @staticmethod
+    def forward(ctx, fmap1, fmap2, block):
+        ctx.block = block
+        return block._prep(fmap1, fmap2)
+
+    @staticmethod
+    def backward(ctx, df1n, df2p):
+        block = ctx.block
+        B, D, H, W, L = block._B, block._D, block._H, block._W, block.num_levels
+        dev = block._device
+        acc1, acc2 = block._grad_acc
+        block._grad_acc = (None, None)
+        if df1n is None:
+            df1n = torch.zeros((B, H, W, D), dtype=torch.float32, device=dev)
+        if df2p is None:
+            df2p = torch.zeros(_alt_sizes(B, D, H, W, L), dtype=torch.float32, device=dev)
+        elif acc2 is None or df2p.data_ptr() != acc2.data_ptr():
+            df2p = df2p.contiguous().clone()  # grad_finish folds in place
+        df1 = torch.empty((B, D, H, W), dtype=torch.float32, device=dev)
+        df2 = torch.empty((B, D, H, W), dtype=torch.float32, device=dev)
+        check(_lib.lib().raftcorr_alt_grad_finish(_ptr(df1n.contiguous()), _ptr(df2p), B, D, H, W, L, _ptr(df1),
+                                                  _ptr(df2), dev.index, _stream(dev)), "raftcorr_alt_grad_finish")
+        return df1, df2, None
+
+
+class _AltLookupFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f1n, f2p, coords, block):
+        ctx.block = block
+        ctx.save_for_backward(f1n, f2p, coords)
+        return block._lookup(f1n, f2p, coords)
+
+    @staticmethod
+    def backward(ctx, gout):
+        f1n, f2p, coords = ctx.saved_tensors
+        block = ctx.block
+        B, D, H, W, L = block._B, block._D, block._H, block._W, block.num_levels
+        dev = block._device
+        acc1, acc2 = block._grad_acc
+        first = acc1 is None
+        if first:  # same single-accumulator scheme as _LookupFn.backward
+            acc1 = torch.zeros((B, H, W, D), dtype=torch.float32, device=dev)
+            acc2 = torch.zeros(_alt_sizes(B, D, H, W, L), dtype=torch.float32, device=dev)
+            block._grad_acc = (acc1, acc2)
+        check(_lib.lib().raftcorr_alt_lookup_bwd(_ptr(f1n), _ptr(f2p), _ptr(coords), _ptr(gout.contiguous()), B, D, H,
+                                                 W, L, block.radius, _ptr(acc1), _ptr(acc2), dev.index, _stream(dev)),
+              "raftcorr_alt_lookup_bwd")
+        # coords: no gradient, exactly like the reference kernel (correlation_kernel.cu:307 returns zeros
+        # and raft.py:143 detaches coords anyway)
+        return (acc1, acc2, None, None) if first else (None, None, None, None)
+
+
+class AlternateCorrBlock:
+    """Memory-efficient on-the-fly correlation; drop-in for raft/core/corr.py:119-167.
+
+    Unlike the reference (whose ``alt_cuda_corr.backward`` is never called from Python) this class is
+    differentiable w.r.t. both feature maps.
+    """
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+        _check_fmaps(fmap1, fmap2, "AlternateCorrBlock")
+        self.num_levels = int(num_levels)
+        self.radius = int(radius)
+        if not 1 <= self.radius <= 4:
+            raise RaftCorrError(f"AlternateCorrBlock: radius must be in [1, 4] (got {radius})")
+        if not 1 <= self.num_levels <= 4:
+            raise RaftCorrError(f"AlternateCorrBlock: num_levels must be in [1, 4] (got {num_levels})")
+        B, D, H, W = fmap1.shape
+        if (H >> (self.num_levels - 1)) < 1 or (W >> (self.num_levels - 1)) < 1:
+            raise RaftCorrError("AlternateCorrBlock: feature maps too small for the number of levels")
+        self._B, self._D, self._H, self._W = B, D, H, W
+        self._device = fmap1.device
+        self._fmaps = (fmap1, fmap2)
+        self._grad_acc = (None, None)
+        fmap1 = fmap1.contiguous()
+        fmap2 = fmap2.contiguous()
+        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+            self._f1n, self._f2p = _AltPrepFn.apply(fmap1, fmap2, self)
+        else:
+            self._f1n, self._f2p = self._prep(fmap1, fmap2)
+
+    def _prep(self, fmap1, fmap2):
+        B, D, H, W, L = self._B, self._D, self._H, self._W, self.num_levels
+        dev = self._device
+        f1n = torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
+        f2p = torch.empty(_alt_sizes(B, D, H, W, L), dtype=torch.float32, device=dev)
+        check(_lib.lib().raftcorr_alt_pyramid(_ptr(fmap1), _ptr(fmap2), B, D, H, W, L, _ptr(f1n), _ptr(f2p),
+                                              dev.index, _stream(dev)), "raftcorr_alt_pyramid")
+        return f1n, f2p
+
+    def _lookup(self, f1n, f2p, coords):
+        B, D, H, W, L = self._B, self._D, self._H, self._W, self.num_levels
+        dev = self._device
+        K = 2 * self.radius + 1
+        out = torch.empty((B, L * K * K, H, W), dtype=torch.float32, device=dev)
+        check(_lib.lib().raftcorr_alt_lookup_fwd(_ptr(f1n), _ptr(f2p), _ptr(coords), B, D, H, W, L, self.radius,
+                                                 _ptr(out), dev.index, _stream(dev)), "raftcorr_alt_lookup_fwd")
+        return out
+
+    def __call__(self, coords):
+        _check_coords(coords, self._B, self._H, self._W, self._device, "AlternateCorrBlock.__call__")
+        coords = coords.contiguous()
+        if torch.is_grad_enabled() and (self._f1n.requires_grad or self._f2p.requires_grad):
+            return _AltLookupFn.apply(self._f1n, self._f2p, coords, self)
+        return self._lookup(self._f1n, self._f2p, coords)
+
+    @property
+    def pyramid(self):
+        """The reference's ``[(fmap1_l, fmap2_l)]`` list, ``num_levels + 1`` entries, NCHW
+        (corr.py:136-140).  Nothing in RAFT reads it; materialised on demand from the inputs."""
+        import torch.nn.functional as F
+
+        f1, f2 = self._fmaps
+        out = [(f1, f2)]
+        for _ in range(self.num_levels):
+            f1 = F.avg_pool2d(f1, 2, stride=2)
+            f2 = F.avg_pool2d(f2, 2, stride=2)
+            out.append((f1, f2))
+        return out

@@ -1,0 +1,322 @@
+// On-the-fly correlation (AlternateCorrBlock, raft/core/corr.py:119-167, and the native
+// alt_cuda_corr extension, raft/alt_cuda_corr/correlation_kernel.cu:18-256) for sm_100a.
+//
+// No volume is materialised: for every source pixel and level the (K+1)x(K+1) lattice of dot
+// products <f1[p], f2_l[floor(y)-r+iy, floor(x)-r+ix]> is computed and bilinearly splatted into
+// K*K outputs (channel iy + K*ix, correlation_kernel.cu:92-95 == CorrBlock's i*K+j order).
+//
+// Differences from the reference kernel (same numbers, different machine mapping):
+//   * all L levels in ONE launch, NHWC feature tensors prepared once (not per call per level);
+//   * a warp owns a source pixel: its f1 vector lives in registers, each lattice point is one
+//     coalesced 128-bit-per-lane read of the f2 vector, 32 partial dots are reduced with a
+//     31-shuffle butterfly transpose instead of 32 x 5 shuffles;
+//   * outputs are accumulated on chip and written once, channel-major, through a shared tile
+//     (the reference read-modify-writes global memory once per 32-channel chunk, :102-114);
+//   * launched on the caller's stream with the caller's device, zero padding by predication.
+#include "common.cuh"
+
+namespace raftcorr {
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kPix = 32;
+constexpr int kTilePitch = 33;
+constexpr int kMaxVec = 4;  // float4 per lane -> C <= 512
+
+__device__ __forceinline__ float clamp_coord(float v) { return fminf(fmaxf(v, -1048576.f), 1048576.f); }
+
+struct AltParams {
+    const float* f1;  // [B][N1][C]
+    AltLevels lv;
+    CoordsView cv;
+    int B, NC, N1, C;  // NC: coordinate sets per pixel (the reference's N, always 1 from Python)
+    float scale;       // 1/sqrt(C) for the fused path, 1 for the raw alt_cuda_corr surface
+    float inv_scale[RAFTCORR_MAX_LEVELS];
+};
+
+// Sum 32 per-lane partials across the warp; lane i ends up with the total of element i.
+__device__ __forceinline__ float transpose_reduce32(float (&p)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool hi = lane & half;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const float send = hi ? p[i] : p[i + half];
+            const float keep = hi ? p[i + half] : p[i];
+            p[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return p[0];
+}
+
+template <int R, int NV>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+alt_fwd_kernel(const AltParams P, float* __restrict__ out) {
+    const int LG = P.lv.L;
+    constexpr int K = 2 * R + 1, K1 = K + 1, NP = K1 * K1, KK = K * K, NT = (KK + 31) / 32;
+    constexpr int NCH = (NP + 31) / 32;
+    const int CH = LG * KK;
+    extern __shared__ float smem[];
+    float* out_s = smem;                       // [CH][kTilePitch]
+    float* patch_s = smem + CH * kTilePitch;   // [kWarps][LG][NCH*32]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bn = blockIdx.y, b = bn / P.NC, p0 = blockIdx.x * kPix;
+    const int nvec = P.C >> 2;
+    float* patch = patch_s + warp * (LG * NCH * 32);
+
+    int ooff[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const int c = lane + 32 * t;
+        const int ix = c / K, iy = c - ix * K;  // channel = iy + K*ix
+        ooff[t] = iy * K1 + ix;
+    }
+
+    for (int q = warp; q < kPix; q += kWarps) {
+        const int p = p0 + q;
+        if (p >= P.N1) break;
+        const float cx = __ldg(P.cv.ptr + bn * P.cv.batch_stride + p * P.cv.pix_stride);
+        const float cy = __ldg(P.cv.ptr + bn * P.cv.batch_stride + P.cv.comp_stride + p * P.cv.pix_stride);
+        float4 a[NV];
+        const float4* f1v = reinterpret_cast<const float4*>(P.f1 + ((int64_t)b * P.N1 + p) * P.C);
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+            a[j] = (lane + 32 * j < nvec) ? __ldg(f1v + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+#pragma unroll 1
+        for (int l = 0; l < LG; ++l) {
+            const int Hl = P.lv.h[l], Wl = P.lv.w[l];
+            const float x = cx * P.inv_scale[l], y = cy * P.inv_scale[l];
+            const float xf = floorf(x), yf = floorf(y);
+            const int x0 = (int)clamp_coord(xf) - R, y0 = (int)clamp_coord(yf) - R;
+            const float4* f2b = reinterpret_cast<const float4*>(P.lv.f2[l] + (int64_t)b * Hl * Wl * P.C);
+#pragma unroll 1
+            for (int ch = 0; ch < NCH; ++ch) {
+                float part[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int e = ch * 32 + i;
+                    const int row = e / K1, col = e - row * K1;
+                    const int yy = y0 + row, xx = x0 + col;
+                    const bool ok = e < NP && yy >= 0 && yy < Hl && xx >= 0 && xx < Wl;
+                    const float4* src = f2b + ((int64_t)yy * Wl + xx) * nvec;
+                    float s = 0.f;
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        if (ok && lane + 32 * j < nvec) {
+                            const float4 v = __ldg(src + lane + 32 * j);
+                            s = fmaf(a[j].x, v.x, s);
+                            s = fmaf(a[j].y, v.y, s);
+                            s = fmaf(a[j].z, v.z, s);
+                            s = fmaf(a[j].w, v.w, s);
+                        }
+                    }
+                    part[i] = s;
+                }
+                patch[l * NCH * 32 + ch * 32 + lane] = transpose_reduce32(part, lane);
+            }
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int l = 0; l < LG; ++l) {
+            const float* S = patch + l * NCH * 32;
+            const float xs = cx * P.inv_scale[l], ys = cy * P.inv_scale[l];
+            const float dx = xs - floorf(xs), dy = ys - floorf(ys);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int c = lane + 32 * t;
+                if (c < KK) {
+                    const int o = ooff[t];
+                    // se*(1-dy)(1-dx) + sw*(1-dy)dx + ne*dy(1-dx) + nw*dy*dx  (correlation_kernel.cu:97-100)
+                    const float top = S[o] + dx * (S[o + 1] - S[o]);
+                    const float bot = S[o + K1] + dx * (S[o + K1 + 1] - S[o + K1]);
+                    out_s[(l * KK + c) * kTilePitch + q] = (top + dy * (bot - top)) * P.scale;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    const int p = p0 + lane;
+    if (p < P.N1) {
+        float* dst = out + (int64_t)bn * CH * P.N1 + p;
+        for (int ch = warp; ch < CH; ch += kWarps) dst[(int64_t)ch * P.N1] = out_s[ch * kTilePitch + lane];
+    }
+}
+
+// Backward (correlation_kernel.cu:122-256 restated): g_e = sum of the <=4 output gradients that a
+// lattice point feeds, then df1[p] += g_e * f2[e] (registers, one vector add per pixel) and
+// df2[e] += g_e * f1[p] (vector red.global.add.v4.f32 instead of one scalar atomic per channel).
+template <int R, int NV>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+alt_bwd_kernel(const AltParams P, const float* __restrict__ grad_out, float* __restrict__ df1) {
+    const int LG = P.lv.L;
+    constexpr int K = 2 * R + 1, K1 = K + 1, NP = K1 * K1, KK = K * K;
+    constexpr int NCH = (NP + 31) / 32;
+    const int CH = LG * KK;
+    extern __shared__ float smem[];
+    float* g_s = smem;  // [CH][kTilePitch]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bn = blockIdx.y, b = bn / P.NC, p0 = blockIdx.x * kPix;
+    const int nvec = P.C >> 2;
+    {
+        const int p = p0 + lane;
+        const float* src = grad_out + (int64_t)bn * CH * P.N1 + p;
+        for (int ch = warp; ch < CH; ch += kWarps)
+            g_s[ch * kTilePitch + lane] = (p < P.N1) ? __ldg(src + (int64_t)ch * P.N1) * P.scale : 0.f;
+    }
+    __syncthreads();
+
+    for (int q = warp; q < kPix; q += kWarps) {
+        const int p = p0 + q;
+        if (p >= P.N1) break;
+        const float cx = __ldg(P.cv.ptr + bn * P.cv.batch_stride + p * P.cv.pix_stride);
+        const float cy = __ldg(P.cv.ptr + bn * P.cv.batch_stride + P.cv.comp_stride + p * P.cv.pix_stride);
+        float4 a[NV], da[NV];
+        const float4* f1v = reinterpret_cast<const float4*>(P.f1 + ((int64_t)b * P.N1 + p) * P.C);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            a[j] = (lane + 32 * j < nvec) ? __ldg(f1v + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            da[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll 1
+        for (int l = 0; l < LG; ++l) {
+            const int Hl = P.lv.h[l], Wl = P.lv.w[l];
+            const float x = cx * P.inv_scale[l], y = cy * P.inv_scale[l];
+            const float xf = floorf(x), yf = floorf(y);
+            const float dx = x - xf, dy = y - yf;
+            const int x0 = (int)clamp_coord(xf) - R, y0 = (int)clamp_coord(yf) - R;
+            const float4* f2b = reinterpret_cast<const float4*>(P.lv.f2[l] + (int64_t)b * Hl * Wl * P.C);
+            float4* d2b = reinterpret_cast<float4*>(P.lv.df2[l] + (int64_t)b * Hl * Wl * P.C);
+            const float* gl = g_s + l * KK * kTilePitch + q;
+#pragma unroll 1
+            for (int ch = 0; ch < NCH; ++ch) {
+                // lane e: gradient reaching lattice point e
+                const int e = ch * 32 + lane;
+                const int row = e / K1, col = e - row * K1;  // row = iy, col = ix
+                float ge = 0.f;
+                if (e < NP) {
+                    if (row < K && col < K) ge += (1.f - dy) * (1.f - dx) * gl[(row + K * col) * kTilePitch];          // se
+                    if (row < K && col >= 1) ge += (1.f - dy) * dx * gl[(row + K * (col - 1)) * kTilePitch];          // sw
+                    if (row >= 1 && col < K) ge += dy * (1.f - dx) * gl[(row - 1 + K * col) * kTilePitch];            // ne
+                    if (row >= 1 && col >= 1) ge += dy * dx * gl[(row - 1 + K * (col - 1)) * kTilePitch];             // nw
+                }
+#pragma unroll 4
+                for (int i = 0; i < 32; ++i) {
+                    const int ee = ch * 32 + i;
+                    if (ee >= NP) break;
+                    const float g = __shfl_sync(0xffffffffu, ge, i);
+                    const int r2 = ee / K1, c2 = ee - r2 * K1;
+                    const int yy = y0 + r2, xx = x0 + c2;
+                    if (yy < 0 || yy >= Hl || xx < 0 || xx >= Wl || g == 0.f) continue;  // warp-uniform
+                    const int64_t off = ((int64_t)yy * Wl + xx) * nvec;
+#pragma unroll
+                    for (int j = 0; j < NV; ++j) {
+                        if (lane + 32 * j < nvec) {
+                            const float4 v = __ldg(f2b + off + lane + 32 * j);
+                            da[j].x = fmaf(g, v.x, da[j].x);
+                            da[j].y = fmaf(g, v.y, da[j].y);
+                            da[j].z = fmaf(g, v.z, da[j].z);
+                            da[j].w = fmaf(g, v.w, da[j].w);
+                            atomicAdd(d2b + off + lane + 32 * j,
+                                      make_float4(g * a[j].x, g * a[j].y, g * a[j].z, g * a[j].w));
+                        }
+                    }
+                }
+            }
+        }
+        float4* d1 = reinterpret_cast<float4*>(df1 + ((int64_t)b * P.N1 + p) * P.C);
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+            if (lane + 32 * j < nvec) atomicAdd(d1 + lane + 32 * j, da[j]);
+    }
+}
+
+template <int R, int NV>
+int run_alt_fwd(const AltParams& P, float* out, cudaStream_t s) {
+    constexpr int K = 2 * R + 1, NP = (K + 1) * (K + 1), NCH = (NP + 31) / 32;
+    const int LG = P.lv.L;
+    const size_t smem = sizeof(float) * (LG * K * K * kTilePitch + kWarps * LG * NCH * 32);
+    auto kern = alt_fwd_kernel<R, NV>;
+    RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(P.N1, kPix), P.B * P.NC);
+    kern<<<grid, kWarps * 32, smem, s>>>(P, out);
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int R, int NV>
+int run_alt_bwd(const AltParams& P, const float* go, float* df1, cudaStream_t s) {
+    constexpr int K = 2 * R + 1;
+    const size_t smem = sizeof(float) * (P.lv.L * K * K * kTilePitch);
+    auto kern = alt_bwd_kernel<R, NV>;
+    RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(P.N1, kPix), P.B * P.NC);
+    kern<<<grid, kWarps * 32, smem, s>>>(P, go, df1);
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+AltParams make_params(const float* f1, const AltLevels& lv, const CoordsView& cv, int B, int NC, int N1, int C,
+                      float scale) {
+    AltParams P{};
+    P.f1 = f1;
+    P.cv = cv;
+    P.B = B;
+    P.NC = NC;
+    P.N1 = N1;
+    P.C = C;
+    P.scale = scale;
+    P.lv = lv;
+    for (int l = 0; l < lv.L; ++l) P.inv_scale[l] = 1.0f / (float)(1 << l);
+    return P;
+}
+
+int check_alt(const AltLevels& lv, int C, int radius) {
+    if (lv.L < 1 || lv.L > 4) return fail("alt: 1..4 levels per call supported (got %d)", lv.L);
+    if (C % 4 != 0 || C > 128 * kMaxVec || C < 4) return fail("alt: C must be a multiple of 4 in [4, 512] (got %d)", C);
+    if (radius < 1 || radius > 4) return fail("alt: radius %d not supported (1..4)", radius);
+    return 0;
+}
+
+}  // namespace
+
+// out: [B*NC][L*K*K][N1]
+int launch_alt_fwd(const float* f1_nhwc, const AltLevels& lv, const CoordsView& cv, int B, int NC, int H1, int W1,
+                   int C, int radius, float scale, float* out, cudaStream_t s) {
+    if (int rc = check_alt(lv, C, radius)) return rc;
+    AltParams P = make_params(f1_nhwc, lv, cv, B, NC, H1 * W1, C, scale);
+    const int nv = C <= 128 ? 1 : (C <= 256 ? 2 : 4);
+#define RC_ALT_CASE(R_)                                            \
+    case R_:                                                       \
+        if (nv == 1) return run_alt_fwd<R_, 1>(P, out, s);         \
+        if (nv == 2) return run_alt_fwd<R_, 2>(P, out, s);         \
+        return run_alt_fwd<R_, 4>(P, out, s);
+    switch (radius) {
+        RC_ALT_CASE(1) RC_ALT_CASE(2) RC_ALT_CASE(3) RC_ALT_CASE(4)
+    }
+#undef RC_ALT_CASE
+    return fail("alt fwd: unreachable");
+}
+
+int launch_alt_bwd(const float* f1_nhwc, const AltLevels& lv, const CoordsView& cv, const float* grad_out, int B,
+                   int NC, int H1, int W1, int C, int radius, float scale, float* df1_nhwc, cudaStream_t s) {
+    if (int rc = check_alt(lv, C, radius)) return rc;
+    AltParams P = make_params(f1_nhwc, lv, cv, B, NC, H1 * W1, C, scale);
+    const int nv = C <= 128 ? 1 : (C <= 256 ? 2 : 4);
+#define RC_ALT_CASE(R_)                                                       \
+    case R_:                                                                  \
+        if (nv == 1) return run_alt_bwd<R_, 1>(P, grad_out, df1_nhwc, s);     \
+        if (nv == 2) return run_alt_bwd<R_, 2>(P, grad_out, df1_nhwc, s);     \
+        return run_alt_bwd<R_, 4>(P, grad_out, df1_nhwc, s);
+    switch (radius) {
+        RC_ALT_CASE(1) RC_ALT_CASE(2) RC_ALT_CASE(3) RC_ALT_CASE(4)
+    }
+#undef RC_ALT_CASE
+    return fail("alt bwd: unreachable");
+}
+
+}  // namespace raftcorr

@@ -1,0 +1,268 @@
+// extern "C" surface of libraftcorr_b200.so -- see include/raftcorr.h for the contract and the
+// reference interfaces each entry point replaces.
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace raftcorr {
+
+char* error_buffer() {
+    static thread_local char buf[512] = {0};
+    return buf;
+}
+
+int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(error_buffer(), 512, fmt, ap);
+    va_end(ap);
+    return 1;
+}
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int check_layout(const raftcorr_pyramid_layout* lay) {
+    RC_REQUIRE(lay != nullptr, "layout is NULL");
+    RC_REQUIRE(lay->L >= 1 && lay->L <= RAFTCORR_MAX_LEVELS, "layout: bad level count %d", lay->L);
+    RC_REQUIRE(lay->B >= 0 && lay->H >= 1 && lay->W >= 1, "layout: bad sizes B=%d H=%d W=%d", lay->B, lay->H, lay->W);
+    for (int l = 0; l < lay->L; ++l)
+        RC_REQUIRE(lay->pitch[l] >= lay->w[l] && lay->h[l] >= 1 && lay->w[l] >= 1, "layout: bad level %d", l);
+    return 0;
+}
+
+int alt_levels(const float* f2pyr, float* df2pyr, int B, int D, int H, int W, int L, AltLevels* out) {
+    RC_REQUIRE(L >= 1 && L <= RAFTCORR_MAX_LEVELS, "alt: bad level count %d", L);
+    out->L = L;
+    int h = H, w = W;
+    int64_t off = 0;
+    for (int l = 0; l < L; ++l) {
+        RC_REQUIRE(h >= 1 && w >= 1, "alt: level %d is empty (H=%d, W=%d)", l, H, W);
+        out->f2[l] = f2pyr ? f2pyr + off : nullptr;
+        out->df2[l] = df2pyr ? df2pyr + off : nullptr;
+        out->h[l] = h;
+        out->w[l] = w;
+        off += (int64_t)align_up((size_t)B * h * w * D, 64);
+        h /= 2;
+        w /= 2;
+    }
+    return 0;
+}
+
+}  // namespace
+}  // namespace raftcorr
+
+using namespace raftcorr;
+
+extern "C" {
+
+int raftcorr_abi_version(void) { return RAFTCORR_ABI_VERSION; }
+
+const char* raftcorr_last_error(void) { return error_buffer(); }
+
+int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* lay, int B, int H, int W, int L) {
+    RC_REQUIRE(lay != nullptr, "layout is NULL");
+    RC_REQUIRE(L >= 1 && L <= RAFTCORR_MAX_LEVELS, "num_levels must be in [1, %d] (got %d)", RAFTCORR_MAX_LEVELS, L);
+    RC_REQUIRE(B >= 0 && H >= 1 && W >= 1, "bad sizes B=%d H=%d W=%d", B, H, W);
+    std::memset(lay, 0, sizeof(*lay));
+    lay->B = B; lay->H = H; lay->W = W; lay->L = L;
+    int h = H, w = W;
+    int64_t off = 0;
+    const int64_t N = (int64_t)H * W;
+    for (int l = 0; l < L; ++l) {
+        // the reference normalises by (W_l - 1) and (H_l - 1) (utils.py:74-75): a 1-pixel level is NaN there
+        RC_REQUIRE(h >= 2 && w >= 2, "pyramid level %d would be %dx%d; the reference divides by (size-1) there "
+                   "(raft/core/utils/utils.py:74-75). Use fewer levels or larger feature maps", l, h, w);
+        lay->h[l] = h;
+        lay->w[l] = w;
+        lay->pitch[l] = (w + 7) / 8 * 8;
+        lay->offset[l] = off;
+        off += (int64_t)align_up((size_t)(B * N * h * lay->pitch[l]), 64);
+        h /= 2;
+        w /= 2;
+    }
+    lay->total_floats = off;
+    return 0;
+}
+
+size_t raftcorr_build_fwd_workspace_bytes(int B, int D, int H, int W, int mode) {
+    if (mode == RAFTCORR_BUILD_TF32_TC)  // two NHWC (K-major), TF32-rounded copies of the feature maps
+        return 2 * align_up((size_t)B * D * H * W * sizeof(float), 1024);
+    return 0;
+}
+
+int raftcorr_build_fwd(const float* fmap1, const float* fmap2, int D, float* pyramid,
+                       const raftcorr_pyramid_layout* lay, int mode, void* workspace, size_t workspace_bytes,
+                       int device, raftcorr_stream_t stream) {
+    if (int rc = check_layout(lay)) return rc;
+    RC_REQUIRE(fmap1 && fmap2 && pyramid, "build_fwd: NULL tensor");
+    RC_REQUIRE(D >= 1, "build_fwd: bad feature dim %d", D);
+    if (lay->B == 0) return 0;
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "build_fwd: cannot select device %d", device);
+    cudaStream_t s = (cudaStream_t)stream;
+    PyramidView pv = make_view(pyramid, *lay);
+    if (mode == RAFTCORR_BUILD_FP32_SIMT) return launch_build_simt(fmap1, fmap2, D, pv, s);
+    if (mode == RAFTCORR_BUILD_TF32_TC) {
+        const size_t need = raftcorr_build_fwd_workspace_bytes(lay->B, D, lay->H, lay->W, mode);
+        RC_REQUIRE(workspace && workspace_bytes >= need, "build_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+        float* f1n = (float*)workspace;
+        float* f2n = (float*)((char*)workspace + need / 2);
+        const int HW = lay->H * lay->W;
+        if (int rc = launch_nchw_to_nhwc(fmap1, f1n, lay->B, D, HW, true, s)) return rc;
+        if (int rc = launch_nchw_to_nhwc(fmap2, f2n, lay->B, D, HW, true, s)) return rc;
+        return launch_build_tc(f1n, f2n, D, pyramid, *lay, device, s);
+    }
+    return fail("build_fwd: unknown mode %d", mode);
+}
+
+int raftcorr_lookup_fwd(const float* pyramid, const raftcorr_pyramid_layout* lay, const float* coords, int radius,
+                        float* out, int device, raftcorr_stream_t stream) {
+    if (int rc = check_layout(lay)) return rc;
+    RC_REQUIRE(pyramid && coords && out, "lookup_fwd: NULL tensor");
+    if (lay->B == 0) return 0;
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "lookup_fwd: cannot select device %d", device);
+    PyramidView pv = make_view(const_cast<float*>(pyramid), *lay);
+    return launch_lookup_fwd(pv, coords, radius, out, (cudaStream_t)stream);
+}
+
+int raftcorr_lookup_bwd(const float* grad_out, const float* coords, const float* pyramid, float* dpyramid,
+                        const raftcorr_pyramid_layout* lay, int radius, float* dcoords, int device,
+                        raftcorr_stream_t stream) {
+    if (int rc = check_layout(lay)) return rc;
+    RC_REQUIRE(grad_out && coords && dpyramid, "lookup_bwd: NULL tensor");
+    RC_REQUIRE(!dcoords || pyramid, "lookup_bwd: dcoords requested without the forward pyramid");
+    if (lay->B == 0) return 0;
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "lookup_bwd: cannot select device %d", device);
+    cudaStream_t s = (cudaStream_t)stream;
+    PyramidView dpv = make_view(dpyramid, *lay);
+    PyramidView fpv{};
+    if (dcoords) {
+        fpv = make_view(const_cast<float*>(pyramid), *lay);
+        RC_CUDA(cudaMemsetAsync(dcoords, 0, sizeof(float) * 2 * (size_t)lay->B * lay->H * lay->W, s));
+    }
+    return launch_lookup_bwd(grad_out, coords, dcoords ? &fpv : nullptr, dpv, radius, dcoords, s);
+}
+
+int raftcorr_build_bwd(float* dpyramid, const raftcorr_pyramid_layout* lay, const float* fmap1, const float* fmap2,
+                       int D, float* dfmap1, float* dfmap2, int device, raftcorr_stream_t stream) {
+    if (int rc = check_layout(lay)) return rc;
+    RC_REQUIRE(dpyramid && fmap1 && fmap2 && dfmap1 && dfmap2, "build_bwd: NULL tensor");
+    if (lay->B == 0) return 0;
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "build_bwd: cannot select device %d", device);
+    cudaStream_t s = (cudaStream_t)stream;
+    PyramidView dpv = make_view(dpyramid, *lay);
+    const int64_t imgs = (int64_t)lay->B * lay->H * lay->W;
+    for (int l = lay->L - 1; l >= 1; --l)  // adjoint of corr.py:41-43, coarse to fine
+        if (int rc = launch_pool_adjoint_level(dpv.lvl[l], dpv.lvl[l - 1], imgs, s)) return rc;
+    return launch_build_bwd_gemms(dpv, fmap1, fmap2, D, dfmap1, dfmap2, s);
+}
+
+int raftcorr_alt_forward(const float* fmap1, const float* fmap2, const float* coords, int B, int N, int H1, int W1,
+                         int H2, int W2, int C, int radius, float* corr, int device, raftcorr_stream_t stream) {
+    RC_REQUIRE(fmap1 && fmap2 && coords && corr, "alt_forward: NULL tensor");
+    RC_REQUIRE(B >= 0 && N >= 1 && H1 >= 1 && W1 >= 1 && H2 >= 1 && W2 >= 1, "alt_forward: bad sizes");
+    if (B == 0) return 0;
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "alt_forward: cannot select device %d", device);
+    AltLevels lv{};
+    lv.L = 1; lv.f2[0] = fmap2; lv.h[0] = H2; lv.w[0] = W2;
+    const int64_t N1 = (int64_t)H1 * W1;
+    CoordsView cv{coords, 2 * N1, 1, 2};  // [B,N,H1,W1,2]
+    return launch_alt_fwd(fmap1, lv, cv, B, N, H1, W1, C, radius, 1.0f, corr, (cudaStream_t)stream);
+}
+
+int raftcorr_alt_backward(const float* fmap1, const float* fmap2, const float* coords, const float* corr_grad, int B,
+                          int N, int H1, int W1, int H2, int W2, int C, int radius, float* fmap1_grad,
+                          float* fmap2_grad, float* coords_grad, int device, raftcorr_stream_t stream) {
+    (void)coords_grad;  // identically zero in the reference (correlation_kernel.cu:307); caller zero-fills
+    RC_REQUIRE(fmap1 && fmap2 && coords && corr_grad && fmap1_grad && fmap2_grad, "alt_backward: NULL tensor");
+    RC_REQUIRE(B >= 0 && N >= 1 && H1 >= 1 && W1 >= 1 && H2 >= 1 && W2 >= 1, "alt_backward: bad sizes");
+    if (B == 0) return 0;
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "alt_backward: cannot select device %d", device);
+    AltLevels lv{};
+    lv.L = 1; lv.f2[0] = fmap2; lv.df2[0] = fmap2_grad; lv.h[0] = H2; lv.w[0] = W2;
+    const int64_t N1 = (int64_t)H1 * W1;
+    CoordsView cv{coords, 2 * N1, 1, 2};
+    return launch_alt_bwd(fmap1, lv, cv, corr_grad, B, N, H1, W1, C, radius, 1.0f, fmap1_grad, (cudaStream_t)stream);
+}
+
+int64_t raftcorr_alt_level_offset(int B, int D, int H, int W, int level) {
+    int h = H, w = W;
+    int64_t off = 0;
+    for (int l = 0; l < level; ++l) {
+        off += (int64_t)align_up((size_t)B * h * w * D, 64);
+        h /= 2;
+        w /= 2;
+    }
+    return off;
+}
+
+int raftcorr_alt_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int L, float* f1_nhwc,
+                         float* f2_pyr, int device, raftcorr_stream_t stream) {
+    RC_REQUIRE(fmap1 && fmap2 && f1_nhwc && f2_pyr, "alt_pyramid: NULL tensor");
+    AltLevels lv{};
+    if (int rc = alt_levels(f2_pyr, nullptr, B, D, H, W, L, &lv)) return rc;
+    if (B == 0) return 0;
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "alt_pyramid: cannot select device %d", device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (int rc = launch_nchw_to_nhwc(fmap1, f1_nhwc, B, D, H * W, false, s)) return rc;
+    if (int rc = launch_nchw_to_nhwc(fmap2, const_cast<float*>(lv.f2[0]), B, D, H * W, false, s)) return rc;
+    for (int l = 1; l < L; ++l)  // corr.py:138-139 (fmap2 side; the pooled fmap1 copies are never read, :158)
+        if (int rc = launch_pool_nhwc(lv.f2[l - 1], const_cast<float*>(lv.f2[l]), B, lv.h[l - 1], lv.w[l - 1], D, s))
+            return rc;
+    return 0;
+}
+
+int raftcorr_alt_lookup_fwd(const float* f1_nhwc, const float* f2_pyr, const float* coords, int B, int D, int H,
+                            int W, int L, int radius, float* out, int device, raftcorr_stream_t stream) {
+    RC_REQUIRE(f1_nhwc && f2_pyr && coords && out, "alt_lookup_fwd: NULL tensor");
+    AltLevels lv{};
+    if (int rc = alt_levels(f2_pyr, nullptr, B, D, H, W, L, &lv)) return rc;
+    if (B == 0) return 0;
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "alt_lookup_fwd: cannot select device %d", device);
+    const int64_t N1 = (int64_t)H * W;
+    CoordsView cv{coords, 2 * N1, N1, 1};  // [B,2,H,W]
+    const float scale = 1.0f / sqrtf((float)D);  // corr.py:167
+    return launch_alt_fwd(f1_nhwc, lv, cv, B, 1, H, W, D, radius, scale, out, (cudaStream_t)stream);
+}
+
+int raftcorr_alt_lookup_bwd(const float* f1_nhwc, const float* f2_pyr, const float* coords, const float* grad_out,
+                            int B, int D, int H, int W, int L, int radius, float* df1_nhwc, float* df2_pyr,
+                            int device, raftcorr_stream_t stream) {
+    RC_REQUIRE(f1_nhwc && f2_pyr && coords && grad_out && df1_nhwc && df2_pyr, "alt_lookup_bwd: NULL tensor");
+    AltLevels lv{};
+    if (int rc = alt_levels(f2_pyr, df2_pyr, B, D, H, W, L, &lv)) return rc;
+    if (B == 0) return 0;
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "alt_lookup_bwd: cannot select device %d", device);
+    const int64_t N1 = (int64_t)H * W;
+    CoordsView cv{coords, 2 * N1, N1, 1};
+    const float scale = 1.0f / sqrtf((float)D);
+    return launch_alt_bwd(f1_nhwc, lv, cv, grad_out, B, 1, H, W, D, radius, scale, df1_nhwc, (cudaStream_t)stream);
+}
+
+int raftcorr_alt_grad_finish(const float* df1_nhwc, float* df2_pyr, int B, int D, int H, int W, int L, float* dfmap1,
+                             float* dfmap2, int device, raftcorr_stream_t stream) {
+    RC_REQUIRE(df1_nhwc && df2_pyr && dfmap1 && dfmap2, "alt_grad_finish: NULL tensor");
+    AltLevels lv{};
+    if (int rc = alt_levels(df2_pyr, df2_pyr, B, D, H, W, L, &lv)) return rc;
+    if (B == 0) return 0;
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "alt_grad_finish: cannot select device %d", device);
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int l = L - 1; l >= 1; --l)
+        if (int rc = launch_pool_adjoint_nhwc(lv.df2[l], lv.df2[l - 1], B, lv.h[l - 1], lv.w[l - 1], D, s)) return rc;
+    if (int rc = launch_nhwc_to_nchw(df1_nhwc, dfmap1, B, D, H * W, s)) return rc;
+    return launch_nhwc_to_nchw(lv.df2[0], dfmap2, B, D, H * W, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// Shared host/device helpers for libraftcorr_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "raftcorr.h"
+
+namespace raftcorr {
+
+// ---- error plumbing (thread-local, no global mutable state shared between callers) ----------
+char* error_buffer();  // defined in api.cu
+int fail(const char* fmt, ...);
+
+#define RC_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return ::raftcorr::fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                                    __LINE__);                                                 \
+    } while (0)
+
+#define RC_REQUIRE(cond, ...)                         \
+    do {                                              \
+        if (!(cond)) return ::raftcorr::fail(__VA_ARGS__); \
+    } while (0)
+
+// RAII device guard: callers may sit on any current device (DataParallel threads).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != device && cudaSetDevice(device) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Per-level view of the pyramid handed to kernels by value.
+struct LevelView {
+    float* base;          // level start
+    int h, w, pitch;      // rows, valid cols, row pitch (floats)
+    int64_t img_stride;   // h * pitch: floats between consecutive source pixels
+};
+
+struct PyramidView {
+    LevelView lvl[RAFTCORR_MAX_LEVELS];
+    int B, N, L;  // N = H*W source pixels
+};
+
+inline PyramidView make_view(float* base, const raftcorr_pyramid_layout& lay) {
+    PyramidView v{};
+    v.B = lay.B;
+    v.N = lay.H * lay.W;
+    v.L = lay.L;
+    for (int l = 0; l < lay.L; ++l) {
+        v.lvl[l].base = base + lay.offset[l];
+        v.lvl[l].h = lay.h[l];
+        v.lvl[l].w = lay.w[l];
+        v.lvl[l].pitch = lay.pitch[l];
+        v.lvl[l].img_stride = (int64_t)lay.h[l] * lay.pitch[l];
+    }
+    return v;
+}
+
+// ---- launchers implemented in the individual .cu files ------------------------------------------
+int launch_nchw_to_nhwc(const float* in, float* out, int B, int D, int HW, bool round_tf32, cudaStream_t s);
+int launch_nhwc_to_nchw(const float* in, float* out, int B, int D, int HW, cudaStream_t s);
+int launch_pool_nhwc(const float* in, float* out, int B, int Hi, int Wi, int D, cudaStream_t s);
+int launch_pool_adjoint_nhwc(const float* gout, float* gin, int B, int Hi, int Wi, int D, cudaStream_t s);
+int launch_pool_level(const LevelView& in, const LevelView& out, int64_t imgs, cudaStream_t s);
+int launch_pool_adjoint_level(const LevelView& coarse, const LevelView& fine, int64_t imgs, cudaStream_t s);
+
+int launch_build_simt(const float* f1, const float* f2, int D, const PyramidView& pv, cudaStream_t s);
+int launch_build_tc(const float* f1_nhwc, const float* f2_nhwc, int D, float* pyramid,
+                    const raftcorr_pyramid_layout& lay, int device, cudaStream_t s);
+int launch_build_bwd_gemms(const PyramidView& dpv, const float* f1, const float* f2, int D, float* df1,
+                           float* df2, cudaStream_t s);
+
+int launch_lookup_fwd(const PyramidView& pv, const float* coords, int radius, float* out, cudaStream_t s);
+int launch_lookup_bwd(const float* grad_out, const float* coords, const PyramidView* pv_fwd,
+                      const PyramidView& dpv, int radius, float* dcoords, cudaStream_t s);
+
+struct AltLevels {
+    const float* f2[RAFTCORR_MAX_LEVELS];  // NHWC [B][h][w][C]
+    float* df2[RAFTCORR_MAX_LEVELS];       // gradients (bwd only)
+    int h[RAFTCORR_MAX_LEVELS], w[RAFTCORR_MAX_LEVELS];
+    int L;
+};
+// coords addressing: value(b, c, p) = coords[b * batch_stride + c * comp_stride + p * pix_stride]
+struct CoordsView {
+    const float* ptr;
+    int64_t batch_stride, comp_stride, pix_stride;
+};
+int launch_alt_fwd(const float* f1_nhwc, const AltLevels& lv, const CoordsView& cv, int B, int NC, int H1, int W1,
+                   int C, int radius, float scale, float* out, cudaStream_t s);
+int launch_alt_bwd(const float* f1_nhwc, const AltLevels& lv, const CoordsView& cv, const float* grad_out, int B,
+                   int NC, int H1, int W1, int C, int radius, float scale, float* df1_nhwc, cudaStream_t s);
+
+}  // namespace raftcorr

@@ -1,0 +1,158 @@
+// Layout / pooling helpers around the hot kernels (all tiny next to the volume):
+//   NCHW <-> NHWC transposes of the feature maps (the tcgen05 build and the on-the-fly path want
+//   the feature dim contiguous = K-major; the reference re-does this permute on every call,
+//   raft/core/corr.py:158-159), 2x2 average pooling (corr.py:42,138-139) and its adjoint.
+#include "common.cuh"
+
+namespace raftcorr {
+
+namespace {
+
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// in [B][D][HW] -> out [B][HW][D]; 32x32 tiles through shared memory, both sides coalesced.
+template <bool ROUND>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int D, int HW) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+    const float* src = in + (int64_t)b * D * HW;
+    float* dst = out + (int64_t)b * D * HW;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int d = d0 + i, p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (d < D && p < HW) ? src[(int64_t)d * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int p = p0 + i, d = d0 + threadIdx.x;
+        if (p < HW && d < D) {
+            float v = tile[threadIdx.x][i];
+            dst[(int64_t)p * D + d] = ROUND ? round_tf32(v) : v;
+        }
+    }
+}
+
+// NHWC 2x2 mean, floor mode: in [B][Hi][Wi][D] -> out [B][Hi/2][Wi/2][D]
+__global__ void pool_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int Hi, int Wi, int D,
+                                 int64_t total) {
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int d = idx % D;
+        int64_t t = idx / D;
+        const int x = t % Wo;
+        t /= Wo;
+        const int y = t % Ho;
+        const int b = t / Ho;
+        const float* s = in + (((int64_t)b * Hi + 2 * y) * Wi + 2 * x) * D + d;
+        out[idx] = (s[0] + s[D] + s[(int64_t)Wi * D] + s[(int64_t)Wi * D + D]) * 0.25f;
+    }
+}
+
+// adjoint: gin [B][Hi][Wi][D] += 0.25 * gout[b][y/2][x/2][d] for (y,x) inside the pooled footprint
+__global__ void pool_adjoint_nhwc_kernel(const float* __restrict__ gout, float* __restrict__ gin, int Hi, int Wi,
+                                         int D, int64_t total) {
+    const int Ho = Hi / 2, Wo = Wi / 2;
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int d = idx % D;
+        int64_t t = idx / D;
+        const int x = t % Wi;
+        t /= Wi;
+        const int y = t % Hi;
+        const int b = t / Hi;
+        if ((y >> 1) < Ho && (x >> 1) < Wo)
+            gin[idx] += 0.25f * gout[(((int64_t)b * Ho + (y >> 1)) * Wo + (x >> 1)) * D + d];
+    }
+}
+
+// Pyramid-level pooling on the pitched volume layout: one thread per output element.
+__global__ void pool_level_kernel(const LevelView in, const LevelView out, int64_t total) {
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int x = idx % out.w;
+        int64_t t = idx / out.w;
+        const int y = t % out.h;
+        const int64_t img = t / out.h;
+        const float* s = in.base + img * in.img_stride + (int64_t)(2 * y) * in.pitch + 2 * x;
+        out.base[img * out.img_stride + (int64_t)y * out.pitch + x] =
+            (s[0] + s[1] + s[in.pitch] + s[in.pitch + 1]) * 0.25f;
+    }
+}
+
+__global__ void pool_adjoint_level_kernel(const LevelView coarse, const LevelView fine, int64_t total) {
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int x = idx % fine.w;
+        int64_t t = idx / fine.w;
+        const int y = t % fine.h;
+        const int64_t img = t / fine.h;
+        if ((y >> 1) < coarse.h && (x >> 1) < coarse.w)
+            fine.base[img * fine.img_stride + (int64_t)y * fine.pitch + x] +=
+                0.25f * coarse.base[img * coarse.img_stride + (int64_t)(y >> 1) * coarse.pitch + (x >> 1)];
+    }
+}
+
+inline int grid_for(int64_t total, int threads) {
+    int64_t g = ceil_div64(total, threads);
+    const int64_t cap = 148 * 16;  // persistent-ish grid-stride: 16 CTAs per SM
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+int launch_nchw_to_nhwc(const float* in, float* out, int B, int D, int HW, bool round, cudaStream_t s) {
+    dim3 grid(ceil_div(HW, 32), ceil_div(D, 32), B), block(32, 8);
+    if (round)
+        nchw_to_nhwc_kernel<true><<<grid, block, 0, s>>>(in, out, D, HW);
+    else
+        nchw_to_nhwc_kernel<false><<<grid, block, 0, s>>>(in, out, D, HW);
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_nhwc_to_nchw(const float* in, float* out, int B, int D, int HW, cudaStream_t s) {
+    // the same tile transpose with the roles of D and HW swapped
+    dim3 grid(ceil_div(D, 32), ceil_div(HW, 32), B), block(32, 8);
+    nchw_to_nhwc_kernel<false><<<grid, block, 0, s>>>(in, out, HW, D);
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_pool_nhwc(const float* in, float* out, int B, int Hi, int Wi, int D, cudaStream_t s) {
+    const int64_t total = (int64_t)B * (Hi / 2) * (Wi / 2) * D;
+    if (total == 0) return 0;
+    pool_nhwc_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, Hi, Wi, D, total);
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_pool_adjoint_nhwc(const float* gout, float* gin, int B, int Hi, int Wi, int D, cudaStream_t s) {
+    const int64_t total = (int64_t)B * Hi * Wi * D;
+    if (total == 0) return 0;
+    pool_adjoint_nhwc_kernel<<<grid_for(total, 256), 256, 0, s>>>(gout, gin, Hi, Wi, D, total);
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_pool_level(const LevelView& in, const LevelView& out, int64_t imgs, cudaStream_t s) {
+    const int64_t total = imgs * out.h * out.w;
+    if (total == 0) return 0;
+    pool_level_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, total);
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_pool_adjoint_level(const LevelView& coarse, const LevelView& fine, int64_t imgs, cudaStream_t s) {
+    const int64_t total = imgs * fine.h * fine.w;
+    if (total == 0) return 0;
+    pool_adjoint_level_kernel<<<grid_for(total, 256), 256, 0, s>>>(coarse, fine, total);
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace raftcorr

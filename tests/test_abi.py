@@ -1,0 +1,95 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/raftcorr.h declares,
+host-only entry points behave, and the Python mirror refuses to run without CUDA tensors."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+
+    g.build()
+    from optical_flow_dnn_b200 import _lib
+
+    return _lib
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "raftcorr.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(raftcorr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported_and_bound(lib):
+    names = declared_symbols()
+    assert len(names) >= 15
+    handle = ctypes.CDLL(lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in raftcorr.h but not exported"
+        assert n in lib.SIGNATURES, f"{n} has no ctypes signature in _lib.py"
+    assert sorted(lib.SIGNATURES) == names
+
+
+def test_library_has_no_python_or_torch_dependency(lib):
+    import subprocess
+
+    out = subprocess.run(["ldd", lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in out and "python" not in out
+
+
+def test_layout_matches_oracle_shapes(lib):
+    from oracle.corr_oracle import level_shapes
+
+    for (B, H, W, L) in [(8, 55, 128, 4), (1, 46, 62, 4), (16, 47, 156, 4), (2, 9, 12, 3)]:
+        lay = lib.make_layout(B, H, W, L)
+        assert [(lay.h[l], lay.w[l]) for l in range(L)] == level_shapes(H, W, L)
+        off = 0
+        for l in range(L):
+            assert lay.pitch[l] % 8 == 0 and lay.pitch[l] >= lay.w[l]
+            assert lay.offset[l] == off and off % 64 == 0
+            off += -(-(B * H * W * lay.h[l] * lay.pitch[l]) // 64) * 64
+        assert lay.total_floats == off
+
+
+def test_layout_rejects_collapsed_levels_and_bad_counts(lib):
+    with pytest.raises(lib.RaftCorrError, match="divides by"):
+        lib.make_layout(1, 8, 8, 4)
+    with pytest.raises(lib.RaftCorrError):
+        lib.make_layout(1, 64, 64, 0)
+    with pytest.raises(lib.RaftCorrError):
+        lib.make_layout(1, 64, 64, 9)
+
+
+def test_null_pointers_are_rejected_without_a_gpu(lib):
+    L = lib.lib()
+    lay = lib.make_layout(1, 16, 16, 2)
+    rc = L.raftcorr_lookup_fwd(None, ctypes.byref(lay), None, 4, None, 0, None)
+    assert rc != 0 and b"NULL" in L.raftcorr_last_error()
+    rc = L.raftcorr_build_fwd(None, None, 16, None, ctypes.byref(lay), 0, None, 0, 0, None)
+    assert rc != 0
+
+
+def test_cpu_tensors_fail_loudly(lib):
+    import torch
+
+    import optical_flow_dnn_b200 as m
+
+    f = torch.zeros(1, 8, 16, 16)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.CorrBlock(f, f)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.AlternateCorrBlock(f, f)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "optical-flow-dnn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text, f"{f} mentions the oracle"

@@ -1,0 +1,300 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes -> libraftcorr_b200.so),
+against (1) golden vectors produced by the reference itself, (2) the CPU oracle on seeded inputs,
+(3) size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (north_star: "fp32-accumulated, <=1e-3 relative on the volume and lookup"), made
+concrete as max|delta| <= tol * max|ref| per tensor:
+    fp32 build mode  : 2e-5   (fp32 re-ordering only)
+    tf32 build mode  : 1e-3   (TF32-rounded operands, fp32 accumulation in TMEM)
+    gradients        : 1e-3 (tf32 forward does not matter: the adjoints are fp32)
+"""
+import numpy as np
+import pytest
+import torch
+
+from make_golden import grad_weights
+from oracle import corr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 2e-5, "tf32": 1e-3}
+MODES = ["fp32", "tf32"]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def rel_err(a, ref):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+    return float(np.abs(a.astype(np.float64) - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def _meta(g):
+    return [int(v) for v in g["meta"]]
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import optical_flow_dnn_b200 as m
+
+    return m
+
+
+# ------------------------------------------------------------------ golden vectors (reference outputs)
+@pytest.mark.parametrize("mode", MODES)
+def test_golden_pyramid_and_lookup(pkg, golden, mode):
+    B, D, H, W, L, r = _meta(golden)
+    blk = pkg.CorrBlock(torch.from_numpy(golden["fmap1"]).to(dev()), torch.from_numpy(golden["fmap2"]).to(dev()),
+                        num_levels=L, radius=r, build_mode=mode)
+    pyr = blk.corr_pyramid
+    assert len(pyr) == L
+    for l in range(L):
+        ref = golden[f"pyr{l}"]
+        assert tuple(pyr[l].shape) == (B * H * W, 1) + ref.shape[-2:]
+        assert rel_err(pyr[l].reshape(ref.shape), ref) <= TOL[mode], f"level {l}"
+    for k in range(3):
+        out = blk(torch.from_numpy(golden[f"coords{k}"]).to(dev()))
+        assert out.shape == golden[f"out{k}"].shape and out.dtype == torch.float32 and out.is_contiguous()
+        assert rel_err(out, golden[f"out64_{k}"]) <= TOL[mode], f"coords set {k}"
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_golden_gradients(pkg, golden, mode):
+    B, D, H, W, L, r = _meta(golden)
+    f1 = torch.from_numpy(golden["fmap1"]).to(dev()).requires_grad_()
+    f2 = torch.from_numpy(golden["fmap2"]).to(dev()).requires_grad_()
+    blk = pkg.CorrBlock(f1, f2, num_levels=L, radius=r, build_mode=mode)
+    loss = 0
+    cs = []
+    for k in range(3):
+        c = torch.from_numpy(golden[f"coords{k}"]).to(dev()).requires_grad_(k == 1)
+        cs.append(c)
+        out = blk(c)
+        w = torch.from_numpy(grad_weights(tuple(out.shape), k).astype(np.float32)).to(dev())
+        loss = loss + (out * w).sum()
+    loss.backward()
+    assert rel_err(f1.grad, golden["df1"]) <= 1e-3
+    assert rel_err(f2.grad, golden["df2"]) <= 1e-3
+    # coordinates gradient (the reference CorrBlock provides it through grid_sample): generic coords only
+    assert rel_err(cs[1].grad, golden["dcoords1"]) <= TOL[mode] * 20
+
+
+def test_golden_alternate(pkg, golden):
+    B, D, H, W, L, r = _meta(golden)
+    f1 = torch.from_numpy(golden["fmap1"]).to(dev()).requires_grad_()
+    f2 = torch.from_numpy(golden["fmap2"]).to(dev()).requires_grad_()
+    blk = pkg.AlternateCorrBlock(f1, f2, num_levels=L, radius=r)
+    loss = 0
+    for k in range(3):
+        out = blk(torch.from_numpy(golden[f"coords{k}"]).to(dev()))
+        assert rel_err(out, golden[f"out64_{k}"]) <= 2e-5
+        w = torch.from_numpy(grad_weights(tuple(out.shape), k).astype(np.float32)).to(dev())
+        loss = loss + (out * w).sum()
+    loss.backward()
+    assert rel_err(f1.grad, golden["df1"]) <= 1e-4
+    assert rel_err(f2.grad, golden["df2"]) <= 1e-4
+    assert len(blk.pyramid) == L + 1
+
+
+def test_alt_cuda_corr_module_surface(pkg, golden):
+    """The native-extension mirror: single level, unscaled, NHWC fmaps, interleaved coords
+    (raft/alt_cuda_corr/correlation.cpp:23-49)."""
+    from optical_flow_dnn_b200 import alt_cuda_corr
+
+    B, D, H, W, L, r = _meta(golden)
+    f1 = torch.from_numpy(golden["fmap1"]).to(dev())
+    f2 = torch.from_numpy(golden["fmap2"]).to(dev())
+    f1n = f1.permute(0, 2, 3, 1).contiguous()
+    for lvl in range(2):
+        f2l = f2
+        for _ in range(lvl):
+            f2l = torch.nn.functional.avg_pool2d(f2l, 2, stride=2)
+        f2n = f2l.permute(0, 2, 3, 1).contiguous()
+        c = torch.from_numpy(golden["coords1"]).to(dev())
+        ci = (c.permute(0, 2, 3, 1) / 2 ** lvl).reshape(B, 1, H, W, 2).contiguous()
+        corr, = alt_cuda_corr.forward(f1n, f2n, ci, r)
+        K = 2 * r + 1
+        assert tuple(corr.shape) == (B, 1, K * K, H, W)
+        ref = golden["out64_1"][:, lvl * K * K:(lvl + 1) * K * K] * np.sqrt(D)
+        assert rel_err(corr[:, 0], ref) <= 2e-5
+        g = torch.from_numpy(grad_weights(tuple(corr.shape), 5).astype(np.float32)).to(dev())
+        d1, d2, dc = alt_cuda_corr.backward(f1n, f2n, ci, g, r)
+        assert d1.shape == f1n.shape and d2.shape == f2n.shape and dc.shape == ci.shape
+        assert float(dc.abs().max()) == 0.0  # correlation_kernel.cu:307
+        # oracle: single-level alt grad == d/dfmaps of <alt_lookup(L=1) * sqrt(D), g>
+        co = (golden["coords1"] / 2 ** lvl).astype(np.float32)
+        e1, e2 = O.alt_grad(golden["fmap1"], f2l.cpu().numpy(), co, g.cpu().numpy()[:, 0] * np.sqrt(D), 1, r, np.float64) \
+            if lvl == 0 else (None, None)
+        if lvl == 0:
+            assert rel_err(d1.permute(0, 3, 1, 2), e1) <= 1e-4
+            assert rel_err(d2.permute(0, 3, 1, 2), e2) <= 1e-4
+    with pytest.raises(RuntimeError):
+        alt_cuda_corr.forward(f1n.cpu(), f2n, ci, r)
+    with pytest.raises(RuntimeError):
+        alt_cuda_corr.forward(f1.permute(0, 2, 3, 1), f2n, ci, r)  # non-contiguous
+
+
+# ------------------------------------------------------------------ seeded inputs vs the CPU oracle
+SEEDED = [
+    # B, D, H, W, L, r   (config 1 shape; an odd KITTI-like shape; tiny)
+    (1, 128, 46, 62, 4, 3),
+    (2, 256, 23, 47, 4, 4),
+    (2, 64, 17, 16, 3, 2),
+    (1, 32, 8, 9, 2, 1),
+]
+
+
+@pytest.mark.parametrize("shape", SEEDED)
+@pytest.mark.parametrize("mode", MODES)
+def test_seeded_vs_oracle(pkg, shape, mode):
+    B, D, H, W, L, r = shape
+    rng = np.random.default_rng(1234)
+    f1 = rng.normal(size=(B, D, H, W)).astype(np.float32)
+    f2 = rng.normal(size=(B, D, H, W)).astype(np.float32)
+    pyr = O.corr_pyramid(f1, f2, L, np.float64)
+    blk = pkg.CorrBlock(torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev()), L, r, build_mode=mode)
+    got = blk.corr_pyramid
+    for l in range(L):
+        assert rel_err(got[l].reshape(pyr[l].shape), pyr[l]) <= TOL[mode], f"level {l}"
+    coords = O.coords_grid(B, H, W)
+    for it in range(3):
+        coords = coords + rng.normal(0, 4.0 if it == 0 else 0.5, coords.shape).astype(np.float32)
+        ref = O.lookup(pyr, coords, r)
+        out = blk(torch.from_numpy(coords).to(dev()))
+        assert rel_err(out, ref) <= TOL[mode]
+    if mode == "fp32":
+        alt = pkg.AlternateCorrBlock(torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev()), L, r)
+        assert rel_err(alt(torch.from_numpy(coords).to(dev())), ref) <= 2e-5
+
+
+def test_c_oracle_agrees_on_gpu_shapes(pkg):
+    """Second, independent checker (plain C loops) on one seeded case."""
+    from oracle import c_oracle as C
+
+    B, D, H, W, L, r = 1, 64, 20, 28, 4, 4
+    rng = np.random.default_rng(5)
+    f1 = rng.normal(size=(B, D, H, W)).astype(np.float32)
+    f2 = rng.normal(size=(B, D, H, W)).astype(np.float32)
+    coords = O.coords_grid(B, H, W) + rng.normal(0, 3.0, (B, 2, H, W)).astype(np.float32)
+    ref = C.lookup(C.corr_pyramid(f1, f2, L), coords, r)
+    blk = pkg.CorrBlock(torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev()), L, r, build_mode="fp32")
+    assert rel_err(blk(torch.from_numpy(coords).to(dev())), ref.astype(np.float64)) <= 2e-5
+
+
+# ------------------------------------------------------------------ full-size properties (config 2 shape)
+@pytest.mark.parametrize("mode", MODES)
+def test_full_size_properties(pkg, mode):
+    """436x1024 -> 55x128 feature maps, D=256, r=4 (BASELINE.json configs[1]), B=2: too big for the
+    CPU oracle in seconds, so check size-independent properties instead."""
+    B, D, H, W, L, r = 2, 256, 55, 128, 4, 4
+    g = torch.Generator(device=dev()).manual_seed(1234)
+    f1 = torch.randn((B, D, H, W), generator=g, device=dev())
+    f2 = torch.randn((B, D, H, W), generator=g, device=dev())
+    blk = pkg.CorrBlock(f1, f2, L, r, build_mode=mode)
+    pyr = blk.corr_pyramid
+    N = H * W
+    v0 = pyr[0].reshape(B, N, H, W)
+    tol = TOL[mode]
+    # (1) checksum of checksums: sum_n V0[m, n] == <f1[m], sum_n f2[n]> / sqrt(D)   (fp64 on device)
+    rowsum = v0.double().sum(dim=(2, 3))
+    expect = torch.einsum("bdm,bd->bm", f1.double().reshape(B, D, N), f2.double().reshape(B, D, N).sum(-1)) / np.sqrt(D)
+    assert float((rowsum - expect).abs().max() / expect.abs().max()) <= tol
+    # (2) random spot checks of single entries against fp64 dot products
+    idx = torch.randint(0, N, (4096, 2), generator=g, device=dev())
+    a = f1.double().reshape(B, D, N)[0][:, idx[:, 0]]
+    b = f2.double().reshape(B, D, N)[0][:, idx[:, 1]]
+    ref = (a * b).sum(0) / np.sqrt(D)
+    got = v0[0].reshape(N, N)[idx[:, 0], idx[:, 1]].double()
+    assert float((got - ref).abs().max()) <= tol * float(v0.abs().max())
+    # (3) each level is the floor-mode 2x2 mean of the previous one (corr.py:41-43)
+    for l in range(1, L):
+        want = torch.nn.functional.avg_pool2d(pyr[l - 1].contiguous(), 2, stride=2)
+        assert tuple(want.shape) == tuple(pyr[l].shape)
+        assert float((want - pyr[l]).abs().max()) <= 1e-5 * float(v0.abs().max())
+    # (4) linearity of the whole path in fmap1
+    blk2 = pkg.CorrBlock(2.0 * f1, f2, L, r, build_mode=mode)
+    coords = torch.from_numpy(O.coords_grid(B, H, W)).to(dev()) + 3.0 * torch.randn((B, 2, H, W), generator=g, device=dev())
+    o1, o2 = blk(coords), blk2(coords)
+    assert float((o2 - 2.0 * o1).abs().max()) <= 1e-5 * float(o1.abs().max())
+    # (5) at integer coordinates the centre tap of level 0 is the volume entry itself
+    cg = torch.from_numpy(O.coords_grid(B, H, W)).to(dev())
+    og = blk(cg)
+    K = 2 * r + 1
+    centre = og[:, r * K + r].reshape(B, N)
+    diag = v0.reshape(B, N, N).diagonal(dim1=1, dim2=2)
+    assert float((centre - diag).abs().max()) == 0.0
+    # (6) lookup == on-the-fly variant (AlternateCorrBlock == CorrBlock)
+    alt = pkg.AlternateCorrBlock(f1, f2, L, r)(coords)
+    assert float((alt - o1).abs().max()) <= tol * float(o1.abs().max())
+    # (7) adjoint identity <lookup(V), g> == <V, lookup^T(g)> through autograd at full size
+    f1g = f1.clone().requires_grad_()
+    blk3 = pkg.CorrBlock(f1g, f2, L, r, build_mode=mode)
+    gsel = torch.randn(o1.shape, generator=g, device=dev())
+    (blk3(coords) * gsel).sum().backward()
+    eps_dir = torch.randn(f1.shape, generator=g, device=dev())
+    lhs = float((f1g.grad.double() * eps_dir.double()).sum())
+    o_dir = pkg.CorrBlock(eps_dir, f2, L, r, build_mode=mode)(coords)  # the path is linear in fmap1
+    rhs = float((o_dir.double() * gsel.double()).sum())
+    assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs), 1.0)
+
+
+# ------------------------------------------------------------------ edge cases / error behaviour
+def test_edge_cases_and_errors(pkg):
+    d = dev()
+    f = torch.randn(1, 16, 16, 16, device=d)
+    with pytest.raises(RuntimeError):
+        pkg.CorrBlock(f.cpu(), f.cpu())
+    with pytest.raises(RuntimeError):
+        pkg.CorrBlock(f, f.double())
+    with pytest.raises(pkg.RaftCorrError):
+        pkg.CorrBlock(f[:, :, :8, :8], f[:, :, :8, :8], num_levels=4)  # level 3 would be 1x1 (NaN in the reference)
+    with pytest.raises(pkg.RaftCorrError):
+        pkg.CorrBlock(f, f, radius=7)
+    blk = pkg.CorrBlock(f, f, num_levels=2, radius=3, build_mode="fp32")
+    with pytest.raises(RuntimeError):
+        blk(torch.zeros(1, 2, 8, 8, device=d))
+    # empty batch
+    e = torch.zeros(0, 16, 16, 16, device=d)
+    out = pkg.CorrBlock(e, e, 2, 3, build_mode="fp32")(torch.zeros(0, 2, 16, 16, device=d))
+    assert tuple(out.shape) == (0, 2 * 49, 16, 16)
+    # non-contiguous inputs are accepted (the reference's matmul / grid_sample accept them too)
+    fn = torch.randn(1, 16, 16, 32, device=d)[..., ::2]
+    cn = torch.randn(1, 16, 16, 2, device=d).permute(0, 3, 1, 2) * 4 + 8
+    o1 = pkg.CorrBlock(fn, fn, 2, 3, build_mode="fp32")(cn)
+    o2 = pkg.CorrBlock(fn.contiguous(), fn.contiguous(), 2, 3, build_mode="fp32")(cn.contiguous())
+    assert torch.equal(o1, o2)
+    # wild coordinates: far outside, huge, NaN -> zeros for every tap that falls outside (zero padding)
+    c = torch.full((1, 2, 16, 16), 1.0e9, device=d)
+    c[0, :, 0, 0] = float("nan")
+    c[0, :, 1, 1] = -3.0e38
+    o = blk(c)
+    assert torch.isfinite(o[:, :, 2:, 2:]).all() and float(o[:, :, 2:, 2:].abs().max()) == 0.0
+    # CorrBlock.corr static method (corr.py:93): [B,H,W,1,H,W]
+    v = pkg.CorrBlock.corr(f, f, build_mode="fp32")
+    assert tuple(v.shape) == (1, 16, 16, 1, 16, 16)
+    ref = torch.einsum("bdm,bdn->bmn", f.reshape(1, 16, 256), f.reshape(1, 16, 256)) / 4.0
+    assert float((v.reshape(1, 256, 256) - ref).abs().max()) <= 1e-4
+
+
+def test_streams_and_determinism(pkg):
+    """Kernels launch on the caller's current stream (the reference used the legacy default stream)
+    and repeated runs are bit-identical (no atomics on the forward path)."""
+    d = dev()
+    g = torch.Generator(device=d).manual_seed(3)
+    f1 = torch.randn((2, 64, 24, 32), generator=g, device=d)
+    f2 = torch.randn((2, 64, 24, 32), generator=g, device=d)
+    coords = torch.from_numpy(O.coords_grid(2, 24, 32)).to(d) + 2.0 * torch.randn((2, 2, 24, 32), generator=g, device=d)
+    outs = []
+    for mode in MODES:
+        a = pkg.CorrBlock(f1, f2, 4, 4, build_mode=mode)(coords)
+        s = torch.cuda.Stream(device=d)
+        s.wait_stream(torch.cuda.current_stream(d))
+        with torch.cuda.stream(s):
+            b = pkg.CorrBlock(f1, f2, 4, 4, build_mode=mode)(coords)
+        s.synchronize()
+        assert torch.equal(a, b), mode
+        outs.append(a)
+    # batch sharding is exact: processing pair 1 alone gives the same bits as inside the batch
+    solo = pkg.CorrBlock(f1[1:], f2[1:], 4, 4, build_mode="fp32")(coords[1:])
+    assert torch.equal(solo, outs[0][1:])
