@@ -88,8 +88,8 @@ int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* lay, int B, int H, int
 }
 
 size_t raftcorr_build_fwd_workspace_bytes(int B, int D, int H, int W, int mode) {
-    if (mode == RAFTCORR_BUILD_TF32_TC)  // two NHWC (K-major), TF32-rounded copies of the feature maps
-        return 2 * align_up((size_t)B * D * H * W * sizeof(float), 1024);
+    if (mode == RAFTCORR_BUILD_TF32_TC)  // two NHWC (K-major), TF32-rounded, K-padded copies of the feature maps
+        return 2 * align_up((size_t)B * tc_feature_pitch(D) * H * W * sizeof(float), 1024);
     return 0;
 }
 
@@ -111,8 +111,9 @@ int raftcorr_build_fwd(const float* fmap1, const float* fmap2, int D, float* pyr
         float* f1n = (float*)workspace;
         float* f2n = (float*)((char*)workspace + need / 2);
         const int HW = lay->H * lay->W;
-        if (int rc = launch_nchw_to_nhwc(fmap1, f1n, lay->B, D, HW, true, s)) return rc;
-        if (int rc = launch_nchw_to_nhwc(fmap2, f2n, lay->B, D, HW, true, s)) return rc;
+        const int Dp = tc_feature_pitch(D);
+        if (int rc = launch_nchw_to_nhwc(fmap1, f1n, lay->B, D, HW, Dp, true, s)) return rc;
+        if (int rc = launch_nchw_to_nhwc(fmap2, f2n, lay->B, D, HW, Dp, true, s)) return rc;
         return launch_build_tc(f1n, f2n, D, pyramid, *lay, device, s);
     }
     return fail("build_fwd: unknown mode %d", mode);
@@ -213,8 +214,8 @@ int raftcorr_alt_pyramid(const float* fmap1, const float* fmap2, int B, int D, i
     DeviceGuard guard(device);
     RC_REQUIRE(guard.ok, "alt_pyramid: cannot select device %d", device);
     cudaStream_t s = (cudaStream_t)stream;
-    if (int rc = launch_nchw_to_nhwc(fmap1, f1_nhwc, B, D, H * W, false, s)) return rc;
-    if (int rc = launch_nchw_to_nhwc(fmap2, const_cast<float*>(lv.f2[0]), B, D, H * W, false, s)) return rc;
+    if (int rc = launch_nchw_to_nhwc(fmap1, f1_nhwc, B, D, H * W, D, false, s)) return rc;
+    if (int rc = launch_nchw_to_nhwc(fmap2, const_cast<float*>(lv.f2[0]), B, D, H * W, D, false, s)) return rc;
     for (int l = 1; l < L; ++l)  // corr.py:138-139 (fmap2 side; the pooled fmap1 copies are never read, :158)
         if (int rc = launch_pool_nhwc(lv.f2[l - 1], const_cast<float*>(lv.f2[l]), B, lv.h[l - 1], lv.w[l - 1], D, s))
             return rc;

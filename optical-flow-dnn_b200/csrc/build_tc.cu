@@ -1,7 +1,489 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// Correlation volume + pyramid build on the 5th-gen tensor cores (RAFTCORR_BUILD_TF32_TC).
+//
+//   V0[b][m][n] = <f1[b][m][:], f2[b][n][:]> / sqrt(D)           (CorrBlock.corr, raft/core/corr.py:93-116)
+//   V_{l+1}     = avg_pool2d(V_l, 2, stride 2) over the target dims (corr.py:41-43)
+//
+// One persistent, warp-specialised kernel replaces the reference's SGEMM + scale + 3 pooling passes:
+//
+//   warp 0  TMA producer : A tile [128 source px][32 k] and B tile [8 x 32 target px][32 k] per k-block,
+//                          128B-swizzled, K-major, straight from the NHWC (TF32-rounded) feature maps;
+//                          B is fetched as a 4-D box over [b][h][w][d] so that one N tile is a spatially
+//                          aligned 8x32 block of target pixels (out-of-range rows/cols are zero-filled).
+//   warp 1  MMA issuer   : tcgen05.mma.cta_group::1.kind::tf32, M=128, N=256, K=8 per instruction,
+//                          fp32 accumulators in TMEM, two 256-column accumulator stages (all 512 columns)
+//                          so the MMAs of tile i+1 overlap the epilogue of tile i.
+//   warp 2  TMEM allocator
+//   warps 4-7 epilogue   : TMEM lane == source pixel, so one thread owns the whole 8x32 target block of
+//                          its source pixel: tcgen05.ld two rows at a time, scale by 1/sqrt(D), stage the
+//                          level-0 rows in swizzled shared memory and TMA-store them ([128 px][128 B] boxes,
+//                          bounds clipped by the tensor map), and reduce 2x2 / 4x4 / 8x8 means in registers
+//                          for levels 1..3 (floor-mode pooling == block means over the floor-cropped region,
+//                          since floor(floor(n/2)/2) == floor(n/4)), written with 128-bit stores.
+//
+// The kernel is bound by the fp32 pyramid write (174 KB per tile vs 4096 tensor cycles per tile),
+// see DESIGN.md; the MMA pipe has slack, the epilogue/TMA-store path is what is tuned.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace raftcorr {
-int launch_build_tc(const float*, const float*, int, float*, const raftcorr_pyramid_layout&, int, cudaStream_t) {
-    return fail("build_fwd: TF32 tensor-core mode not built yet");
+
+namespace {
+
+constexpr int kTileM = 128;       // source pixels per tile (TMEM lanes)
+constexpr int kTileH = 8;         // target rows per tile
+constexpr int kTileW = 32;        // target cols per tile
+constexpr int kTileN = kTileH * kTileW;  // 256 = UMMA N
+constexpr int kBlockK = 32;       // floats per k-block = one 128-byte swizzle row
+constexpr int kUmmaK = 8;         // tf32: 32 bytes per instruction
+constexpr int kStages = 3;
+constexpr int kABytes = kTileM * kBlockK * 4;   // 16 KB
+constexpr int kBBytes = kTileN * kBlockK * 4;   // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;  // 48 KB
+constexpr int kRowTileBytes = kTileM * kTileW * 4;  // 16 KB: one target row for 128 source pixels
+constexpr int kStoreBufBytes = 2 * kRowTileBytes;   // two rows per phase
+constexpr int kNumStoreBufs = 2;
+constexpr int kSmemBytes = kStages * kStageBytes + kNumStoreBufs * kStoreBufBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kThreads = 256;
+constexpr int kEpilogueThreads = 128;
+constexpr uint32_t kTmemCols = 512;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trapped launch (reported by the next CUDA call) instead of a hang.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
+//   bits [0,14) start >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, 1) | [32,46) SBO >> 4 = 64
+//   bits [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// kind::tf32 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), both K-major,
+// N>>3 at bits 17-22, M>>4 at bits 24-28.
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
+                                ((uint32_t)(kTileM >> 4) << 24);
+
+struct BuildParams {
+    float* lvl_base[4];     // pooled levels 1..3 (index by level); [0] unused (TMA path)
+    int lvl_h[4], lvl_w[4], lvl_pitch[4];
+    int64_t lvl_img_stride[4];
+    int B, N1, H2, W2, L;
+    int m_tiles, bands, w_tiles, k_blocks;
+    int total_tiles;
+    float scale;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_out, const BuildParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment: required by the 128B swizzle atoms of TMA and UMMA
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t stage_base = smem_base;                                  // kStages x (A | B)
+    const uint32_t store_base = smem_base + kStages * kStageBytes;          // kNumStoreBufs x 2 rows
+    const uint32_t bar_base = store_base + kNumStoreBufs * kStoreBufBytes;  // mbarriers (8 B each)
+    const uint32_t full_bar = bar_base;                       // [kStages]
+    const uint32_t empty_bar = bar_base + 8 * kStages;        // [kStages]
+    const uint32_t tfull_bar = bar_base + 16 * kStages;       // [2]
+    const uint32_t tempty_bar = tfull_bar + 16;               // [2]
+    const uint32_t tmem_slot = tempty_bar + 16;               // u32 written by tcgen05.alloc
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar + 8 * s, 1);
+            mbar_init(empty_bar + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar + 8 * a, 1);
+            mbar_init(tempty_bar + 8 * a, kEpilogueThreads);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+    const int tiles_per_m = P.bands * P.w_tiles;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+                const int wt = t % P.w_tiles;
+                const int band = (t / P.w_tiles) % P.bands;
+                const int mt = (t / tiles_per_m) % P.m_tiles;
+                const int b = t / (tiles_per_m * P.m_tiles);
+                for (int kb = 0; kb < P.k_blocks; ++kb) {
+                    mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+                    const uint32_t sa = stage_base + stage * kStageBytes;
+                    const uint32_t sb = sa + kABytes;
+                    mbar_expect_tx(full_bar + 8 * stage, kStageBytes);
+                    tma_load_3d(sa, &map_a, full_bar + 8 * stage, kb * kBlockK, mt * kTileM, b);
+                    tma_load_4d(sb, &map_b, full_bar + 8 * stage, kb * kBlockK, wt * kTileW, band * kTileH, b);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kTileN;
+                for (int kb = 0; kb < P.k_blocks; ++kb) {
+                    mbar_wait(full_bar + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = stage_base + stage * kStageBytes;
+                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t bdesc = make_smem_desc(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        // advance 32 bytes along K inside the swizzle row: +2 in the (>>4) start-address field
+                        tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(empty_bar + 8 * stage);  // frees the smem slot when these MMAs retire
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;                  // == warp % 4: TMEM lane quarter this warp may access
+        const int ml = ew * 32 + lane;            // source pixel inside the tile == TMEM lane
+        const bool issuer = (threadIdx.x == 4 * 32);
+        const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+        const uint32_t swz = (uint32_t)(ml & 7);
+        int it = 0;
+        int buf = 0;
+        for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+            const int wt = t % P.w_tiles;
+            const int band = (t / P.w_tiles) % P.bands;
+            const int mt = (t / tiles_per_m) % P.m_tiles;
+            const int b = t / (tiles_per_m * P.m_tiles);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int m = mt * kTileM + ml;
+            const bool m_ok = m < P.N1;
+            const int w0 = wt * kTileW;
+
+            mbar_wait(tfull_bar + 8 * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + lane_addr + acc * kTileN;
+
+            float l1prev[16], l2prev[8];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                float ra[32], rb[32];
+                tmem_ld32(t_acc + (2 * p) * kTileW, ra);
+                tmem_ld32(t_acc + (2 * p + 1) * kTileW, rb);
+                tmem_ld_wait();
+                if (p == 3) {  // all of this accumulator is in registers: hand it back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(tempty_bar + 8 * acc);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    ra[j] *= P.scale;
+                    rb[j] *= P.scale;
+                }
+                // ---- level 0: two rows -> swizzled staging -> TMA store
+                const uint32_t sa = store_base + buf * kStoreBufBytes + ml * 128;
+                const uint32_t sb = sa + kRowTileBytes;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t off = ((uint32_t)j ^ swz) << 4;
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(ra[4 * j]),
+                                 "f"(ra[4 * j + 1]), "f"(ra[4 * j + 2]), "f"(ra[4 * j + 3])
+                                 : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + off), "f"(rb[4 * j]),
+                                 "f"(rb[4 * j + 1]), "f"(rb[4 * j + 2]), "f"(rb[4 * j + 3])
+                                 : "memory");
+                }
+                fence_proxy_async();
+                // the other buffer (used by the previous phase) must have been read out before the next
+                // phase overwrites it; waiting here, one phase late, keeps one store group in flight
+                if (issuer) tma_store_wait_read_all();
+                named_bar_sync(1, kEpilogueThreads);
+                if (issuer) {
+                    const uint32_t s0 = store_base + buf * kStoreBufBytes;
+                    const int h = band * kTileH + 2 * p;
+                    tma_store_4d(&map_out, s0, w0, h, mt * kTileM, b);
+                    tma_store_4d(&map_out, s0 + kRowTileBytes, w0, h + 1, mt * kTileM, b);
+                    tma_store_commit();
+                }
+                buf ^= 1;
+                // ---- levels 1..3: thread-local block means, 128-bit stores
+                if (P.L > 1) {
+                    float l1[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) l1[j] = (ra[2 * j] + ra[2 * j + 1] + rb[2 * j] + rb[2 * j + 1]) * 0.25f;
+                    const int h1 = band * 4 + p;
+                    if (m_ok && h1 < P.lvl_h[1]) {
+                        float* dst = P.lvl_base[1] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[1] +
+                                     (int64_t)h1 * P.lvl_pitch[1] + (w0 >> 1);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if ((w0 >> 1) + 4 * q + 4 <= P.lvl_pitch[1])
+                                *reinterpret_cast<float4*>(dst + 4 * q) =
+                                    make_float4(l1[4 * q], l1[4 * q + 1], l1[4 * q + 2], l1[4 * q + 3]);
+                    }
+                    if (P.L > 2) {
+                        if ((p & 1) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) l1prev[j] = l1[j];
+                        } else {
+                            float l2[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                l2[j] = (l1prev[2 * j] + l1prev[2 * j + 1] + l1[2 * j] + l1[2 * j + 1]) * 0.25f;
+                            const int h2 = band * 2 + (p >> 1);
+                            if (m_ok && h2 < P.lvl_h[2]) {
+                                float* dst = P.lvl_base[2] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[2] +
+                                             (int64_t)h2 * P.lvl_pitch[2] + (w0 >> 2);
+#pragma unroll
+                                for (int q = 0; q < 2; ++q)
+                                    if ((w0 >> 2) + 4 * q + 4 <= P.lvl_pitch[2])
+                                        *reinterpret_cast<float4*>(dst + 4 * q) =
+                                            make_float4(l2[4 * q], l2[4 * q + 1], l2[4 * q + 2], l2[4 * q + 3]);
+                            }
+                            if (P.L > 3) {
+                                if (p == 1) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) l2prev[j] = l2[j];
+                                } else {
+                                    float l3[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        l3[j] = (l2prev[2 * j] + l2prev[2 * j + 1] + l2[2 * j] + l2[2 * j + 1]) * 0.25f;
+                                    if (m_ok && band < P.lvl_h[3] && (w0 >> 3) + 4 <= P.lvl_pitch[3]) {
+                                        float* dst = P.lvl_base[3] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[3] +
+                                                     (int64_t)band * P.lvl_pitch[3] + (w0 >> 3);
+                                        *reinterpret_cast<float4*>(dst) = make_float4(l3[0], l3[1], l3[2], l3[3]);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (issuer) tma_store_wait_all();  // global writes complete before the CTA exits
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+    static EncodeTiledFn cached = nullptr;  // immutable once resolved; benign if two threads race to set it
+    if (!cached) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        RC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        RC_REQUIRE(qres == cudaDriverEntryPointSuccess && fn, "cuTensorMapEncodeTiled not available from the driver");
+        cached = (EncodeTiledFn)fn;
+    }
+    *out = cached;
+    return 0;
+}
+
+int encode(EncodeTiledFn fn, CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+           const cuuint32_t* box, CUtensorMapL2promotion promo, const char* what) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+    return 0;
+}
+
+}  // namespace
+
+int tc_feature_pitch(int D) { return (D + kBlockK - 1) / kBlockK * kBlockK; }
+
+// f1n/f2n: [B][H*W][Dp] fp32, TF32-rounded, zero-padded to Dp = tc_feature_pitch(D)
+int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, const raftcorr_pyramid_layout& lay,
+                    int device, cudaStream_t s) {
+    RC_REQUIRE(lay.L <= 4, "tf32 build: at most 4 pyramid levels are fused (got %d); use the fp32 mode", lay.L);
+    EncodeTiledFn fn;
+    if (int rc = get_encode_fn(&fn)) return rc;
+    const int B = lay.B, H = lay.H, W = lay.W, N1 = H * W;
+    const int Dp = tc_feature_pitch(D);
+
+    CUtensorMap map_a, map_b, map_out;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)Dp, (cuuint64_t)N1, (cuuint64_t)B};
+        cuuint64_t strides[2] = {(cuuint64_t)Dp * 4, (cuuint64_t)N1 * Dp * 4};
+        cuuint32_t box[3] = {kBlockK, kTileM, 1};
+        if (int rc = encode(fn, &map_a, (void*)f1n, 3, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap1"))
+            return rc;
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Dp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)Dp * 4, (cuuint64_t)W * Dp * 4, (cuuint64_t)N1 * Dp * 4};
+        cuuint32_t box[4] = {kBlockK, kTileW, kTileH, 1};
+        if (int rc = encode(fn, &map_b, (void*)f2n, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2"))
+            return rc;
+    }
+    {
+        const int64_t img = (int64_t)lay.h[0] * lay.pitch[0];
+        cuuint64_t dims[4] = {(cuuint64_t)lay.w[0], (cuuint64_t)lay.h[0], (cuuint64_t)N1, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)lay.pitch[0] * 4, (cuuint64_t)img * 4, (cuuint64_t)N1 * img * 4};
+        cuuint32_t box[4] = {kTileW, 1, kTileM, 1};
+        if (int rc = encode(fn, &map_out, (void*)(pyramid + lay.offset[0]), 4, dims, strides, box,
+                            CU_TENSOR_MAP_L2_PROMOTION_NONE, "volume"))
+            return rc;
+    }
+
+    BuildParams P{};
+    for (int l = 0; l < lay.L; ++l) {
+        P.lvl_base[l] = pyramid + lay.offset[l];
+        P.lvl_h[l] = lay.h[l];
+        P.lvl_w[l] = lay.w[l];
+        P.lvl_pitch[l] = lay.pitch[l];
+        P.lvl_img_stride[l] = (int64_t)lay.h[l] * lay.pitch[l];
+    }
+    P.B = B; P.N1 = N1; P.H2 = H; P.W2 = W; P.L = lay.L;
+    P.m_tiles = ceil_div(N1, kTileM);
+    P.bands = ceil_div(H, kTileH);
+    P.w_tiles = ceil_div(W, kTileW);
+    P.k_blocks = Dp / kBlockK;
+    const int64_t total = (int64_t)B * P.m_tiles * P.bands * P.w_tiles;
+    RC_REQUIRE(total < (1LL << 31), "tf32 build: too many tiles");
+    P.total_tiles = (int)total;
+    P.scale = 1.0f / sqrtf((float)D);  // corr.py:116
+
+    int sms = 0;
+    RC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    RC_CUDA(cudaFuncSetAttribute(build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    const int grid = P.total_tiles < sms ? P.total_tiles : sms;
+    build_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(map_a, map_b, map_out, P);
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace raftcorr

@@ -15,13 +15,14 @@ __device__ __forceinline__ float round_tf32(float x) {
 }
 
 // in [B][D][HW] -> out [B][HW][D]; 32x32 tiles through shared memory, both sides coalesced.
+// Dout >= D is the output row pitch; channels [D, Dout) are zero-filled (K padding for the tensor-core path).
 template <bool ROUND>
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int D, int HW) {
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int D, int HW, int Dout) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int p0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
     const float* src = in + (int64_t)b * D * HW;
-    float* dst = out + (int64_t)b * D * HW;
+    float* dst = out + (int64_t)b * Dout * HW;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int d = d0 + i, p = p0 + threadIdx.x;
         tile[i][threadIdx.x] = (d < D && p < HW) ? src[(int64_t)d * HW + p] : 0.f;
@@ -29,9 +30,9 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int p = p0 + i, d = d0 + threadIdx.x;
-        if (p < HW && d < D) {
+        if (p < HW && d < Dout) {
             float v = tile[threadIdx.x][i];
-            dst[(int64_t)p * D + d] = ROUND ? round_tf32(v) : v;
+            dst[(int64_t)p * Dout + d] = ROUND ? round_tf32(v) : v;
         }
     }
 }
@@ -105,12 +106,12 @@ inline int grid_for(int64_t total, int threads) {
 
 }  // namespace
 
-int launch_nchw_to_nhwc(const float* in, float* out, int B, int D, int HW, bool round, cudaStream_t s) {
-    dim3 grid(ceil_div(HW, 32), ceil_div(D, 32), B), block(32, 8);
+int launch_nchw_to_nhwc(const float* in, float* out, int B, int D, int HW, int Dout, bool round, cudaStream_t s) {
+    dim3 grid(ceil_div(HW, 32), ceil_div(Dout, 32), B), block(32, 8);
     if (round)
-        nchw_to_nhwc_kernel<true><<<grid, block, 0, s>>>(in, out, D, HW);
+        nchw_to_nhwc_kernel<true><<<grid, block, 0, s>>>(in, out, D, HW, Dout);
     else
-        nchw_to_nhwc_kernel<false><<<grid, block, 0, s>>>(in, out, D, HW);
+        nchw_to_nhwc_kernel<false><<<grid, block, 0, s>>>(in, out, D, HW, Dout);
     RC_CUDA(cudaGetLastError());
     return 0;
 }
@@ -118,7 +119,7 @@ int launch_nchw_to_nhwc(const float* in, float* out, int B, int D, int HW, bool 
 int launch_nhwc_to_nchw(const float* in, float* out, int B, int D, int HW, cudaStream_t s) {
     // the same tile transpose with the roles of D and HW swapped
     dim3 grid(ceil_div(D, 32), ceil_div(HW, 32), B), block(32, 8);
-    nchw_to_nhwc_kernel<false><<<grid, block, 0, s>>>(in, out, HW, D);
+    nchw_to_nhwc_kernel<false><<<grid, block, 0, s>>>(in, out, HW, D, HW);
     RC_CUDA(cudaGetLastError());
     return 0;
 }
