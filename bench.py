@@ -182,6 +182,14 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    if args.l2_fetch:
+        import ctypes
+
+        from optical_flow_dnn_b200 import _lib
+        prev = ctypes.c_int(0)
+        _lib.check(_lib.lib().raftcorr_set_l2_fetch_granularity(args.l2_fetch, local_rank, ctypes.byref(prev)), "l2 fetch")
+        if rank == 0:
+            print(f"[bench] L2 fetch granularity {prev.value} -> {args.l2_fetch} bytes", file=sys.stderr)
     B, D, H, W, L, r = (SHAPE[k] for k in "BDHWLr")
     B = args.batch or B
     iters = args.iters
@@ -333,6 +341,7 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("RAFTCORR_BUILD_MODE", "tf32"), choices=["tf32", "fp32"])
     ap.add_argument("--batch", type=int, default=0, help="frame pairs per GPU (default 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--l2-fetch", type=int, default=0, help="set cudaLimitMaxL2FetchGranularity (32/64/128) first")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -68,6 +68,12 @@ enum {
 int raftcorr_abi_version(void);
 const char* raftcorr_last_error(void);
 
+/* Tuning knob (process-wide CUDA device limit, not per call): cudaLimitMaxL2FetchGranularity for
+ * `device`, in bytes (32, 64 or 128).  The lookup is a sparse gather of 40-byte runs; the default
+ * 64-byte DRAM->L2 fill granularity doubles its DRAM traffic.  Returns the previous value through
+ * *previous when non-NULL. */
+int raftcorr_set_l2_fetch_granularity(int bytes, int device, int* previous);
+
 /* Host-only helper: fill *layout for a [B,D,H,W] pair of feature maps and L levels.
  * Fails if L < 1, L > RAFTCORR_MAX_LEVELS or a level would collapse below 2x2 (the reference
  * divides by (W_l - 1), utils.py:74-75, and yields NaN there). */

@@ -37,6 +37,7 @@ _LAYP = ctypes.POINTER(PyramidLayout)
 SIGNATURES = {
     "raftcorr_abi_version": (_c_int, []),
     "raftcorr_last_error": (ctypes.c_char_p, []),
+    "raftcorr_set_l2_fetch_granularity": (_c_int, [_c_int, _c_int, ctypes.POINTER(_c_int)]),
     "raftcorr_pyramid_layout_init": (_c_int, [_LAYP, _c_int, _c_int, _c_int, _c_int]),
     "raftcorr_build_fwd_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "raftcorr_build_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _LAYP, _c_int, _c_void_p, _c_size_t,

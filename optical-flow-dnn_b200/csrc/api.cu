@@ -62,6 +62,17 @@ int raftcorr_abi_version(void) { return RAFTCORR_ABI_VERSION; }
 
 const char* raftcorr_last_error(void) { return error_buffer(); }
 
+int raftcorr_set_l2_fetch_granularity(int bytes, int device, int* previous) {
+    RC_REQUIRE(bytes == 32 || bytes == 64 || bytes == 128, "L2 fetch granularity must be 32, 64 or 128 (got %d)", bytes);
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "cannot select device %d", device);
+    size_t prev = 0;
+    RC_CUDA(cudaDeviceGetLimit(&prev, cudaLimitMaxL2FetchGranularity));
+    if (previous) *previous = (int)prev;
+    RC_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
+    return 0;
+}
+
 int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* lay, int B, int H, int W, int L) {
     RC_REQUIRE(lay != nullptr, "layout is NULL");
     RC_REQUIRE(L >= 1 && L <= RAFTCORR_MAX_LEVELS, "num_levels must be in [1, %d] (got %d)", RAFTCORR_MAX_LEVELS, L);
@@ -97,9 +108,9 @@ int raftcorr_build_fwd(const float* fmap1, const float* fmap2, int D, float* pyr
                        const raftcorr_pyramid_layout* lay, int mode, void* workspace, size_t workspace_bytes,
                        int device, raftcorr_stream_t stream) {
     if (int rc = check_layout(lay)) return rc;
+    if (lay->B == 0) return 0;  // empty batch: nothing to do (and no storage behind the pointers)
     RC_REQUIRE(fmap1 && fmap2 && pyramid, "build_fwd: NULL tensor");
     RC_REQUIRE(D >= 1, "build_fwd: bad feature dim %d", D);
-    if (lay->B == 0) return 0;
     DeviceGuard guard(device);
     RC_REQUIRE(guard.ok, "build_fwd: cannot select device %d", device);
     cudaStream_t s = (cudaStream_t)stream;
@@ -122,8 +133,8 @@ int raftcorr_build_fwd(const float* fmap1, const float* fmap2, int D, float* pyr
 int raftcorr_lookup_fwd(const float* pyramid, const raftcorr_pyramid_layout* lay, const float* coords, int radius,
                         float* out, int device, raftcorr_stream_t stream) {
     if (int rc = check_layout(lay)) return rc;
-    RC_REQUIRE(pyramid && coords && out, "lookup_fwd: NULL tensor");
     if (lay->B == 0) return 0;
+    RC_REQUIRE(pyramid && coords && out, "lookup_fwd: NULL tensor");
     DeviceGuard guard(device);
     RC_REQUIRE(guard.ok, "lookup_fwd: cannot select device %d", device);
     PyramidView pv = make_view(const_cast<float*>(pyramid), *lay);
@@ -134,9 +145,9 @@ int raftcorr_lookup_bwd(const float* grad_out, const float* coords, const float*
                         const raftcorr_pyramid_layout* lay, int radius, float* dcoords, int device,
                         raftcorr_stream_t stream) {
     if (int rc = check_layout(lay)) return rc;
+    if (lay->B == 0) return 0;
     RC_REQUIRE(grad_out && coords && dpyramid, "lookup_bwd: NULL tensor");
     RC_REQUIRE(!dcoords || pyramid, "lookup_bwd: dcoords requested without the forward pyramid");
-    if (lay->B == 0) return 0;
     DeviceGuard guard(device);
     RC_REQUIRE(guard.ok, "lookup_bwd: cannot select device %d", device);
     cudaStream_t s = (cudaStream_t)stream;
@@ -152,8 +163,8 @@ int raftcorr_lookup_bwd(const float* grad_out, const float* coords, const float*
 int raftcorr_build_bwd(float* dpyramid, const raftcorr_pyramid_layout* lay, const float* fmap1, const float* fmap2,
                        int D, float* dfmap1, float* dfmap2, int device, raftcorr_stream_t stream) {
     if (int rc = check_layout(lay)) return rc;
-    RC_REQUIRE(dpyramid && fmap1 && fmap2 && dfmap1 && dfmap2, "build_bwd: NULL tensor");
     if (lay->B == 0) return 0;
+    RC_REQUIRE(dpyramid && fmap1 && fmap2 && dfmap1 && dfmap2, "build_bwd: NULL tensor");
     DeviceGuard guard(device);
     RC_REQUIRE(guard.ok, "build_bwd: cannot select device %d", device);
     cudaStream_t s = (cudaStream_t)stream;
@@ -166,7 +177,7 @@ int raftcorr_build_bwd(float* dpyramid, const raftcorr_pyramid_layout* lay, cons
 
 int raftcorr_alt_forward(const float* fmap1, const float* fmap2, const float* coords, int B, int N, int H1, int W1,
                          int H2, int W2, int C, int radius, float* corr, int device, raftcorr_stream_t stream) {
-    RC_REQUIRE(fmap1 && fmap2 && coords && corr, "alt_forward: NULL tensor");
+    RC_REQUIRE(B == 0 || (fmap1 && fmap2 && coords && corr), "alt_forward: NULL tensor");
     RC_REQUIRE(B >= 0 && N >= 1 && H1 >= 1 && W1 >= 1 && H2 >= 1 && W2 >= 1, "alt_forward: bad sizes");
     if (B == 0) return 0;
     DeviceGuard guard(device);
@@ -182,7 +193,7 @@ int raftcorr_alt_backward(const float* fmap1, const float* fmap2, const float* c
                           int N, int H1, int W1, int H2, int W2, int C, int radius, float* fmap1_grad,
                           float* fmap2_grad, float* coords_grad, int device, raftcorr_stream_t stream) {
     (void)coords_grad;  // identically zero in the reference (correlation_kernel.cu:307); caller zero-fills
-    RC_REQUIRE(fmap1 && fmap2 && coords && corr_grad && fmap1_grad && fmap2_grad, "alt_backward: NULL tensor");
+    RC_REQUIRE(B == 0 || (fmap1 && fmap2 && coords && corr_grad && fmap1_grad && fmap2_grad), "alt_backward: NULL tensor");
     RC_REQUIRE(B >= 0 && N >= 1 && H1 >= 1 && W1 >= 1 && H2 >= 1 && W2 >= 1, "alt_backward: bad sizes");
     if (B == 0) return 0;
     DeviceGuard guard(device);
@@ -207,7 +218,7 @@ int64_t raftcorr_alt_level_offset(int B, int D, int H, int W, int level) {
 
 int raftcorr_alt_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int L, float* f1_nhwc,
                          float* f2_pyr, int device, raftcorr_stream_t stream) {
-    RC_REQUIRE(fmap1 && fmap2 && f1_nhwc && f2_pyr, "alt_pyramid: NULL tensor");
+    RC_REQUIRE(B == 0 || (fmap1 && fmap2 && f1_nhwc && f2_pyr), "alt_pyramid: NULL tensor");
     AltLevels lv{};
     if (int rc = alt_levels(f2_pyr, nullptr, B, D, H, W, L, &lv)) return rc;
     if (B == 0) return 0;
@@ -224,7 +235,7 @@ int raftcorr_alt_pyramid(const float* fmap1, const float* fmap2, int B, int D, i
 
 int raftcorr_alt_lookup_fwd(const float* f1_nhwc, const float* f2_pyr, const float* coords, int B, int D, int H,
                             int W, int L, int radius, float* out, int device, raftcorr_stream_t stream) {
-    RC_REQUIRE(f1_nhwc && f2_pyr && coords && out, "alt_lookup_fwd: NULL tensor");
+    RC_REQUIRE(B == 0 || (f1_nhwc && f2_pyr && coords && out), "alt_lookup_fwd: NULL tensor");
     AltLevels lv{};
     if (int rc = alt_levels(f2_pyr, nullptr, B, D, H, W, L, &lv)) return rc;
     if (B == 0) return 0;
@@ -239,7 +250,7 @@ int raftcorr_alt_lookup_fwd(const float* f1_nhwc, const float* f2_pyr, const flo
 int raftcorr_alt_lookup_bwd(const float* f1_nhwc, const float* f2_pyr, const float* coords, const float* grad_out,
                             int B, int D, int H, int W, int L, int radius, float* df1_nhwc, float* df2_pyr,
                             int device, raftcorr_stream_t stream) {
-    RC_REQUIRE(f1_nhwc && f2_pyr && coords && grad_out && df1_nhwc && df2_pyr, "alt_lookup_bwd: NULL tensor");
+    RC_REQUIRE(B == 0 || (f1_nhwc && f2_pyr && coords && grad_out && df1_nhwc && df2_pyr), "alt_lookup_bwd: NULL tensor");
     AltLevels lv{};
     if (int rc = alt_levels(f2_pyr, df2_pyr, B, D, H, W, L, &lv)) return rc;
     if (B == 0) return 0;
@@ -253,7 +264,7 @@ int raftcorr_alt_lookup_bwd(const float* f1_nhwc, const float* f2_pyr, const flo
 
 int raftcorr_alt_grad_finish(const float* df1_nhwc, float* df2_pyr, int B, int D, int H, int W, int L, float* dfmap1,
                              float* dfmap2, int device, raftcorr_stream_t stream) {
-    RC_REQUIRE(df1_nhwc && df2_pyr && dfmap1 && dfmap2, "alt_grad_finish: NULL tensor");
+    RC_REQUIRE(B == 0 || (df1_nhwc && df2_pyr && dfmap1 && dfmap2), "alt_grad_finish: NULL tensor");
     AltLevels lv{};
     if (int rc = alt_levels(df2_pyr, df2_pyr, B, D, H, W, L, &lv)) return rc;
     if (B == 0) return 0;

@@ -1,0 +1,17 @@
+#!/bin/bash
+# gpurun payload: full GPU test-suite + smoke + bench (+ L2-fetch experiment) + ncu full capture of build and lookup
+set -u
+OUT=gpurun_out; TAG=${1:-p1}; mkdir -p $OUT
+timeout 1500 python -m pytest tests -m gpu -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?"; tail -5 $OUT/${TAG}_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?"; tail -4 $OUT/${TAG}_smoke.log
+timeout 600 python bench.py --steps 20 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"; cat $OUT/${TAG}_bench.json
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --l2-fetch 32 > $OUT/${TAG}_bench_l2f32.json 2> $OUT/${TAG}_bench_l2f32.err; echo "bench l2f32 exit $?"; cat $OUT/${TAG}_bench_l2f32.json
+timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_plain.log 2>&1 &&
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/${TAG}_launches.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu1.log 2>&1
+echo "ncu launches exit $?"
+timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_plain2.log 2>&1 &&
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:build_tc_kernel|lookup_fwd" -s 39 -c 2 -f -o $OUT/${TAG}_prof \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu2.log 2>&1
+echo "ncu full exit $?"
+ls -la $OUT | tail -15
