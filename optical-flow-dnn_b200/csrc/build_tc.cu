@@ -135,6 +135,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// 256-bit global store: one full 32-byte sector per thread (two 128-bit stores would each send a
+// half-filled sector through the L1->XBAR path, which is what bounds this kernel)
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                 "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
@@ -338,10 +345,8 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         float* dst = P.lvl_base[1] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[1] +
                                      (int64_t)h1 * P.lvl_pitch[1] + (w0 >> 1);
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if ((w0 >> 1) + 4 * q + 4 <= P.lvl_pitch[1])
-                                *reinterpret_cast<float4*>(dst + 4 * q) =
-                                    make_float4(l1[4 * q], l1[4 * q + 1], l1[4 * q + 2], l1[4 * q + 3]);
+                        for (int q = 0; q < 2; ++q)
+                            if ((w0 >> 1) + 8 * q + 8 <= P.lvl_pitch[1]) st_global_v8(dst + 8 * q, l1 + 8 * q);
                     }
                     if (P.L > 2) {
                         if ((p & 1) == 0) {
@@ -356,11 +361,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             if (m_ok && h2 < P.lvl_h[2]) {
                                 float* dst = P.lvl_base[2] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[2] +
                                              (int64_t)h2 * P.lvl_pitch[2] + (w0 >> 2);
-#pragma unroll
-                                for (int q = 0; q < 2; ++q)
-                                    if ((w0 >> 2) + 4 * q + 4 <= P.lvl_pitch[2])
-                                        *reinterpret_cast<float4*>(dst + 4 * q) =
-                                            make_float4(l2[4 * q], l2[4 * q + 1], l2[4 * q + 2], l2[4 * q + 3]);
+                                if ((w0 >> 2) + 8 <= P.lvl_pitch[2]) st_global_v8(dst, l2);
                             }
                             if (P.L > 3) {
                                 if (p == 1) {

@@ -79,47 +79,100 @@ __device__ __forceinline__ void fetch_patches(const GroupView& g, int b, int p, 
     }
 }
 
+// ---- forward ---------------------------------------------------------------------------------
+// One 256-bit load per lane fetches a whole 32-byte sector of a patch row (rows are sector aligned:
+// the pitch is a multiple of 8 floats), so a (pixel, level) patch is ONE load instruction:
+// lane -> (row, sector) with NS = ceil((7 + K + 1) / 8) sectors per row.  The sectors are parked in
+// shared memory unshifted; the sub-sector offset ox = x0 & 7 is applied when the K*K outputs read
+// their four taps.
+template <int R>
+struct FwdGeo {
+    static constexpr int K = 2 * R + 1;
+    static constexpr int K1 = K + 1;
+    static constexpr int NS = (7 + K1 + 7) / 8;        // 32-byte sectors a patch row can straddle
+    static constexpr int TASKS = K1 * NS;              // <= 32 for R <= 4
+    static constexpr int PITCH = NS * 8 + 4;           // floats; +4 keeps rows 16-byte aligned, spreads banks
+    static constexpr int PATCH = K1 * PITCH;
+    static constexpr int KK = K * K;
+    static constexpr int NT = (KK + 31) / 32;
+    static_assert(TASKS <= 32, "one load instruction per (pixel, level)");
+};
+
+__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
+    asm("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+
 template <int R, int LG>
 __global__ void __launch_bounds__(kWarps * 32, 4)
 lookup_fwd_kernel(const GroupView g, const float* __restrict__ coords, float* __restrict__ out) {
-    using G = Geo<R>;
+    using G = FwdGeo<R>;
     constexpr int CH = LG * G::KK;
-    extern __shared__ float smem[];
-    float* out_s = smem;                                 // [CH][kTilePitch]
-    float* patch_s = smem + CH * kTilePitch;             // [kWarps][LG][NP]
+    extern __shared__ __align__(16) float smem[];
+    float* out_s = smem;                                                  // [CH][kTilePitch]
+    float* patch_s = smem + ((CH * kTilePitch + 3) & ~3);                 // [kWarps][LG][PATCH], 16-byte aligned
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y, p0 = blockIdx.x * kPix;
     const int N = g.N;
 
-    LaneGeo<R, LG> lg;
-    lg.init(lane);
+    const int trow = lane / G::NS, tsec = lane - trow * G::NS;  // this lane's (row, sector) of every patch
+    const bool tactive = lane < G::TASKS;
     int ooff[G::NT];
 #pragma unroll
     for (int t = 0; t < G::NT; ++t) {
         const int c = lane + 32 * t;
         const int i = c / G::K, j = c - i * G::K;  // channel c = i*K + j: i along x, j along y
-        ooff[t] = j * G::K1 + i;
+        ooff[t] = j * G::PITCH + i;
     }
-    float* patch = patch_s + warp * (LG * G::NP);
+    float* patch = patch_s + warp * (LG * G::PATCH);
 
     for (int q = warp; q < kPix; q += kWarps) {
         const int p = p0 + q;
         if (p >= N) break;
         const float cx = __ldg(coords + ((int64_t)b * 2 + 0) * N + p);
         const float cy = __ldg(coords + ((int64_t)b * 2 + 1) * N + p);
-        float v[LG][G::NK], fx[LG], fy[LG];
-        int x0[LG], y0[LG];
-        fetch_patches<R, LG>(g, b, p, cx, cy, lane, lg, v, fx, fy, x0, y0);
+        float v[LG][8], fx[LG], fy[LG];
+        int ox[LG], cc[LG];
+        bool ok[LG];
+        // phase A: all levels' loads are issued back to back (out-of-range lanes read the level base
+        // and are zeroed afterwards, so no load sits behind a branch)
 #pragma unroll
-        for (int l = 0; l < LG; ++l)
+        for (int l = 0; l < LG; ++l) {
+            const LevelView& lv = g.lvl[l];
+            const float x = cx * g.inv_scale[l], y = cy * g.inv_scale[l];
+            const float xf = floorf(x), yf = floorf(y);
+            fx[l] = x - xf;
+            fy[l] = y - yf;
+            const int x0 = (int)clamp_coord(xf) - R, y0 = (int)clamp_coord(yf) - R;
+            ox[l] = x0 & 7;
+            const int yy = y0 + trow;
+            cc[l] = (x0 & ~7) + 8 * tsec;
+            ok[l] = tactive && yy >= 0 && yy < lv.h && cc[l] >= 0 && cc[l] < lv.w;
+            const float* src = lv.base + ((int64_t)b * N + p) * lv.img_stride + (int64_t)yy * lv.pitch + cc[l];
+            ldg256(ok[l] ? src : lv.base, v[l]);
+        }
+        // phase B: zero padding (whole sector outside, or row tail inside the pitch padding)
 #pragma unroll
-            for (int k = 0; k < G::NK; ++k)
-                if (lane + 32 * k < G::NP) patch[l * G::NP + lane + 32 * k] = v[l][k];
+        for (int l = 0; l < LG; ++l) {
+            const int w = g.lvl[l].w;
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (!ok[l] || cc[l] + e >= w) v[l][e] = 0.f;
+        }
+        if (tactive) {
+#pragma unroll
+            for (int l = 0; l < LG; ++l) {
+                float4* dst = reinterpret_cast<float4*>(patch + l * G::PATCH + trow * G::PITCH + tsec * 8);
+                dst[0] = make_float4(v[l][0], v[l][1], v[l][2], v[l][3]);
+                dst[1] = make_float4(v[l][4], v[l][5], v[l][6], v[l][7]);
+            }
+        }
         __syncwarp();
 #pragma unroll
         for (int l = 0; l < LG; ++l) {
-            const float* P = patch + l * G::NP;
+            const float* P = patch + l * G::PATCH + ox[l];
             const float ax = fx[l], ay = fy[l];
 #pragma unroll
             for (int t = 0; t < G::NT; ++t) {
@@ -127,7 +180,7 @@ lookup_fwd_kernel(const GroupView g, const float* __restrict__ coords, float* __
                 if (c < G::KK) {
                     const int o = ooff[t];
                     const float top = P[o] + ax * (P[o + 1] - P[o]);
-                    const float bot = P[o + G::K1] + ax * (P[o + G::K1 + 1] - P[o + G::K1]);
+                    const float bot = P[o + G::PITCH] + ax * (P[o + G::PITCH + 1] - P[o + G::PITCH]);
                     out_s[(l * G::KK + c) * kTilePitch + q] = top + ay * (bot - top);
                 }
             }
@@ -261,8 +314,8 @@ GroupView make_group(const PyramidView& pv, int l0, int lg, int radius) {
 
 template <int R, int LG>
 int run_fwd(const GroupView& g, const float* coords, float* out, cudaStream_t s) {
-    using G = Geo<R>;
-    const size_t smem = sizeof(float) * (LG * G::KK * kTilePitch + kWarps * LG * G::NP);
+    using G = FwdGeo<R>;
+    const size_t smem = sizeof(float) * (((LG * G::KK * kTilePitch + 3) & ~3) + kWarps * LG * G::PATCH);
     auto kern = lookup_fwd_kernel<R, LG>;
     RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(g.N, kPix), g.B);
