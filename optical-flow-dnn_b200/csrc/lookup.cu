@@ -80,45 +80,94 @@ __device__ __forceinline__ void fetch_patches(const GroupView& g, int b, int p, 
 }
 
 // ---- forward ---------------------------------------------------------------------------------
-// One 256-bit load per lane fetches a whole 32-byte sector of a patch row (rows are sector aligned:
-// the pitch is a multiple of 8 floats), so a (pixel, level) patch is ONE load instruction:
-// lane -> (row, sector) with NS = ceil((7 + K + 1) / 8) sectors per row.  The sectors are parked in
-// shared memory unshifted; the sub-sector offset ox = x0 & 7 is applied when the K*K outputs read
-// their four taps.
+// Patch rows start on 32-byte sectors (the pitch is a multiple of 8 floats), so a (pixel, level)
+// patch is K+1 rows x NS sectors.  Each lane copies 16-byte chunks of those sectors straight from
+// global to shared memory with cp.async (no register staging; out-of-range chunks and row tails are
+// zero-filled by the copy's src-size operand = grid_sample's zero padding).  Every warp keeps the
+// copies of its NEXT pixel in flight while it evaluates the current one (double-buffered patches),
+// which is what keeps enough bytes in flight to cover HBM latency at 2 CTAs/SM.  The sub-sector
+// offset ox = x0 & 7 is applied when the K*K outputs read their four taps.
 template <int R>
 struct FwdGeo {
     static constexpr int K = 2 * R + 1;
     static constexpr int K1 = K + 1;
     static constexpr int NS = (7 + K1 + 7) / 8;        // 32-byte sectors a patch row can straddle
-    static constexpr int TASKS = K1 * NS;              // <= 32 for R <= 4
-    static constexpr int PITCH = NS * 8 + 4;           // floats; +4 keeps rows 16-byte aligned, spreads banks
+    static constexpr int PITCH = NS * 8;               // floats per staged patch row
+    static constexpr int CHUNKS = NS * 2;              // 16-byte chunks per row
+    static constexpr int TASKS = K1 * CHUNKS;          // cp.async tasks per (pixel, level)
+    static constexpr int NTK = (TASKS + 31) / 32;      // per lane
     static constexpr int PATCH = K1 * PITCH;
     static constexpr int KK = K * K;
     static constexpr int NT = (KK + 31) / 32;
-    static_assert(TASKS <= 32, "one load instruction per (pixel, level)");
 };
 
-__device__ __forceinline__ void ldg256(const float* p, float (&v)[8]) {
-    asm("ld.global.nc.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "l"(p));
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int R, int LG>
+struct FwdLane {
+    int row[FwdGeo<R>::NTK], col[FwdGeo<R>::NTK];  // this lane's (patch row, first float of its 16-byte chunk)
+    uint32_t dst[FwdGeo<R>::NTK];                  // byte offset inside one level's patch
+    bool on[FwdGeo<R>::NTK];
+    __device__ __forceinline__ void init(int lane) {
+        using G = FwdGeo<R>;
+#pragma unroll
+        for (int k = 0; k < G::NTK; ++k) {
+            const int t = lane + 32 * k;
+            row[k] = t / G::CHUNKS;
+            col[k] = (t - row[k] * G::CHUNKS) * 4;
+            dst[k] = (uint32_t)(row[k] * G::PITCH + col[k]) * 4u;
+            on[k] = t < G::TASKS;
+        }
+    }
+};
+
+// issue the copies of one source pixel's patches (all levels of the group) into `patch_smem`
+template <int R, int LG>
+__device__ __forceinline__ void prefetch_pixel(const GroupView& g, int b, int p, float cx, float cy,
+                                               const FwdLane<R, LG>& ln, uint32_t patch_smem) {
+    using G = FwdGeo<R>;
+#pragma unroll
+    for (int l = 0; l < LG; ++l) {
+        const LevelView& lv = g.lvl[l];
+        const int x0 = (int)clamp_coord(floorf(cx * g.inv_scale[l])) - R;
+        const int y0 = (int)clamp_coord(floorf(cy * g.inv_scale[l])) - R;
+        const int xs = x0 & ~7;
+        const float* img = lv.base + ((int64_t)b * g.N + p) * lv.img_stride;
+#pragma unroll
+        for (int k = 0; k < G::NTK; ++k) {
+            if (ln.on[k]) {
+                const int yy = y0 + ln.row[k], cc = xs + ln.col[k];
+                const bool ok = yy >= 0 && yy < lv.h && cc >= 0 && cc < lv.w;
+                int bytes = (lv.w - cc) * 4;          // row tail inside the pitch padding -> partial copy
+                bytes = ok ? (bytes < 16 ? bytes : 16) : 0;
+                const float* src = ok ? img + (int64_t)yy * lv.pitch + cc : lv.base;
+                cp_async16_zfill(patch_smem + (uint32_t)(l * G::PATCH) * 4u + ln.dst[k], src, bytes);
+            }
+        }
+    }
 }
 
 template <int R, int LG>
-__global__ void __launch_bounds__(kWarps * 32, 4)
+__global__ void __launch_bounds__(kWarps * 32, 2)
 lookup_fwd_kernel(const GroupView g, const float* __restrict__ coords, float* __restrict__ out) {
     using G = FwdGeo<R>;
     constexpr int CH = LG * G::KK;
+    constexpr int PIX_PER_WARP = kPix / kWarps;
     extern __shared__ __align__(16) float smem[];
-    float* out_s = smem;                                                  // [CH][kTilePitch]
-    float* patch_s = smem + ((CH * kTilePitch + 3) & ~3);                 // [kWarps][LG][PATCH], 16-byte aligned
+    float* out_s = smem;                                       // [CH][kTilePitch]
+    float* patch_s = smem + ((CH * kTilePitch + 3) & ~3);      // [kWarps][2][LG][PATCH], 16-byte aligned
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y, p0 = blockIdx.x * kPix;
     const int N = g.N;
 
-    const int trow = lane / G::NS, tsec = lane - trow * G::NS;  // this lane's (row, sector) of every patch
-    const bool tactive = lane < G::TASKS;
+    FwdLane<R, LG> ln;
+    ln.init(lane);
     int ooff[G::NT];
 #pragma unroll
     for (int t = 0; t < G::NT; ++t) {
@@ -126,54 +175,42 @@ lookup_fwd_kernel(const GroupView g, const float* __restrict__ coords, float* __
         const int i = c / G::K, j = c - i * G::K;  // channel c = i*K + j: i along x, j along y
         ooff[t] = j * G::PITCH + i;
     }
-    float* patch = patch_s + warp * (LG * G::PATCH);
+    float* patch = patch_s + warp * (2 * LG * G::PATCH);
+    const uint32_t patch_u32 = (uint32_t)__cvta_generic_to_shared(patch);
 
-    for (int q = warp; q < kPix; q += kWarps) {
+    // this warp's pixels: q = warp + kWarps * n  (coordinates for all of them up front)
+    float cxs[PIX_PER_WARP], cys[PIX_PER_WARP];
+#pragma unroll
+    for (int n = 0; n < PIX_PER_WARP; ++n) {
+        const int p = p0 + warp + kWarps * n;
+        const bool v = p < N;
+        cxs[n] = v ? __ldg(coords + ((int64_t)b * 2 + 0) * N + p) : 0.f;
+        cys[n] = v ? __ldg(coords + ((int64_t)b * 2 + 1) * N + p) : 0.f;
+    }
+    if (p0 + warp < N) prefetch_pixel<R, LG>(g, b, p0 + warp, cxs[0], cys[0], ln, patch_u32);
+    cp_async_commit();
+
+#pragma unroll
+    for (int n = 0; n < PIX_PER_WARP; ++n) {
+        const int q = warp + kWarps * n;
         const int p = p0 + q;
         if (p >= N) break;
-        const float cx = __ldg(coords + ((int64_t)b * 2 + 0) * N + p);
-        const float cy = __ldg(coords + ((int64_t)b * 2 + 1) * N + p);
-        float v[LG][8], fx[LG], fy[LG];
-        int ox[LG], cc[LG];
-        bool ok[LG];
-        // phase A: all levels' loads are issued back to back (out-of-range lanes read the level base
-        // and are zeroed afterwards, so no load sits behind a branch)
-#pragma unroll
-        for (int l = 0; l < LG; ++l) {
-            const LevelView& lv = g.lvl[l];
-            const float x = cx * g.inv_scale[l], y = cy * g.inv_scale[l];
-            const float xf = floorf(x), yf = floorf(y);
-            fx[l] = x - xf;
-            fy[l] = y - yf;
-            const int x0 = (int)clamp_coord(xf) - R, y0 = (int)clamp_coord(yf) - R;
-            ox[l] = x0 & 7;
-            const int yy = y0 + trow;
-            cc[l] = (x0 & ~7) + 8 * tsec;
-            ok[l] = tactive && yy >= 0 && yy < lv.h && cc[l] >= 0 && cc[l] < lv.w;
-            const float* src = lv.base + ((int64_t)b * N + p) * lv.img_stride + (int64_t)yy * lv.pitch + cc[l];
-            ldg256(ok[l] ? src : lv.base, v[l]);
-        }
-        // phase B: zero padding (whole sector outside, or row tail inside the pitch padding)
-#pragma unroll
-        for (int l = 0; l < LG; ++l) {
-            const int w = g.lvl[l].w;
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-                if (!ok[l] || cc[l] + e >= w) v[l][e] = 0.f;
-        }
-        if (tactive) {
-#pragma unroll
-            for (int l = 0; l < LG; ++l) {
-                float4* dst = reinterpret_cast<float4*>(patch + l * G::PATCH + trow * G::PITCH + tsec * 8);
-                dst[0] = make_float4(v[l][0], v[l][1], v[l][2], v[l][3]);
-                dst[1] = make_float4(v[l][4], v[l][5], v[l][6], v[l][7]);
-            }
-        }
+        const int buf = n & 1;
+        if (n + 1 < PIX_PER_WARP && p + kWarps < N)
+            prefetch_pixel<R, LG>(g, b, p + kWarps, cxs[n + 1 < PIX_PER_WARP ? n + 1 : n],
+                                  cys[n + 1 < PIX_PER_WARP ? n + 1 : n], ln,
+                                  patch_u32 + (uint32_t)((buf ^ 1) * LG * G::PATCH) * 4u);
+        cp_async_commit();
+        cp_async_wait<1>();  // everything but the group just committed has landed
         __syncwarp();
+        const float* pbuf = patch + buf * (LG * G::PATCH);
 #pragma unroll
         for (int l = 0; l < LG; ++l) {
-            const float* P = patch + l * G::PATCH + ox[l];
-            const float ax = fx[l], ay = fy[l];
+            const float x = cxs[n] * g.inv_scale[l], y = cys[n] * g.inv_scale[l];
+            const float xf = floorf(x), yf = floorf(y);
+            const float ax = x - xf, ay = y - yf;
+            const int ox = ((int)clamp_coord(xf) - R) & 7;
+            const float* P = pbuf + l * G::PATCH + ox;
 #pragma unroll
             for (int t = 0; t < G::NT; ++t) {
                 const int c = lane + 32 * t;
@@ -185,8 +222,9 @@ lookup_fwd_kernel(const GroupView g, const float* __restrict__ coords, float* __
                 }
             }
         }
-        __syncwarp();
+        __syncwarp();  // the buffer is refilled by the prefetch issued in the next iteration
     }
+    cp_async_wait<0>();
     __syncthreads();
     // channel-major write-out: one warp store = 32 consecutive pixels of one channel
     const int p = p0 + lane;
@@ -315,7 +353,7 @@ GroupView make_group(const PyramidView& pv, int l0, int lg, int radius) {
 template <int R, int LG>
 int run_fwd(const GroupView& g, const float* coords, float* out, cudaStream_t s) {
     using G = FwdGeo<R>;
-    const size_t smem = sizeof(float) * (((LG * G::KK * kTilePitch + 3) & ~3) + kWarps * LG * G::PATCH);
+    const size_t smem = sizeof(float) * (((LG * G::KK * kTilePitch + 3) & ~3) + kWarps * 2 * LG * G::PATCH);
     auto kern = lookup_fwd_kernel<R, LG>;
     RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(g.N, kPix), g.B);
