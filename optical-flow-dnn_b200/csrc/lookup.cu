@@ -96,7 +96,8 @@ struct FwdGeo {
     static constexpr int CHUNKS = NS * 2;              // 16-byte chunks per row
     static constexpr int TASKS = K1 * CHUNKS;          // cp.async tasks per (pixel, level)
     static constexpr int NTK = (TASKS + 31) / 32;      // per lane
-    static constexpr int PATCH = K1 * PITCH;
+    static constexpr int ROWS = (NTK * 32 + CHUNKS - 1) / CHUNKS;  // K1 rows + padding rows hit by idle tasks
+    static constexpr int PATCH = ROWS * PITCH;
     static constexpr int KK = K * K;
     static constexpr int NT = (KK + 31) / 32;
 };
@@ -108,12 +109,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Per-lane constants: which 16-byte chunks of a patch this lane copies.  Tasks past the end of the
+// patch (the last partial warp-load) land in one padding row per level with a zero-byte copy, so the
+// copy loop has no divergent branch.
 template <int R, int LG>
 struct FwdLane {
-    int row[FwdGeo<R>::NTK], col[FwdGeo<R>::NTK];  // this lane's (patch row, first float of its 16-byte chunk)
-    uint32_t dst[FwdGeo<R>::NTK];                  // byte offset inside one level's patch
-    bool on[FwdGeo<R>::NTK];
-    __device__ __forceinline__ void init(int lane) {
+    int row[FwdGeo<R>::NTK], col[FwdGeo<R>::NTK];
+    int goff[LG][FwdGeo<R>::NTK];   // row * pitch_l + col: float offset from the patch's first sector
+    uint32_t dst[FwdGeo<R>::NTK];   // byte offset inside one level's staged patch
+    __device__ __forceinline__ void init(int lane, const GroupView& g) {
         using G = FwdGeo<R>;
 #pragma unroll
         for (int k = 0; k < G::NTK; ++k) {
@@ -121,33 +125,41 @@ struct FwdLane {
             row[k] = t / G::CHUNKS;
             col[k] = (t - row[k] * G::CHUNKS) * 4;
             dst[k] = (uint32_t)(row[k] * G::PITCH + col[k]) * 4u;
-            on[k] = t < G::TASKS;
+#pragma unroll
+            for (int l = 0; l < LG; ++l) goff[l][k] = row[k] * g.lvl[l].pitch + col[k];
         }
     }
 };
 
+struct PixelGeo {  // per (pixel, level): fractional offsets and the sub-sector shift of the staged patch
+    float fx, fy;
+    int ox;
+};
+
 // issue the copies of one source pixel's patches (all levels of the group) into `patch_smem`
 template <int R, int LG>
-__device__ __forceinline__ void prefetch_pixel(const GroupView& g, int b, int p, float cx, float cy,
-                                               const FwdLane<R, LG>& ln, uint32_t patch_smem) {
+__device__ __forceinline__ void prefetch_pixel(const GroupView& g, int64_t bp, float cx, float cy,
+                                               const FwdLane<R, LG>& ln, uint32_t patch_smem, PixelGeo (&pg)[LG]) {
     using G = FwdGeo<R>;
 #pragma unroll
     for (int l = 0; l < LG; ++l) {
         const LevelView& lv = g.lvl[l];
-        const int x0 = (int)clamp_coord(floorf(cx * g.inv_scale[l])) - R;
-        const int y0 = (int)clamp_coord(floorf(cy * g.inv_scale[l])) - R;
+        const float x = cx * g.inv_scale[l], y = cy * g.inv_scale[l];
+        const int xi = __float2int_rd(x), yi = __float2int_rd(y);
+        pg[l].fx = x - (float)xi;
+        pg[l].fy = y - (float)yi;
+        const int x0 = xi - R, y0 = yi - R;
+        pg[l].ox = x0 & 7;
         const int xs = x0 & ~7;
-        const float* img = lv.base + ((int64_t)b * g.N + p) * lv.img_stride;
+        const float* rb = lv.base + bp * lv.img_stride + ((int64_t)y0 * lv.pitch + xs);
 #pragma unroll
         for (int k = 0; k < G::NTK; ++k) {
-            if (ln.on[k]) {
-                const int yy = y0 + ln.row[k], cc = xs + ln.col[k];
-                const bool ok = yy >= 0 && yy < lv.h && cc >= 0 && cc < lv.w;
-                int bytes = (lv.w - cc) * 4;          // row tail inside the pitch padding -> partial copy
-                bytes = ok ? (bytes < 16 ? bytes : 16) : 0;
-                const float* src = ok ? img + (int64_t)yy * lv.pitch + cc : lv.base;
-                cp_async16_zfill(patch_smem + (uint32_t)(l * G::PATCH) * 4u + ln.dst[k], src, bytes);
-            }
+            const int yy = y0 + ln.row[k], cc = xs + ln.col[k];
+            const bool ok = ln.row[k] < G::K1 && (unsigned)yy < (unsigned)lv.h && (unsigned)cc < (unsigned)lv.w;
+            int bytes = (lv.w - cc) * 4;  // row tail inside the pitch padding -> partial copy, rest zero-filled
+            bytes = ok ? (bytes < 16 ? bytes : 16) : 0;
+            cp_async16_zfill(patch_smem + (uint32_t)(l * G::PATCH) * 4u + ln.dst[k], ok ? rb + ln.goff[l][k] : lv.base,
+                             bytes);
         }
     }
 }
@@ -167,7 +179,7 @@ lookup_fwd_kernel(const GroupView g, const float* __restrict__ coords, float* __
     const int N = g.N;
 
     FwdLane<R, LG> ln;
-    ln.init(lane);
+    ln.init(lane, g);
     int ooff[G::NT];
 #pragma unroll
     for (int t = 0; t < G::NT; ++t) {
@@ -178,16 +190,19 @@ lookup_fwd_kernel(const GroupView g, const float* __restrict__ coords, float* __
     float* patch = patch_s + warp * (2 * LG * G::PATCH);
     const uint32_t patch_u32 = (uint32_t)__cvta_generic_to_shared(patch);
 
-    // this warp's pixels: q = warp + kWarps * n  (coordinates for all of them up front)
+    // this warp's pixels: q = warp + kWarps * n.  Coordinates are clamped once: anything beyond
+    // +-2^20 px is outside every level anyway and float->int stays defined (NaN -> -2^20).
     float cxs[PIX_PER_WARP], cys[PIX_PER_WARP];
 #pragma unroll
     for (int n = 0; n < PIX_PER_WARP; ++n) {
         const int p = p0 + warp + kWarps * n;
         const bool v = p < N;
-        cxs[n] = v ? __ldg(coords + ((int64_t)b * 2 + 0) * N + p) : 0.f;
-        cys[n] = v ? __ldg(coords + ((int64_t)b * 2 + 1) * N + p) : 0.f;
+        cxs[n] = clamp_coord(v ? __ldg(coords + ((int64_t)b * 2 + 0) * N + p) : 0.f);
+        cys[n] = clamp_coord(v ? __ldg(coords + ((int64_t)b * 2 + 1) * N + p) : 0.f);
     }
-    if (p0 + warp < N) prefetch_pixel<R, LG>(g, b, p0 + warp, cxs[0], cys[0], ln, patch_u32);
+    PixelGeo cur[LG], nxt[LG];
+    const int64_t bp0 = (int64_t)b * N + p0 + warp;
+    if (p0 + warp < N) prefetch_pixel<R, LG>(g, bp0, cxs[0], cys[0], ln, patch_u32, nxt);
     cp_async_commit();
 
 #pragma unroll
@@ -196,21 +211,20 @@ lookup_fwd_kernel(const GroupView g, const float* __restrict__ coords, float* __
         const int p = p0 + q;
         if (p >= N) break;
         const int buf = n & 1;
+#pragma unroll
+        for (int l = 0; l < LG; ++l) cur[l] = nxt[l];
         if (n + 1 < PIX_PER_WARP && p + kWarps < N)
-            prefetch_pixel<R, LG>(g, b, p + kWarps, cxs[n + 1 < PIX_PER_WARP ? n + 1 : n],
+            prefetch_pixel<R, LG>(g, bp0 + kWarps * (n + 1), cxs[n + 1 < PIX_PER_WARP ? n + 1 : n],
                                   cys[n + 1 < PIX_PER_WARP ? n + 1 : n], ln,
-                                  patch_u32 + (uint32_t)((buf ^ 1) * LG * G::PATCH) * 4u);
+                                  patch_u32 + (uint32_t)((buf ^ 1) * LG * G::PATCH) * 4u, nxt);
         cp_async_commit();
         cp_async_wait<1>();  // everything but the group just committed has landed
         __syncwarp();
         const float* pbuf = patch + buf * (LG * G::PATCH);
 #pragma unroll
         for (int l = 0; l < LG; ++l) {
-            const float x = cxs[n] * g.inv_scale[l], y = cys[n] * g.inv_scale[l];
-            const float xf = floorf(x), yf = floorf(y);
-            const float ax = x - xf, ay = y - yf;
-            const int ox = ((int)clamp_coord(xf) - R) & 7;
-            const float* P = pbuf + l * G::PATCH + ox;
+            const float ax = cur[l].fx, ay = cur[l].fy;
+            const float* P = pbuf + l * G::PATCH + cur[l].ox;
 #pragma unroll
             for (int t = 0; t < G::NT; ++t) {
                 const int c = lane + 32 * t;
