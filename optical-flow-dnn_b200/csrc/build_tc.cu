@@ -22,9 +22,7 @@
 //
 // The kernel is bound by the fp32 pyramid write (174 KB per tile vs 4096 tensor cycles per tile),
 // see DESIGN.md; the MMA pipe has slack, the epilogue/TMA-store path is what is tuned.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tma_util.cuh"
 
 namespace raftcorr {
 
@@ -48,61 +46,7 @@ constexpr int kThreads = 256;
 constexpr int kEpilogueThreads = 128;
 constexpr uint32_t kTmemCols = 512;
 
-// ---- PTX wrappers -------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug becomes a trapped launch (reported by the next CUDA call) instead of a hang.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-    }
-}
-
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
-                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
+// ---- tcgen05 PTX wrappers (mbarrier / TMA wrappers live in tma_util.cuh) -------------------------
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -191,9 +135,9 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_out) : "memory");
+        prefetch_tensormap(&map_a);
+        prefetch_tensormap(&map_b);
+        prefetch_tensormap(&map_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -204,7 +148,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_init(tfull_bar + 8 * a, 1);
             mbar_init(tempty_bar + 8 * a, kEpilogueThreads);
         }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_mbar_init();
     }
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
@@ -396,32 +340,6 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 }
 
 // ---- host side ----------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int get_encode_fn(EncodeTiledFn* out) {
-    static EncodeTiledFn cached = nullptr;  // immutable once resolved; benign if two threads race to set it
-    if (!cached) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        RC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        RC_REQUIRE(qres == cudaDriverEntryPointSuccess && fn, "cuTensorMapEncodeTiled not available from the driver");
-        cached = (EncodeTiledFn)fn;
-    }
-    *out = cached;
-    return 0;
-}
-
-int encode(EncodeTiledFn fn, CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-           const cuuint32_t* box, CUtensorMapL2promotion promo, const char* what) {
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    RC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
-    return 0;
-}
-
 }  // namespace
 
 int tc_feature_pitch(int D) { return (D + kBlockK - 1) / kBlockK * kBlockK; }
@@ -440,14 +358,16 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
         cuuint64_t dims[3] = {(cuuint64_t)Dp, (cuuint64_t)N1, (cuuint64_t)B};
         cuuint64_t strides[2] = {(cuuint64_t)Dp * 4, (cuuint64_t)N1 * Dp * 4};
         cuuint32_t box[3] = {kBlockK, kTileM, 1};
-        if (int rc = encode(fn, &map_a, (void*)f1n, 3, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap1"))
+        if (int rc = encode_f32_map(fn, &map_a, (void*)f1n, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap1"))
             return rc;
     }
     {
         cuuint64_t dims[4] = {(cuuint64_t)Dp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)Dp * 4, (cuuint64_t)W * Dp * 4, (cuuint64_t)N1 * Dp * 4};
         cuuint32_t box[4] = {kBlockK, kTileW, kTileH, 1};
-        if (int rc = encode(fn, &map_b, (void*)f2n, 4, dims, strides, box, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2"))
+        if (int rc = encode_f32_map(fn, &map_b, (void*)f2n, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2"))
             return rc;
     }
     {
@@ -455,8 +375,8 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
         cuuint64_t dims[4] = {(cuuint64_t)lay.w[0], (cuuint64_t)lay.h[0], (cuuint64_t)N1, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)lay.pitch[0] * 4, (cuuint64_t)img * 4, (cuuint64_t)N1 * img * 4};
         cuuint32_t box[4] = {kTileW, 1, kTileM, 1};
-        if (int rc = encode(fn, &map_out, (void*)(pyramid + lay.offset[0]), 4, dims, strides, box,
-                            CU_TENSOR_MAP_L2_PROMOTION_NONE, "volume"))
+        if (int rc = encode_f32_map(fn, &map_out, (void*)(pyramid + lay.offset[0]), 4, dims, strides, box,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, "volume"))
             return rc;
     }
 

@@ -8,15 +8,14 @@
 // contiguous 40-byte runs), parks it in shared memory, and evaluates the K*K outputs from it.
 // Results are transposed through a [channels][32 pixels] shared tile so that global stores are
 // full 128-byte lines along W of the [B, C, H, W] output (no NHWC->NCHW pass as in corr.py:91).
-#include "common.cuh"
+#include <cstdlib>
+#include <cstring>
+
+#include "lookup_common.cuh"
 
 namespace raftcorr {
 
 namespace {
-
-constexpr int kWarps = 8;
-constexpr int kPix = 32;       // source pixels per CTA = one output line per channel
-constexpr int kTilePitch = 33; // +1 float: conflict-free column writes / row reads
 
 template <int R>
 struct Geo {
@@ -27,19 +26,6 @@ struct Geo {
     static constexpr int KK = K * K;              // outputs per (pixel, level)
     static constexpr int NT = (KK + 31) / 32;     // outputs per lane
 };
-
-struct GroupView {  // <= 4 consecutive levels handled by one launch
-    LevelView lvl[4];
-    float inv_scale[4];  // 2^-level
-    int B, N;
-    int ch0, ctot;       // first output channel of this group, total channels
-};
-
-__device__ __forceinline__ float clamp_coord(float v) {
-    // keeps float->int conversion defined for wild coordinates; everything this far out is
-    // outside every level anyway (zero padding).  NaN maps to -2^20 (all taps out of range).
-    return fminf(fmaxf(v, -1048576.f), 1048576.f);
-}
 
 template <int R, int LG>
 struct LaneGeo {
@@ -350,20 +336,6 @@ lookup_bwd_kernel(const GroupView dg, const GroupView fg, const float* __restric
     }
 }
 
-GroupView make_group(const PyramidView& pv, int l0, int lg, int radius) {
-    GroupView g{};
-    const int KK = (2 * radius + 1) * (2 * radius + 1);
-    for (int l = 0; l < lg; ++l) {
-        g.lvl[l] = pv.lvl[l0 + l];
-        g.inv_scale[l] = 1.0f / (float)(1 << (l0 + l));
-    }
-    g.B = pv.B;
-    g.N = pv.N;
-    g.ch0 = l0 * KK;
-    g.ctot = pv.L * KK;
-    return g;
-}
-
 template <int R, int LG>
 int run_fwd(const GroupView& g, const float* coords, float* out, cudaStream_t s) {
     using G = FwdGeo<R>;
@@ -419,7 +391,28 @@ int dispatch_bwd(int lg, const GroupView& dg, const GroupView* fg, const float* 
 
 }  // namespace
 
+GroupView make_group(const PyramidView& pv, int l0, int lg, int radius) {
+    GroupView g{};
+    const int KK = (2 * radius + 1) * (2 * radius + 1);
+    for (int l = 0; l < lg; ++l) {
+        g.lvl[l] = pv.lvl[l0 + l];
+        g.inv_scale[l] = 1.0f / (float)(1 << (l0 + l));
+    }
+    g.B = pv.B;
+    g.N = pv.N;
+    g.ch0 = l0 * KK;
+    g.ctot = pv.L * KK;
+    return g;
+}
+
+// RAFTCORR_LOOKUP=tma|cpasync selects the forward implementation (read once per call; default: tma).
+static bool use_tma_lookup() {
+    const char* e = std::getenv("RAFTCORR_LOOKUP");
+    return !(e && std::strcmp(e, "cpasync") == 0);
+}
+
 int launch_lookup_fwd(const PyramidView& pv, const float* coords, int radius, float* out, cudaStream_t s) {
+    if (use_tma_lookup()) return launch_lookup_fwd_tma(pv, coords, radius, out, s);
     for (int l0 = 0; l0 < pv.L; l0 += 4) {
         const int lg = pv.L - l0 < 4 ? pv.L - l0 : 4;
         GroupView g = make_group(pv, l0, lg, radius);

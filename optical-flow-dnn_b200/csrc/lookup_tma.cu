@@ -1,0 +1,190 @@
+// Correlation lookup forward, TMA variant (CorrBlock.__call__, raft/core/corr.py:45-91).
+//
+// A (pixel, level) patch is exactly what a tiled TMA load describes: a (K+1) x (K+1) box at an
+// arbitrary (signed) element coordinate of the 3-D tensor [B*N][H_l][W_l], with out-of-range elements
+// ZERO-FILLED by the hardware -- grid_sample's padding_mode='zeros' for free, and no per-element
+// address / bounds arithmetic on the SM: one elected lane issues ONE cp.async.bulk.tensor per level.
+// Each warp owns two patch buffers and two mbarriers and keeps the next pixel's boxes in flight while
+// it evaluates the current pixel; results are transposed through a [channels][32 px] shared tile and
+// stored channel-major with full 128-byte lines, as in lookup.cu.
+#include "lookup_common.cuh"
+#include "tma_util.cuh"
+
+namespace raftcorr {
+
+namespace {
+
+template <int R>
+struct TmaGeo {
+    static constexpr int K = 2 * R + 1;
+    static constexpr int K1 = K + 1;
+    static constexpr int BC = (K1 + 3) / 4 * 4;            // box columns: 16-byte multiple
+    static constexpr int BOX_BYTES = BC * K1 * 4;
+    static constexpr int SLOT = (BOX_BYTES + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
+    static constexpr int KK = K * K;
+    static constexpr int NT = (KK + 31) / 32;
+};
+
+struct LookupMaps {
+    CUtensorMap m[4];
+};
+
+template <int R, int LG>
+__global__ void __launch_bounds__(kWarps * 32, 3)
+lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g, const float* __restrict__ coords,
+                      float* __restrict__ out) {
+    using G = TmaGeo<R>;
+    constexpr int CH = LG * G::KK;
+    constexpr int PIX_PER_WARP = kPix / kWarps;
+    constexpr int WARP_PATCH = 2 * LG * G::SLOT;  // bytes: double-buffered patches of one warp
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    // [kWarps][2][LG][SLOT] patches | [kWarps][2] mbarriers | out_s [CH][kTilePitch]
+    const uint32_t bar_base = base + kWarps * WARP_PATCH;
+    float* out_s = reinterpret_cast<float*>(gen + kWarps * WARP_PATCH + kWarps * 16);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, p0 = blockIdx.x * kPix;
+    const int N = g.N;
+    const uint32_t my_patch = base + warp * WARP_PATCH;
+    const float* my_patch_gen = reinterpret_cast<const float*>(gen + warp * WARP_PATCH);
+    const uint32_t my_bar = bar_base + warp * 16;
+
+    if (lane == 0) {
+        mbar_init(my_bar, 1);
+        mbar_init(my_bar + 8, 1);
+        fence_mbar_init();
+        if (warp == 0) {
+#pragma unroll
+            for (int l = 0; l < LG; ++l) prefetch_tensormap(&maps.m[l]);
+        }
+    }
+    __syncwarp();
+
+    int ooff[G::NT];
+#pragma unroll
+    for (int t = 0; t < G::NT; ++t) {
+        const int c = lane + 32 * t;
+        const int i = c / G::K, j = c - i * G::K;  // channel c = i*K + j: i along x, j along y
+        ooff[t] = j * G::BC + i;
+    }
+
+    float cxs[PIX_PER_WARP], cys[PIX_PER_WARP];
+#pragma unroll
+    for (int n = 0; n < PIX_PER_WARP; ++n) {
+        const int p = p0 + warp + kWarps * n;
+        const bool v = p < N;
+        cxs[n] = clamp_coord(v ? __ldg(coords + ((int64_t)b * 2 + 0) * N + p) : 0.f);
+        cys[n] = clamp_coord(v ? __ldg(coords + ((int64_t)b * 2 + 1) * N + p) : 0.f);
+    }
+
+    auto issue = [&](int n, int buf) {  // lane 0 only
+        const int img = b * N + p0 + warp + kWarps * n;
+        mbar_expect_tx(my_bar + 8 * buf, LG * G::BOX_BYTES);
+#pragma unroll
+        for (int l = 0; l < LG; ++l) {
+            const int x0 = __float2int_rd(cxs[n] * g.inv_scale[l]) - R;
+            const int y0 = __float2int_rd(cys[n] * g.inv_scale[l]) - R;
+            tma_load_3d(my_patch + (buf * LG + l) * G::SLOT, &maps.m[l], my_bar + 8 * buf, x0, y0, img);
+        }
+    };
+
+    if (lane == 0 && p0 + warp < N) issue(0, 0);
+
+#pragma unroll
+    for (int n = 0; n < PIX_PER_WARP; ++n) {
+        const int q = warp + kWarps * n;
+        const int p = p0 + q;
+        if (p >= N) break;
+        const int buf = n & 1;
+        if (lane == 0 && n + 1 < PIX_PER_WARP && p + kWarps < N) {
+            fence_proxy_async();  // the other buffer was just read through the generic proxy
+            issue(n + 1, buf ^ 1);
+        }
+        mbar_wait(my_bar + 8 * buf, (n >> 1) & 1);
+        const float* pbuf = my_patch_gen + buf * (LG * G::SLOT / 4);
+#pragma unroll
+        for (int l = 0; l < LG; ++l) {
+            const float x = cxs[n] * g.inv_scale[l], y = cys[n] * g.inv_scale[l];
+            const float ax = x - floorf(x), ay = y - floorf(y);
+            const float* P = pbuf + l * (G::SLOT / 4);
+#pragma unroll
+            for (int t = 0; t < G::NT; ++t) {
+                const int c = lane + 32 * t;
+                if (c < G::KK) {
+                    const int o = ooff[t];
+                    const float top = P[o] + ax * (P[o + 1] - P[o]);
+                    const float bot = P[o + G::BC] + ax * (P[o + G::BC + 1] - P[o + G::BC]);
+                    out_s[(l * G::KK + c) * kTilePitch + q] = top + ay * (bot - top);
+                }
+            }
+        }
+        __syncwarp();  // all lanes are done with `buf` before lane 0 refills it next iteration
+    }
+    __syncthreads();
+    const int p = p0 + lane;
+    if (p < N) {
+        float* dst = out + ((int64_t)b * g.ctot + g.ch0) * N + p;
+        for (int ch = warp; ch < CH; ch += kWarps) dst[(int64_t)ch * N] = out_s[ch * kTilePitch + lane];
+    }
+}
+
+template <int R, int LG>
+int run_fwd_tma(const LookupMaps& maps, const GroupView& g, const float* coords, float* out, cudaStream_t s) {
+    using G = TmaGeo<R>;
+    const size_t smem = 128 + (size_t)kWarps * 2 * LG * G::SLOT + kWarps * 16 + sizeof(float) * LG * G::KK * kTilePitch;
+    auto kern = lookup_fwd_tma_kernel<R, LG>;
+    RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(g.N, kPix), g.B);
+    kern<<<grid, kWarps * 32, smem, s>>>(maps, g, coords, out);
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int R>
+int dispatch_fwd_tma(int lg, const LookupMaps& maps, const GroupView& g, const float* coords, float* out,
+                     cudaStream_t s) {
+    switch (lg) {
+        case 1: return run_fwd_tma<R, 1>(maps, g, coords, out, s);
+        case 2: return run_fwd_tma<R, 2>(maps, g, coords, out, s);
+        case 3: return run_fwd_tma<R, 3>(maps, g, coords, out, s);
+        default: return run_fwd_tma<R, 4>(maps, g, coords, out, s);
+    }
+}
+
+}  // namespace
+
+int launch_lookup_fwd_tma(const PyramidView& pv, const float* coords, int radius, float* out, cudaStream_t s) {
+    EncodeTiledFn fn;
+    if (int rc = get_encode_fn(&fn)) return rc;
+    const int K1 = 2 * radius + 2, BC = (K1 + 3) / 4 * 4;
+    for (int l0 = 0; l0 < pv.L; l0 += 4) {
+        const int lg = pv.L - l0 < 4 ? pv.L - l0 : 4;
+        GroupView g = make_group(pv, l0, lg, radius);
+        LookupMaps maps;
+        for (int l = 0; l < lg; ++l) {
+            const LevelView& lv = pv.lvl[l0 + l];
+            // logical width = W_l (not the pitch): columns in the row padding read as zeros, like everything outside
+            cuuint64_t dims[3] = {(cuuint64_t)lv.w, (cuuint64_t)lv.h, (cuuint64_t)pv.B * pv.N};
+            cuuint64_t strides[2] = {(cuuint64_t)lv.pitch * 4, (cuuint64_t)lv.img_stride * 4};
+            cuuint32_t box[3] = {(cuuint32_t)BC, (cuuint32_t)K1, 1};
+            if (int rc = encode_f32_map(fn, &maps.m[l], (void*)lv.base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_NONE, "pyramid level"))
+                return rc;
+        }
+        for (int l = lg; l < 4; ++l) maps.m[l] = maps.m[0];
+        int rc;
+        switch (radius) {
+            case 1: rc = dispatch_fwd_tma<1>(lg, maps, g, coords, out, s); break;
+            case 2: rc = dispatch_fwd_tma<2>(lg, maps, g, coords, out, s); break;
+            case 3: rc = dispatch_fwd_tma<3>(lg, maps, g, coords, out, s); break;
+            case 4: rc = dispatch_fwd_tma<4>(lg, maps, g, coords, out, s); break;
+            default: return fail("lookup: radius %d not supported (1..4)", radius);
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace raftcorr
