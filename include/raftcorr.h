@@ -89,6 +89,18 @@ int raftcorr_build_fwd(const float* fmap1, const float* fmap2, int D, float* pyr
 int raftcorr_lookup_fwd(const float* pyramid, const raftcorr_pyramid_layout* layout, const float* coords,
                         int radius, float* out, int device, raftcorr_stream_t stream);
 
+/* The same lookup with the per-pyramid setup (TMA tensor maps, launch geometry) done once: RAFT calls
+ * the lookup 12-32 times per volume (raft.py:141-144).  The plan is a caller-owned HOST blob, valid as
+ * long as `pyramid` and `layout` are; initialise it after raftcorr_build_fwd, reuse it for every call. */
+#define RAFTCORR_LOOKUP_PLAN_BYTES 2048
+typedef struct raftcorr_lookup_plan {
+    unsigned char opaque[RAFTCORR_LOOKUP_PLAN_BYTES];
+} raftcorr_lookup_plan;
+int raftcorr_lookup_plan_init(raftcorr_lookup_plan* plan, const float* pyramid, const raftcorr_pyramid_layout* layout,
+                              int radius, int device);
+int raftcorr_lookup_fwd_planned(const raftcorr_lookup_plan* plan, const float* coords, float* out, int device,
+                                raftcorr_stream_t stream);
+
 /* Adjoint of the lookup: dpyramid (same layout, ACCUMULATED into -- zero it once, then call once
  * per refinement iteration) += scatter of grad_out[B, L*(2r+1)^2, H, W].
  * dcoords [B,2,H,W] is optional (NULL to skip); when given, pyramid must be the forward pyramid. */

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libraftcorr_b200.so")
 MAX_LEVELS = 8
 BUILD_FP32_SIMT = 0
 BUILD_TF32_TC = 1
+LOOKUP_PLAN_BYTES = 2048
 
 
 class RaftCorrError(RuntimeError):
@@ -43,6 +44,8 @@ SIGNATURES = {
     "raftcorr_build_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _LAYP, _c_int, _c_void_p, _c_size_t,
                                      _c_int, _c_void_p]),
     "raftcorr_lookup_fwd": (_c_int, [_c_void_p, _LAYP, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p]),
+    "raftcorr_lookup_plan_init": (_c_int, [_c_void_p, _c_void_p, _LAYP, _c_int, _c_int]),
+    "raftcorr_lookup_fwd_planned": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "raftcorr_lookup_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _LAYP, _c_int, _c_void_p, _c_int,
                                       _c_void_p]),
     "raftcorr_build_bwd": (_c_int, [_c_void_p, _LAYP, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int,

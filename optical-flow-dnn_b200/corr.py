@@ -159,6 +159,8 @@ class CorrBlock:
         self._device = fmap1.device
         self._layout = _lib.make_layout(B, H, W, self.num_levels)
         self._grad_acc = None
+        self._plan = None
+        self._plan_ptr = 0
         fmap1 = fmap1.contiguous()
         fmap2 = fmap2.contiguous()
         if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
@@ -181,8 +183,15 @@ class CorrBlock:
         lay, dev = self._layout, self._device
         K = 2 * self.radius + 1
         out = torch.empty((self._B, self.num_levels * K * K, self._H, self._W), dtype=torch.float32, device=dev)
-        check(_lib.lib().raftcorr_lookup_fwd(_ptr(pyr), ctypes.byref(lay), _ptr(coords), self.radius, _ptr(out),
-                                             dev.index, _stream(dev)), "raftcorr_lookup_fwd")
+        L = _lib.lib()
+        if self._plan is None or self._plan_ptr != pyr.data_ptr():
+            # per-pyramid setup (tensor maps, launch geometry) once; every refinement iteration reuses it
+            self._plan = ctypes.create_string_buffer(_lib.LOOKUP_PLAN_BYTES)
+            check(L.raftcorr_lookup_plan_init(self._plan, _ptr(pyr), ctypes.byref(lay), self.radius, dev.index),
+                  "raftcorr_lookup_plan_init")
+            self._plan_ptr = pyr.data_ptr()
+        check(L.raftcorr_lookup_fwd_planned(self._plan, _ptr(coords), _ptr(out), dev.index, _stream(dev)),
+              "raftcorr_lookup_fwd_planned")
         return out
 
     # -- reference surface ----------------------------------------------------------------------

@@ -3,7 +3,7 @@
 #include <cmath>
 #include <cstring>
 
-#include "common.cuh"
+#include "lookup_common.cuh"
 
 namespace raftcorr {
 
@@ -139,6 +139,31 @@ int raftcorr_lookup_fwd(const float* pyramid, const raftcorr_pyramid_layout* lay
     RC_REQUIRE(guard.ok, "lookup_fwd: cannot select device %d", device);
     PyramidView pv = make_view(const_cast<float*>(pyramid), *lay);
     return launch_lookup_fwd(pv, coords, radius, out, (cudaStream_t)stream);
+}
+
+int raftcorr_lookup_plan_init(raftcorr_lookup_plan* plan, const float* pyramid, const raftcorr_pyramid_layout* lay,
+                              int radius, int device) {
+    RC_REQUIRE(plan != nullptr, "lookup_plan_init: plan is NULL");
+    if (int rc = check_layout(lay)) return rc;
+    std::memset(plan, 0, sizeof(*plan));
+    if (lay->B == 0) return 0;
+    RC_REQUIRE(pyramid, "lookup_plan_init: NULL pyramid");
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "lookup_plan_init: cannot select device %d", device);
+    PyramidView pv = make_view(const_cast<float*>(pyramid), *lay);
+    return lookup_plan_init(plan->opaque, pv, radius);
+}
+
+int raftcorr_lookup_fwd_planned(const raftcorr_lookup_plan* plan, const float* coords, float* out, int device,
+                                raftcorr_stream_t stream) {
+    RC_REQUIRE(plan != nullptr, "lookup_fwd_planned: plan is NULL");
+    bool empty = true;
+    for (int i = 0; i < 16 && empty; ++i) empty = plan->opaque[i] == 0;
+    if (empty) return 0;  // plan of an empty batch
+    RC_REQUIRE(coords && out, "lookup_fwd_planned: NULL tensor");
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "lookup_fwd_planned: cannot select device %d", device);
+    return lookup_plan_run(plan->opaque, coords, out, (cudaStream_t)stream);
 }
 
 int raftcorr_lookup_bwd(const float* grad_out, const float* coords, const float* pyramid, float* dpyramid,

@@ -406,9 +406,20 @@ GroupView make_group(const PyramidView& pv, int l0, int lg, int radius) {
 }
 
 // RAFTCORR_LOOKUP=tma|cpasync selects the forward implementation (read once per call; default: tma).
-static bool use_tma_lookup() {
+bool use_tma_lookup() {
     const char* e = std::getenv("RAFTCORR_LOOKUP");
     return !(e && std::strcmp(e, "cpasync") == 0);
+}
+
+int launch_lookup_fwd_group_cpasync(int radius, int lg, const GroupView& g, const float* coords, float* out,
+                                    cudaStream_t s) {
+    switch (radius) {
+        case 1: return dispatch_fwd<1>(lg, g, coords, out, s);
+        case 2: return dispatch_fwd<2>(lg, g, coords, out, s);
+        case 3: return dispatch_fwd<3>(lg, g, coords, out, s);
+        case 4: return dispatch_fwd<4>(lg, g, coords, out, s);
+        default: return fail("lookup: radius %d not supported (1..4)", radius);
+    }
 }
 
 int launch_lookup_fwd(const PyramidView& pv, const float* coords, int radius, float* out, cudaStream_t s) {

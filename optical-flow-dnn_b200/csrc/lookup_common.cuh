@@ -24,5 +24,10 @@ __device__ __forceinline__ float clamp_coord(float v) {
 
 GroupView make_group(const PyramidView& pv, int l0, int lg, int radius);
 int launch_lookup_fwd_tma(const PyramidView& pv, const float* coords, int radius, float* out, cudaStream_t s);
+bool use_tma_lookup();
+int launch_lookup_fwd_group_cpasync(int radius, int lg, const GroupView& g, const float* coords, float* out,
+                                    cudaStream_t s);
+int lookup_plan_init(void* plan_blob, const PyramidView& pv, int radius);
+int lookup_plan_run(const void* plan_blob, const float* coords, float* out, cudaStream_t s);
 
 }  // namespace raftcorr

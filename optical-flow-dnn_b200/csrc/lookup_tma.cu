@@ -1,12 +1,17 @@
 // Correlation lookup forward, TMA variant (CorrBlock.__call__, raft/core/corr.py:45-91).
 //
-// A (pixel, level) patch is exactly what a tiled TMA load describes: a (K+1) x (K+1) box at an
-// arbitrary (signed) element coordinate of the 3-D tensor [B*N][H_l][W_l], with out-of-range elements
-// ZERO-FILLED by the hardware -- grid_sample's padding_mode='zeros' for free, and no per-element
-// address / bounds arithmetic on the SM: one elected lane issues ONE cp.async.bulk.tensor per level.
+// A (pixel, level) patch is exactly what a tiled TMA load describes: a box at a signed element
+// coordinate of the 3-D tensor [B*N][H_l][W_l], with out-of-range elements ZERO-FILLED by the hardware
+// -- grid_sample's padding_mode='zeros' for free, and no per-element address / bounds arithmetic on
+// the SM: one elected lane issues ONE cp.async.bulk.tensor per level.  The only hardware rule is that
+// the innermost start coordinate is 16-byte aligned (measured: scripts/probe/tma_probe.cu traps with
+// 'illegal instruction' otherwise), so the box starts at x0 & ~3 and is K+1+3 columns wide (rounded to
+// 4); the 0..3 column shift is applied when the outputs read their taps.
 // Each warp owns two patch buffers and two mbarriers and keeps the next pixel's boxes in flight while
 // it evaluates the current pixel; results are transposed through a [channels][32 px] shared tile and
 // stored channel-major with full 128-byte lines, as in lookup.cu.
+#include <cstring>
+
 #include "lookup_common.cuh"
 #include "tma_util.cuh"
 
@@ -18,7 +23,7 @@ template <int R>
 struct TmaGeo {
     static constexpr int K = 2 * R + 1;
     static constexpr int K1 = K + 1;
-    static constexpr int BC = (K1 + 3) / 4 * 4;            // box columns: 16-byte multiple
+    static constexpr int BC = (K1 + 3 + 3) / 4 * 4;        // box columns: covers any 0..3 start shift, 16-byte multiple
     static constexpr int BOX_BYTES = BC * K1 * 4;
     static constexpr int SLOT = (BOX_BYTES + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
     static constexpr int KK = K * K;
@@ -30,7 +35,7 @@ struct LookupMaps {
 };
 
 template <int R, int LG>
-__global__ void __launch_bounds__(kWarps * 32, 3)
+__global__ void __launch_bounds__(kWarps * 32, 2)
 lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g, const float* __restrict__ coords,
                       float* __restrict__ out) {
     using G = TmaGeo<R>;
@@ -62,12 +67,13 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
     }
     __syncwarp();
 
-    int ooff[G::NT];
+    int ooff[G::NT], och[G::NT];
 #pragma unroll
     for (int t = 0; t < G::NT; ++t) {
         const int c = lane + 32 * t;
-        const int i = c / G::K, j = c - i * G::K;  // channel c = i*K + j: i along x, j along y
+        const int j = c / G::K, i = c - j * G::K;  // lanes run along x inside a patch row (fewest bank conflicts)
         ooff[t] = j * G::BC + i;
+        och[t] = i * G::K + j;                     // output channel: i (x offset) major, corr.py:66-78
     }
 
     float cxs[PIX_PER_WARP], cys[PIX_PER_WARP];
@@ -86,7 +92,7 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
         for (int l = 0; l < LG; ++l) {
             const int x0 = __float2int_rd(cxs[n] * g.inv_scale[l]) - R;
             const int y0 = __float2int_rd(cys[n] * g.inv_scale[l]) - R;
-            tma_load_3d(my_patch + (buf * LG + l) * G::SLOT, &maps.m[l], my_bar + 8 * buf, x0, y0, img);
+            tma_load_3d(my_patch + (buf * LG + l) * G::SLOT, &maps.m[l], my_bar + 8 * buf, x0 & ~3, y0, img);
         }
     };
 
@@ -107,8 +113,9 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
 #pragma unroll
         for (int l = 0; l < LG; ++l) {
             const float x = cxs[n] * g.inv_scale[l], y = cys[n] * g.inv_scale[l];
-            const float ax = x - floorf(x), ay = y - floorf(y);
-            const float* P = pbuf + l * (G::SLOT / 4);
+            const float xf = floorf(x);
+            const float ax = x - xf, ay = y - floorf(y);
+            const float* P = pbuf + l * (G::SLOT / 4) + (((int)xf - R) & 3);
 #pragma unroll
             for (int t = 0; t < G::NT; ++t) {
                 const int c = lane + 32 * t;
@@ -116,7 +123,7 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
                     const int o = ooff[t];
                     const float top = P[o] + ax * (P[o + 1] - P[o]);
                     const float bot = P[o + G::BC] + ax * (P[o + G::BC + 1] - P[o + G::BC]);
-                    out_s[(l * G::KK + c) * kTilePitch + q] = top + ay * (bot - top);
+                    out_s[(l * G::KK + och[t]) * kTilePitch + q] = top + ay * (bot - top);
                 }
             }
         }
@@ -155,36 +162,73 @@ int dispatch_fwd_tma(int lg, const LookupMaps& maps, const GroupView& g, const f
 
 }  // namespace
 
-int launch_lookup_fwd_tma(const PyramidView& pv, const float* coords, int radius, float* out, cudaStream_t s) {
+// ---- plans: tensor maps + launch geometry encoded once per pyramid, reused by every refinement iteration
+struct LookupPlanData {
+    uint32_t magic;
+    int radius, groups, lg[2];
+    GroupView g[2];
+    LookupMaps maps[2];
+};
+static_assert(sizeof(LookupPlanData) <= RAFTCORR_LOOKUP_PLAN_BYTES, "plan blob too small");
+constexpr uint32_t kPlanMagic = 0x52434c50u;  // "RCLP"
+
+int lookup_plan_init(void* plan_blob, const PyramidView& pv, int radius) {
+    RC_REQUIRE(radius >= 1 && radius <= 4, "lookup: radius %d not supported (1..4)", radius);
     EncodeTiledFn fn;
     if (int rc = get_encode_fn(&fn)) return rc;
-    const int K1 = 2 * radius + 2, BC = (K1 + 3) / 4 * 4;
+    LookupPlanData plan;
+    std::memset(&plan, 0, sizeof(plan));
+    plan.magic = kPlanMagic;
+    plan.radius = radius;
+    const int K1 = 2 * radius + 2, BC = (K1 + 3 + 3) / 4 * 4;
     for (int l0 = 0; l0 < pv.L; l0 += 4) {
+        const int gi = plan.groups++;
         const int lg = pv.L - l0 < 4 ? pv.L - l0 : 4;
-        GroupView g = make_group(pv, l0, lg, radius);
-        LookupMaps maps;
+        plan.lg[gi] = lg;
+        plan.g[gi] = make_group(pv, l0, lg, radius);
         for (int l = 0; l < lg; ++l) {
             const LevelView& lv = pv.lvl[l0 + l];
             // logical width = W_l (not the pitch): columns in the row padding read as zeros, like everything outside
             cuuint64_t dims[3] = {(cuuint64_t)lv.w, (cuuint64_t)lv.h, (cuuint64_t)pv.B * pv.N};
             cuuint64_t strides[2] = {(cuuint64_t)lv.pitch * 4, (cuuint64_t)lv.img_stride * 4};
             cuuint32_t box[3] = {(cuuint32_t)BC, (cuuint32_t)K1, 1};
-            if (int rc = encode_f32_map(fn, &maps.m[l], (void*)lv.base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                        CU_TENSOR_MAP_L2_PROMOTION_NONE, "pyramid level"))
+            if (int rc = encode_f32_map(fn, &plan.maps[gi].m[l], (void*)lv.base, 3, dims, strides, box,
+                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, "pyramid level"))
                 return rc;
         }
-        for (int l = lg; l < 4; ++l) maps.m[l] = maps.m[0];
+        for (int l = lg; l < 4; ++l) plan.maps[gi].m[l] = plan.maps[gi].m[0];
+    }
+    std::memcpy(plan_blob, &plan, sizeof(plan));
+    return 0;
+}
+
+int lookup_plan_run(const void* plan_blob, const float* coords, float* out, cudaStream_t s) {
+    LookupPlanData plan;  // local, properly aligned copy (the caller's blob is plain bytes)
+    std::memcpy(&plan, plan_blob, sizeof(plan));
+    RC_REQUIRE(plan.magic == kPlanMagic, "lookup plan is not initialised");
+    const bool tma = use_tma_lookup();
+    for (int gi = 0; gi < plan.groups; ++gi) {
         int rc;
-        switch (radius) {
-            case 1: rc = dispatch_fwd_tma<1>(lg, maps, g, coords, out, s); break;
-            case 2: rc = dispatch_fwd_tma<2>(lg, maps, g, coords, out, s); break;
-            case 3: rc = dispatch_fwd_tma<3>(lg, maps, g, coords, out, s); break;
-            case 4: rc = dispatch_fwd_tma<4>(lg, maps, g, coords, out, s); break;
-            default: return fail("lookup: radius %d not supported (1..4)", radius);
+        if (!tma) {
+            rc = launch_lookup_fwd_group_cpasync(plan.radius, plan.lg[gi], plan.g[gi], coords, out, s);
+            if (rc) return rc;
+            continue;
+        }
+        switch (plan.radius) {
+            case 1: rc = dispatch_fwd_tma<1>(plan.lg[gi], plan.maps[gi], plan.g[gi], coords, out, s); break;
+            case 2: rc = dispatch_fwd_tma<2>(plan.lg[gi], plan.maps[gi], plan.g[gi], coords, out, s); break;
+            case 3: rc = dispatch_fwd_tma<3>(plan.lg[gi], plan.maps[gi], plan.g[gi], coords, out, s); break;
+            default: rc = dispatch_fwd_tma<4>(plan.lg[gi], plan.maps[gi], plan.g[gi], coords, out, s); break;
         }
         if (rc) return rc;
     }
     return 0;
+}
+
+int launch_lookup_fwd_tma(const PyramidView& pv, const float* coords, int radius, float* out, cudaStream_t s) {
+    alignas(64) unsigned char blob[RAFTCORR_LOOKUP_PLAN_BYTES];
+    if (int rc = lookup_plan_init(blob, pv, radius)) return rc;
+    return lookup_plan_run(blob, coords, out, s);
 }
 
 }  // namespace raftcorr
