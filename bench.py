@@ -220,12 +220,18 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     with torch.no_grad():
-        for _ in range(max(args.warmup, 3)):
-            blk, out = step()
-        barrier()
+        # start the clock sampler BEFORE the warm-up: nvidia-smi's start-up (NVML init) takes ~100 ms and
+        # contends for the driver; only its steady 100 ms polling should overlap the timed region
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        for _ in range(max(args.warmup, 3)):
+            blk, out = step()
+        if rank == 0:
+            t_wait = time.time()
+            while sampler.proc and not sampler.lines and time.time() - t_wait < 3.0:
+                time.sleep(0.01)
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -334,7 +340,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--iters", type=int, default=12, help="lookups per build (metric: 12)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

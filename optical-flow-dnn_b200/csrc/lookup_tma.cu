@@ -19,6 +19,9 @@ namespace raftcorr {
 
 namespace {
 
+constexpr int kBufs = 3;                 // patch ring per warp: two pixels in flight while one is evaluated
+constexpr int kBarBytes = 8 * kBufs + 8;  // per-warp mbarrier block (padded to 16 bytes)
+
 template <int R>
 struct TmaGeo {
     static constexpr int K = 2 * R + 1;
@@ -41,24 +44,24 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
     using G = TmaGeo<R>;
     constexpr int CH = LG * G::KK;
     constexpr int PIX_PER_WARP = kPix / kWarps;
-    constexpr int WARP_PATCH = 2 * LG * G::SLOT;  // bytes: double-buffered patches of one warp
+    constexpr int WARP_PATCH = kBufs * LG * G::SLOT;  // bytes: this warp's ring of patch buffers
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-    // [kWarps][2][LG][SLOT] patches | [kWarps][2] mbarriers | out_s [CH][kTilePitch]
+    // [kWarps][kBufs][LG][SLOT] patches | [kWarps][kBufs] mbarriers | out_s [CH][kTilePitch]
     const uint32_t bar_base = base + kWarps * WARP_PATCH;
-    float* out_s = reinterpret_cast<float*>(gen + kWarps * WARP_PATCH + kWarps * 16);
+    float* out_s = reinterpret_cast<float*>(gen + kWarps * WARP_PATCH + kWarps * kBarBytes);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y, p0 = blockIdx.x * kPix;
     const int N = g.N;
     const uint32_t my_patch = base + warp * WARP_PATCH;
     const float* my_patch_gen = reinterpret_cast<const float*>(gen + warp * WARP_PATCH);
-    const uint32_t my_bar = bar_base + warp * 16;
+    const uint32_t my_bar = bar_base + warp * kBarBytes;
 
     if (lane == 0) {
-        mbar_init(my_bar, 1);
-        mbar_init(my_bar + 8, 1);
+#pragma unroll
+        for (int i = 0; i < kBufs; ++i) mbar_init(my_bar + 8 * i, 1);
         fence_mbar_init();
         if (warp == 0) {
 #pragma unroll
@@ -96,19 +99,25 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
         }
     };
 
-    if (lane == 0 && p0 + warp < N) issue(0, 0);
+    // prologue: kBufs-1 pixels in flight before the first one is consumed
+    if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < kBufs - 1 && n < PIX_PER_WARP; ++n)
+            if (p0 + warp + kWarps * n < N) issue(n, n);
+    }
 
 #pragma unroll
     for (int n = 0; n < PIX_PER_WARP; ++n) {
         const int q = warp + kWarps * n;
         const int p = p0 + q;
         if (p >= N) break;
-        const int buf = n & 1;
-        if (lane == 0 && n + 1 < PIX_PER_WARP && p + kWarps < N) {
-            fence_proxy_async();  // the other buffer was just read through the generic proxy
-            issue(n + 1, buf ^ 1);
+        const int buf = n % kBufs;
+        constexpr int kAhead = kBufs - 1;
+        if (lane == 0 && n + kAhead < PIX_PER_WARP && p + kAhead * kWarps < N) {
+            fence_proxy_async();  // that buffer was read through the generic proxy one iteration ago
+            issue(n + kAhead, (n + kAhead) % kBufs);
         }
-        mbar_wait(my_bar + 8 * buf, (n >> 1) & 1);
+        mbar_wait(my_bar + 8 * buf, (n / kBufs) & 1);
         const float* pbuf = my_patch_gen + buf * (LG * G::SLOT / 4);
 #pragma unroll
         for (int l = 0; l < LG; ++l) {
@@ -140,7 +149,7 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
 template <int R, int LG>
 int run_fwd_tma(const LookupMaps& maps, const GroupView& g, const float* coords, float* out, cudaStream_t s) {
     using G = TmaGeo<R>;
-    const size_t smem = 128 + (size_t)kWarps * 2 * LG * G::SLOT + kWarps * 16 + sizeof(float) * LG * G::KK * kTilePitch;
+    const size_t smem = 128 + (size_t)kWarps * kBufs * LG * G::SLOT + kWarps * kBarBytes + sizeof(float) * LG * G::KK * kTilePitch;
     auto kern = lookup_fwd_tma_kernel<R, LG>;
     RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(g.N, kPix), g.B);
