@@ -42,8 +42,8 @@ constexpr int kRowTileBytes = kTileM * kTileW * 4;  // 16 KB: one target row for
 constexpr int kStoreBufBytes = 2 * kRowTileBytes;   // two rows per phase
 constexpr int kNumStoreBufs = 2;
 constexpr int kSmemBytes = kStages * kStageBytes + kNumStoreBufs * kStoreBufBytes + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int kThreads = 256;
-constexpr int kEpilogueThreads = 128;
+constexpr int kThreads = 384;          // 4 control warps + 8 epilogue warps
+constexpr int kEpilogueThreads = 256;
 constexpr uint32_t kTmemCols = 512;
 
 // ---- tcgen05 PTX wrappers (mbarrier / TMA wrappers live in tma_util.cuh) -------------------------
@@ -85,6 +85,17 @@ __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
     asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
                  "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                  : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -214,8 +225,12 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
-        const int ew = warp - 4;                  // == warp % 4: TMEM lane quarter this warp may access
+        // ===================== epilogue (8 warps) =====================
+        // warp % 4 selects the TMEM lane quarter (hardware rule), (warp - 4) / 4 the column half: every
+        // source pixel's 8x32 target block is split between two threads (16 columns each), which halves
+        // the serial TMEM->registers->smem chain per warp and puts two epilogue warps on every scheduler.
+        const int ew = warp & 3;
+        const int cg = (warp - 4) >> 2;           // column half: target columns [16*cg, 16*cg + 16)
         const int ml = ew * 32 + lane;            // source pixel inside the tile == TMEM lane
         const bool issuer = (threadIdx.x == 4 * 32);
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
@@ -231,25 +246,26 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m = mt * kTileM + ml;
             const bool m_ok = m < P.N1;
-            const int w0 = wt * kTileW;
+            const int w0 = wt * kTileW;          // first level-0 column of the tile
+            const int c0 = w0 + 16 * cg;         // first level-0 column of this thread
 
             mbar_wait(tfull_bar + 8 * acc, acc_phase);
             tc_fence_after();
-            const uint32_t t_acc = tmem_base + lane_addr + acc * kTileN;
+            const uint32_t t_acc = tmem_base + lane_addr + acc * kTileN + 16 * cg;
 
-            float l1prev[16], l2prev[8];
+            float l1prev[8], l2prev[4];
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
-                float ra[32], rb[32];
-                tmem_ld32(t_acc + (2 * p) * kTileW, ra);
-                tmem_ld32(t_acc + (2 * p + 1) * kTileW, rb);
+                float ra[16], rb[16];
+                tmem_ld16(t_acc + (2 * p) * kTileW, ra);
+                tmem_ld16(t_acc + (2 * p + 1) * kTileW, rb);
                 tmem_ld_wait();
                 if (p == 3) {  // all of this accumulator is in registers: hand it back to the MMA warp
                     tc_fence_before();
                     mbar_arrive(tempty_bar + 8 * acc);
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < 16; ++j) {
                     ra[j] *= P.scale;
                     rb[j] *= P.scale;
                 }
@@ -257,8 +273,8 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const uint32_t sa = store_base + buf * kStoreBufBytes + ml * 128;
                 const uint32_t sb = sa + kRowTileBytes;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t off = ((uint32_t)j ^ swz) << 4;
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t off = ((uint32_t)(4 * cg + j) ^ swz) << 4;
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(ra[4 * j]),
                                  "f"(ra[4 * j + 1]), "f"(ra[4 * j + 2]), "f"(ra[4 * j + 3])
                                  : "memory");
@@ -279,48 +295,41 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     tma_store_commit();
                 }
                 buf ^= 1;
-                // ---- levels 1..3: thread-local block means, 128-bit stores
+                // ---- levels 1..3: thread-local block means.  Values past a level's width/height are never
+                // stored (w/h guards), values in the row padding are harmless (nothing reads the padding).
                 if (P.L > 1) {
-                    float l1[16];
+                    float l1[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) l1[j] = (ra[2 * j] + ra[2 * j + 1] + rb[2 * j] + rb[2 * j + 1]) * 0.25f;
+                    for (int j = 0; j < 8; ++j) l1[j] = (ra[2 * j] + ra[2 * j + 1] + rb[2 * j] + rb[2 * j + 1]) * 0.25f;
                     const int h1 = band * 4 + p;
-                    if (m_ok && h1 < P.lvl_h[1]) {
-                        float* dst = P.lvl_base[1] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[1] +
-                                     (int64_t)h1 * P.lvl_pitch[1] + (w0 >> 1);
-#pragma unroll
-                        for (int q = 0; q < 2; ++q)
-                            if ((w0 >> 1) + 8 * q + 8 <= P.lvl_pitch[1]) st_global_v8(dst + 8 * q, l1 + 8 * q);
-                    }
+                    if (m_ok && h1 < P.lvl_h[1] && (c0 >> 1) + 8 <= P.lvl_pitch[1])
+                        st_global_v8(P.lvl_base[1] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[1] +
+                                         (int64_t)h1 * P.lvl_pitch[1] + (c0 >> 1), l1);
                     if (P.L > 2) {
                         if ((p & 1) == 0) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) l1prev[j] = l1[j];
+                            for (int j = 0; j < 8; ++j) l1prev[j] = l1[j];
                         } else {
-                            float l2[8];
+                            float l2[4];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
+                            for (int j = 0; j < 4; ++j)
                                 l2[j] = (l1prev[2 * j] + l1prev[2 * j + 1] + l1[2 * j] + l1[2 * j + 1]) * 0.25f;
                             const int h2 = band * 2 + (p >> 1);
-                            if (m_ok && h2 < P.lvl_h[2]) {
-                                float* dst = P.lvl_base[2] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[2] +
-                                             (int64_t)h2 * P.lvl_pitch[2] + (w0 >> 2);
-                                if ((w0 >> 2) + 8 <= P.lvl_pitch[2]) st_global_v8(dst, l2);
-                            }
+                            if (m_ok && h2 < P.lvl_h[2] && (c0 >> 2) + 4 <= P.lvl_pitch[2])
+                                *reinterpret_cast<float4*>(P.lvl_base[2] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[2] +
+                                                           (int64_t)h2 * P.lvl_pitch[2] + (c0 >> 2)) =
+                                    make_float4(l2[0], l2[1], l2[2], l2[3]);
                             if (P.L > 3) {
                                 if (p == 1) {
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) l2prev[j] = l2[j];
+                                    for (int j = 0; j < 4; ++j) l2prev[j] = l2[j];
                                 } else {
-                                    float l3[4];
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j)
-                                        l3[j] = (l2prev[2 * j] + l2prev[2 * j + 1] + l2[2 * j] + l2[2 * j + 1]) * 0.25f;
-                                    if (m_ok && band < P.lvl_h[3] && (w0 >> 3) + 4 <= P.lvl_pitch[3]) {
-                                        float* dst = P.lvl_base[3] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[3] +
-                                                     (int64_t)band * P.lvl_pitch[3] + (w0 >> 3);
-                                        *reinterpret_cast<float4*>(dst) = make_float4(l3[0], l3[1], l3[2], l3[3]);
-                                    }
+                                    const float l3a = (l2prev[0] + l2prev[1] + l2[0] + l2[1]) * 0.25f;
+                                    const float l3b = (l2prev[2] + l2prev[3] + l2[2] + l2[3]) * 0.25f;
+                                    if (m_ok && band < P.lvl_h[3] && (c0 >> 3) + 2 <= P.lvl_pitch[3])
+                                        *reinterpret_cast<float2*>(P.lvl_base[3] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[3] +
+                                                                   (int64_t)band * P.lvl_pitch[3] + (c0 >> 3)) =
+                                            make_float2(l3a, l3b);
                                 }
                             }
                         }
