@@ -304,10 +304,17 @@ def run_ours(args):
             "lookup": {"ms_per_launch": l_ms, "achieved_gbs": B * lb / (l_ms * 1e-3) / 1e9,
                        "share_of_step": 1.0 - build_share},
         }
+        lookup_name = "lookup_fwd_kernel<4,4>" if os.environ.get("RAFTCORR_LOOKUP") == "cpasync" else "lookup_fwd_tma_kernel<4,4>"
         if build_share >= 0.5:
-            dom, ach, alg = "corr_build (" + mode + ")", kern["build"]["achieved_gbs"], B * bb
+            dom, ach, alg = ("build_tc_kernel" if mode == "tf32" else "sgemm_kernel"), kern["build"]["achieved_gbs"], B * bb
         else:
-            dom, ach, alg = "lookup_fwd_kernel<4,4>", kern["lookup"]["achieved_gbs"], B * lb
+            dom, ach, alg = lookup_name, kern["lookup"]["achieved_gbs"], B * lb
+        traffic = None
+        try:  # per-launch DRAM bytes of that kernel from the committed ncu --set full capture (same B, shape)
+            if B == SHAPE["B"]:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
+        except Exception:
+            traffic = None
         launches_per_step = (3 if mode == "tf32" else 1 + (L - 1)) + iters
         cpu = cpu_port_run(3, 1, iters, SHAPE) if world == 1 and not args.no_cpu_baseline else None
         line = {
@@ -325,7 +332,7 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                         "traffic": None, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+                         "traffic": traffic, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
             "kernels": kern,
         }
         if cpu:
