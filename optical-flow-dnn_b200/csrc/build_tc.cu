@@ -22,6 +22,8 @@
 //
 // The kernel is bound by the fp32 pyramid write (174 KB per tile vs 4096 tensor cycles per tile),
 // see DESIGN.md; the MMA pipe has slack, the epilogue/TMA-store path is what is tuned.
+#include <cstdlib>
+
 #include "tma_util.cuh"
 
 namespace raftcorr {
@@ -51,6 +53,23 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mcast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                  int c3, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -122,11 +141,12 @@ struct BuildParams {
     int lvl_h[4], lvl_w[4], lvl_pitch[4];
     int64_t lvl_img_stride[4];
     int B, N1, H2, W2, L;
-    int m_tiles, bands, w_tiles, k_blocks;
+    int m_tiles, m_groups, bands, w_tiles, k_blocks;  // m_groups = ceil(m_tiles / cluster size)
     int total_tiles;
     float scale;
 };
 
+template <int CL>  // CTAs per cluster sharing one B (target) tile through TMA multicast: 1 or 2
 __global__ void __launch_bounds__(kThreads, 1)
 build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_out, const BuildParams P) {
@@ -153,7 +173,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_bar + 8 * s, 1);
-            mbar_init(empty_bar + 8 * s, 1);
+            mbar_init(empty_bar + 8 * s, CL);  // every CTA of the cluster must have consumed the stage
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar + 8 * a, 1);
@@ -167,9 +187,12 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts / arrives remotely
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+    const int crank = CL > 1 ? (int)(blockIdx.x % CL) : 0;      // rank inside the cluster (cluster dims = (CL,1,1))
+    const int first = (int)(blockIdx.x / CL), stride = (int)(gridDim.x / CL);
 
     const int tiles_per_m = P.bands * P.w_tiles;
 
@@ -178,18 +201,25 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+            for (int t = first; t < P.total_tiles; t += stride) {
                 const int wt = t % P.w_tiles;
                 const int band = (t / P.w_tiles) % P.bands;
-                const int mt = (t / tiles_per_m) % P.m_tiles;
-                const int b = t / (tiles_per_m * P.m_tiles);
+                const int mt = ((t / tiles_per_m) % P.m_groups) * CL + crank;  // may be a dummy tile past the end
+                const int b = t / (tiles_per_m * P.m_groups);
                 for (int kb = 0; kb < P.k_blocks; ++kb) {
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                     const uint32_t sa = stage_base + stage * kStageBytes;
                     const uint32_t sb = sa + kABytes;
                     mbar_expect_tx(full_bar + 8 * stage, kStageBytes);
                     tma_load_3d(sa, &map_a, full_bar + 8 * stage, kb * kBlockK, mt * kTileM, b);
-                    tma_load_4d(sb, &map_b, full_bar + 8 * stage, kb * kBlockK, wt * kTileW, band * kTileH, b);
+                    if (CL == 1) {
+                        tma_load_4d(sb, &map_b, full_bar + 8 * stage, kb * kBlockK, wt * kTileW, band * kTileH, b);
+                    } else {
+                        // this CTA fetches 1/CL of the B tile (kTileH/CL target rows) and multicasts it into the
+                        // same smem offset of every CTA of the cluster; each full barrier collects all CL parts
+                        tma_load_4d_mcast(sb + crank * (kBBytes / CL), &map_b, full_bar + 8 * stage, kb * kBlockK,
+                                          wt * kTileW, band * kTileH + crank * (kTileH / CL), b, (uint16_t)((1u << CL) - 1));
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -200,7 +230,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+            for (int t = first; t < P.total_tiles; t += stride, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator
@@ -218,7 +248,8 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
                                     (kb | k) != 0 ? 1u : 0u);
                     }
-                    tc_commit(empty_bar + 8 * stage);  // frees the smem slot when these MMAs retire
+                    if (CL == 1) tc_commit(empty_bar + 8 * stage);  // frees the smem slot when these MMAs retire
+                    else tc_commit_mcast(empty_bar + 8 * stage, (uint16_t)((1u << CL) - 1));  // ... in every CTA of the cluster
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
@@ -237,11 +268,11 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const uint32_t swz = (uint32_t)(ml & 7);
         int it = 0;
         int buf = 0;
-        for (int t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++it) {
+        for (int t = first; t < P.total_tiles; t += stride, ++it) {
             const int wt = t % P.w_tiles;
             const int band = (t / P.w_tiles) % P.bands;
-            const int mt = (t / tiles_per_m) % P.m_tiles;
-            const int b = t / (tiles_per_m * P.m_tiles);
+            const int mt = ((t / tiles_per_m) % P.m_groups) * CL + crank;
+            const int b = t / (tiles_per_m * P.m_groups);
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
             const int m = mt * kTileM + ml;
@@ -341,7 +372,8 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into / arrive on it
+    else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
@@ -361,6 +393,9 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
     if (int rc = get_encode_fn(&fn)) return rc;
     const int B = lay.B, H = lay.H, W = lay.W, N1 = H * W;
     const int Dp = tc_feature_pitch(D);
+    // RAFTCORR_BUILD_CLUSTER=1|2: CTAs per cluster sharing the B tile by TMA multicast (default 2)
+    const char* ce = std::getenv("RAFTCORR_BUILD_CLUSTER");
+    const int cl = (ce && ce[0] == '1') ? 1 : 2;
 
     CUtensorMap map_a, map_b, map_out;
     {
@@ -374,7 +409,7 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
     {
         cuuint64_t dims[4] = {(cuuint64_t)Dp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)Dp * 4, (cuuint64_t)W * Dp * 4, (cuuint64_t)N1 * Dp * 4};
-        cuuint32_t box[4] = {kBlockK, kTileW, kTileH, 1};
+        cuuint32_t box[4] = {kBlockK, kTileW, (cuuint32_t)(kTileH / cl), 1};
         if (int rc = encode_f32_map(fn, &map_b, (void*)f2n, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2"))
             return rc;
@@ -399,19 +434,38 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
     }
     P.B = B; P.N1 = N1; P.H2 = H; P.W2 = W; P.L = lay.L;
     P.m_tiles = ceil_div(N1, kTileM);
+    P.m_groups = ceil_div(P.m_tiles, cl);
     P.bands = ceil_div(H, kTileH);
     P.w_tiles = ceil_div(W, kTileW);
     P.k_blocks = Dp / kBlockK;
-    const int64_t total = (int64_t)B * P.m_tiles * P.bands * P.w_tiles;
+    const int64_t total = (int64_t)B * P.m_groups * P.bands * P.w_tiles;  // tiles per cluster rank
     RC_REQUIRE(total < (1LL << 31), "tf32 build: too many tiles");
     P.total_tiles = (int)total;
     P.scale = 1.0f / sqrtf((float)D);  // corr.py:116
 
     int sms = 0;
     RC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    RC_CUDA(cudaFuncSetAttribute(build_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    const int grid = P.total_tiles < sms ? P.total_tiles : sms;
-    build_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(map_a, map_b, map_out, P);
+    const int max_clusters = sms / cl;
+    const int clusters = P.total_tiles < max_clusters ? P.total_tiles : max_clusters;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * cl);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cl == 2) {
+        RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<2>, map_a, map_b, map_out, P));
+    } else {
+        RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<1>, map_a, map_b, map_out, P));
+    }
     RC_CUDA(cudaGetLastError());
     return 0;
 }
