@@ -109,10 +109,12 @@ int raftcorr_lookup_bwd(const float* grad_out, const float* coords, const float*
                         raftcorr_stream_t stream);
 
 /* Adjoint of the build.  dpyramid is CONSUMED (pooled-level gradients are folded into level 0
- * in place); dfmap1/dfmap2 [B,D,H,W] are overwritten. */
+ * in place; in TF32 mode level 0 is also rounded to TF32); dfmap1/dfmap2 [B,D,H,W] are overwritten.
+ * mode as in raftcorr_build_fwd: TF32 runs the two products on tcgen05 (D <= 256, else CUDA cores). */
+size_t raftcorr_build_bwd_workspace_bytes(int B, int D, int H, int W, int mode);
 int raftcorr_build_bwd(float* dpyramid, const raftcorr_pyramid_layout* layout, const float* fmap1,
-                       const float* fmap2, int D, float* dfmap1, float* dfmap2, int device,
-                       raftcorr_stream_t stream);
+                       const float* fmap2, int D, float* dfmap1, float* dfmap2, int mode, void* workspace,
+                       size_t workspace_bytes, int device, raftcorr_stream_t stream);
 
 /* alt_cuda_corr.forward (correlation.cpp:23-33, correlation_kernel.cu:260-286), same tensors:
  * fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C] (NHWC), coords [B,N,H1,W1,2] (x,y interleaved),

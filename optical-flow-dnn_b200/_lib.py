@@ -48,8 +48,9 @@ SIGNATURES = {
     "raftcorr_lookup_fwd_planned": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
     "raftcorr_lookup_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _LAYP, _c_int, _c_void_p, _c_int,
                                       _c_void_p]),
+    "raftcorr_build_bwd_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "raftcorr_build_bwd": (_c_int, [_c_void_p, _LAYP, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int,
-                                     _c_void_p]),
+                                     _c_void_p, _c_size_t, _c_int, _c_void_p]),
     "raftcorr_alt_forward": (_c_int, [_c_void_p] * 3 + [_c_int] * 8 + [_c_void_p, _c_int, _c_void_p]),
     "raftcorr_alt_backward": (_c_int, [_c_void_p] * 4 + [_c_int] * 8 + [_c_void_p] * 3 + [_c_int, _c_void_p]),
     "raftcorr_alt_level_offset": (_c_i64, [_c_int] * 5),

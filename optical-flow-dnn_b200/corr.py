@@ -91,8 +91,12 @@ class _BuildFn(torch.autograd.Function):
         df1 = torch.empty_like(fmap1)
         df2 = torch.empty_like(fmap2)
         dev = fmap1.device
-        check(_lib.lib().raftcorr_build_bwd(_ptr(dpyr), ctypes.byref(lay), _ptr(fmap1), _ptr(fmap2), block._D,
-                                            _ptr(df1), _ptr(df2), dev.index, _stream(dev)), "raftcorr_build_bwd")
+        L = _lib.lib()
+        ws_bytes = L.raftcorr_build_bwd_workspace_bytes(block._B, block._D, block._H, block._W, block._mode)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+        check(L.raftcorr_build_bwd(_ptr(dpyr), ctypes.byref(lay), _ptr(fmap1), _ptr(fmap2), block._D, _ptr(df1),
+                                   _ptr(df2), block._mode, _ptr(ws), ws_bytes, dev.index, _stream(dev)),
+              "raftcorr_build_bwd")
         return df1, df2, None
 
 

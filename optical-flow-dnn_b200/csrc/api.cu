@@ -185,19 +185,32 @@ int raftcorr_lookup_bwd(const float* grad_out, const float* coords, const float*
     return launch_lookup_bwd(grad_out, coords, dcoords ? &fpv : nullptr, dpv, radius, dcoords, s);
 }
 
+size_t raftcorr_build_bwd_workspace_bytes(int B, int D, int H, int W, int mode) {
+    if (mode == RAFTCORR_BUILD_TF32_TC && build_bwd_tc_supported(D)) return build_bwd_tc_workspace_bytes(B, D, H, W);
+    return 0;
+}
+
 int raftcorr_build_bwd(float* dpyramid, const raftcorr_pyramid_layout* lay, const float* fmap1, const float* fmap2,
-                       int D, float* dfmap1, float* dfmap2, int device, raftcorr_stream_t stream) {
+                       int D, float* dfmap1, float* dfmap2, int mode, void* workspace, size_t workspace_bytes,
+                       int device, raftcorr_stream_t stream) {
     if (int rc = check_layout(lay)) return rc;
     if (lay->B == 0) return 0;
     RC_REQUIRE(dpyramid && fmap1 && fmap2 && dfmap1 && dfmap2, "build_bwd: NULL tensor");
+    RC_REQUIRE(mode == RAFTCORR_BUILD_FP32_SIMT || mode == RAFTCORR_BUILD_TF32_TC, "build_bwd: unknown mode %d", mode);
     DeviceGuard guard(device);
     RC_REQUIRE(guard.ok, "build_bwd: cannot select device %d", device);
     cudaStream_t s = (cudaStream_t)stream;
     PyramidView dpv = make_view(dpyramid, *lay);
     const int64_t imgs = (int64_t)lay->B * lay->H * lay->W;
+    const bool tc = mode == RAFTCORR_BUILD_TF32_TC && build_bwd_tc_supported(D);  // D > 256: CUDA-core GEMMs
     for (int l = lay->L - 1; l >= 1; --l)  // adjoint of corr.py:41-43, coarse to fine
-        if (int rc = launch_pool_adjoint_level(dpv.lvl[l], dpv.lvl[l - 1], imgs, s)) return rc;
-    return launch_build_bwd_gemms(dpv, fmap1, fmap2, D, dfmap1, dfmap2, s);
+        if (int rc = launch_pool_adjoint_level(dpv.lvl[l], dpv.lvl[l - 1], imgs, tc && l == 1, s)) return rc;
+    if (!tc) return launch_build_bwd_gemms(dpv, fmap1, fmap2, D, dfmap1, dfmap2, s);
+    if (lay->L == 1)
+        if (int rc = launch_round_level(dpv.lvl[0], imgs, s)) return rc;
+    const size_t need = build_bwd_tc_workspace_bytes(lay->B, D, lay->H, lay->W);
+    RC_REQUIRE(workspace && workspace_bytes >= need, "build_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return launch_build_bwd_tc(dpv, fmap1, fmap2, D, dfmap1, dfmap2, workspace, device, s);
 }
 
 int raftcorr_alt_forward(const float* fmap1, const float* fmap2, const float* coords, int B, int N, int H1, int W1,

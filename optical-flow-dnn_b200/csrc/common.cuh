@@ -78,7 +78,13 @@ int launch_nhwc_to_nchw(const float* in, float* out, int B, int D, int HW, cudaS
 int launch_pool_nhwc(const float* in, float* out, int B, int Hi, int Wi, int D, cudaStream_t s);
 int launch_pool_adjoint_nhwc(const float* gout, float* gin, int B, int Hi, int Wi, int D, cudaStream_t s);
 int launch_pool_level(const LevelView& in, const LevelView& out, int64_t imgs, cudaStream_t s);
-int launch_pool_adjoint_level(const LevelView& coarse, const LevelView& fine, int64_t imgs, cudaStream_t s);
+int launch_pool_adjoint_level(const LevelView& coarse, const LevelView& fine, int64_t imgs, bool round_tf32_out,
+                              cudaStream_t s);
+int launch_round_level(const LevelView& lv, int64_t imgs, cudaStream_t s);
+bool build_bwd_tc_supported(int D);
+size_t build_bwd_tc_workspace_bytes(int B, int D, int H, int W);
+int launch_build_bwd_tc(const PyramidView& dpv, const float* f1, const float* f2, int D, float* df1, float* df2,
+                        void* workspace, int device, cudaStream_t s);
 
 int launch_build_simt(const float* f1, const float* f2, int D, const PyramidView& pv, cudaStream_t s);
 int launch_build_tc(const float* f1_nhwc, const float* f2_nhwc, int D, float* pyramid,

@@ -124,6 +124,7 @@ __global__ void pool_level_kernel(const LevelView in, const LevelView out, int64
     }
 }
 
+template <bool ROUND>
 __global__ void pool_adjoint_level_kernel(const LevelView coarse, const LevelView fine, int64_t total) {
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
@@ -131,9 +132,13 @@ __global__ void pool_adjoint_level_kernel(const LevelView coarse, const LevelVie
         int64_t t = idx / fine.w;
         const int y = t % fine.h;
         const int64_t img = t / fine.h;
+        float* dst = fine.base + img * fine.img_stride + (int64_t)y * fine.pitch + x;
+        float v = *dst;
         if ((y >> 1) < coarse.h && (x >> 1) < coarse.w)
-            fine.base[img * fine.img_stride + (int64_t)y * fine.pitch + x] +=
-                0.25f * coarse.base[img * coarse.img_stride + (int64_t)(y >> 1) * coarse.pitch + (x >> 1)];
+            v += 0.25f * coarse.base[img * coarse.img_stride + (int64_t)(y >> 1) * coarse.pitch + (x >> 1)];
+        else if (!ROUND)
+            continue;
+        *dst = ROUND ? round_tf32(v) : v;  // ROUND: the folded level 0 feeds the tensor-core backward GEMMs
     }
 }
 
@@ -187,10 +192,14 @@ int launch_pool_level(const LevelView& in, const LevelView& out, int64_t imgs, c
     return 0;
 }
 
-int launch_pool_adjoint_level(const LevelView& coarse, const LevelView& fine, int64_t imgs, cudaStream_t s) {
+int launch_pool_adjoint_level(const LevelView& coarse, const LevelView& fine, int64_t imgs, bool round_tf32_out,
+                              cudaStream_t s) {
     const int64_t total = imgs * fine.h * fine.w;
     if (total == 0) return 0;
-    pool_adjoint_level_kernel<<<grid_for(total, 256), 256, 0, s>>>(coarse, fine, total);
+    if (round_tf32_out)
+        pool_adjoint_level_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(coarse, fine, total);
+    else
+        pool_adjoint_level_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(coarse, fine, total);
     RC_CUDA(cudaGetLastError());
     return 0;
 }
