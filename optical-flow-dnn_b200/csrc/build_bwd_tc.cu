@@ -5,7 +5,8 @@
 //            A = dV0 rows: K-major straight from the gradient pyramid  ([128 m][32 w] boxes, one target row)
 //            B = F2 [d][n]: K-major from a TF32-rounded, row-padded NCHW copy
 //   GEMM 2:  dF2[b][d][n] = s * sum_m dV0[b][m][n] * F1[b][d][m]      M = n (target px), N = d, K = m
-//            A = dV0^T: the reduction index m is the STRIDED one -> MN-major UMMA operand; a 128-pixel
+//            A = dV0^T: the reduction index m is the STRIDED one -> MN-major UMMA operand (TF32 needs the
+//                SWIZZLE_128B_BASE32B layout, TMA mode 128B_ATOM_32B, see tc_util.cuh); a 128-pixel
 //                target tile is 4 rows x 32 cols, fetched as four [32 m][32 w] boxes (one per row)
 //            B = F1 [d][m]: K-major from a TF32-rounded, padded copy
 //
@@ -126,7 +127,7 @@ build_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     for (int k = 0; k < kBK / 8; ++k) {
                         // K-major: +32 bytes inside the swizzle row; MN-major: next 8-row atom (+1024 bytes)
                         const uint64_t adesc = MODE == 1 ? make_smem_desc(sa) + (uint64_t)(2 * k)
-                                                         : make_smem_desc_mn(sa + k * 1024, 4096, 1024);
+                                                         : make_smem_desc_mn_tf32(sa + k * 1024, 4096);
                         tc_mma_tf32(d_tmem, adesc, bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     tc_commit(empty_bar + 8 * stage);
@@ -277,7 +278,7 @@ int launch_build_bwd_tc(const PyramidView& dpv, const float* f1, const float* f2
     {   // ---- GEMM 2: dF2
         CUtensorMap map_a, map_b;
         cuuint32_t boxa[4] = {32, 1, kBK, 1};
-        if (int rc = encode_f32_map(fn, &map_a, (void*)g0.base, 4, gdims, gstr, boxa, CU_TENSOR_MAP_SWIZZLE_128B,
+        if (int rc = encode_f32_map(fn, &map_a, (void*)g0.base, 4, gdims, gstr, boxa, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, "dV0 (columns)"))
             return rc;
         cuuint64_t bd[3] = {(cuuint64_t)N1p, (cuuint64_t)D, (cuuint64_t)B};

@@ -87,15 +87,19 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 
 
-// MN-major, 128B-swizzled operand tile (the reduction index is the STRIDED one in memory): atoms of
-// 8 k-rows x 128 bytes (32 fp32 along M/N), atoms along K `sbo` bytes apart, along M/N `lbo` bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+// MN-major TF32 operand tile (the reduction index is the STRIDED one in memory).  Measured with
+// scripts/probe/umma_mn_probe.cu: kind::tf32 only accepts MN-major operands in the
+// SWIZZLE_128B_BASE32B layout (descriptor layout type 1; plain SWIZZLE_128B silently yields zeros):
+// atoms of 4 k-rows x 128 bytes (32 fp32 along M/N) whose 32-byte chunks are XOR-swizzled by the row
+// (address bits 5-6 ^= bits 7-8) -- what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+// SBO = 512 bytes between 4-row k-groups, LBO = bytes between 32-element M/N chunks.
+__device__ __forceinline__ uint64_t make_smem_desc_mn_tf32(uint32_t smem_addr, uint32_t lbo) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
-    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)(512 >> 4) << 32;
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;
     return d;
 }
 

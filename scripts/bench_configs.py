@@ -73,7 +73,14 @@ def train_config(name, B, D, H, W, L, r, iters, cls, kw, reps=5):
         loss = 0
         for c, w in zip(coords, ws): loss = loss + (blk(c) * w).sum()
         loss.backward()
-    ms = timeit(step, reps, warm=2)
+    for _ in range(2): step()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):  # step latency: one step in flight at a time (median of per-step device times)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); step(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
     print(json.dumps({"config": name, "shape": [B, D, H, W, L, r], "iters": iters, "class": cls.__name__, **kw, "ms_per_step_fwd_bwd": ms,
                       "pairs_per_s": B / (ms * 1e-3)}))
 
@@ -97,7 +104,7 @@ if "2" in which:
     fwd_config("2 RAFT-basic 436x1024 B8 32it", 8, 256, 55, 128, 4, 4, 32, "tf32")
     fwd_config("2 RAFT-basic 436x1024 B1 32it", 1, 256, 55, 128, 4, 4, 32, "tf32")
 if "3" in which:
-    train_config("3 training 368x496 B10 12it fwd+bwd", 10, 256, 46, 62, 4, 4, 12, rc.CorrBlock, {"build_mode": "tf32"})
+    train_config("3 training 368x496 B10 12it fwd+bwd", 10, 256, 46, 62, 4, 4, 12, rc.CorrBlock, {"build_mode": "tf32"}, reps=20)
     train_config("3 training (alternate) B2 2it fwd+bwd", 2, 256, 46, 62, 4, 4, 2, rc.AlternateCorrBlock, {}, reps=2)
 if "4" in which:
     fwd_config("4 raft_uncertainty KITTI 375x1242 B16 24it", 16, 256, 47, 156, 4, 4, 24, "tf32", reps=10)
