@@ -381,7 +381,7 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
         RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<2>, map_a, map_b, map_out, P));
     } else {
         RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<1>, map_a, map_b, map_out, P));
+        build_tc_kernel<1><<<clusters, kThreads, kSmemBytes, s>>>(map_a, map_b, map_out, P);
     }
     RC_CUDA(cudaGetLastError());
     return 0;

@@ -124,21 +124,35 @@ __global__ void pool_level_kernel(const LevelView in, const LevelView out, int64
     }
 }
 
+// Adjoint of one pooling level on the pitched layout: fine[y][x] += coarse[y/2][x/2] / 4 inside the pooled
+// footprint.  One thread per 4 consecutive fine elements (rows are 32-byte aligned: pitch % 8 == 0), so
+// the pass streams float4s; values written into the row padding are harmless (nothing reads it).
 template <bool ROUND>
-__global__ void pool_adjoint_level_kernel(const LevelView coarse, const LevelView fine, int64_t total) {
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+__global__ void pool_adjoint_level_kernel(const LevelView coarse, const LevelView fine, int64_t total4) {
+    const int q4 = fine.pitch >> 2;  // float4 chunks per fine row
+    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total4;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        const int x = idx % fine.w;
-        int64_t t = idx / fine.w;
-        const int y = t % fine.h;
+        const int xq = (int)(idx % q4);
+        int64_t t = idx / q4;
+        const int y = (int)(t % fine.h);
         const int64_t img = t / fine.h;
-        float* dst = fine.base + img * fine.img_stride + (int64_t)y * fine.pitch + x;
-        float v = *dst;
-        if ((y >> 1) < coarse.h && (x >> 1) < coarse.w)
-            v += 0.25f * coarse.base[img * coarse.img_stride + (int64_t)(y >> 1) * coarse.pitch + (x >> 1)];
-        else if (!ROUND)
+        const int x = xq * 4;
+        if (x >= fine.w) continue;
+        float4* dst = reinterpret_cast<float4*>(fine.base + img * fine.img_stride + (int64_t)y * fine.pitch + x);
+        float4 v = *dst;
+        const int yc = y >> 1, xc = x >> 1;
+        if (yc < coarse.h) {
+            const float* c = coarse.base + img * coarse.img_stride + (int64_t)yc * coarse.pitch + xc;
+            const float c0 = xc < coarse.w ? 0.25f * c[0] : 0.f;
+            const float c1 = xc + 1 < coarse.w ? 0.25f * c[1] : 0.f;
+            v.x += c0; v.y += c0; v.z += c1; v.w += c1;
+        } else if (!ROUND) {
             continue;
-        *dst = ROUND ? round_tf32(v) : v;  // ROUND: the folded level 0 feeds the tensor-core backward GEMMs
+        }
+        if (ROUND) {  // the folded level 0 feeds the tensor-core backward GEMMs
+            v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+        }
+        *dst = v;
     }
 }
 
@@ -194,7 +208,7 @@ int launch_pool_level(const LevelView& in, const LevelView& out, int64_t imgs, c
 
 int launch_pool_adjoint_level(const LevelView& coarse, const LevelView& fine, int64_t imgs, bool round_tf32_out,
                               cudaStream_t s) {
-    const int64_t total = imgs * fine.h * fine.w;
+    const int64_t total = imgs * fine.h * (fine.pitch >> 2);
     if (total == 0) return 0;
     if (round_tf32_out)
         pool_adjoint_level_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(coarse, fine, total);
