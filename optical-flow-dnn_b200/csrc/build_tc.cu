@@ -13,12 +13,14 @@
 //                          fp32 accumulators in TMEM, two 256-column accumulator stages (all 512 columns)
 //                          so the MMAs of tile i+1 overlap the epilogue of tile i.
 //   warp 2  TMEM allocator
-//   warps 4-7 epilogue   : TMEM lane == source pixel, so one thread owns the whole 8x32 target block of
+//   warps 4-7  epilogue A: TMEM lane == source pixel, so one thread owns the whole 8x32 target block of
 //                          its source pixel: tcgen05.ld two rows at a time, scale by 1/sqrt(D), stage the
 //                          level-0 rows in swizzled shared memory and TMA-store them ([128 px][128 B] boxes,
-//                          bounds clipped by the tensor map), and reduce 2x2 / 4x4 / 8x8 means in registers
+//                          double-buffered, bounds clipped by the tensor map).
+//   warps 8-11 epilogue B: read the same accumulator again and reduce 2x2 / 4x4 / 8x8 means in registers
 //                          for levels 1..3 (floor-mode pooling == block means over the floor-cropped region,
-//                          since floor(floor(n/2)/2) == floor(n/4)), written with 128-bit stores.
+//                          since floor(floor(n/2)/2) == floor(n/4)); 256-bit stores, off the critical path
+//                          of the level-0 store pipeline.
 //
 // The kernel is bound by the fp32 pyramid write (174 KB per tile vs 4096 tensor cycles per tile),
 // see DESIGN.md; the MMA pipe has slack, the epilogue/TMA-store path is what is tuned.
@@ -172,14 +174,12 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tc_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
             }
         }
-    } else if (warp >= 4) {
-        // ===================== epilogue (8 warps) =====================
-        // warp % 4 selects the TMEM lane quarter (hardware rule), (warp - 4) / 4 the column half: every
-        // source pixel's 8x32 target block is split between two threads (16 columns each), which halves
-        // the serial TMEM->registers->smem chain per warp and puts two epilogue warps on every scheduler.
-        const int ew = warp & 3;
-        const int cg = (warp - 4) >> 2;           // column half: target columns [16*cg, 16*cg + 16)
-        const int ml = ew * 32 + lane;            // source pixel inside the tile == TMEM lane
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== epilogue A (warps 4-7): level 0 =====================
+        // TMEM lane == source pixel: each thread moves the 8x32 block of its source pixel, two rows at a
+        // time: tcgen05.ld -> scale -> swizzled smem staging -> TMA store of [128 px][128 B] boxes.
+        const int ew = warp & 3;                  // TMEM lane quarter this warp may access (hardware rule)
+        const int ml = ew * 32 + lane;
         const bool issuer = (threadIdx.x == 4 * 32);
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
         const uint32_t swz = (uint32_t)(ml & 7);
@@ -191,101 +191,128 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int mt = ((t / tiles_per_m) % P.m_groups) * CL + crank;
             const int b = t / (tiles_per_m * P.m_groups);
             const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
-            const int m = mt * kTileM + ml;
-            const bool m_ok = m < P.N1;
-            const int w0 = wt * kTileW;          // first level-0 column of the tile
-            const int c0 = w0 + 16 * cg;         // first level-0 column of this thread
-
-            mbar_wait(tfull_bar + 8 * acc, acc_phase);
+            mbar_wait(tfull_bar + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t t_acc = tmem_base + lane_addr + acc * kTileN + 16 * cg;
-
-            float l1prev[8], l2prev[4];
+            const uint32_t t_acc = tmem_base + lane_addr + acc * kTileN;
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
-                float ra[16], rb[16];
-                tmem_ld16(t_acc + (2 * p) * kTileW, ra);
-                tmem_ld16(t_acc + (2 * p + 1) * kTileW, rb);
+                float ra[32], rb[32];
+                tmem_ld32(t_acc + (2 * p) * kTileW, ra);
+                tmem_ld32(t_acc + (2 * p + 1) * kTileW, rb);
                 tmem_ld_wait();
-                if (p == 3) {  // all of this accumulator is in registers: hand it back to the MMA warp
+                if (p == 3) {  // this warp has read all of the accumulator
                     tc_fence_before();
                     mbar_arrive(tempty_bar + 8 * acc);
                 }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    ra[j] *= P.scale;
-                    rb[j] *= P.scale;
-                }
-                // ---- level 0: two rows -> swizzled staging -> TMA store
                 const uint32_t sa = store_base + buf * kStoreBufBytes + ml * 128;
                 const uint32_t sb = sa + kRowTileBytes;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t off = ((uint32_t)(4 * cg + j) ^ swz) << 4;
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(ra[4 * j]),
-                                 "f"(ra[4 * j + 1]), "f"(ra[4 * j + 2]), "f"(ra[4 * j + 3])
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t off = ((uint32_t)j ^ swz) << 4;
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(ra[4 * j] * P.scale),
+                                 "f"(ra[4 * j + 1] * P.scale), "f"(ra[4 * j + 2] * P.scale), "f"(ra[4 * j + 3] * P.scale)
                                  : "memory");
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + off), "f"(rb[4 * j]),
-                                 "f"(rb[4 * j + 1]), "f"(rb[4 * j + 2]), "f"(rb[4 * j + 3])
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + off), "f"(rb[4 * j] * P.scale),
+                                 "f"(rb[4 * j + 1] * P.scale), "f"(rb[4 * j + 2] * P.scale), "f"(rb[4 * j + 3] * P.scale)
                                  : "memory");
                 }
                 fence_proxy_async();
                 // the other buffer (used by the previous phase) must have been read out before the next
                 // phase overwrites it; waiting here, one phase late, keeps one store group in flight
                 if (issuer) tma_store_wait_read_all();
-                named_bar_sync(1, kEpilogueThreads);
+                named_bar_sync(1, 128);
                 if (issuer) {
                     const uint32_t s0 = store_base + buf * kStoreBufBytes;
                     const int h = band * kTileH + 2 * p;
-                    tma_store_4d(&map_out, s0, w0, h, mt * kTileM, b);
-                    tma_store_4d(&map_out, s0 + kRowTileBytes, w0, h + 1, mt * kTileM, b);
+                    tma_store_4d(&map_out, s0, wt * kTileW, h, mt * kTileM, b);
+                    tma_store_4d(&map_out, s0 + kRowTileBytes, wt * kTileW, h + 1, mt * kTileM, b);
                     tma_store_commit();
                 }
                 buf ^= 1;
-                // ---- levels 1..3: thread-local block means.  Values past a level's width/height are never
-                // stored (w/h guards), values in the row padding are harmless (nothing reads the padding).
-                if (P.L > 1) {
-                    float l1[8];
+            }
+        }
+        if (issuer) tma_store_wait_all();  // global writes complete before the CTA exits
+    } else if (warp >= 8) {
+        // ===================== epilogue B (warps 8-11): levels 1..3 =====================
+        // Re-reads the same accumulator from TMEM (cheap) so that the pooled levels never sit on the
+        // critical path of the level-0 store pipeline.  Floor-mode cascaded pooling == block means over
+        // the floor-cropped region, so 2x2 / 4x4 / 8x8 means are thread-local register reductions; the
+        // 1/sqrt(D) scale is applied to the means.  Full 32-byte sectors per store (levels 1, 2).
+        const int ew = warp & 3;
+        const int ml = ew * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+        const float q = 0.25f * P.scale;
+        int it = 0;
+        for (int t = first; t < P.total_tiles; t += stride, ++it) {
+            const int wt = t % P.w_tiles;
+            const int band = (t / P.w_tiles) % P.bands;
+            const int mt = ((t / tiles_per_m) % P.m_groups) * CL + crank;
+            const int b = t / (tiles_per_m * P.m_groups);
+            const int acc = it & 1;
+            const int m = mt * kTileM + ml;
+            const bool m_ok = m < P.N1;
+            const int w0 = wt * kTileW;
+            mbar_wait(tfull_bar + 8 * acc, (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_acc = tmem_base + lane_addr + acc * kTileN;
+            if (P.L <= 1) {  // nothing to pool: just release the accumulator
+                tc_fence_before();
+                mbar_arrive(tempty_bar + 8 * acc);
+                continue;
+            }
+            const int64_t pix = (int64_t)b * P.N1 + m;
+            float l1prev[16], l2prev[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) l1[j] = (ra[2 * j] + ra[2 * j + 1] + rb[2 * j] + rb[2 * j + 1]) * 0.25f;
-                    const int h1 = band * 4 + p;
-                    if (m_ok && h1 < P.lvl_h[1] && (c0 >> 1) + 8 <= P.lvl_pitch[1])
-                        st_global_v8(P.lvl_base[1] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[1] +
-                                         (int64_t)h1 * P.lvl_pitch[1] + (c0 >> 1), l1);
-                    if (P.L > 2) {
-                        if ((p & 1) == 0) {
+            for (int p = 0; p < 4; ++p) {
+                float ra[32], rb[32];
+                tmem_ld32(t_acc + (2 * p) * kTileW, ra);
+                tmem_ld32(t_acc + (2 * p + 1) * kTileW, rb);
+                tmem_ld_wait();
+                if (p == 3) {
+                    tc_fence_before();
+                    mbar_arrive(tempty_bar + 8 * acc);
+                }
+                float l1[16];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) l1prev[j] = l1[j];
-                        } else {
-                            float l2[4];
+                for (int j = 0; j < 16; ++j) l1[j] = (ra[2 * j] + ra[2 * j + 1] + rb[2 * j] + rb[2 * j + 1]) * q;
+                const int h1 = band * 4 + p;
+                if (m_ok && h1 < P.lvl_h[1]) {
+                    float* dst = P.lvl_base[1] + pix * P.lvl_img_stride[1] + (int64_t)h1 * P.lvl_pitch[1] + (w0 >> 1);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                l2[j] = (l1prev[2 * j] + l1prev[2 * j + 1] + l1[2 * j] + l1[2 * j + 1]) * 0.25f;
-                            const int h2 = band * 2 + (p >> 1);
-                            if (m_ok && h2 < P.lvl_h[2] && (c0 >> 2) + 4 <= P.lvl_pitch[2])
-                                *reinterpret_cast<float4*>(P.lvl_base[2] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[2] +
-                                                           (int64_t)h2 * P.lvl_pitch[2] + (c0 >> 2)) =
-                                    make_float4(l2[0], l2[1], l2[2], l2[3]);
-                            if (P.L > 3) {
-                                if (p == 1) {
+                    for (int c = 0; c < 2; ++c)
+                        if ((w0 >> 1) + 8 * c + 8 <= P.lvl_pitch[1]) st_global_v8(dst + 8 * c, l1 + 8 * c);
+                }
+                if (P.L > 2) {
+                    if ((p & 1) == 0) {
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j) l2prev[j] = l2[j];
-                                } else {
-                                    const float l3a = (l2prev[0] + l2prev[1] + l2[0] + l2[1]) * 0.25f;
-                                    const float l3b = (l2prev[2] + l2prev[3] + l2[2] + l2[3]) * 0.25f;
-                                    if (m_ok && band < P.lvl_h[3] && (c0 >> 3) + 2 <= P.lvl_pitch[3])
-                                        *reinterpret_cast<float2*>(P.lvl_base[3] + ((int64_t)b * P.N1 + m) * P.lvl_img_stride[3] +
-                                                                   (int64_t)band * P.lvl_pitch[3] + (c0 >> 3)) =
-                                            make_float2(l3a, l3b);
-                                }
+                        for (int j = 0; j < 16; ++j) l1prev[j] = l1[j];
+                    } else {
+                        float l2[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            l2[j] = (l1prev[2 * j] + l1prev[2 * j + 1] + l1[2 * j] + l1[2 * j + 1]) * 0.25f;
+                        const int h2 = band * 2 + (p >> 1);
+                        if (m_ok && h2 < P.lvl_h[2] && (w0 >> 2) + 8 <= P.lvl_pitch[2])
+                            st_global_v8(P.lvl_base[2] + pix * P.lvl_img_stride[2] + (int64_t)h2 * P.lvl_pitch[2] + (w0 >> 2), l2);
+                        if (P.L > 3) {
+                            if (p == 1) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) l2prev[j] = l2[j];
+                            } else {
+                                float4 l3;
+                                l3.x = (l2prev[0] + l2prev[1] + l2[0] + l2[1]) * 0.25f;
+                                l3.y = (l2prev[2] + l2prev[3] + l2[2] + l2[3]) * 0.25f;
+                                l3.z = (l2prev[4] + l2prev[5] + l2[4] + l2[5]) * 0.25f;
+                                l3.w = (l2prev[6] + l2prev[7] + l2[6] + l2[7]) * 0.25f;
+                                if (m_ok && band < P.lvl_h[3] && (w0 >> 3) + 4 <= P.lvl_pitch[3])
+                                    *reinterpret_cast<float4*>(P.lvl_base[3] + pix * P.lvl_img_stride[3] +
+                                                               (int64_t)band * P.lvl_pitch[3] + (w0 >> 3)) = l3;
                             }
                         }
                     }
                 }
             }
         }
-        if (issuer) tma_store_wait_all();  // global writes complete before the CTA exits
     }
 
     tc_fence_before();
