@@ -13,6 +13,10 @@
 //   * outputs are accumulated on chip and written once, channel-major, through a shared tile
 //     (the reference read-modify-writes global memory once per 32-channel chunk, :102-114);
 //   * launched on the caller's stream with the caller's device, zero padding by predication.
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace raftcorr {
@@ -146,6 +150,171 @@ alt_fwd_kernel(const AltParams P, float* __restrict__ out) {
     }
 }
 
+// Sum 64 per-lane partials (index c = 0..63) across the warp; lane i ends up with the totals of
+// elements 2i (returned in p[0]) and 2i+1 (p[1]).  62 shuffles for 64 sums.
+__device__ __forceinline__ void transpose_reduce64(float (&p)[64], int lane) {
+#pragma unroll
+    for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+        const bool hi = lane & off;
+#pragma unroll
+        for (int j = 0; j < n; ++j) {
+            const float send = hi ? p[j] : p[j + n];
+            const float keep = hi ? p[j + n] : p[j];
+            p[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
+// Grouped forward: a warp owns FOUR consecutive source pixels.  When the flow is locally smooth their
+// (K+1)^2 windows overlap almost completely, so the warp walks the UNION box once: every f2 vector is
+// fetched once and dotted with all four f1 vectors held in registers (4x fewer L1/L2 bytes -- the
+// single-pixel kernel above is bound by exactly that traffic).  Partial dots of 16 lattice points x 4
+// pixels are reduced with a 62-shuffle transpose; each lane then drops its two sums into the per-pixel
+// patches they belong to.  If the windows are far apart (union > 2x one window) the pixels are walked
+// one by one through the same code path, so arbitrary coordinates stay correct.
+template <int R, int NV>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+alt_fwd_group_kernel(const AltParams P, float* __restrict__ out) {
+    const int LG = P.lv.L;
+    constexpr int K = 2 * R + 1, K1 = K + 1, NP = K1 * K1, KK = K * K, NT = (KK + 31) / 32;
+    constexpr int G = 4;           // pixels per warp: kPix == kWarps * G
+    constexpr int UMAX = 2 * NP;   // largest union box walked in one go
+    const int CH = LG * KK;
+    extern __shared__ float smem[];
+    float* out_s = smem;                       // [CH][kTilePitch]
+    float* patch_s = smem + CH * kTilePitch;   // [kWarps][G][LG][NP]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bn = blockIdx.y, b = bn / P.NC, p0 = blockIdx.x * kPix + warp * G;
+    const int nvec = P.C >> 2;
+    float* patch = patch_s + warp * (G * LG * NP);
+
+    int ooff[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const int c = lane + 32 * t;
+        const int ix = c / K, iy = c - ix * K;  // channel = iy + K*ix
+        ooff[t] = iy * K1 + ix;
+    }
+
+    float cx[G], cy[G];
+    float4 a[G][NV];
+    bool valid[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int p = p0 + g;
+        valid[g] = p < P.N1;
+        const int pc = valid[g] ? p : P.N1 - 1;
+        cx[g] = clamp_coord(__ldg(P.cv.ptr + bn * P.cv.batch_stride + pc * P.cv.pix_stride));
+        cy[g] = clamp_coord(__ldg(P.cv.ptr + bn * P.cv.batch_stride + P.cv.comp_stride + pc * P.cv.pix_stride));
+        const float4* f1v = reinterpret_cast<const float4*>(P.f1 + ((int64_t)b * P.N1 + pc) * P.C);
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+            a[g][j] = (lane + 32 * j < nvec) ? __ldg(f1v + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (p0 < P.N1) {
+#pragma unroll 1
+        for (int l = 0; l < LG; ++l) {
+            const int Hl = P.lv.h[l], Wl = P.lv.w[l];
+            int x0[G], y0[G];
+            int ux0 = INT_MAX, uy0 = INT_MAX, ux1 = INT_MIN, uy1 = INT_MIN;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                x0[g] = __float2int_rd(cx[g] * P.inv_scale[l]) - R;
+                y0[g] = __float2int_rd(cy[g] * P.inv_scale[l]) - R;
+                ux0 = min(ux0, x0[g]); uy0 = min(uy0, y0[g]);
+                ux1 = max(ux1, x0[g] + K1); uy1 = max(uy1, y0[g] + K1);
+            }
+            const bool joint = (int64_t)(ux1 - ux0) * (uy1 - uy0) <= UMAX;
+            const float4* f2b = reinterpret_cast<const float4*>(P.lv.f2[l] + (int64_t)b * Hl * Wl * P.C);
+            const int qsel = lane >> 3;  // pixel whose sums this lane receives after the transpose
+            const int qx0 = qsel == 0 ? x0[0] : qsel == 1 ? x0[1] : qsel == 2 ? x0[2] : x0[3];
+            const int qy0 = qsel == 0 ? y0[0] : qsel == 1 ? y0[1] : qsel == 2 ? y0[2] : y0[3];
+            float* qpatch = patch + (qsel * LG + l) * NP;
+            const int nbox = joint ? 1 : G;
+#pragma unroll 1
+            for (int bx = 0; bx < nbox; ++bx) {
+                int bx0 = ux0, by0 = uy0, bw = ux1 - ux0, bh = uy1 - uy0;
+                if (!joint) {
+                    bx0 = bx == 0 ? x0[0] : bx == 1 ? x0[1] : bx == 2 ? x0[2] : x0[3];
+                    by0 = bx == 0 ? y0[0] : bx == 1 ? y0[1] : bx == 2 ? y0[2] : y0[3];
+                    bw = K1; bh = K1;
+                }
+                const int cnt = bw * bh;
+                int row = 0, col = 0;  // walking position inside the box (warp-uniform)
+#pragma unroll 1
+                for (int e0 = 0; e0 < cnt; e0 += 16) {
+                    float part[64];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int yy = by0 + row, xx = bx0 + col;
+                        const bool ok = e0 + i < cnt && yy >= 0 && yy < Hl && xx >= 0 && xx < Wl;
+                        const float4* src = f2b + ((int64_t)yy * Wl + xx) * nvec;
+                        float sg[G];
+#pragma unroll
+                        for (int g = 0; g < G; ++g) sg[g] = 0.f;
+#pragma unroll
+                        for (int j = 0; j < NV; ++j) {
+                            if (ok && lane + 32 * j < nvec) {
+                                const float4 v = __ldg(src + lane + 32 * j);
+#pragma unroll
+                                for (int g = 0; g < G; ++g) {
+                                    sg[g] = fmaf(a[g][j].x, v.x, sg[g]);
+                                    sg[g] = fmaf(a[g][j].y, v.y, sg[g]);
+                                    sg[g] = fmaf(a[g][j].z, v.z, sg[g]);
+                                    sg[g] = fmaf(a[g][j].w, v.w, sg[g]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int g = 0; g < G; ++g) part[g * 16 + i] = sg[g];
+                        if (++col == bw) { col = 0; ++row; }
+                    }
+                    transpose_reduce64(part, lane);
+                    // this lane now holds pixel qsel's sums for points e0 + 2*(lane&7) + {0,1}
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int e = e0 + 2 * (lane & 7) + k;
+                        if (e < cnt) {
+                            const int er = e / bw, ec = e - er * bw;
+                            const int wr = by0 + er - qy0, wc = bx0 + ec - qx0;  // position inside pixel qsel's window
+                            if (wr >= 0 && wr < K1 && wc >= 0 && wc < K1) qpatch[wr * K1 + wc] = part[k];
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (!valid[g]) continue;
+        const int q = warp * G + g;
+#pragma unroll 1
+        for (int l = 0; l < LG; ++l) {
+            const float* S = patch + (g * LG + l) * NP;
+            const float xs = cx[g] * P.inv_scale[l], ys = cy[g] * P.inv_scale[l];
+            const float dx = xs - floorf(xs), dy = ys - floorf(ys);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const int c = lane + 32 * t;
+                if (c < KK) {
+                    const int o = ooff[t];
+                    const float top = S[o] + dx * (S[o + 1] - S[o]);
+                    const float bot = S[o + K1] + dx * (S[o + K1 + 1] - S[o + K1]);
+                    out_s[(l * KK + c) * kTilePitch + q] = (top + dy * (bot - top)) * P.scale;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int p = blockIdx.x * kPix + lane;
+    if (p < P.N1) {
+        float* dst = out + (int64_t)bn * CH * P.N1 + p;
+        for (int ch = warp; ch < CH; ch += kWarps) dst[(int64_t)ch * P.N1] = out_s[ch * kTilePitch + lane];
+    }
+}
+
 // Backward (correlation_kernel.cu:122-256 restated): g_e = sum of the <=4 output gradients that a
 // lattice point feeds, then df1[p] += g_e * f2[e] (registers, one vector add per pixel) and
 // df2[e] += g_e * f1[p] (vector red.global.add.v4.f32 instead of one scalar atomic per channel).
@@ -239,8 +408,12 @@ template <int R, int NV>
 int run_alt_fwd(const AltParams& P, float* out, cudaStream_t s) {
     constexpr int K = 2 * R + 1, NP = (K + 1) * (K + 1), NCH = (NP + 31) / 32;
     const int LG = P.lv.L;
-    const size_t smem = sizeof(float) * (LG * K * K * kTilePitch + kWarps * LG * NCH * 32);
-    auto kern = alt_fwd_kernel<R, NV>;
+    // RAFTCORR_ALT=single selects the one-pixel-per-warp kernel (A/B switch); default: grouped
+    const char* e = std::getenv("RAFTCORR_ALT");
+    const bool single = e && std::strcmp(e, "single") == 0;
+    const size_t smem = single ? sizeof(float) * (LG * K * K * kTilePitch + kWarps * LG * NCH * 32)
+                               : sizeof(float) * (LG * K * K * kTilePitch + kWarps * 4 * LG * NP);
+    auto kern = single ? alt_fwd_kernel<R, NV> : alt_fwd_group_kernel<R, NV>;
     RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(P.N1, kPix), P.B * P.NC);
     kern<<<grid, kWarps * 32, smem, s>>>(P, out);
