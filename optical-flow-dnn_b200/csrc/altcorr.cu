@@ -168,9 +168,9 @@ __device__ __forceinline__ void transpose_reduce64(float (&p)[64], int lane) {
 // Grouped forward: a warp owns FOUR consecutive source pixels.  When the flow is locally smooth their
 // (K+1)^2 windows overlap almost completely, so the warp walks the UNION box once: every f2 vector is
 // fetched once and dotted with all four f1 vectors held in registers (4x fewer L1/L2 bytes -- the
-// single-pixel kernel above is bound by exactly that traffic).  Partial dots of 16 lattice points x 4
-// pixels are reduced with a 62-shuffle transpose; each lane then drops its two sums into the per-pixel
-// patches they belong to.  If the windows are far apart (union > 2x one window) the pixels are walked
+// single-pixel kernel above is bound by exactly that traffic).  Partial dots of 8 lattice points x 4
+// pixels are reduced with a 31-shuffle transpose; each lane then drops its sum into the per-pixel
+// patch it belongs to.  If the windows are far apart (union > 2x one window) the pixels are walked
 // one by one through the same code path, so arbitrary coordinates stay correct.
 template <int R, int NV>
 __global__ void __launch_bounds__(kWarps * 32, 2)
@@ -243,43 +243,46 @@ alt_fwd_group_kernel(const AltParams P, float* __restrict__ out) {
                 const int cnt = bw * bh;
                 int row = 0, col = 0;  // walking position inside the box (warp-uniform)
 #pragma unroll 1
-                for (int e0 = 0; e0 < cnt; e0 += 16) {
-                    float part[64];
+                for (int e0 = 0; e0 < cnt; e0 += 8) {
+                    float part[32];  // [pixel g][point i]: g * 8 + i
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int yy = by0 + row, xx = bx0 + col;
-                        const bool ok = e0 + i < cnt && yy >= 0 && yy < Hl && xx >= 0 && xx < Wl;
-                        const float4* src = f2b + ((int64_t)yy * Wl + xx) * nvec;
-                        float sg[G];
+                    for (int hb = 0; hb < 2; ++hb) {
+                        // four points at a time: all their loads are issued before the FMAs that use them
+                        float4 v[4][NV];
+                        bool okp[4];
 #pragma unroll
-                        for (int g = 0; g < G; ++g) sg[g] = 0.f;
+                        for (int i = 0; i < 4; ++i) {
+                            const int yy = by0 + row, xx = bx0 + col;
+                            okp[i] = e0 + hb * 4 + i < cnt && yy >= 0 && yy < Hl && xx >= 0 && xx < Wl;
+                            const float4* src = okp[i] ? f2b + ((int64_t)yy * Wl + xx) * nvec : f2b;
 #pragma unroll
-                        for (int j = 0; j < NV; ++j) {
-                            if (ok && lane + 32 * j < nvec) {
-                                const float4 v = __ldg(src + lane + 32 * j);
+                            for (int j = 0; j < NV; ++j)
+                                v[i][j] = (lane + 32 * j < nvec) ? __ldg(src + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (++col == bw) { col = 0; ++row; }
+                        }
 #pragma unroll
-                                for (int g = 0; g < G; ++g) {
-                                    sg[g] = fmaf(a[g][j].x, v.x, sg[g]);
-                                    sg[g] = fmaf(a[g][j].y, v.y, sg[g]);
-                                    sg[g] = fmaf(a[g][j].z, v.z, sg[g]);
-                                    sg[g] = fmaf(a[g][j].w, v.w, sg[g]);
+                        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                            for (int g = 0; g < G; ++g) {
+                                float sg = 0.f;
+#pragma unroll
+                                for (int j = 0; j < NV; ++j) {
+                                    sg = fmaf(a[g][j].x, v[i][j].x, sg);
+                                    sg = fmaf(a[g][j].y, v[i][j].y, sg);
+                                    sg = fmaf(a[g][j].z, v[i][j].z, sg);
+                                    sg = fmaf(a[g][j].w, v[i][j].w, sg);
                                 }
+                                part[g * 8 + hb * 4 + i] = okp[i] ? sg : 0.f;
                             }
                         }
-#pragma unroll
-                        for (int g = 0; g < G; ++g) part[g * 16 + i] = sg[g];
-                        if (++col == bw) { col = 0; ++row; }
                     }
-                    transpose_reduce64(part, lane);
-                    // this lane now holds pixel qsel's sums for points e0 + 2*(lane&7) + {0,1}
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        const int e = e0 + 2 * (lane & 7) + k;
-                        if (e < cnt) {
-                            const int er = e / bw, ec = e - er * bw;
-                            const int wr = by0 + er - qy0, wc = bx0 + ec - qx0;  // position inside pixel qsel's window
-                            if (wr >= 0 && wr < K1 && wc >= 0 && wc < K1) qpatch[wr * K1 + wc] = part[k];
-                        }
+                    // lane -> (pixel lane>>3, point e0 + (lane&7)) after the 31-shuffle transpose
+                    const float sum = transpose_reduce32(part, lane);
+                    const int e = e0 + (lane & 7);
+                    if (e < cnt) {
+                        const int er = e / bw, ec = e - er * bw;
+                        const int wr = by0 + er - qy0, wc = bx0 + ec - qx0;  // position inside pixel qsel's window
+                        if (wr >= 0 && wr < K1 && wc >= 0 && wc < K1) qpatch[wr * K1 + wc] = sum;
                     }
                 }
             }
