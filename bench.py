@@ -148,7 +148,7 @@ def cpu_port_run(steps, warmup, iters, shape, seed=1234):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return 0
+        return None
     r = cpu_port_run(args.steps, max(args.warmup, 1), args.iters, SHAPE)
     line = {
         "impl": "reference", "metric": METRIC, "value": r["pairs_per_s"], "unit": UNIT, "n_gpus": args.gpus,
@@ -160,8 +160,7 @@ def run_reference(args):
         "e2e": {"value": r["pairs_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
-    return 0
+    return line
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
@@ -314,6 +313,7 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, e2e_ms = float(t[0]), float(t[1])
 
+    line = None
     if rank == 0:
         hbm, bf16, peak_src = peaks()
         bb, lb, flops = algorithmic_bytes(D, H, W, L, r)
@@ -361,10 +361,25 @@ def run_ours(args):
         if cpu:
             line["cpu_baseline"] = {"value": cpu["pairs_per_s"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                                     "sample": cpu["sample"]}
-        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return line if rank == 0 else None
+
+
+class _StdoutToStderr:
+    """Everything a library prints on fd 1 while we run (e.g. NCCL's version banner) goes to stderr, so that
+    stdout carries exactly ONE line: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
 
 
 def main():
@@ -379,9 +394,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--l2-fetch", type=int, default=0, help="set cudaLimitMaxL2FetchGranularity (32/64/128) first")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    line = None
+    with _StdoutToStderr():
+        line = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
 
 
 if __name__ == "__main__":

@@ -298,3 +298,50 @@ def test_streams_and_determinism(pkg):
     # batch sharding is exact: processing pair 1 alone gives the same bits as inside the batch
     solo = pkg.CorrBlock(f1[1:], f2[1:], 4, 4, build_mode="fp32")(coords[1:])
     assert torch.equal(solo, outs[0][1:])
+
+
+# ------------------------------------------------------------------ implementation variants agree
+def test_kernel_variants_agree(pkg, monkeypatch):
+    """The A/B switches kept in the library (cp.async vs TMA lookup, single vs grouped on-the-fly kernel,
+    1- vs 2-CTA build) must produce the same numbers; planned and unplanned C entry points too."""
+    import ctypes
+
+    from optical_flow_dnn_b200 import _lib
+
+    d = dev()
+    g = torch.Generator(device=d).manual_seed(11)
+    B, D, H, W, L, r = 2, 128, 30, 45, 4, 4
+    f1 = torch.randn((B, D, H, W), generator=g, device=d)
+    f2 = torch.randn((B, D, H, W), generator=g, device=d)
+    coords = torch.from_numpy(O.coords_grid(B, H, W)).to(d) + 3.0 * torch.randn((B, 2, H, W), generator=g, device=d)
+    coords[0, :, 0, :5] = torch.tensor([[-7.3, 0.0, 44.0, 100.5, 3.999], [2.0, -0.5, 29.0, 1.0, 29.999]], device=d)
+
+    monkeypatch.setenv("RAFTCORR_BUILD_CLUSTER", "1")
+    blk = pkg.CorrBlock(f1, f2, L, r)
+    monkeypatch.setenv("RAFTCORR_BUILD_CLUSTER", "2")
+    blk2 = pkg.CorrBlock(f1, f2, L, r)
+    for a, c in zip(blk.corr_pyramid, blk2.corr_pyramid):  # views exclude the (never written) row padding
+        assert torch.equal(a, c)
+    monkeypatch.setenv("RAFTCORR_LOOKUP", "tma")
+    o_tma = blk(coords)
+    o_tma2 = blk2(coords)
+    monkeypatch.setenv("RAFTCORR_LOOKUP", "cpasync")
+    o_cp = blk(coords)
+    assert torch.equal(o_tma, o_tma2)
+    assert float((o_tma - o_cp).abs().max()) <= 1e-6 * float(o_tma.abs().max())
+    # unplanned C entry point == planned one
+    out = torch.empty_like(o_tma)
+    monkeypatch.setenv("RAFTCORR_LOOKUP", "tma")
+    rc_ = _lib.lib().raftcorr_lookup_fwd(ctypes.c_void_p(blk._pyr.data_ptr()), ctypes.byref(blk._layout),
+                                         ctypes.c_void_p(coords.data_ptr()), r, ctypes.c_void_p(out.data_ptr()), d.index,
+                                         ctypes.c_void_p(torch.cuda.current_stream(d).cuda_stream))
+    assert rc_ == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out, o_tma)
+    # on-the-fly: grouped vs single-pixel kernel
+    alt = pkg.AlternateCorrBlock(f1, f2, L, r)
+    monkeypatch.setenv("RAFTCORR_ALT", "group")
+    a_g = alt(coords)
+    monkeypatch.setenv("RAFTCORR_ALT", "single")
+    a_s = alt(coords)
+    assert float((a_g - a_s).abs().max()) <= 2e-6 * float(a_s.abs().max())
