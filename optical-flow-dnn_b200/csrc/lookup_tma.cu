@@ -27,7 +27,6 @@ struct TmaGeo {
     static constexpr int K = 2 * R + 1;
     static constexpr int K1 = K + 1;
     static constexpr int BC = (K1 + 3 + 3) / 4 * 4;        // box columns: covers any 0..3 start shift, 16-byte multiple
-    static constexpr int BCN = (K1 + 3) / 4 * 4;           // narrow box: enough when the shift is <= BCN - K1
     static constexpr int BOX_BYTES = BC * K1 * 4;
     static constexpr int SLOT = (BOX_BYTES + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
     static constexpr int KK = K * K;
@@ -35,8 +34,7 @@ struct TmaGeo {
 };
 
 struct LookupMaps {
-    CUtensorMap m[4];  // wide boxes  (BC columns)
-    CUtensorMap n[4];  // narrow boxes (BCN columns): 16 fewer bytes per row fetched, fewer 64-byte DRAM fills
+    CUtensorMap m[4];
 };
 
 template <int R, int LG>
@@ -72,13 +70,12 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
     }
     __syncwarp();
 
-    int oj[G::NT], oi[G::NT], och[G::NT];
+    int ooff[G::NT], och[G::NT];
 #pragma unroll
     for (int t = 0; t < G::NT; ++t) {
         const int c = lane + 32 * t;
         const int j = c / G::K, i = c - j * G::K;  // lanes run along x inside a patch row (fewest bank conflicts)
-        oj[t] = j;
-        oi[t] = i;
+        ooff[t] = j * G::BC + i;
         och[t] = i * G::K + j;                     // output channel: i (x offset) major, corr.py:66-78
     }
 
@@ -93,20 +90,12 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
 
     auto issue = [&](int n, int buf) {  // lane 0 only
         const int img = b * N + p0 + warp + kWarps * n;
-        int x0[LG], y0[LG];
-        uint32_t bytes = 0;
+        mbar_expect_tx(my_bar + 8 * buf, LG * G::BOX_BYTES);
 #pragma unroll
         for (int l = 0; l < LG; ++l) {
-            x0[l] = __float2int_rd(cxs[n] * g.inv_scale[l]) - R;
-            y0[l] = __float2int_rd(cys[n] * g.inv_scale[l]) - R;
-            bytes += ((x0[l] & 3) + G::K1 <= G::BCN ? G::BCN : G::BC) * G::K1 * 4;
-        }
-        mbar_expect_tx(my_bar + 8 * buf, bytes);
-#pragma unroll
-        for (int l = 0; l < LG; ++l) {
-            const bool narrow = (x0[l] & 3) + G::K1 <= G::BCN;
-            tma_load_3d(my_patch + (buf * LG + l) * G::SLOT, narrow ? &maps.n[l] : &maps.m[l], my_bar + 8 * buf,
-                        x0[l] & ~3, y0[l], img);
+            const int x0 = __float2int_rd(cxs[n] * g.inv_scale[l]) - R;
+            const int y0 = __float2int_rd(cys[n] * g.inv_scale[l]) - R;
+            tma_load_3d(my_patch + (buf * LG + l) * G::SLOT, &maps.m[l], my_bar + 8 * buf, x0 & ~3, y0, img);
         }
     };
 
@@ -135,16 +124,14 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
             const float x = cxs[n] * g.inv_scale[l], y = cys[n] * g.inv_scale[l];
             const float xf = floorf(x);
             const float ax = x - xf, ay = y - floorf(y);
-            const int ox = ((int)xf - R) & 3;
-            const int pitch = ox + G::K1 <= G::BCN ? G::BCN : G::BC;  // the box this pixel-level was fetched with
-            const float* P = pbuf + l * (G::SLOT / 4) + ox;
+            const float* P = pbuf + l * (G::SLOT / 4) + (((int)xf - R) & 3);
 #pragma unroll
             for (int t = 0; t < G::NT; ++t) {
                 const int c = lane + 32 * t;
                 if (c < G::KK) {
-                    const int o = oj[t] * pitch + oi[t];
+                    const int o = ooff[t];
                     const float top = P[o] + ax * (P[o + 1] - P[o]);
-                    const float bot = P[o + pitch] + ax * (P[o + pitch + 1] - P[o + pitch]);
+                    const float bot = P[o + G::BC] + ax * (P[o + G::BC + 1] - P[o + G::BC]);
                     out_s[(l * G::KK + och[t]) * kTilePitch + q] = top + ay * (bot - top);
                 }
             }
@@ -202,7 +189,7 @@ int lookup_plan_init(void* plan_blob, const PyramidView& pv, int radius) {
     std::memset(&plan, 0, sizeof(plan));
     plan.magic = kPlanMagic;
     plan.radius = radius;
-    const int K1 = 2 * radius + 2, BC = (K1 + 3 + 3) / 4 * 4, BCN = (K1 + 3) / 4 * 4;
+    const int K1 = 2 * radius + 2, BC = (K1 + 3 + 3) / 4 * 4;
     for (int l0 = 0; l0 < pv.L; l0 += 4) {
         const int gi = plan.groups++;
         const int lg = pv.L - l0 < 4 ? pv.L - l0 : 4;
@@ -217,15 +204,8 @@ int lookup_plan_init(void* plan_blob, const PyramidView& pv, int radius) {
             if (int rc = encode_f32_map(fn, &plan.maps[gi].m[l], (void*)lv.base, 3, dims, strides, box,
                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, "pyramid level"))
                 return rc;
-            cuuint32_t boxn[3] = {(cuuint32_t)BCN, (cuuint32_t)K1, 1};
-            if (int rc = encode_f32_map(fn, &plan.maps[gi].n[l], (void*)lv.base, 3, dims, strides, boxn,
-                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, "pyramid level (narrow)"))
-                return rc;
         }
-        for (int l = lg; l < 4; ++l) {
-            plan.maps[gi].m[l] = plan.maps[gi].m[0];
-            plan.maps[gi].n[l] = plan.maps[gi].n[0];
-        }
+        for (int l = lg; l < 4; ++l) plan.maps[gi].m[l] = plan.maps[gi].m[0];
     }
     std::memcpy(plan_blob, &plan, sizeof(plan));
     return 0;
