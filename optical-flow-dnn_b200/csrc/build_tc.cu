@@ -49,11 +49,23 @@ constexpr int kSmemBytes = kStages * kStageBytes + kNumStoreBufs * kStoreBufByte
 constexpr int kThreads = 384;          // 4 control warps + 8 epilogue warps
 constexpr int kEpilogueThreads = 256;
 constexpr uint32_t kTmemCols = 512;
+constexpr int kDefaultBuildMode = 0;
 
 // kind::tf32 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), both K-major,
 // N>>3 at bits 17-22, M>>4 at bits 24-28.
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileN >> 3) << 17) |
                                 ((uint32_t)(kTileM >> 4) << 24);
+
+constexpr uint32_t kInstrDesc2 = make_idesc_tf32(2 * kTileM, kTileN, false, false);  // cta_group::2: M = 256 over the pair
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> the pair's leader
+
+template <bool PAIR>
+__device__ __forceinline__ void tempty_arrive(uint32_t bar) {
+    if (PAIR)  // the leader's MMA thread waits for the epilogues of BOTH CTAs
+        asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+    else
+        mbar_arrive(bar);
+}
 
 struct BuildParams {
     float* lvl_base[4];     // pooled levels 1..3 (index by level); [0] unused (TMA path)
@@ -65,10 +77,15 @@ struct BuildParams {
     float scale;
 };
 
-template <int CL>  // CTAs per cluster sharing one B (target) tile through TMA multicast: 1 or 2
+// MODE 0: one CTA per tile.  MODE 1: CTA pair, each loads half of the B tile and TMA-multicasts it to both
+// (every CTA still ingests the whole tile).  MODE 2: CTA pair issuing ONE tcgen05.mma.cta_group::2 (M = 256):
+// each CTA keeps only its half of B in shared memory, so the operand ingress per SM drops by a third.
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_out, const BuildParams P) {
+    constexpr int CL = MODE == 0 ? 1 : 2;
+    constexpr bool PAIR_MMA = MODE == 2;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle atoms of TMA and UMMA
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -92,18 +109,24 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full_bar + 8 * s, 1);
-            mbar_init(empty_bar + 8 * s, CL);  // every CTA of the cluster must have consumed the stage
+            mbar_init(empty_bar + 8 * s, MODE == 1 ? 2 : 1);  // multicast pair: both CTAs must have consumed the stage
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar + 8 * a, 1);
-            mbar_init(tempty_bar + 8 * a, kEpilogueThreads);
+            mbar_init(tempty_bar + 8 * a, PAIR_MMA ? 2 * kEpilogueThreads : kEpilogueThreads);  // pair MMA: both CTAs' epilogues
         }
         fence_mbar_init();
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR_MMA) {  // both CTAs of the pair allocate the same columns (same warp id, same smem slot)
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     if (CL > 1) cluster_sync_all();  // peers' barriers are initialised before anyone multicasts / arrives remotely
@@ -129,6 +152,15 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                     const uint32_t sa = stage_base + stage * kStageBytes;
                     const uint32_t sb = sa + kABytes;
+                    if (PAIR_MMA) {
+                        // both CTAs' loads complete on the LEADER's barrier (peer bit cleared); it expects both halves
+                        const uint32_t lead_bar = (full_bar + 8 * stage) & kPeerBitMask;
+                        if (crank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * (kABytes + kBBytes / 2));
+                        tma_load_3d_2sm(sa, &map_a, lead_bar, kb * kBlockK, mt * kTileM, b);
+                        tma_load_4d_2sm(sb, &map_b, lead_bar, kb * kBlockK, wt * kTileW, band * kTileH + crank * (kTileH / 2), b);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(full_bar + 8 * stage, kStageBytes);
                     tma_load_3d(sa, &map_a, full_bar + 8 * stage, kb * kBlockK, mt * kTileM, b);
                     if (CL == 1) {
@@ -144,8 +176,8 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (pair MMA: the leader CTA issues for both) =====================
+        if (lane == 0 && !(PAIR_MMA && crank != 0)) {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -164,14 +196,20 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < kBlockK / kUmmaK; ++k) {
                         // advance 32 bytes along K inside the swizzle row: +2 in the (>>4) start-address field
-                        tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
-                                    (kb | k) != 0 ? 1u : 0u);
+                        if (PAIR_MMA)
+                            tc_mma_tf32_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc2,
+                                            (kb | k) != 0 ? 1u : 0u);
+                        else
+                            tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
+                                        (kb | k) != 0 ? 1u : 0u);
                     }
-                    if (CL == 1) tc_commit(empty_bar + 8 * stage);  // frees the smem slot when these MMAs retire
-                    else tc_commit_mcast(empty_bar + 8 * stage, (uint16_t)((1u << CL) - 1));  // ... in every CTA of the cluster
+                    if (MODE == 0) tc_commit(empty_bar + 8 * stage);  // frees the smem slot when these MMAs retire
+                    else if (MODE == 1) tc_commit_mcast(empty_bar + 8 * stage, 3);  // ... in both CTAs of the pair
+                    else tc_commit_2sm_mcast(empty_bar + 8 * stage, 3);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
+                if (PAIR_MMA) tc_commit_2sm_mcast(tfull_bar + 8 * acc, 3);  // accumulators complete in both CTAs
+                else tc_commit(tfull_bar + 8 * acc);                        // accumulator complete -> epilogue
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -202,7 +240,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tmem_ld_wait();
                 if (p == 3) {  // this warp has read all of the accumulator
                     tc_fence_before();
-                    mbar_arrive(tempty_bar + 8 * acc);
+                    tempty_arrive<PAIR_MMA>(tempty_bar + 8 * acc);
                 }
                 const uint32_t sa = store_base + buf * kStoreBufBytes + ml * 128;
                 const uint32_t sb = sa + kRowTileBytes;
@@ -257,7 +295,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const uint32_t t_acc = tmem_base + lane_addr + acc * kTileN;
             if (P.L <= 1) {  // nothing to pool: just release the accumulator
                 tc_fence_before();
-                mbar_arrive(tempty_bar + 8 * acc);
+                tempty_arrive<PAIR_MMA>(tempty_bar + 8 * acc);
                 continue;
             }
             const int64_t pix = (int64_t)b * P.N1 + m;
@@ -270,7 +308,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 tmem_ld_wait();
                 if (p == 3) {
                     tc_fence_before();
-                    mbar_arrive(tempty_bar + 8 * acc);
+                    tempty_arrive<PAIR_MMA>(tempty_bar + 8 * acc);
                 }
                 float l1[16];
 #pragma unroll
@@ -320,7 +358,10 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        if (PAIR_MMA)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 
@@ -337,9 +378,11 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
     if (int rc = get_encode_fn(&fn)) return rc;
     const int B = lay.B, H = lay.H, W = lay.W, N1 = H * W;
     const int Dp = tc_feature_pitch(D);
-    // RAFTCORR_BUILD_CLUSTER=1|2: CTAs per cluster sharing the B tile by TMA multicast (default 1: measured slower with 2 on B200, see profiles/README.md)
+    // RAFTCORR_BUILD_CLUSTER: 1 = one CTA per tile, 2 = CTA pair with TMA multicast of B (measured slower),
+    // 3 = CTA pair issuing tcgen05.mma.cta_group::2 (each CTA ingests only half of B)
     const char* ce = std::getenv("RAFTCORR_BUILD_CLUSTER");
-    const int cl = (ce && ce[0] == '2') ? 2 : 1;
+    const int mode = (ce && ce[0] == '2') ? 1 : (ce && ce[0] == '3') ? 2 : kDefaultBuildMode;
+    const int cl = mode == 0 ? 1 : 2;
 
     CUtensorMap map_a, map_b, map_out;
     {
@@ -403,12 +446,15 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cl == 2) {
+    if (mode == 2) {
         RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<2>, map_a, map_b, map_out, P));
-    } else {
+    } else if (mode == 1) {
         RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        build_tc_kernel<1><<<clusters, kThreads, kSmemBytes, s>>>(map_a, map_b, map_out, P);
+        RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<1>, map_a, map_b, map_out, P));
+    } else {
+        RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        build_tc_kernel<0><<<clusters, kThreads, kSmemBytes, s>>>(map_a, map_b, map_out, P);
     }
     RC_CUDA(cudaGetLastError());
     return 0;
