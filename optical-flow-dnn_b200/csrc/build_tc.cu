@@ -373,7 +373,7 @@ int tc_feature_pitch(int D) { return (D + kBlockK - 1) / kBlockK * kBlockK; }
 // f1n/f2n: [B][H*W][Dp] fp32, TF32-rounded, zero-padded to Dp = tc_feature_pitch(D)
 int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, const raftcorr_pyramid_layout& lay,
                     int device, cudaStream_t s) {
-    RC_REQUIRE(lay.L <= 4, "tf32 build: at most 4 pyramid levels are fused (got %d); use the fp32 mode", lay.L);
+    const int fusedL = lay.L < 4 ? lay.L : 4;  // levels 0..3 come out of the epilogue; deeper ones are pooled afterwards
     EncodeTiledFn fn;
     if (int rc = get_encode_fn(&fn)) return rc;
     const int B = lay.B, H = lay.H, W = lay.W, N1 = H * W;
@@ -412,14 +412,14 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
     }
 
     BuildParams P{};
-    for (int l = 0; l < lay.L; ++l) {
+    for (int l = 0; l < fusedL; ++l) {
         P.lvl_base[l] = pyramid + lay.offset[l];
         P.lvl_h[l] = lay.h[l];
         P.lvl_w[l] = lay.w[l];
         P.lvl_pitch[l] = lay.pitch[l];
         P.lvl_img_stride[l] = (int64_t)lay.h[l] * lay.pitch[l];
     }
-    P.B = B; P.N1 = N1; P.H2 = H; P.W2 = W; P.L = lay.L;
+    P.B = B; P.N1 = N1; P.H2 = H; P.W2 = W; P.L = fusedL;
     P.m_tiles = ceil_div(N1, kTileM);
     P.m_groups = ceil_div(P.m_tiles, cl);
     P.bands = ceil_div(H, kTileH);
@@ -457,6 +457,11 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
         build_tc_kernel<0><<<clusters, kThreads, kSmemBytes, s>>>(map_a, map_b, map_out, P);
     }
     RC_CUDA(cudaGetLastError());
+    if (lay.L > fusedL) {  // never used by RAFT (num_levels = 4); kept correct rather than rejected
+        PyramidView pv = make_view(pyramid, lay);
+        for (int l = fusedL; l < lay.L; ++l)
+            if (int rc = launch_pool_level(pv.lvl[l - 1], pv.lvl[l], (int64_t)B * N1, s)) return rc;
+    }
     return 0;
 }
 

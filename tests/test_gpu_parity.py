@@ -345,3 +345,16 @@ def test_kernel_variants_agree(pkg, monkeypatch):
     monkeypatch.setenv("RAFTCORR_ALT", "single")
     a_s = alt(coords)
     assert float((a_g - a_s).abs().max()) <= 2e-6 * float(a_s.abs().max())
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_five_levels(pkg, mode):
+    """More levels than RAFT uses (the fused epilogue covers 4; deeper ones are pooled afterwards)."""
+    B, D, H, W, L, r = 1, 32, 40, 48, 5, 2
+    rng = np.random.default_rng(9)
+    f1 = rng.normal(size=(B, D, H, W)).astype(np.float32)
+    f2 = rng.normal(size=(B, D, H, W)).astype(np.float32)
+    coords = O.coords_grid(B, H, W) + rng.normal(0, 3.0, (B, 2, H, W)).astype(np.float32)
+    ref = O.lookup(O.corr_pyramid(f1, f2, L, np.float64), coords, r)
+    blk = pkg.CorrBlock(torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev()), L, r, build_mode=mode)
+    assert rel_err(blk(torch.from_numpy(coords).to(dev())), ref) <= TOL[mode]
