@@ -74,6 +74,7 @@ struct BuildParams {
     int B, N1, H2, W2, L;
     int m_tiles, m_groups, bands, w_tiles, k_blocks;  // m_groups = ceil(m_tiles / cluster size)
     int total_tiles;
+    int lsu_store;  // A/B: level-0 rows leave through LSU stores instead of TMA
     float scale;
 };
 
@@ -254,17 +255,38 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                  "f"(rb[4 * j + 1] * P.scale), "f"(rb[4 * j + 2] * P.scale), "f"(rb[4 * j + 3] * P.scale)
                                  : "memory");
                 }
-                fence_proxy_async();
-                // the other buffer (used by the previous phase) must have been read out before the next
-                // phase overwrites it; waiting here, one phase late, keeps one store group in flight
-                if (issuer) tma_store_wait_read_all();
-                named_bar_sync(1, 128);
-                if (issuer) {
+                if (P.lsu_store) {
+                    // A/B variant: drain the staged rows with coalesced 128-bit stores (8 lanes per 128-byte row)
+                    // instead of TMA, so that the TMA unit only carries the operand loads
+                    named_bar_sync(1, 128);
                     const uint32_t s0 = store_base + buf * kStoreBufBytes;
-                    const int h = band * kTileH + 2 * p;
-                    tma_store_4d(&map_out, s0, wt * kTileW, h, mt * kTileM, b);
-                    tma_store_4d(&map_out, s0 + kRowTileBytes, wt * kTileW, h + 1, mt * kTileM, b);
-                    tma_store_commit();
+                    const int tid = threadIdx.x - 128;
+#pragma unroll 4
+                    for (int k = 0; k < 16; ++k) {
+                        const int idx = k * 128 + tid;
+                        const int rr = idx >> 3, c16 = idx & 7;       // staged row (0..255), 16-byte chunk in it
+                        const int mm = mt * kTileM + (rr & 127), hh = band * kTileH + 2 * p + (rr >> 7);
+                        const int ww = wt * kTileW + c16 * 4;
+                        float4 v;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                     : "r"(s0 + rr * 128 + ((c16 ^ (rr & 7)) << 4)));
+                        if (mm < P.N1 && hh < P.lvl_h[0] && ww + 4 <= P.lvl_pitch[0])
+                            *reinterpret_cast<float4*>(P.lvl_base[0] + ((int64_t)b * P.N1 + mm) * P.lvl_img_stride[0] +
+                                                       (int64_t)hh * P.lvl_pitch[0] + ww) = v;
+                    }
+                } else {
+                    fence_proxy_async();
+                    // the other buffer (used by the previous phase) must have been read out before the next
+                    // phase overwrites it; waiting here, one phase late, keeps one store group in flight
+                    if (issuer) tma_store_wait_read_all();
+                    named_bar_sync(1, 128);
+                    if (issuer) {
+                        const uint32_t s0 = store_base + buf * kStoreBufBytes;
+                        const int h = band * kTileH + 2 * p;
+                        tma_store_4d(&map_out, s0, wt * kTileW, h, mt * kTileM, b);
+                        tma_store_4d(&map_out, s0 + kRowTileBytes, wt * kTileW, h + 1, mt * kTileM, b);
+                        tma_store_commit();
+                    }
                 }
                 buf ^= 1;
             }
@@ -429,6 +451,7 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
     RC_REQUIRE(total < (1LL << 31), "tf32 build: too many tiles");
     P.total_tiles = (int)total;
     P.scale = 1.0f / sqrtf((float)D);  // corr.py:116
+    { const char* e = std::getenv("RAFTCORR_BUILD_STORE"); P.lsu_store = (e && e[0] == 'l') ? 1 : 0; }
 
     int sms = 0;
     RC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
