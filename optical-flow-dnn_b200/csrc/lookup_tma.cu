@@ -7,9 +7,8 @@
 // the innermost start coordinate is 16-byte aligned (measured: scripts/probe/tma_probe.cu traps with
 // 'illegal instruction' otherwise), so the box starts at x0 & ~3 and is K+1+3 columns wide (rounded to
 // 4); the 0..3 column shift is applied when the outputs read their taps.
-// A dedicated producer warp (lane = source pixel) computes the box origins once per pixel and serves the
-// eight consumer warps through per-warp rings of three patch buffers (full/empty mbarriers); the
-// consumers only wait, evaluate and transpose results through a [channels][32 px] shared tile that is
+// Each warp owns two patch buffers and two mbarriers and keeps the next pixel's boxes in flight while
+// it evaluates the current pixel; results are transposed through a [channels][32 px] shared tile and
 // stored channel-major with full 128-byte lines, as in lookup.cu.
 #include <cstring>
 
@@ -38,138 +37,123 @@ struct LookupMaps {
     CUtensorMap m[4];
 };
 
-constexpr int kLookupThreads = (kWarps + 1) * 32;  // 8 consumer warps + 1 TMA producer warp
-
 template <int R, int LG>
-__global__ void __launch_bounds__(kLookupThreads, 2)
+__global__ void __launch_bounds__(kWarps * 32, 2)
 lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g, const float* __restrict__ coords,
                       float* __restrict__ out) {
     using G = TmaGeo<R>;
     constexpr int CH = LG * G::KK;
     constexpr int PIX_PER_WARP = kPix / kWarps;
-    constexpr int WARP_PATCH = kBufs * LG * G::SLOT;  // bytes: one consumer warp's ring of patch buffers
+    constexpr int WARP_PATCH = kBufs * LG * G::SLOT;  // bytes: this warp's ring of patch buffers
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-    // [kWarps][kBufs][LG][SLOT] patches | full[kWarps][kBufs], empty[kWarps][kBufs] mbarriers | out_s [CH][kTilePitch]
-    const uint32_t full_base = base + kWarps * WARP_PATCH;
-    const uint32_t empty_base = full_base + kWarps * kBufs * 8;
-    float* out_s = reinterpret_cast<float*>(gen + kWarps * WARP_PATCH + 2 * kWarps * kBufs * 8);
+    // [kWarps][kBufs][LG][SLOT] patches | [kWarps][kBufs] mbarriers | out_s [CH][kTilePitch]
+    const uint32_t bar_base = base + kWarps * WARP_PATCH;
+    float* out_s = reinterpret_cast<float*>(gen + kWarps * WARP_PATCH + kWarps * kBarBytes);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y, p0 = blockIdx.x * kPix;
     const int N = g.N;
+    const uint32_t my_patch = base + warp * WARP_PATCH;
+    const float* my_patch_gen = reinterpret_cast<const float*>(gen + warp * WARP_PATCH);
+    const uint32_t my_bar = bar_base + warp * kBarBytes;
 
-    if (threadIdx.x < kWarps * kBufs) {
-        mbar_init(full_base + 8 * threadIdx.x, 1);
-        mbar_init(empty_base + 8 * threadIdx.x, 1);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kBufs; ++i) mbar_init(my_bar + 8 * i, 1);
         fence_mbar_init();
+        if (warp == 0) {
+#pragma unroll
+            for (int l = 0; l < LG; ++l) prefetch_tensormap(&maps.m[l]);
+        }
     }
-    __syncthreads();
+    __syncwarp();
 
-    if (warp == kWarps) {
-        // ===================== producer warp: lane q owns source pixel p0 + q =====================
-        // Coordinates are loaded coalesced and the per-level box origins computed once per pixel (not once
-        // per lane of a consumer warp); pixels are then served in order, lane 0 issuing one TMA box per level.
-        if (lane < LG) prefetch_tensormap(&maps.m[lane]);
-        const int p = p0 + lane;
+    int ooff[G::NT], och[G::NT];
+#pragma unroll
+    for (int t = 0; t < G::NT; ++t) {
+        const int c = lane + 32 * t;
+        const int j = c / G::K, i = c - j * G::K;  // lanes run along x inside a patch row (fewest bank conflicts)
+        ooff[t] = j * G::BC + i;
+        och[t] = i * G::K + j;                     // output channel: i (x offset) major, corr.py:66-78
+    }
+
+    float cxs[PIX_PER_WARP], cys[PIX_PER_WARP];
+#pragma unroll
+    for (int n = 0; n < PIX_PER_WARP; ++n) {
+        const int p = p0 + warp + kWarps * n;
         const bool v = p < N;
-        const float cx = clamp_coord(v ? __ldg(coords + ((int64_t)b * 2 + 0) * N + p) : 0.f);
-        const float cy = clamp_coord(v ? __ldg(coords + ((int64_t)b * 2 + 1) * N + p) : 0.f);
-        int x0[LG], y0[LG];
+        cxs[n] = clamp_coord(v ? __ldg(coords + ((int64_t)b * 2 + 0) * N + p) : 0.f);
+        cys[n] = clamp_coord(v ? __ldg(coords + ((int64_t)b * 2 + 1) * N + p) : 0.f);
+    }
+
+    auto issue = [&](int n, int buf) {  // lane 0 only
+        const int img = b * N + p0 + warp + kWarps * n;
+        mbar_expect_tx(my_bar + 8 * buf, LG * G::BOX_BYTES);
 #pragma unroll
         for (int l = 0; l < LG; ++l) {
-            x0[l] = (__float2int_rd(cx * g.inv_scale[l]) - R) & ~3;  // 16-byte aligned box start
-            y0[l] = __float2int_rd(cy * g.inv_scale[l]) - R;
+            const int x0 = __float2int_rd(cxs[n] * g.inv_scale[l]) - R;
+            const int y0 = __float2int_rd(cys[n] * g.inv_scale[l]) - R;
+            tma_load_3d(my_patch + (buf * LG + l) * G::SLOT, &maps.m[l], my_bar + 8 * buf, x0 & ~3, y0, img);
         }
-#pragma unroll 1
-        for (int n = 0; n < PIX_PER_WARP; ++n) {
-            const int buf = n % kBufs;
-#pragma unroll 1
-            for (int w = 0; w < kWarps; ++w) {
-                const int q = w + kWarps * n;
-                if (p0 + q >= N) break;
-                const uint32_t slot = w * kBufs + buf;
-                if (n >= kBufs) mbar_wait(empty_base + 8 * slot, ((n / kBufs) - 1) & 1);  // consumer released it
-                int bx[LG], by[LG];
+    };
+
+    // prologue: kBufs-1 pixels in flight before the first one is consumed
+    if (lane == 0) {
 #pragma unroll
-                for (int l = 0; l < LG; ++l) {
-                    bx[l] = __shfl_sync(0xffffffffu, x0[l], q);
-                    by[l] = __shfl_sync(0xffffffffu, y0[l], q);
-                }
-                if (lane == 0) {
-                    const uint32_t fb = full_base + 8 * slot;
-                    mbar_expect_tx(fb, LG * G::BOX_BYTES);
+        for (int n = 0; n < kBufs - 1 && n < PIX_PER_WARP; ++n)
+            if (p0 + warp + kWarps * n < N) issue(n, n);
+    }
+
 #pragma unroll
-                    for (int l = 0; l < LG; ++l)
-                        tma_load_3d(base + w * WARP_PATCH + (buf * LG + l) * G::SLOT, &maps.m[l], fb, bx[l], by[l],
-                                    b * N + p0 + q);
-                }
-            }
+    for (int n = 0; n < PIX_PER_WARP; ++n) {
+        const int q = warp + kWarps * n;
+        const int p = p0 + q;
+        if (p >= N) break;
+        const int buf = n % kBufs;
+        constexpr int kAhead = kBufs - 1;
+        if (lane == 0 && n + kAhead < PIX_PER_WARP && p + kAhead * kWarps < N) {
+            fence_proxy_async();  // that buffer was read through the generic proxy one iteration ago
+            issue(n + kAhead, (n + kAhead) % kBufs);
         }
-    } else {
-        // ===================== consumer warps: evaluate the K*K outputs of each staged patch =====================
-        int ooff[G::NT], och[G::NT];
+        mbar_wait(my_bar + 8 * buf, (n / kBufs) & 1);
+        const float* pbuf = my_patch_gen + buf * (LG * G::SLOT / 4);
 #pragma unroll
-        for (int t = 0; t < G::NT; ++t) {
-            const int c = lane + 32 * t;
-            const int j = c / G::K, i = c - j * G::K;  // lanes run along x inside a patch row (fewest bank conflicts)
-            ooff[t] = j * G::BC + i;
-            och[t] = i * G::K + j;                     // output channel: i (x offset) major, corr.py:66-78
-        }
-        const float* my_patch = reinterpret_cast<const float*>(gen + warp * WARP_PATCH);
+        for (int l = 0; l < LG; ++l) {
+            const float x = cxs[n] * g.inv_scale[l], y = cys[n] * g.inv_scale[l];
+            const float xf = floorf(x);
+            const float ax = x - xf, ay = y - floorf(y);
+            const float* P = pbuf + l * (G::SLOT / 4) + (((int)xf - R) & 3);
 #pragma unroll
-        for (int n = 0; n < PIX_PER_WARP; ++n) {
-            const int q = warp + kWarps * n;
-            const int p = p0 + q;
-            if (p >= N) break;
-            const int buf = n % kBufs;
-            const float cx = clamp_coord(__ldg(coords + ((int64_t)b * 2 + 0) * N + p));
-            const float cy = clamp_coord(__ldg(coords + ((int64_t)b * 2 + 1) * N + p));
-            mbar_wait(full_base + 8 * (warp * kBufs + buf), (n / kBufs) & 1);
-            const float* pbuf = my_patch + buf * (LG * G::SLOT / 4);
-#pragma unroll
-            for (int l = 0; l < LG; ++l) {
-                const float x = cx * g.inv_scale[l], y = cy * g.inv_scale[l];
-                const float xf = floorf(x);
-                const float ax = x - xf, ay = y - floorf(y);
-                const float* P = pbuf + l * (G::SLOT / 4) + (((int)xf - R) & 3);
-#pragma unroll
-                for (int t = 0; t < G::NT; ++t) {
-                    const int c = lane + 32 * t;
-                    if (c < G::KK) {
-                        const int o = ooff[t];
-                        const float top = P[o] + ax * (P[o + 1] - P[o]);
-                        const float bot = P[o + G::BC] + ax * (P[o + G::BC + 1] - P[o + G::BC]);
-                        out_s[(l * G::KK + och[t]) * kTilePitch + q] = top + ay * (bot - top);
-                    }
-                }
-            }
-            if (n + kBufs < PIX_PER_WARP) {  // this buffer is refilled later: hand it back to the producer
-                __syncwarp();
-                if (lane == 0) {
-                    fence_proxy_async();  // generic-proxy reads before the async-proxy refill
-                    mbar_arrive(empty_base + 8 * (warp * kBufs + buf));
+            for (int t = 0; t < G::NT; ++t) {
+                const int c = lane + 32 * t;
+                if (c < G::KK) {
+                    const int o = ooff[t];
+                    const float top = P[o] + ax * (P[o + 1] - P[o]);
+                    const float bot = P[o + G::BC] + ax * (P[o + G::BC + 1] - P[o + G::BC]);
+                    out_s[(l * G::KK + och[t]) * kTilePitch + q] = top + ay * (bot - top);
                 }
             }
         }
+        __syncwarp();  // all lanes are done with `buf` before lane 0 refills it next iteration
     }
     __syncthreads();
     const int p = p0 + lane;
     if (p < N) {
         float* dst = out + ((int64_t)b * g.ctot + g.ch0) * N + p;
-        for (int ch = warp; ch < CH; ch += kWarps + 1) dst[(int64_t)ch * N] = out_s[ch * kTilePitch + lane];
+        for (int ch = warp; ch < CH; ch += kWarps) dst[(int64_t)ch * N] = out_s[ch * kTilePitch + lane];
     }
 }
 
 template <int R, int LG>
 int run_fwd_tma(const LookupMaps& maps, const GroupView& g, const float* coords, float* out, cudaStream_t s) {
     using G = TmaGeo<R>;
-    const size_t smem = 128 + (size_t)kWarps * kBufs * LG * G::SLOT + 2 * kWarps * kBufs * 8 + sizeof(float) * LG * G::KK * kTilePitch;
+    const size_t smem = 128 + (size_t)kWarps * kBufs * LG * G::SLOT + kWarps * kBarBytes + sizeof(float) * LG * G::KK * kTilePitch;
     auto kern = lookup_fwd_tma_kernel<R, LG>;
     RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(g.N, kPix), g.B);
-    kern<<<grid, kLookupThreads, smem, s>>>(maps, g, coords, out);
+    kern<<<grid, kWarps * 32, smem, s>>>(maps, g, coords, out);
     RC_CUDA(cudaGetLastError());
     return 0;
 }
