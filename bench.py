@@ -337,7 +337,8 @@ def run_ours(args):
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(dom)
         except Exception:
             traffic = None
-        launches_per_step = (3 if mode == "tf32" else 1 + (L - 1)) + iters
+        # tf32: 1 paired NCHW->NHWC transpose + build_tc; fp32: sgemm + (L-1) pooling passes; + one lookup per iteration
+        launches_per_step = (2 if mode == "tf32" else 1 + (L - 1)) + iters
         cpu = cpu_port_run(3, 1, iters, SHAPE) if world == 1 and not args.no_cpu_baseline else None
         line = {
             "metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,

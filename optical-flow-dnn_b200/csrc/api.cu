@@ -123,8 +123,7 @@ int raftcorr_build_fwd(const float* fmap1, const float* fmap2, int D, float* pyr
         float* f2n = (float*)((char*)workspace + need / 2);
         const int HW = lay->H * lay->W;
         const int Dp = tc_feature_pitch(D);
-        if (int rc = launch_nchw_to_nhwc(fmap1, f1n, lay->B, D, HW, Dp, true, s)) return rc;
-        if (int rc = launch_nchw_to_nhwc(fmap2, f2n, lay->B, D, HW, Dp, true, s)) return rc;
+        if (int rc = launch_nchw_to_nhwc_pair(fmap1, f1n, fmap2, f2n, lay->B, D, HW, Dp, true, s)) return rc;
         return launch_build_tc(f1n, f2n, D, pyramid, *lay, device, s);
     }
     return fail("build_fwd: unknown mode %d", mode);
@@ -263,8 +262,8 @@ int raftcorr_alt_pyramid(const float* fmap1, const float* fmap2, int B, int D, i
     DeviceGuard guard(device);
     RC_REQUIRE(guard.ok, "alt_pyramid: cannot select device %d", device);
     cudaStream_t s = (cudaStream_t)stream;
-    if (int rc = launch_nchw_to_nhwc(fmap1, f1_nhwc, B, D, H * W, D, false, s)) return rc;
-    if (int rc = launch_nchw_to_nhwc(fmap2, const_cast<float*>(lv.f2[0]), B, D, H * W, D, false, s)) return rc;
+    if (int rc = launch_nchw_to_nhwc_pair(fmap1, f1_nhwc, fmap2, const_cast<float*>(lv.f2[0]), B, D, H * W, D, false, s))
+        return rc;
     for (int l = 1; l < L; ++l)  // corr.py:138-139 (fmap2 side; the pooled fmap1 copies are never read, :158)
         if (int rc = launch_pool_nhwc(lv.f2[l - 1], const_cast<float*>(lv.f2[l]), B, lv.h[l - 1], lv.w[l - 1], D, s))
             return rc;

@@ -23,7 +23,10 @@
 //                          of the level-0 store pipeline.
 //
 // The kernel is bound by the fp32 pyramid write (174 KB per tile vs 4096 tensor cycles per tile),
-// see DESIGN.md; the MMA pipe has slack, the epilogue/TMA-store path is what is tuned.
+// see DESIGN.md; the MMA pipe has slack, the epilogue/TMA-store path is what is tuned.  Ablations on
+// B200 (B=8, 55x128, D=256, L=4; profiles/README.md): level-0 stores alone 280 us (6.0 TB/s), + pooled
+// levels 418 us, + operand loads 541 us -- the operand ingress (384 KB per tile) competes with the
+// stores for the SM<->L2 port (l1tex2xbar 75 % busy), it is not hidden behind them.
 #include <cstdlib>
 
 #include "tc_util.cuh"
@@ -38,14 +41,12 @@ constexpr int kTileW = 32;        // target cols per tile
 constexpr int kTileN = kTileH * kTileW;  // 256 = UMMA N
 constexpr int kBlockK = 32;       // floats per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 8;         // tf32: 32 bytes per instruction
-constexpr int kStages = 3;
 constexpr int kABytes = kTileM * kBlockK * 4;   // 16 KB
 constexpr int kBBytes = kTileN * kBlockK * 4;   // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;  // 48 KB
 constexpr int kRowTileBytes = kTileM * kTileW * 4;  // 16 KB: one target row for 128 source pixels
-constexpr int kStoreBufBytes = 2 * kRowTileBytes;   // two rows per phase
-constexpr int kNumStoreBufs = 2;
-constexpr int kSmemBytes = kStages * kStageBytes + kNumStoreBufs * kStoreBufBytes + 1024 /*align*/ + 256 /*barriers*/;
+// pipeline shape: NS operand stages, NB level-0 store buffers of RP target rows each
+constexpr int smem_bytes(int ns, int nb, int rp) { return ns * kStageBytes + nb * rp * kRowTileBytes + 1024 /*align*/ + 256 /*barriers*/; }
 constexpr int kThreads = 384;          // 4 control warps + 8 epilogue warps
 constexpr int kEpilogueThreads = 256;
 constexpr uint32_t kTmemCols = 512;
@@ -81,12 +82,16 @@ struct BuildParams {
 // MODE 0: one CTA per tile.  MODE 1: CTA pair, each loads half of the B tile and TMA-multicasts it to both
 // (every CTA still ingests the whole tile).  MODE 2: CTA pair issuing ONE tcgen05.mma.cta_group::2 (M = 256):
 // each CTA keeps only its half of B in shared memory, so the operand ingress per SM drops by a third.
-template <int MODE>
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+template <int MODE, int kStages = 3, int kNumStoreBufs = 2, int RP = 2>
 __global__ void __launch_bounds__(kThreads, 1)
 build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_out, const BuildParams P) {
     constexpr int CL = MODE == 0 ? 1 : 2;
     constexpr bool PAIR_MMA = MODE == 2;
+    constexpr int kStoreBufBytes = RP * kRowTileBytes;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle atoms of TMA and UMMA
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -234,12 +239,12 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             tc_fence_after();
             const uint32_t t_acc = tmem_base + lane_addr + acc * kTileN;
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
+            for (int p = 0; p < kTileH / RP; ++p) {
                 float ra[32], rb[32];
-                tmem_ld32(t_acc + (2 * p) * kTileW, ra);
-                tmem_ld32(t_acc + (2 * p + 1) * kTileW, rb);
+                tmem_ld32(t_acc + (RP * p) * kTileW, ra);
+                if (RP == 2) tmem_ld32(t_acc + (2 * p + 1) * kTileW, rb);
                 tmem_ld_wait();
-                if (p == 3) {  // this warp has read all of the accumulator
+                if (p == kTileH / RP - 1) {  // this warp has read all of the accumulator
                     tc_fence_before();
                     tempty_arrive<PAIR_MMA>(tempty_bar + 8 * acc);
                 }
@@ -251,11 +256,12 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(ra[4 * j] * P.scale),
                                  "f"(ra[4 * j + 1] * P.scale), "f"(ra[4 * j + 2] * P.scale), "f"(ra[4 * j + 3] * P.scale)
                                  : "memory");
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + off), "f"(rb[4 * j] * P.scale),
-                                 "f"(rb[4 * j + 1] * P.scale), "f"(rb[4 * j + 2] * P.scale), "f"(rb[4 * j + 3] * P.scale)
-                                 : "memory");
+                    if (RP == 2)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + off), "f"(rb[4 * j] * P.scale),
+                                     "f"(rb[4 * j + 1] * P.scale), "f"(rb[4 * j + 2] * P.scale), "f"(rb[4 * j + 3] * P.scale)
+                                     : "memory");
                 }
-                if (P.lsu_store) {
+                if (P.lsu_store && RP == 2) {
                     // A/B variant: drain the staged rows with coalesced 128-bit stores (8 lanes per 128-byte row)
                     // instead of TMA, so that the TMA unit only carries the operand loads
                     named_bar_sync(1, 128);
@@ -276,19 +282,19 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     }
                 } else {
                     fence_proxy_async();
-                    // the other buffer (used by the previous phase) must have been read out before the next
-                    // phase overwrites it; waiting here, one phase late, keeps one store group in flight
-                    if (issuer) tma_store_wait_read_all();
+                    // the buffer the NEXT phase overwrites (used kNumStoreBufs-1 phases ago) must have been read
+                    // out; waiting here, one phase early, keeps kNumStoreBufs-1 store groups in flight
+                    if (issuer) tma_store_wait_read_n<kNumStoreBufs - 2>();
                     named_bar_sync(1, 128);
                     if (issuer) {
                         const uint32_t s0 = store_base + buf * kStoreBufBytes;
-                        const int h = band * kTileH + 2 * p;
+                        const int h = band * kTileH + RP * p;
                         tma_store_4d(&map_out, s0, wt * kTileW, h, mt * kTileM, b);
-                        tma_store_4d(&map_out, s0 + kRowTileBytes, wt * kTileW, h + 1, mt * kTileM, b);
+                        if (RP == 2) tma_store_4d(&map_out, s0 + kRowTileBytes, wt * kTileW, h + 1, mt * kTileM, b);
                         tma_store_commit();
                     }
                 }
-                buf ^= 1;
+                if (++buf == kNumStoreBufs) buf = 0;
             }
         }
         if (issuer) tma_store_wait_all();  // global writes complete before the CTA exits
@@ -460,6 +466,7 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * cl);
     cfg.blockDim = dim3(kThreads);
+    constexpr int kSmemBytes = smem_bytes(3, 2, 2);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -476,8 +483,29 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
         RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<1>, map_a, map_b, map_out, P));
     } else {
-        RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        build_tc_kernel<0><<<clusters, kThreads, kSmemBytes, s>>>(map_a, map_b, map_out, P);
+        // RAFTCORR_BUILD_PIPE = <operand stages><store buffers><rows per buffer>.  Measured on B200 (B=8, 55x128,
+        // L=4): at D=256 three stages are needed (2: 646 us, 3: 540, 4: 547) and deeper store buffering changes
+        // nothing; at D<=128 the MMA side has slack and operand loads running far ahead only steal bandwidth
+        // from the store pipeline, so two stages are faster (420 vs 462 us).
+        const char* pe = std::getenv("RAFTCORR_BUILD_PIPE");
+        const int pipe = pe ? atoi(pe) : (P.k_blocks <= 4 ? 222 : 322);
+#define RAFTCORR_PIPE_CASE(NS, NB, RP)                                                                                  \
+    case NS * 100 + NB * 10 + RP: {                                                                                     \
+        static_assert(smem_bytes(NS, NB, RP) <= 232448, "pipeline does not fit shared memory");                         \
+        RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<0, NS, NB, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                     smem_bytes(NS, NB, RP)));                                                          \
+        build_tc_kernel<0, NS, NB, RP><<<clusters, kThreads, smem_bytes(NS, NB, RP), s>>>(map_a, map_b, map_out, P);    \
+        break;                                                                                                          \
+    }
+        switch (pipe) {
+            RAFTCORR_PIPE_CASE(3, 2, 2)
+            RAFTCORR_PIPE_CASE(2, 2, 2)
+            RAFTCORR_PIPE_CASE(2, 4, 2)
+            RAFTCORR_PIPE_CASE(3, 4, 1)
+            RAFTCORR_PIPE_CASE(4, 2, 1)
+            default: return fail("RAFTCORR_BUILD_PIPE=%d is not a compiled pipeline shape", pipe);
+        }
+#undef RAFTCORR_PIPE_CASE
     }
     RC_CUDA(cudaGetLastError());
     if (lay.L > fusedL) {  // never used by RAFT (num_levels = 4); kept correct rather than rejected

@@ -73,6 +73,8 @@ inline PyramidView make_view(float* base, const raftcorr_pyramid_layout& lay) {
 
 // ---- launchers implemented in the individual .cu files ------------------------------------------
 int launch_nchw_to_nhwc(const float* in, float* out, int B, int D, int HW, int Dout, bool round_tf32, cudaStream_t s);
+int launch_nchw_to_nhwc_pair(const float* in1, float* out1, const float* in2, float* out2, int B, int D, int HW,
+                             int Dout, bool round, cudaStream_t s);
 int tc_feature_pitch(int D);  // K padding of the tensor-core build (multiple of 32 floats)
 int launch_nhwc_to_nchw(const float* in, float* out, int B, int D, int HW, cudaStream_t s);
 int launch_pool_nhwc(const float* in, float* out, int B, int Hi, int Wi, int D, cudaStream_t s);

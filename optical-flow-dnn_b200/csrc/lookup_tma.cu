@@ -10,6 +10,7 @@
 // Each warp owns two patch buffers and two mbarriers and keeps the next pixel's boxes in flight while
 // it evaluates the current pixel; results are transposed through a [channels][32 px] shared tile and
 // stored channel-major with full 128-byte lines, as in lookup.cu.
+#include <cstdlib>
 #include <cstring>
 
 #include "lookup_common.cuh"
@@ -19,8 +20,8 @@ namespace raftcorr {
 
 namespace {
 
-constexpr int kBufs = 3;                 // patch ring per warp: two pixels in flight while one is evaluated
-constexpr int kBarBytes = 8 * kBufs + 8;  // per-warp mbarrier block (padded to 16 bytes)
+constexpr int kDefaultRingDepth = 3;
+constexpr int kBarBytes = 32;  // per-warp mbarrier block: up to 3 barriers, padded
 
 template <int R>
 struct TmaGeo {
@@ -37,8 +38,10 @@ struct LookupMaps {
     CUtensorMap m[4];
 };
 
-template <int R, int LG>
-__global__ void __launch_bounds__(kWarps * 32, 2)
+// kBufs = patch ring depth per warp.  3 (two pixels in flight while one is evaluated) fits two CTAs per SM
+// at r=4; 2 fits three CTAs (24 warps) with the same number of patches in flight per SM.
+template <int R, int LG, int kBufs>
+__global__ void __launch_bounds__(kWarps * 32, kBufs == 2 ? 3 : 2)
 lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g, const float* __restrict__ coords,
                       float* __restrict__ out) {
     using G = TmaGeo<R>;
@@ -146,16 +149,30 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
     }
 }
 
-template <int R, int LG>
-int run_fwd_tma(const LookupMaps& maps, const GroupView& g, const float* coords, float* out, cudaStream_t s) {
+template <int R, int LG, int kBufs>
+int run_fwd_tma_bufs(const LookupMaps& maps, const GroupView& g, const float* coords, float* out, cudaStream_t s) {
     using G = TmaGeo<R>;
     const size_t smem = 128 + (size_t)kWarps * kBufs * LG * G::SLOT + kWarps * kBarBytes + sizeof(float) * LG * G::KK * kTilePitch;
-    auto kern = lookup_fwd_tma_kernel<R, LG>;
+    auto kern = lookup_fwd_tma_kernel<R, LG, kBufs>;
     RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(g.N, kPix), g.B);
     kern<<<grid, kWarps * 32, smem, s>>>(maps, g, coords, out);
     RC_CUDA(cudaGetLastError());
     return 0;
+}
+
+inline int lookup_ring_depth() {  // RAFTCORR_LOOKUP_BUFS=2|3 (A/B switch)
+    static const int depth = [] {
+        const char* e = std::getenv("RAFTCORR_LOOKUP_BUFS");
+        return (e && e[0] == '2') ? 2 : (e && e[0] == '3') ? 3 : kDefaultRingDepth;
+    }();
+    return depth;
+}
+
+template <int R, int LG>
+int run_fwd_tma(const LookupMaps& maps, const GroupView& g, const float* coords, float* out, cudaStream_t s) {
+    return lookup_ring_depth() == 2 ? run_fwd_tma_bufs<R, LG, 2>(maps, g, coords, out, s)
+                                    : run_fwd_tma_bufs<R, LG, 3>(maps, g, coords, out, s);
 }
 
 template <int R>

@@ -41,13 +41,16 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restr
 // tensor-core build calls it on both feature maps before every volume, so it should run near copy speed.
 template <bool ROUND>
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_wide_kernel(const float* __restrict__ in, float* __restrict__ out, int D, int HW, int Dout) {
+nchw_to_nhwc_wide_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ in2,
+                         float* __restrict__ out2, int B, int D, int HW, int Dout) {
     __shared__ float tile[32][129];
-    const int b = blockIdx.z;
+    // blockIdx.z in [B, 2B) handles the second map of a pair (both feature maps in one launch)
+    const bool second = (int)blockIdx.z >= B;
+    const int b = second ? blockIdx.z - B : blockIdx.z;
     const int p0 = blockIdx.x * 128, d0 = blockIdx.y * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* src = in + (int64_t)b * D * HW;
-    float* dst = out + (int64_t)b * Dout * HW;
+    const float* src = (second ? in2 : in) + (int64_t)b * D * HW;
+    float* dst = (second ? out2 : out) + (int64_t)b * Dout * HW;
     float r[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {      // channel rows warp, warp+8, ...
@@ -164,14 +167,19 @@ inline int grid_for(int64_t total, int threads) {
 
 }  // namespace
 
-int launch_nchw_to_nhwc(const float* in, float* out, int B, int D, int HW, int Dout, bool round, cudaStream_t s) {
-    dim3 grid(ceil_div(HW, 128), ceil_div(Dout, 32), B);
+int launch_nchw_to_nhwc_pair(const float* in1, float* out1, const float* in2, float* out2, int B, int D, int HW,
+                             int Dout, bool round, cudaStream_t s) {
+    dim3 grid(ceil_div(HW, 128), ceil_div(Dout, 32), in2 ? 2 * B : B);
     if (round)
-        nchw_to_nhwc_wide_kernel<true><<<grid, 256, 0, s>>>(in, out, D, HW, Dout);
+        nchw_to_nhwc_wide_kernel<true><<<grid, 256, 0, s>>>(in1, out1, in2, out2, B, D, HW, Dout);
     else
-        nchw_to_nhwc_wide_kernel<false><<<grid, 256, 0, s>>>(in, out, D, HW, Dout);
+        nchw_to_nhwc_wide_kernel<false><<<grid, 256, 0, s>>>(in1, out1, in2, out2, B, D, HW, Dout);
     RC_CUDA(cudaGetLastError());
     return 0;
+}
+
+int launch_nchw_to_nhwc(const float* in, float* out, int B, int D, int HW, int Dout, bool round, cudaStream_t s) {
+    return launch_nchw_to_nhwc_pair(in, out, nullptr, nullptr, B, D, HW, Dout, round, s);
 }
 
 int launch_nhwc_to_nchw(const float* in, float* out, int B, int D, int HW, cudaStream_t s) {

@@ -17,4 +17,4 @@ for D in [int(x) for x in (sys.argv[1:] or ["256"])]:
             for _ in range(20): blk = rc.CorrBlock(f1, f2, LV, 4)
             e1.record(); torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) / 20 * 1e3)
-        print(f"L={LV} D={D}: build group (2 transposes + build_tc) {min(ts):.1f} us (trials {' '.join('%.0f' % t for t in ts)})")
+        print(f"L={LV} D={D}: build group (transpose + build_tc) {min(ts):.1f} us (trials {' '.join('%.0f' % t for t in ts)})")

@@ -322,6 +322,15 @@ def test_kernel_variants_agree(pkg, monkeypatch):
     blk2 = pkg.CorrBlock(f1, f2, L, r)
     for a, c in zip(blk.corr_pyramid, blk2.corr_pyramid):  # views exclude the (never written) row padding
         assert torch.equal(a, c)
+    monkeypatch.setenv("RAFTCORR_BUILD_CLUSTER", "1")
+    for pipe in ("322", "222", "242", "341", "421"):  # operand stages / store buffers / rows per buffer
+        monkeypatch.setenv("RAFTCORR_BUILD_PIPE", pipe)
+        for a, c in zip(blk.corr_pyramid, pkg.CorrBlock(f1, f2, L, r).corr_pyramid):
+            assert torch.equal(a, c), pipe
+    monkeypatch.setenv("RAFTCORR_BUILD_PIPE", "999")
+    with pytest.raises(pkg.RaftCorrError, match="pipeline shape"):
+        pkg.CorrBlock(f1, f2, L, r)
+    monkeypatch.delenv("RAFTCORR_BUILD_PIPE")
     monkeypatch.setenv("RAFTCORR_LOOKUP", "tma")
     o_tma = blk(coords)
     o_tma2 = blk2(coords)
