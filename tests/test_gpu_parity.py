@@ -334,6 +334,9 @@ def test_kernel_variants_agree(pkg, monkeypatch):
     monkeypatch.setenv("RAFTCORR_LOOKUP", "tma")
     o_tma = blk(coords)
     o_tma2 = blk2(coords)
+    monkeypatch.setenv("RAFTCORR_LOOKUP_BUFS", "2")  # 2-deep patch ring, 3 CTAs per SM
+    assert torch.equal(blk(coords), o_tma)
+    monkeypatch.delenv("RAFTCORR_LOOKUP_BUFS")
     monkeypatch.setenv("RAFTCORR_LOOKUP", "cpasync")
     o_cp = blk(coords)
     assert torch.equal(o_tma, o_tma2)
