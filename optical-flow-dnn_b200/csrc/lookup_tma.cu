@@ -31,7 +31,10 @@ struct TmaGeo {
     static constexpr int BOX_BYTES = BC * K1 * 4;
     static constexpr int SLOT = (BOX_BYTES + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
     static constexpr int KK = K * K;
-    static constexpr int NT = (KK + 31) / 32;
+    // evaluation: lane = (x offset i, row group jg); a lane produces RPL vertically adjacent outputs of column i
+    // from RPL+1 horizontal lerps, so every patch value is loaded once per two outputs instead of once per tap
+    static constexpr int GROUPS = (32 / K) < K ? (32 / K) : K;
+    static constexpr int RPL = (K + GROUPS - 1) / GROUPS;
 };
 
 struct LookupMaps {
@@ -73,14 +76,12 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
     }
     __syncwarp();
 
-    int ooff[G::NT], och[G::NT];
-#pragma unroll
-    for (int t = 0; t < G::NT; ++t) {
-        const int c = lane + 32 * t;
-        const int j = c / G::K, i = c - j * G::K;  // lanes run along x inside a patch row (fewest bank conflicts)
-        ooff[t] = j * G::BC + i;
-        och[t] = i * G::K + j;                     // output channel: i (x offset) major, corr.py:66-78
-    }
+    // lanes run along x inside a patch row (fewest bank conflicts); lanes >= K * GROUPS idle during evaluation
+    const int jg = lane / G::K, li = lane - jg * G::K;
+    const int j0 = jg * G::RPL;
+    const bool lane_on = jg < G::GROUPS;
+    const int lane_off = j0 * G::BC + li;       // first tap of this lane inside a patch
+    const int lane_ch = li * G::K + j0;         // output channel: i (x offset) major, corr.py:66-78
 
     float cxs[PIX_PER_WARP], cys[PIX_PER_WARP];
 #pragma unroll
@@ -127,16 +128,22 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
             const float x = cxs[n] * g.inv_scale[l], y = cys[n] * g.inv_scale[l];
             const float xf = floorf(x);
             const float ax = x - xf, ay = y - floorf(y);
-            const float* P = pbuf + l * (G::SLOT / 4) + (((int)xf - R) & 3);
+            const float* P = pbuf + l * (G::SLOT / 4) + (((int)xf - R) & 3) + lane_off;
+            if (lane_on) {
+                float h[G::RPL + 1];
 #pragma unroll
-            for (int t = 0; t < G::NT; ++t) {
-                const int c = lane + 32 * t;
-                if (c < G::KK) {
-                    const int o = ooff[t];
-                    const float top = P[o] + ax * (P[o + 1] - P[o]);
-                    const float bot = P[o + G::BC] + ax * (P[o + G::BC + 1] - P[o + G::BC]);
-                    out_s[(l * G::KK + och[t]) * kTilePitch + q] = top + ay * (bot - top);
+                for (int rr = 0; rr <= G::RPL; ++rr) {
+                    if (j0 + rr <= G::K) {  // the last group may own fewer than RPL rows
+                        const float a = P[rr * G::BC], c = P[rr * G::BC + 1];
+                        h[rr] = a + ax * (c - a);
+                    } else {
+                        h[rr] = 0.f;
+                    }
                 }
+                float* o = out_s + (l * G::KK + lane_ch) * kTilePitch + q;
+#pragma unroll
+                for (int k = 0; k < G::RPL; ++k)
+                    if (j0 + k < G::K) o[k * kTilePitch] = h[k] + ay * (h[k + 1] - h[k]);
             }
         }
         __syncwarp();  // all lanes are done with `buf` before lane 0 refills it next iteration
