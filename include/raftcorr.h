@@ -136,13 +136,21 @@ int raftcorr_alt_backward(const float* fmap1_nhwc, const float* fmap2_nhwc, cons
  * f1_nhwc [B,H,W,D] <- transpose(fmap1); f2_pyramid_nhwc <- levels l<L of avg-pooled fmap2, NHWC,
  * level l at float offset raftcorr_alt_level_offset(B,D,H,W,l), dense [B][H_l][W_l][D]. */
 int64_t raftcorr_alt_level_offset(int B, int D, int H, int W, int level);
-int raftcorr_alt_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int L,
+/* mode RAFTCORR_BUILD_TF32_TC additionally rounds every stored feature to TF32 (round to nearest), which is what
+ * the tensor-core lookup below multiplies; RAFTCORR_BUILD_FP32_SIMT stores exact fp32. */
+int raftcorr_alt_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int L, int mode,
                          float* f1_nhwc, float* f2_pyramid_nhwc, int device, raftcorr_stream_t stream);
 
-/* AlternateCorrBlock.__call__ (corr.py:142-167) fused over all L levels, incl. the 1/sqrt(D). */
+/* AlternateCorrBlock.__call__ (corr.py:142-167) fused over all L levels, incl. the 1/sqrt(D).
+ * mode RAFTCORR_BUILD_FP32_SIMT: exact fp32 dot products on the CUDA cores, one warp per source pixel (the
+ *   arithmetic of correlation_kernel.cu:18-119); no work space.
+ * mode RAFTCORR_BUILD_TF32_TC: blocks of 8x16 source pixels against the bounding box of their windows as TF32
+ *   tcgen05 GEMM tiles, windows gathered from the accumulators; needs D % 32 == 0, a pyramid built with the same
+ *   mode, and raftcorr_alt_lookup_workspace_bytes() bytes of 16-byte aligned device work space. */
+size_t raftcorr_alt_lookup_workspace_bytes(int B, int H, int W, int L, int mode);
 int raftcorr_alt_lookup_fwd(const float* f1_nhwc, const float* f2_pyramid_nhwc, const float* coords, int B,
-                            int D, int H, int W, int L, int radius, float* out, int device,
-                            raftcorr_stream_t stream);
+                            int D, int H, int W, int L, int radius, int mode, float* out, void* workspace,
+                            size_t workspace_bytes, int device, raftcorr_stream_t stream);
 
 /* Gradient of raftcorr_alt_lookup_fwd w.r.t. the NHWC feature tensors (accumulated into
  * df1_nhwc [B,H,W,D] and df2_pyramid_nhwc, same layout as the forward pyramid; zero them first). */

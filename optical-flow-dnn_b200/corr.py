@@ -295,10 +295,21 @@ class AlternateCorrBlock:
 
     Unlike the reference (whose ``alt_cuda_corr.backward`` is never called from Python) this class is
     differentiable w.r.t. both feature maps.
+
+    ``build_mode`` (extension; RAFT never passes it): ``"tf32"`` evaluates blocks of source pixels against the
+    bounding box of their windows on the tcgen05 tensor cores (needs ``D % 32 == 0``), ``"fp32"`` computes
+    exact fp32 dot products on the CUDA cores.  Default: :func:`set_default_build_mode` /
+    ``RAFTCORR_BUILD_MODE`` when the feature dim allows it, else ``"fp32"``.
     """
 
-    def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, build_mode=None):
         _check_fmaps(fmap1, fmap2, "AlternateCorrBlock")
+        mode = build_mode or (_default_mode if fmap1.shape[1] % 32 == 0 else "fp32")
+        if mode not in _MODES:
+            raise ValueError(f"unknown build mode {mode!r} (expected one of {sorted(_MODES)})")
+        if mode == "tf32" and fmap1.shape[1] % 32 != 0:
+            raise RaftCorrError("AlternateCorrBlock: build_mode='tf32' needs a feature dim that is a multiple of 32")
+        self._mode = _MODES[mode]
         self.num_levels = int(num_levels)
         self.radius = int(radius)
         if not 1 <= self.radius <= 4:
@@ -324,8 +335,10 @@ class AlternateCorrBlock:
         dev = self._device
         f1n = torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
         f2p = torch.empty(_alt_sizes(B, D, H, W, L), dtype=torch.float32, device=dev)
-        check(_lib.lib().raftcorr_alt_pyramid(_ptr(fmap1), _ptr(fmap2), B, D, H, W, L, _ptr(f1n), _ptr(f2p),
-                                              dev.index, _stream(dev)), "raftcorr_alt_pyramid")
+        check(_lib.lib().raftcorr_alt_pyramid(_ptr(fmap1), _ptr(fmap2), B, D, H, W, L, self._mode, _ptr(f1n),
+                                              _ptr(f2p), dev.index, _stream(dev)), "raftcorr_alt_pyramid")
+        ws_bytes = int(_lib.lib().raftcorr_alt_lookup_workspace_bytes(B, H, W, L, self._mode))
+        self._ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         return f1n, f2p
 
     def _lookup(self, f1n, f2p, coords):
@@ -334,7 +347,8 @@ class AlternateCorrBlock:
         K = 2 * self.radius + 1
         out = torch.empty((B, L * K * K, H, W), dtype=torch.float32, device=dev)
         check(_lib.lib().raftcorr_alt_lookup_fwd(_ptr(f1n), _ptr(f2p), _ptr(coords), B, D, H, W, L, self.radius,
-                                                 _ptr(out), dev.index, _stream(dev)), "raftcorr_alt_lookup_fwd")
+                                                 self._mode, _ptr(out), _ptr(self._ws), self._ws.numel(), dev.index,
+                                                 _stream(dev)), "raftcorr_alt_lookup_fwd")
         return out
 
     def __call__(self, coords):

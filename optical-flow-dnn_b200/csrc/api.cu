@@ -253,8 +253,10 @@ int64_t raftcorr_alt_level_offset(int B, int D, int H, int W, int level) {
     return off;
 }
 
-int raftcorr_alt_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int L, float* f1_nhwc,
-                         float* f2_pyr, int device, raftcorr_stream_t stream) {
+int raftcorr_alt_pyramid(const float* fmap1, const float* fmap2, int B, int D, int H, int W, int L, int mode,
+                         float* f1_nhwc, float* f2_pyr, int device, raftcorr_stream_t stream) {
+    RC_REQUIRE(mode == RAFTCORR_BUILD_FP32_SIMT || mode == RAFTCORR_BUILD_TF32_TC, "alt_pyramid: unknown mode %d", mode);
+    const bool round = mode == RAFTCORR_BUILD_TF32_TC;  // the tensor-core lookup wants round-to-nearest TF32 operands
     RC_REQUIRE(B == 0 || (fmap1 && fmap2 && f1_nhwc && f2_pyr), "alt_pyramid: NULL tensor");
     AltLevels lv{};
     if (int rc = alt_levels(f2_pyr, nullptr, B, D, H, W, L, &lv)) return rc;
@@ -262,17 +264,23 @@ int raftcorr_alt_pyramid(const float* fmap1, const float* fmap2, int B, int D, i
     DeviceGuard guard(device);
     RC_REQUIRE(guard.ok, "alt_pyramid: cannot select device %d", device);
     cudaStream_t s = (cudaStream_t)stream;
-    if (int rc = launch_nchw_to_nhwc_pair(fmap1, f1_nhwc, fmap2, const_cast<float*>(lv.f2[0]), B, D, H * W, D, false, s))
+    if (int rc = launch_nchw_to_nhwc_pair(fmap1, f1_nhwc, fmap2, const_cast<float*>(lv.f2[0]), B, D, H * W, D, round, s))
         return rc;
     for (int l = 1; l < L; ++l)  // corr.py:138-139 (fmap2 side; the pooled fmap1 copies are never read, :158)
-        if (int rc = launch_pool_nhwc(lv.f2[l - 1], const_cast<float*>(lv.f2[l]), B, lv.h[l - 1], lv.w[l - 1], D, s))
+        if (int rc = launch_pool_nhwc(lv.f2[l - 1], const_cast<float*>(lv.f2[l]), B, lv.h[l - 1], lv.w[l - 1], D, round, s))
             return rc;
     return 0;
 }
 
+size_t raftcorr_alt_lookup_workspace_bytes(int B, int H, int W, int L, int mode) {
+    return mode == RAFTCORR_BUILD_TF32_TC ? alt_tc_workspace_bytes(B, H, W, L) : 0;
+}
+
 int raftcorr_alt_lookup_fwd(const float* f1_nhwc, const float* f2_pyr, const float* coords, int B, int D, int H,
-                            int W, int L, int radius, float* out, int device, raftcorr_stream_t stream) {
+                            int W, int L, int radius, int mode, float* out, void* workspace, size_t workspace_bytes,
+                            int device, raftcorr_stream_t stream) {
     RC_REQUIRE(B == 0 || (f1_nhwc && f2_pyr && coords && out), "alt_lookup_fwd: NULL tensor");
+    RC_REQUIRE(mode == RAFTCORR_BUILD_FP32_SIMT || mode == RAFTCORR_BUILD_TF32_TC, "alt_lookup_fwd: unknown mode %d", mode);
     AltLevels lv{};
     if (int rc = alt_levels(f2_pyr, nullptr, B, D, H, W, L, &lv)) return rc;
     if (B == 0) return 0;
@@ -281,6 +289,9 @@ int raftcorr_alt_lookup_fwd(const float* f1_nhwc, const float* f2_pyr, const flo
     const int64_t N1 = (int64_t)H * W;
     CoordsView cv{coords, 2 * N1, N1, 1};  // [B,2,H,W]
     const float scale = 1.0f / sqrtf((float)D);  // corr.py:167
+    if (mode == RAFTCORR_BUILD_TF32_TC)
+        return launch_alt_fwd_tc(f1_nhwc, lv, cv, B, H, W, D, radius, scale, out, workspace, workspace_bytes, device,
+                                 (cudaStream_t)stream);
     return launch_alt_fwd(f1_nhwc, lv, cv, B, 1, H, W, D, radius, scale, out, (cudaStream_t)stream);
 }
 

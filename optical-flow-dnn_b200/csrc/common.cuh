@@ -77,7 +77,7 @@ int launch_nchw_to_nhwc_pair(const float* in1, float* out1, const float* in2, fl
                              int Dout, bool round, cudaStream_t s);
 int tc_feature_pitch(int D);  // K padding of the tensor-core build (multiple of 32 floats)
 int launch_nhwc_to_nchw(const float* in, float* out, int B, int D, int HW, cudaStream_t s);
-int launch_pool_nhwc(const float* in, float* out, int B, int Hi, int Wi, int D, cudaStream_t s);
+int launch_pool_nhwc(const float* in, float* out, int B, int Hi, int Wi, int D, bool round_tf32, cudaStream_t s);
 int launch_pool_adjoint_nhwc(const float* gout, float* gin, int B, int Hi, int Wi, int D, cudaStream_t s);
 int launch_pool_level(const LevelView& in, const LevelView& out, int64_t imgs, cudaStream_t s);
 int launch_pool_adjoint_level(const LevelView& coarse, const LevelView& fine, int64_t imgs, bool round_tf32_out,
@@ -111,6 +111,10 @@ struct CoordsView {
 };
 int launch_alt_fwd(const float* f1_nhwc, const AltLevels& lv, const CoordsView& cv, int B, int NC, int H1, int W1,
                    int C, int radius, float scale, float* out, cudaStream_t s);
+size_t alt_tc_workspace_bytes(int B, int H, int W, int L);
+int launch_alt_fwd_tc(const float* f1_nhwc, const AltLevels& lv, const CoordsView& cv, int B, int H, int W, int C,
+                      int radius, float scale, float* out, void* workspace, size_t workspace_bytes, int device,
+                      cudaStream_t s);
 int launch_alt_bwd(const float* f1_nhwc, const AltLevels& lv, const CoordsView& cv, const float* grad_out, int B,
                    int NC, int H1, int W1, int C, int radius, float scale, float* df1_nhwc, cudaStream_t s);
 

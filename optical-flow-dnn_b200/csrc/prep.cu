@@ -80,6 +80,7 @@ nchw_to_nhwc_wide_kernel(const float* __restrict__ in, float* __restrict__ out, 
 }
 
 // NHWC 2x2 mean, floor mode: in [B][Hi][Wi][D] -> out [B][Hi/2][Wi/2][D]
+template <bool ROUND>
 __global__ void pool_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out, int Hi, int Wi, int D,
                                  int64_t total) {
     const int Ho = Hi / 2, Wo = Wi / 2;
@@ -92,7 +93,8 @@ __global__ void pool_nhwc_kernel(const float* __restrict__ in, float* __restrict
         const int y = t % Ho;
         const int b = t / Ho;
         const float* s = in + (((int64_t)b * Hi + 2 * y) * Wi + 2 * x) * D + d;
-        out[idx] = (s[0] + s[D] + s[(int64_t)Wi * D] + s[(int64_t)Wi * D + D]) * 0.25f;
+        const float v = (s[0] + s[D] + s[(int64_t)Wi * D] + s[(int64_t)Wi * D + D]) * 0.25f;
+        out[idx] = ROUND ? round_tf32(v) : v;
     }
 }
 
@@ -190,10 +192,13 @@ int launch_nhwc_to_nchw(const float* in, float* out, int B, int D, int HW, cudaS
     return 0;
 }
 
-int launch_pool_nhwc(const float* in, float* out, int B, int Hi, int Wi, int D, cudaStream_t s) {
+int launch_pool_nhwc(const float* in, float* out, int B, int Hi, int Wi, int D, bool round, cudaStream_t s) {
     const int64_t total = (int64_t)B * (Hi / 2) * (Wi / 2) * D;
     if (total == 0) return 0;
-    pool_nhwc_kernel<<<grid_for(total, 256), 256, 0, s>>>(in, out, Hi, Wi, D, total);
+    if (round)
+        pool_nhwc_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(in, out, Hi, Wi, D, total);
+    else
+        pool_nhwc_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(in, out, Hi, Wi, D, total);
     RC_CUDA(cudaGetLastError());
     return 0;
 }

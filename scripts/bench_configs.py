@@ -85,15 +85,15 @@ def train_config(name, B, D, H, W, L, r, iters, cls, kw, reps=5):
                       "pairs_per_s": B / (ms * 1e-3)}))
 
 
-def alt_config(name, B, D, H, W, L, r, reps=5):
+def alt_config(name, B, D, H, W, L, r, reps=5, mode="tf32"):
     f1, f2, coords = inputs(B, D, H, W, 2)
     with torch.no_grad():
-        blk = rc.AlternateCorrBlock(f1, f2, L, r)
-        ms_ctor = timeit(lambda: rc.AlternateCorrBlock(f1, f2, L, r), reps)
+        blk = rc.AlternateCorrBlock(f1, f2, L, r, build_mode=mode)
+        ms_ctor = timeit(lambda: rc.AlternateCorrBlock(f1, f2, L, r, build_mode=mode), reps)
         ms = timeit(lambda: blk(coords[1]), reps)
     *_, ab, af, _ = alg_bytes(D, H, W, L, r)
-    print(json.dumps({"config": name, "shape": [B, D, H, W, L, r], "ctor_ms": ms_ctor, "lookup_ms": ms, "pair_iters_per_s": B / (ms * 1e-3),
-                      "alg_gbs": B * ab / ms / 1e6, "tflops_fp32": B * af / ms / 1e9}))
+    print(json.dumps({"config": name, "mode": mode, "shape": [B, D, H, W, L, r], "ctor_ms": ms_ctor, "lookup_ms": ms,
+                      "pair_iters_per_s": B / (ms * 1e-3), "alg_gbs": B * ab / ms / 1e6, "alg_tflops": B * af / ms / 1e9}))
 
 
 which = sys.argv[1:] or ["1", "2", "3", "4", "5a", "5b"]
@@ -109,6 +109,8 @@ if "3" in which:
 if "4" in which:
     fwd_config("4 raft_uncertainty KITTI 375x1242 B16 24it", 16, 256, 47, 156, 4, 4, 24, "tf32", reps=10)
 if "5a" in which:
-    alt_config("5a alt 1080x1920 B4", 4, 256, 135, 240, 4, 4)
+    alt_config("5a alt 1080x1920 B4", 4, 256, 135, 240, 4, 4, mode="tf32")
+    alt_config("5a alt 1080x1920 B4", 4, 256, 135, 240, 4, 4, mode="fp32")
 if "5b" in which:
-    alt_config("5b alt 2160x3840 B4", 4, 256, 270, 480, 4, 4, reps=3)
+    alt_config("5b alt 2160x3840 B4", 4, 256, 270, 480, 4, 4, reps=3, mode="tf32")
+    alt_config("5b alt 2160x3840 B4", 4, 256, 270, 480, 4, 4, reps=3, mode="fp32")

@@ -80,20 +80,26 @@ def test_golden_gradients(pkg, golden, mode):
     assert rel_err(cs[1].grad, golden["dcoords1"]) <= TOL[mode] * 20
 
 
-def test_golden_alternate(pkg, golden):
+ALT_TOL = {"fp32": 2e-5, "tf32": 1e-3}  # on-the-fly path: exact fp32 dots vs TF32 tensor-core tiles
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_golden_alternate(pkg, golden, mode):
     B, D, H, W, L, r = _meta(golden)
+    if mode == "tf32" and D % 32:
+        pytest.skip("the tensor-core on-the-fly kernel needs D % 32 == 0")
     f1 = torch.from_numpy(golden["fmap1"]).to(dev()).requires_grad_()
     f2 = torch.from_numpy(golden["fmap2"]).to(dev()).requires_grad_()
-    blk = pkg.AlternateCorrBlock(f1, f2, num_levels=L, radius=r)
+    blk = pkg.AlternateCorrBlock(f1, f2, num_levels=L, radius=r, build_mode=mode)
     loss = 0
     for k in range(3):
         out = blk(torch.from_numpy(golden[f"coords{k}"]).to(dev()))
-        assert rel_err(out, golden[f"out64_{k}"]) <= 2e-5
+        assert rel_err(out, golden[f"out64_{k}"]) <= ALT_TOL[mode]
         w = torch.from_numpy(grad_weights(tuple(out.shape), k).astype(np.float32)).to(dev())
         loss = loss + (out * w).sum()
     loss.backward()
-    assert rel_err(f1.grad, golden["df1"]) <= 1e-4
-    assert rel_err(f2.grad, golden["df2"]) <= 1e-4
+    assert rel_err(f1.grad, golden["df1"]) <= (1e-4 if mode == "fp32" else 1e-3)
+    assert rel_err(f2.grad, golden["df2"]) <= (1e-4 if mode == "fp32" else 1e-3)
     assert len(blk.pyramid) == L + 1
 
 
@@ -163,9 +169,9 @@ def test_seeded_vs_oracle(pkg, shape, mode):
         ref = O.lookup(pyr, coords, r)
         out = blk(torch.from_numpy(coords).to(dev()))
         assert rel_err(out, ref) <= TOL[mode]
-    if mode == "fp32":
-        alt = pkg.AlternateCorrBlock(torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev()), L, r)
-        assert rel_err(alt(torch.from_numpy(coords).to(dev())), ref) <= 2e-5
+    if mode == "fp32" or D % 32 == 0:
+        alt = pkg.AlternateCorrBlock(torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev()), L, r, build_mode=mode)
+        assert rel_err(alt(torch.from_numpy(coords).to(dev())), ref) <= ALT_TOL[mode]
 
 
 def test_c_oracle_agrees_on_gpu_shapes(pkg):
@@ -225,7 +231,7 @@ def test_full_size_properties(pkg, mode):
     diag = v0.reshape(B, N, N).diagonal(dim1=1, dim2=2)
     assert float((centre - diag).abs().max()) == 0.0
     # (6) lookup == on-the-fly variant (AlternateCorrBlock == CorrBlock)
-    alt = pkg.AlternateCorrBlock(f1, f2, L, r)(coords)
+    alt = pkg.AlternateCorrBlock(f1, f2, L, r, build_mode=mode)(coords)
     assert float((alt - o1).abs().max()) <= tol * float(o1.abs().max())
     # (7) adjoint identity <lookup(V), g> == <V, lookup^T(g)> through autograd at full size
     f1g = f1.clone().requires_grad_()
@@ -351,12 +357,46 @@ def test_kernel_variants_agree(pkg, monkeypatch):
     torch.cuda.synchronize()
     assert torch.equal(out, o_tma)
     # on-the-fly: grouped vs single-pixel kernel
-    alt = pkg.AlternateCorrBlock(f1, f2, L, r)
+    alt = pkg.AlternateCorrBlock(f1, f2, L, r, build_mode="fp32")
     monkeypatch.setenv("RAFTCORR_ALT", "group")
     a_g = alt(coords)
     monkeypatch.setenv("RAFTCORR_ALT", "single")
     a_s = alt(coords)
     assert float((a_g - a_s).abs().max()) <= 2e-6 * float(a_s.abs().max())
+    # ... and the tensor-core tiles (TF32 operands) against the exact fp32 dots
+    a_t = pkg.AlternateCorrBlock(f1, f2, L, r, build_mode="tf32")(coords)
+    assert float((a_t - a_s).abs().max()) <= 1e-3 * float(a_s.abs().max())
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 8, 16, 1, 1), (2, 64, 19, 37, 3, 2), (1, 96, 33, 21, 4, 3), (2, 128, 24, 50, 4, 4)])
+def test_alt_tensor_core_blocks(pkg, shape):
+    """The tensor-core on-the-fly kernel on sizes that are not multiples of its 8x16 source block / 8x32 lattice
+    tile, for every radius, with coherent, incoherent, integer, far-out-of-range and NaN coordinates."""
+    B, D, H, W, L, r = shape
+    rng = np.random.default_rng(5)
+    f1 = rng.normal(size=(B, D, H, W)).astype(np.float32)
+    f2 = rng.normal(size=(B, D, H, W)).astype(np.float32)
+    pyr = O.corr_pyramid(f1, f2, L, np.float64)
+    scale = max(float(np.abs(p).max()) for p in pyr)
+    alt = pkg.AlternateCorrBlock(torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev()), L, r, build_mode="tf32")
+    grid = O.coords_grid(B, H, W)
+    smooth = grid + np.float32(2.3) + rng.normal(0, 0.3, grid.shape).astype(np.float32)
+    wild = grid + rng.normal(0, 12.0, grid.shape).astype(np.float32)
+    far = grid.copy()
+    far[:, 0, : H // 2] += 1e4   # whole rows outside every level
+    far[:, 1, :, : W // 3] -= 777.25
+    for name, coords in (("integer", grid), ("smooth", smooth), ("wild", wild), ("far", far)):
+        ref = O.lookup(pyr, coords, r)
+        out = alt(torch.from_numpy(coords).to(dev())).cpu().numpy()
+        assert np.abs(out - ref).max() <= 1e-3 * scale, name
+    nan = smooth.copy()
+    nan[0, 0, 1, 2] = np.nan
+    out = alt(torch.from_numpy(nan).to(dev())).cpu().numpy()
+    ref = O.lookup(pyr, smooth, r)
+    mask = np.ones_like(out, dtype=bool)
+    mask[0, :, 1, 2] = False
+    assert np.abs(out - ref)[mask].max() <= 1e-3 * scale
+    assert np.all(out[0, :, 1, 2] == 0)  # NaN coordinate -> every tap out of range (same rule as the lookup)
 
 
 @pytest.mark.parametrize("mode", MODES)
