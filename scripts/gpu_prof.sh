@@ -14,4 +14,10 @@ timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}
 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:build_tc_kernel|lookup_fwd" -s 39 -c 2 -f -o $OUT/${TAG}_prof \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu2.log 2>&1
 echo "ncu full exit $?"
-ls -la $OUT | tail -15
+
+timeout 600 python scripts/bench_configs.py > $OUT/${TAG}_configs.jsonl 2> $OUT/${TAG}_configs.err; echo "configs exit $?"; cat $OUT/${TAG}_configs.jsonl
+timeout 300 python scripts/alt_tc_stats.py a b > $OUT/${TAG}_alt_tc_stats.txt 2>&1; echo "alt stats exit $?"; cat $OUT/${TAG}_alt_tc_stats.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:alt_fwd_tc" -s 2 -c 1 -f -o $OUT/${TAG}_prof_alt \
+    python scripts/alt_tc_stats.py a > $OUT/${TAG}_ncu3.log 2>&1
+echo "ncu alt exit $?"
+ls -la $OUT | tail -20
