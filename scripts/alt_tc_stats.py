@@ -23,12 +23,14 @@ def run(tag, B, D, H, W, L, r, sigma, smooth, reps=5):
         e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     bb = blk._ws.view(torch.int32).view(-1, L, 4)
-    tiles = (bb[..., 2] * bb[..., 3]).sum(0).tolist()
+    tiles = ((bb[..., 2] & 0xffff) * bb[..., 3]).sum(0).tolist()
+    square = ((bb[..., 2] >> 16) * (bb[..., 2] & 0xffff) * bb[..., 3]).sum(0).tolist()
     nblk = bb.shape[0]
     K = 2 * r + 1
     useful = B * H * W * L * (K + 1) ** 2
-    done = sum(tiles) * 128 * 256
-    print(f"{tag}: {ms*1e3:8.1f} us  blocks={nblk} lattice tiles/level={tiles} per block={sum(tiles)/nblk:.1f} "
+    tile_n = 128 if (D <= 256 and os.environ.get("RAFTCORR_ALT_TC", "")[:1] == "r") else 256  # resident-A kernel: 8x16 tiles
+    done = sum(tiles) * 128 * tile_n
+    print(f"{tag}: {ms*1e3:8.1f} us  blocks={nblk} lattice tiles/level={tiles} (16x16: {square}) (x{tile_n} pts) per block={sum(tiles)/nblk:.1f} "
           f"redundancy={done/useful:.2f}x  MMA TFLOP/s={done*2*D/ms/1e9:.0f}  us/tile={ms*1e3*148/max(sum(tiles),1):.2f}")
 which = sys.argv[1:] or ["a"]
 for w in which:

@@ -364,8 +364,15 @@ def test_kernel_variants_agree(pkg, monkeypatch):
     a_s = alt(coords)
     assert float((a_g - a_s).abs().max()) <= 2e-6 * float(a_s.abs().max())
     # ... and the tensor-core tiles (TF32 operands) against the exact fp32 dots
-    a_t = pkg.AlternateCorrBlock(f1, f2, L, r, build_mode="tf32")(coords)
+    alt_t = pkg.AlternateCorrBlock(f1, f2, L, r, build_mode="tf32")
+    a_t = alt_t(coords)
     assert float((a_t - a_s).abs().max()) <= 1e-3 * float(a_s.abs().max())
+    # ... whose variants (8x32-only lattice tiles; fmap1 block resident in tensor memory) differ by summation order only
+    for var, val in (("RAFTCORR_ALT_SQUARE", "0"), ("RAFTCORR_ALT_TC", "resident")):
+        monkeypatch.setenv(var, val)
+        a_v = alt_t(coords)
+        monkeypatch.delenv(var)
+        assert float((a_v - a_t).abs().max()) <= 2e-6 * float(a_t.abs().max()), var
 
 
 @pytest.mark.parametrize("shape", [(1, 32, 8, 16, 1, 1), (2, 64, 19, 37, 3, 2), (1, 96, 33, 21, 4, 3), (2, 128, 24, 50, 4, 4)])
