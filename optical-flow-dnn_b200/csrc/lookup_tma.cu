@@ -83,6 +83,12 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
     const int lane_off = j0 * G::BC + li;       // first tap of this lane inside a patch
     const int lane_ch = li * G::K + j0;         // output channel: i (x offset) major, corr.py:66-78
 
+    // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the stream (the
+    // launch carries cudaLaunchAttributeProgrammaticStreamSerialization); from here on its results are visible.
+    // Our own dependents may be scheduled as soon as every CTA of this grid has got this far.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
     float cxs[PIX_PER_WARP], cys[PIX_PER_WARP];
 #pragma unroll
     for (int n = 0; n < PIX_PER_WARP; ++n) {
@@ -156,15 +162,31 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
     }
 }
 
+inline bool lookup_pdl() {  // RAFTCORR_LOOKUP_PDL=0 launches without programmatic stream serialization (A/B switch)
+    static const bool on = [] {
+        const char* e = std::getenv("RAFTCORR_LOOKUP_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 template <int R, int LG, int kBufs>
 int run_fwd_tma_bufs(const LookupMaps& maps, const GroupView& g, const float* coords, float* out, cudaStream_t s) {
     using G = TmaGeo<R>;
     const size_t smem = 128 + (size_t)kWarps * kBufs * LG * G::SLOT + kWarps * kBarBytes + sizeof(float) * LG * G::KK * kTilePitch;
     auto kern = lookup_fwd_tma_kernel<R, LG, kBufs>;
     RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(ceil_div(g.N, kPix), g.B);
-    kern<<<grid, kWarps * 32, smem, s>>>(maps, g, coords, out);
-    RC_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(ceil_div(g.N, kPix), g.B);
+    cfg.blockDim = dim3(kWarps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = lookup_pdl() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RC_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, g, coords, out));
     return 0;
 }
 
