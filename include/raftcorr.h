@@ -56,6 +56,13 @@ typedef struct raftcorr_pyramid_layout {
     int32_t pitch[RAFTCORR_MAX_LEVELS];
     int64_t offset[RAFTCORR_MAX_LEVELS];
     int64_t total_floats;
+    int32_t interleaved; /* 0: rows one after the other, element (y,x) at y*pitch + x.
+                            1: ROW PAIRS interleaved, element (y,x) at (y/2)*(2*pitch) + 2*x + (y%2), ceil(h/2) pair rows
+                               per image (an odd last row is paired with zeros).  A (K+1)x(K+1) lookup window is then
+                               ~(K+1)/2 runs of 2(K+1) floats instead of K+1 runs of K+1: fewer, longer DRAM bursts.
+                               The tensor-core build writes and the lookup reads either; gradient pyramids and the
+                               fp32 build use 0. */
+    int32_t reserved_;
 } raftcorr_pyramid_layout;
 
 /* Build precision modes for raftcorr_build_fwd. */
@@ -76,8 +83,8 @@ int raftcorr_set_l2_fetch_granularity(int bytes, int device, int* previous);
 
 /* Host-only helper: fill *layout for a [B,D,H,W] pair of feature maps and L levels.
  * Fails if L < 1, L > RAFTCORR_MAX_LEVELS or a level would collapse below 2x2 (the reference
- * divides by (W_l - 1), utils.py:74-75, and yields NaN there). */
-int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* layout, int B, int H, int W, int L);
+ * divides by (W_l - 1), utils.py:74-75, and yields NaN there).  `interleaved`: see the struct. */
+int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* layout, int B, int H, int W, int L, int interleaved);
 
 /* CorrBlock.__init__ (corr.py:18-43): pyramid <- all-pairs <f1,f2>/sqrt(D) + L-1 poolings. */
 size_t raftcorr_build_fwd_workspace_bytes(int B, int D, int H, int W, int mode);

@@ -27,7 +27,7 @@ class PyramidLayout(ctypes.Structure):
         ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("L", ctypes.c_int32),
         ("h", ctypes.c_int32 * MAX_LEVELS), ("w", ctypes.c_int32 * MAX_LEVELS),
         ("pitch", ctypes.c_int32 * MAX_LEVELS), ("offset", ctypes.c_int64 * MAX_LEVELS),
-        ("total_floats", ctypes.c_int64),
+        ("total_floats", ctypes.c_int64), ("interleaved", ctypes.c_int32), ("reserved_", ctypes.c_int32),
     ]
 
 
@@ -39,7 +39,7 @@ SIGNATURES = {
     "raftcorr_abi_version": (_c_int, []),
     "raftcorr_last_error": (ctypes.c_char_p, []),
     "raftcorr_set_l2_fetch_granularity": (_c_int, [_c_int, _c_int, ctypes.POINTER(_c_int)]),
-    "raftcorr_pyramid_layout_init": (_c_int, [_LAYP, _c_int, _c_int, _c_int, _c_int]),
+    "raftcorr_pyramid_layout_init": (_c_int, [_LAYP, _c_int, _c_int, _c_int, _c_int, _c_int]),
     "raftcorr_build_fwd_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "raftcorr_build_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _LAYP, _c_int, _c_void_p, _c_size_t,
                                      _c_int, _c_void_p]),
@@ -90,7 +90,7 @@ def check(status: int, what: str):
         raise RaftCorrError(f"{what}: {msg.decode() if msg else 'unknown error'}")
 
 
-def make_layout(B: int, H: int, W: int, L: int) -> PyramidLayout:
+def make_layout(B: int, H: int, W: int, L: int, interleaved: bool = False) -> PyramidLayout:
     lay = PyramidLayout()
-    check(lib().raftcorr_pyramid_layout_init(ctypes.byref(lay), B, H, W, L), "pyramid layout")
+    check(lib().raftcorr_pyramid_layout_init(ctypes.byref(lay), B, H, W, L, 1 if interleaved else 0), "pyramid layout")
     return lay

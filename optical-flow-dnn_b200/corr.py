@@ -161,7 +161,12 @@ class CorrBlock:
         B, D, H, W = fmap1.shape
         self._B, self._D, self._H, self._W = B, D, H, W
         self._device = fmap1.device
-        self._layout = _lib.make_layout(B, H, W, self.num_levels)
+        # the tensor-core build writes row pairs interleaved (fewer, longer DRAM runs per lookup window);
+        # gradient pyramids are row-major inside the library whatever this says, and never larger
+        # (RAFTCORR_PYRAMID_LAYOUT=rowmajor keeps the old layout: A/B switch, needed by the cp.async lookup and the
+        # CTA-pair build experiments)
+        il = mode == "tf32" and os.environ.get("RAFTCORR_PYRAMID_LAYOUT", "interleaved") != "rowmajor"
+        self._layout = _lib.make_layout(B, H, W, self.num_levels, interleaved=il)
         self._grad_acc = None
         self._plan = None
         self._plan_ptr = 0
@@ -208,15 +213,23 @@ class CorrBlock:
 
     @property
     def corr_pyramid(self):
-        """The reference's list of ``[B*H*W, 1, H_l, W_l]`` tensors (corr.py:35-43), as strided views
-        into the single pyramid buffer (rows are padded to a multiple of 8 floats)."""
+        """The reference's list of ``[B*H*W, 1, H_l, W_l]`` tensors (corr.py:35-43).  fp32 build mode: strided
+        views into the single pyramid buffer (rows are padded to a multiple of 8 floats).  tf32 build mode: the
+        buffer stores row pairs interleaved, so the levels are de-interleaved copies (nothing in RAFT reads
+        this attribute; the lookup works on the buffer)."""
         lay = self._layout
         N = self._H * self._W
         out = []
         for l in range(self.num_levels):
             h, w, p = lay.h[l], lay.w[l], lay.pitch[l]
-            flat = self._pyr[lay.offset[l]: lay.offset[l] + self._B * N * h * p]
-            out.append(flat.view(self._B * N, 1, h, p)[..., :w])
+            if lay.interleaved:
+                hp = (h + 1) // 2
+                flat = self._pyr[lay.offset[l]: lay.offset[l] + self._B * N * hp * 2 * p]
+                lvl = flat.view(self._B * N, hp, p, 2).permute(0, 1, 3, 2).reshape(self._B * N, 1, 2 * hp, p)
+                out.append(lvl[:, :, :h, :w])
+            else:
+                flat = self._pyr[lay.offset[l]: lay.offset[l] + self._B * N * h * p]
+                out.append(flat.view(self._B * N, 1, h, p)[..., :w])
         return out
 
     @staticmethod

@@ -73,12 +73,13 @@ int raftcorr_set_l2_fetch_granularity(int bytes, int device, int* previous) {
     return 0;
 }
 
-int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* lay, int B, int H, int W, int L) {
+int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* lay, int B, int H, int W, int L, int interleaved) {
     RC_REQUIRE(lay != nullptr, "layout is NULL");
     RC_REQUIRE(L >= 1 && L <= RAFTCORR_MAX_LEVELS, "num_levels must be in [1, %d] (got %d)", RAFTCORR_MAX_LEVELS, L);
     RC_REQUIRE(B >= 0 && H >= 1 && W >= 1, "bad sizes B=%d H=%d W=%d", B, H, W);
     std::memset(lay, 0, sizeof(*lay));
     lay->B = B; lay->H = H; lay->W = W; lay->L = L;
+    lay->interleaved = interleaved ? 1 : 0;
     int h = H, w = W;
     int64_t off = 0;
     const int64_t N = (int64_t)H * W;
@@ -90,7 +91,8 @@ int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* lay, int B, int H, int
         lay->w[l] = w;
         lay->pitch[l] = (w + 7) / 8 * 8;
         lay->offset[l] = off;
-        off += (int64_t)align_up((size_t)(B * N * h * lay->pitch[l]), 64);
+        const int64_t rows = interleaved ? (h + 1) / 2 * 2 : h;  // an odd last row is paired with a row of zeros
+        off += (int64_t)align_up((size_t)(B * N * rows * lay->pitch[l]), 64);
         h /= 2;
         w /= 2;
     }
@@ -115,7 +117,10 @@ int raftcorr_build_fwd(const float* fmap1, const float* fmap2, int D, float* pyr
     RC_REQUIRE(guard.ok, "build_fwd: cannot select device %d", device);
     cudaStream_t s = (cudaStream_t)stream;
     PyramidView pv = make_view(pyramid, *lay);
-    if (mode == RAFTCORR_BUILD_FP32_SIMT) return launch_build_simt(fmap1, fmap2, D, pv, s);
+    if (mode == RAFTCORR_BUILD_FP32_SIMT) {
+        RC_REQUIRE(!lay->interleaved, "build_fwd: the fp32 build writes the row-major pyramid layout only");
+        return launch_build_simt(fmap1, fmap2, D, pv, s);
+    }
     if (mode == RAFTCORR_BUILD_TF32_TC) {
         const size_t need = raftcorr_build_fwd_workspace_bytes(lay->B, D, lay->H, lay->W, mode);
         RC_REQUIRE(workspace && workspace_bytes >= need, "build_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
@@ -175,7 +180,10 @@ int raftcorr_lookup_bwd(const float* grad_out, const float* coords, const float*
     DeviceGuard guard(device);
     RC_REQUIRE(guard.ok, "lookup_bwd: cannot select device %d", device);
     cudaStream_t s = (cudaStream_t)stream;
-    PyramidView dpv = make_view(dpyramid, *lay);
+    // gradient pyramids are always row-major (they feed the backward GEMMs); `lay` describes the forward pyramid
+    raftcorr_pyramid_layout glay;
+    if (int rc = raftcorr_pyramid_layout_init(&glay, lay->B, lay->H, lay->W, lay->L, 0)) return rc;
+    PyramidView dpv = make_view(dpyramid, glay);
     PyramidView fpv{};
     if (dcoords) {
         fpv = make_view(const_cast<float*>(pyramid), *lay);
@@ -199,7 +207,9 @@ int raftcorr_build_bwd(float* dpyramid, const raftcorr_pyramid_layout* lay, cons
     DeviceGuard guard(device);
     RC_REQUIRE(guard.ok, "build_bwd: cannot select device %d", device);
     cudaStream_t s = (cudaStream_t)stream;
-    PyramidView dpv = make_view(dpyramid, *lay);
+    raftcorr_pyramid_layout glay;  // gradient pyramids are always row-major, whatever the forward layout is
+    if (int rc = raftcorr_pyramid_layout_init(&glay, lay->B, lay->H, lay->W, lay->L, 0)) return rc;
+    PyramidView dpv = make_view(dpyramid, glay);
     const int64_t imgs = (int64_t)lay->B * lay->H * lay->W;
     const bool tc = mode == RAFTCORR_BUILD_TF32_TC && build_bwd_tc_supported(D);  // D > 256: CUDA-core GEMMs
     for (int l = lay->L - 1; l >= 1; --l)  // adjoint of corr.py:41-43, coarse to fine

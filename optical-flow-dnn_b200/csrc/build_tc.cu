@@ -85,12 +85,14 @@ struct BuildParams {
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
-template <int MODE, int kStages = 3, int kNumStoreBufs = 2, int RP = 2>
+// IL: the pyramid is written with row pairs interleaved (raftcorr_pyramid_layout::interleaved); needs RP == 2.
+template <int MODE, int kStages = 3, int kNumStoreBufs = 2, int RP = 2, bool IL = false>
 __global__ void __launch_bounds__(kThreads, 1)
 build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_out, const BuildParams P) {
     constexpr int CL = MODE == 0 ? 1 : 2;
     constexpr bool PAIR_MMA = MODE == 2;
+    static_assert(!IL || RP == 2, "the interleaved layout stores whole row pairs");
     constexpr int kStoreBufBytes = RP * kRowTileBytes;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle atoms of TMA and UMMA
@@ -253,6 +255,16 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const uint32_t off = ((uint32_t)j ^ swz) << 4;
+                    if (IL) {
+                        // the two rows leave as ONE run (a0 b0 a1 b1 ...): first box = target columns 0..15, second = 16..31
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(ra[2 * j] * P.scale),
+                                     "f"(rb[2 * j] * P.scale), "f"(ra[2 * j + 1] * P.scale), "f"(rb[2 * j + 1] * P.scale)
+                                     : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + off), "f"(ra[16 + 2 * j] * P.scale),
+                                     "f"(rb[16 + 2 * j] * P.scale), "f"(ra[17 + 2 * j] * P.scale), "f"(rb[17 + 2 * j] * P.scale)
+                                     : "memory");
+                        continue;
+                    }
                     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(ra[4 * j] * P.scale),
                                  "f"(ra[4 * j + 1] * P.scale), "f"(ra[4 * j + 2] * P.scale), "f"(ra[4 * j + 3] * P.scale)
                                  : "memory");
@@ -261,7 +273,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                      "f"(rb[4 * j + 1] * P.scale), "f"(rb[4 * j + 2] * P.scale), "f"(rb[4 * j + 3] * P.scale)
                                      : "memory");
                 }
-                if (P.lsu_store && RP == 2) {
+                if (P.lsu_store && RP == 2 && !IL) {
                     // A/B variant: drain the staged rows with coalesced 128-bit stores (8 lanes per 128-byte row)
                     // instead of TMA, so that the TMA unit only carries the operand loads
                     named_bar_sync(1, 128);
@@ -289,8 +301,13 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     if (issuer) {
                         const uint32_t s0 = store_base + buf * kStoreBufBytes;
                         const int h = band * kTileH + RP * p;
-                        tma_store_4d(&map_out, s0, wt * kTileW, h, mt * kTileM, b);
-                        if (RP == 2) tma_store_4d(&map_out, s0 + kRowTileBytes, wt * kTileW, h + 1, mt * kTileM, b);
+                        if (IL) {  // map_out: [2 * W interleaved floats][pair rows][N1][B]
+                            tma_store_4d(&map_out, s0, wt * (2 * kTileW), h >> 1, mt * kTileM, b);
+                            tma_store_4d(&map_out, s0 + kRowTileBytes, wt * (2 * kTileW) + kTileW, h >> 1, mt * kTileM, b);
+                        } else {
+                            tma_store_4d(&map_out, s0, wt * kTileW, h, mt * kTileM, b);
+                            if (RP == 2) tma_store_4d(&map_out, s0 + kRowTileBytes, wt * kTileW, h + 1, mt * kTileM, b);
+                        }
                         tma_store_commit();
                     }
                 }
@@ -342,37 +359,77 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 16; ++j) l1[j] = (ra[2 * j] + ra[2 * j + 1] + rb[2 * j] + rb[2 * j + 1]) * q;
                 const int h1 = band * 4 + p;
-                if (m_ok && h1 < P.lvl_h[1]) {
+                if (IL) {
+                    // interleaved: rows (h1-1, h1) form a pair and leave together at odd p; an odd last row is paired with zeros
+                    if ((p & 1) && m_ok && h1 - 1 < P.lvl_h[1]) {
+                        const bool odd_ok = h1 < P.lvl_h[1];
+                        float* dst = P.lvl_base[1] + pix * P.lvl_img_stride[1] + (int64_t)(h1 >> 1) * (2 * P.lvl_pitch[1]) + w0;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if ((w0 >> 1) + 4 * c + 4 <= P.lvl_pitch[1]) {
+                                float v[8];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    v[2 * e] = l1prev[4 * c + e];
+                                    v[2 * e + 1] = odd_ok ? l1[4 * c + e] : 0.f;
+                                }
+                                st_global_v8(dst + 8 * c, v);
+                            }
+                    }
+                } else if (m_ok && h1 < P.lvl_h[1]) {
                     float* dst = P.lvl_base[1] + pix * P.lvl_img_stride[1] + (int64_t)h1 * P.lvl_pitch[1] + (w0 >> 1);
 #pragma unroll
                     for (int c = 0; c < 2; ++c)
                         if ((w0 >> 1) + 8 * c + 8 <= P.lvl_pitch[1]) st_global_v8(dst + 8 * c, l1 + 8 * c);
                 }
-                if (P.L > 2) {
-                    if ((p & 1) == 0) {
+                if ((p & 1) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) l1prev[j] = l1[j];
-                    } else {
-                        float l2[8];
+                    for (int j = 0; j < 16; ++j) l1prev[j] = l1[j];
+                } else if (P.L > 2) {
+                    float l2[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            l2[j] = (l1prev[2 * j] + l1prev[2 * j + 1] + l1[2 * j] + l1[2 * j + 1]) * 0.25f;
-                        const int h2 = band * 2 + (p >> 1);
-                        if (m_ok && h2 < P.lvl_h[2] && (w0 >> 2) + 8 <= P.lvl_pitch[2])
-                            st_global_v8(P.lvl_base[2] + pix * P.lvl_img_stride[2] + (int64_t)h2 * P.lvl_pitch[2] + (w0 >> 2), l2);
-                        if (P.L > 3) {
-                            if (p == 1) {
+                    for (int j = 0; j < 8; ++j)
+                        l2[j] = (l1prev[2 * j] + l1prev[2 * j + 1] + l1[2 * j] + l1[2 * j + 1]) * 0.25f;
+                    const int h2 = band * 2 + (p >> 1);
+                    if (IL) {
+                        if (p == 3 && m_ok && h2 - 1 < P.lvl_h[2]) {
+                            const bool odd_ok = h2 < P.lvl_h[2];
+                            float* dst = P.lvl_base[2] + pix * P.lvl_img_stride[2] + (int64_t)band * (2 * P.lvl_pitch[2]) + (w0 >> 1);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) l2prev[j] = l2[j];
+                            for (int c = 0; c < 2; ++c)
+                                if ((w0 >> 2) + 4 * c + 4 <= P.lvl_pitch[2]) {
+                                    float v[8];
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        v[2 * e] = l2prev[4 * c + e];
+                                        v[2 * e + 1] = odd_ok ? l2[4 * c + e] : 0.f;
+                                    }
+                                    st_global_v8(dst + 8 * c, v);
+                                }
+                        }
+                    } else if (m_ok && h2 < P.lvl_h[2] && (w0 >> 2) + 8 <= P.lvl_pitch[2]) {
+                        st_global_v8(P.lvl_base[2] + pix * P.lvl_img_stride[2] + (int64_t)h2 * P.lvl_pitch[2] + (w0 >> 2), l2);
+                    }
+                    if (p == 1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) l2prev[j] = l2[j];
+                    } else if (P.L > 3) {
+                        float4 l3;
+                        l3.x = (l2prev[0] + l2prev[1] + l2[0] + l2[1]) * 0.25f;
+                        l3.y = (l2prev[2] + l2prev[3] + l2[2] + l2[3]) * 0.25f;
+                        l3.z = (l2prev[4] + l2prev[5] + l2[4] + l2[5]) * 0.25f;
+                        l3.w = (l2prev[6] + l2prev[7] + l2[6] + l2[7]) * 0.25f;
+                        if (m_ok && band < P.lvl_h[3] && (w0 >> 3) + 4 <= P.lvl_pitch[3]) {
+                            if (IL) {
+                                // one level-3 row per tile: its 4 values go to every other slot of the pair row; the tile
+                                // that owns the last (even) row of an odd-height level also writes the zero partner row
+                                float* dst = P.lvl_base[3] + pix * P.lvl_img_stride[3] + (int64_t)(band >> 1) * (2 * P.lvl_pitch[3]) +
+                                             (w0 >> 2) + (band & 1);
+                                dst[0] = l3.x; dst[2] = l3.y; dst[4] = l3.z; dst[6] = l3.w;
+                                if (!(band & 1) && band + 1 >= P.lvl_h[3]) dst[1] = dst[3] = dst[5] = dst[7] = 0.f;
                             } else {
-                                float4 l3;
-                                l3.x = (l2prev[0] + l2prev[1] + l2[0] + l2[1]) * 0.25f;
-                                l3.y = (l2prev[2] + l2prev[3] + l2[2] + l2[3]) * 0.25f;
-                                l3.z = (l2prev[4] + l2prev[5] + l2[4] + l2[5]) * 0.25f;
-                                l3.w = (l2prev[6] + l2prev[7] + l2[6] + l2[7]) * 0.25f;
-                                if (m_ok && band < P.lvl_h[3] && (w0 >> 3) + 4 <= P.lvl_pitch[3])
-                                    *reinterpret_cast<float4*>(P.lvl_base[3] + pix * P.lvl_img_stride[3] +
-                                                               (int64_t)band * P.lvl_pitch[3] + (w0 >> 3)) = l3;
+                                *reinterpret_cast<float4*>(P.lvl_base[3] + pix * P.lvl_img_stride[3] +
+                                                           (int64_t)band * P.lvl_pitch[3] + (w0 >> 3)) = l3;
                             }
                         }
                     }
@@ -429,7 +486,18 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2"))
             return rc;
     }
-    {
+    const bool il = lay.interleaved != 0;
+    RC_REQUIRE(!il || mode == 0, "tf32 build: the interleaved pyramid layout needs the single-CTA kernel");
+    if (il) {  // level 0 as [2 * W interleaved floats][pair rows][N1][B]
+        const int hp = (lay.h[0] + 1) / 2;
+        const int64_t img = (int64_t)hp * 2 * lay.pitch[0];
+        cuuint64_t dims[4] = {(cuuint64_t)lay.w[0] * 2, (cuuint64_t)hp, (cuuint64_t)N1, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)lay.pitch[0] * 8, (cuuint64_t)img * 4, (cuuint64_t)N1 * img * 4};
+        cuuint32_t box[4] = {kTileW, 1, kTileM, 1};
+        if (int rc = encode_f32_map(fn, &map_out, (void*)(pyramid + lay.offset[0]), 4, dims, strides, box,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, "volume (row pairs)"))
+            return rc;
+    } else {
         const int64_t img = (int64_t)lay.h[0] * lay.pitch[0];
         cuuint64_t dims[4] = {(cuuint64_t)lay.w[0], (cuuint64_t)lay.h[0], (cuuint64_t)N1, (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)lay.pitch[0] * 4, (cuuint64_t)img * 4, (cuuint64_t)N1 * img * 4};
@@ -445,7 +513,7 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
         P.lvl_h[l] = lay.h[l];
         P.lvl_w[l] = lay.w[l];
         P.lvl_pitch[l] = lay.pitch[l];
-        P.lvl_img_stride[l] = (int64_t)lay.h[l] * lay.pitch[l];
+        P.lvl_img_stride[l] = (int64_t)(il ? (lay.h[l] + 1) / 2 * 2 : lay.h[l]) * lay.pitch[l];
     }
     P.B = B; P.N1 = N1; P.H2 = H; P.W2 = W; P.L = fusedL;
     P.m_tiles = ceil_div(N1, kTileM);
@@ -489,21 +557,30 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
         // from the store pipeline, so two stages are faster (420 vs 462 us).
         const char* pe = std::getenv("RAFTCORR_BUILD_PIPE");
         const int pipe = pe ? atoi(pe) : (P.k_blocks <= 4 ? 222 : 322);
-#define RAFTCORR_PIPE_CASE(NS, NB, RP)                                                                                  \
+#define RAFTCORR_PIPE_CASE(NS, NB, RP, IL_)                                                                             \
     case NS * 100 + NB * 10 + RP: {                                                                                     \
         static_assert(smem_bytes(NS, NB, RP) <= 232448, "pipeline does not fit shared memory");                         \
-        RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<0, NS, NB, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+        RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<0, NS, NB, RP, IL_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                      smem_bytes(NS, NB, RP)));                                                          \
-        build_tc_kernel<0, NS, NB, RP><<<clusters, kThreads, smem_bytes(NS, NB, RP), s>>>(map_a, map_b, map_out, P);    \
+        build_tc_kernel<0, NS, NB, RP, IL_><<<clusters, kThreads, smem_bytes(NS, NB, RP), s>>>(map_a, map_b, map_out, P); \
         break;                                                                                                          \
     }
-        switch (pipe) {
-            RAFTCORR_PIPE_CASE(3, 2, 2)
-            RAFTCORR_PIPE_CASE(2, 2, 2)
-            RAFTCORR_PIPE_CASE(2, 4, 2)
-            RAFTCORR_PIPE_CASE(3, 4, 1)
-            RAFTCORR_PIPE_CASE(4, 2, 1)
-            default: return fail("RAFTCORR_BUILD_PIPE=%d is not a compiled pipeline shape", pipe);
+        if (il) {
+            switch (pipe) {
+                RAFTCORR_PIPE_CASE(3, 2, 2, true)
+                RAFTCORR_PIPE_CASE(2, 2, 2, true)
+                RAFTCORR_PIPE_CASE(2, 4, 2, true)
+                default: return fail("RAFTCORR_BUILD_PIPE=%d is not a compiled pipeline shape for the interleaved layout", pipe);
+            }
+        } else {
+            switch (pipe) {
+                RAFTCORR_PIPE_CASE(3, 2, 2, false)
+                RAFTCORR_PIPE_CASE(2, 2, 2, false)
+                RAFTCORR_PIPE_CASE(2, 4, 2, false)
+                RAFTCORR_PIPE_CASE(3, 4, 1, false)
+                RAFTCORR_PIPE_CASE(4, 2, 1, false)
+                default: return fail("RAFTCORR_BUILD_PIPE=%d is not a compiled pipeline shape", pipe);
+            }
         }
 #undef RAFTCORR_PIPE_CASE
     }

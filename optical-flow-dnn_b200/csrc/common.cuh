@@ -48,7 +48,12 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 struct LevelView {
     float* base;          // level start
     int h, w, pitch;      // rows, valid cols, row pitch (floats)
-    int64_t img_stride;   // h * pitch: floats between consecutive source pixels
+    int il;               // 1: row pairs interleaved (raftcorr_pyramid_layout::interleaved)
+    int64_t img_stride;   // floats between consecutive source pixels: h * pitch (il: 2 * ceil(h/2) * pitch)
+    // offset of element (y, x) inside one image
+    __host__ __device__ __forceinline__ int64_t at(int y, int x) const {
+        return il ? (int64_t)(y >> 1) * (2 * pitch) + 2 * x + (y & 1) : (int64_t)y * pitch + x;
+    }
 };
 
 struct PyramidView {
@@ -66,7 +71,8 @@ inline PyramidView make_view(float* base, const raftcorr_pyramid_layout& lay) {
         v.lvl[l].h = lay.h[l];
         v.lvl[l].w = lay.w[l];
         v.lvl[l].pitch = lay.pitch[l];
-        v.lvl[l].img_stride = (int64_t)lay.h[l] * lay.pitch[l];
+        v.lvl[l].il = lay.interleaved;
+        v.lvl[l].img_stride = (int64_t)(lay.interleaved ? (lay.h[l] + 1) / 2 * 2 : lay.h[l]) * lay.pitch[l];
     }
     return v;
 }

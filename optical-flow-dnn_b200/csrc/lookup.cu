@@ -60,7 +60,7 @@ __device__ __forceinline__ void fetch_patches(const GroupView& g, int b, int p, 
         for (int k = 0; k < G::NK; ++k) {
             const int yy = y0[l] + lg.erow[k], xx = x0[l] + lg.ecol[k];
             const bool ok = (lane + 32 * k < G::NP) && yy >= 0 && yy < lv.h && xx >= 0 && xx < lv.w;
-            v[l][k] = ok ? __ldg(img + (int64_t)yy * lv.pitch + xx) : 0.f;
+            v[l][k] = ok ? __ldg(img + lv.at(yy, xx)) : 0.f;
         }
     }
 }
@@ -318,7 +318,7 @@ lookup_bwd_kernel(const GroupView dg, const GroupView fg, const float* __restric
                     if (col >= 1 && row < G::K) acc += fx * (1.f - fy) * gl[((col - 1) * G::K + row) * kTilePitch];
                     if (col < G::K && row >= 1) acc += (1.f - fx) * fy * gl[(col * G::K + row - 1) * kTilePitch];
                     if (col >= 1 && row >= 1) acc += fx * fy * gl[((col - 1) * G::K + row - 1) * kTilePitch];
-                    atomicAdd(img + (int64_t)yy * lv.pitch + xx, acc);
+                    atomicAdd(img + lv.at(yy, xx), acc);
                 }
             }
         }
@@ -413,6 +413,7 @@ bool use_tma_lookup() {
 
 int launch_lookup_fwd_group_cpasync(int radius, int lg, const GroupView& g, const float* coords, float* out,
                                     cudaStream_t s) {
+    RC_REQUIRE(!g.lvl[0].il, "lookup: RAFTCORR_LOOKUP=cpasync reads the row-major pyramid layout only (fp32 build mode)");
     switch (radius) {
         case 1: return dispatch_fwd<1>(lg, g, coords, out, s);
         case 2: return dispatch_fwd<2>(lg, g, coords, out, s);
@@ -424,6 +425,7 @@ int launch_lookup_fwd_group_cpasync(int radius, int lg, const GroupView& g, cons
 
 int launch_lookup_fwd(const PyramidView& pv, const float* coords, int radius, float* out, cudaStream_t s) {
     if (use_tma_lookup()) return launch_lookup_fwd_tma(pv, coords, radius, out, s);
+    RC_REQUIRE(!pv.lvl[0].il, "lookup: RAFTCORR_LOOKUP=cpasync reads the row-major pyramid layout only (fp32 build mode)");
     for (int l0 = 0; l0 < pv.L; l0 += 4) {
         const int lg = pv.L - l0 < 4 ? pv.L - l0 : 4;
         GroupView g = make_group(pv, l0, lg, radius);

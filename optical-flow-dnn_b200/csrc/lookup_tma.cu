@@ -23,12 +23,16 @@ namespace {
 constexpr int kDefaultRingDepth = 3;
 constexpr int kBarBytes = 32;  // per-warp mbarrier block: up to 3 barriers, padded
 
-template <int R>
+// IL = row pairs interleaved (raftcorr_pyramid_layout::interleaved): the window is (K+1)/2 + 1 pair rows of
+// 2 * (K+1 + 1) floats -- half as many, longer DRAM runs (the box starts at an even column: 16-byte rule again).
+template <int R, bool IL>
 struct TmaGeo {
     static constexpr int K = 2 * R + 1;
     static constexpr int K1 = K + 1;
-    static constexpr int BC = (K1 + 3 + 3) / 4 * 4;        // box columns: covers any 0..3 start shift, 16-byte multiple
-    static constexpr int BOX_BYTES = BC * K1 * 4;
+    // row-major: box columns cover any 0..3 start shift, 16-byte multiple
+    static constexpr int BC = IL ? 2 * ((K1 + 1 + 1) / 2 * 2) : (K1 + 3 + 3) / 4 * 4;  // floats per box row
+    static constexpr int BR = IL ? K1 / 2 + 1 : K1;                                     // box rows
+    static constexpr int BOX_BYTES = BC * BR * 4;
     static constexpr int SLOT = (BOX_BYTES + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
     static constexpr int KK = K * K;
     // evaluation: lane = (x offset i, row group jg); a lane produces RPL vertically adjacent outputs of column i
@@ -43,11 +47,11 @@ struct LookupMaps {
 
 // kBufs = patch ring depth per warp.  3 (two pixels in flight while one is evaluated) fits two CTAs per SM
 // at r=4; 2 fits three CTAs (24 warps) with the same number of patches in flight per SM.
-template <int R, int LG, int kBufs>
+template <int R, int LG, int kBufs, bool IL>
 __global__ void __launch_bounds__(kWarps * 32, kBufs == 2 ? 3 : 2)
 lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g, const float* __restrict__ coords,
                       float* __restrict__ out) {
-    using G = TmaGeo<R>;
+    using G = TmaGeo<R, IL>;
     constexpr int CH = LG * G::KK;
     constexpr int PIX_PER_WARP = kPix / kWarps;
     constexpr int WARP_PATCH = kBufs * LG * G::SLOT;  // bytes: this warp's ring of patch buffers
@@ -80,8 +84,20 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
     const int jg = lane / G::K, li = lane - jg * G::K;
     const int j0 = jg * G::RPL;
     const bool lane_on = jg < G::GROUPS;
-    const int lane_off = j0 * G::BC + li;       // first tap of this lane inside a patch
+    const int lane_off = j0 * G::BC + li;       // first tap of this lane inside a patch (row-major patches)
     const int lane_ch = li * G::K + j0;         // output channel: i (x offset) major, corr.py:66-78
+    // interleaved patches: tap (row Y, col X) sits at (Y >> 1) * BC + 2 * X + (Y & 1); the lane's rows are
+    // Y = (y0 & 1) + j0 + rr, so two small tables (window starting on an even / odd row) cover it
+    int il_row[2][G::RPL + 1];
+    if (IL) {
+#pragma unroll
+        for (int sy = 0; sy < 2; ++sy)
+#pragma unroll
+            for (int rr = 0; rr <= G::RPL; ++rr) {
+                const int Y = sy + j0 + rr;
+                il_row[sy][rr] = (Y >> 1) * G::BC + (Y & 1);
+            }
+    }
 
     // Programmatic dependent launch: everything above overlaps the tail of the previous kernel in the stream (the
     // launch carries cudaLaunchAttributeProgrammaticStreamSerialization); from here on its results are visible.
@@ -105,7 +121,10 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
         for (int l = 0; l < LG; ++l) {
             const int x0 = __float2int_rd(cxs[n] * g.inv_scale[l]) - R;
             const int y0 = __float2int_rd(cys[n] * g.inv_scale[l]) - R;
-            tma_load_3d(my_patch + (buf * LG + l) * G::SLOT, &maps.m[l], my_bar + 8 * buf, x0 & ~3, y0, img);
+            if (IL)  // inner coordinate counts interleaved floats: 2 * column, 16-byte aligned at even columns
+                tma_load_3d(my_patch + (buf * LG + l) * G::SLOT, &maps.m[l], my_bar + 8 * buf, 2 * (x0 & ~1), y0 >> 1, img);
+            else
+                tma_load_3d(my_patch + (buf * LG + l) * G::SLOT, &maps.m[l], my_bar + 8 * buf, x0 & ~3, y0, img);
         }
     };
 
@@ -134,13 +153,16 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
             const float x = cxs[n] * g.inv_scale[l], y = cys[n] * g.inv_scale[l];
             const float xf = floorf(x);
             const float ax = x - xf, ay = y - floorf(y);
-            const float* P = pbuf + l * (G::SLOT / 4) + (((int)xf - R) & 3) + lane_off;
+            const float* P = IL ? pbuf + l * (G::SLOT / 4) + 2 * ((((int)xf - R) & 1) + li)
+                                : pbuf + l * (G::SLOT / 4) + (((int)xf - R) & 3) + lane_off;
+            const int sy = IL ? (((int)floorf(y) - R) & 1) : 0;
             if (lane_on) {
                 float h[G::RPL + 1];
 #pragma unroll
                 for (int rr = 0; rr <= G::RPL; ++rr) {
                     if (j0 + rr <= G::K) {  // the last group may own fewer than RPL rows
-                        const float a = P[rr * G::BC], c = P[rr * G::BC + 1];
+                        const int o = IL ? (sy ? il_row[1][rr] : il_row[0][rr]) : rr * G::BC;
+                        const float a = P[o], c = P[o + (IL ? 2 : 1)];
                         h[rr] = a + ax * (c - a);
                     } else {
                         h[rr] = 0.f;
@@ -170,11 +192,11 @@ inline bool lookup_pdl() {  // RAFTCORR_LOOKUP_PDL=0 launches without programmat
     return on;
 }
 
-template <int R, int LG, int kBufs>
+template <int R, int LG, int kBufs, bool IL>
 int run_fwd_tma_bufs(const LookupMaps& maps, const GroupView& g, const float* coords, float* out, cudaStream_t s) {
-    using G = TmaGeo<R>;
+    using G = TmaGeo<R, IL>;
     const size_t smem = 128 + (size_t)kWarps * kBufs * LG * G::SLOT + kWarps * kBarBytes + sizeof(float) * LG * G::KK * kTilePitch;
-    auto kern = lookup_fwd_tma_kernel<R, LG, kBufs>;
+    auto kern = lookup_fwd_tma_kernel<R, LG, kBufs, IL>;
     RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(ceil_div(g.N, kPix), g.B);
@@ -200,8 +222,9 @@ inline int lookup_ring_depth() {  // RAFTCORR_LOOKUP_BUFS=2|3 (A/B switch)
 
 template <int R, int LG>
 int run_fwd_tma(const LookupMaps& maps, const GroupView& g, const float* coords, float* out, cudaStream_t s) {
-    return lookup_ring_depth() == 2 ? run_fwd_tma_bufs<R, LG, 2>(maps, g, coords, out, s)
-                                    : run_fwd_tma_bufs<R, LG, 3>(maps, g, coords, out, s);
+    if (g.lvl[0].il) return run_fwd_tma_bufs<R, LG, 3, true>(maps, g, coords, out, s);
+    return lookup_ring_depth() == 2 ? run_fwd_tma_bufs<R, LG, 2, false>(maps, g, coords, out, s)
+                                    : run_fwd_tma_bufs<R, LG, 3, false>(maps, g, coords, out, s);
 }
 
 template <int R>
@@ -235,7 +258,9 @@ int lookup_plan_init(void* plan_blob, const PyramidView& pv, int radius) {
     std::memset(&plan, 0, sizeof(plan));
     plan.magic = kPlanMagic;
     plan.radius = radius;
-    const int K1 = 2 * radius + 2, BC = (K1 + 3 + 3) / 4 * 4;
+    const int K1 = 2 * radius + 2;
+    const bool il = pv.lvl[0].il != 0;
+    const int BC = il ? 2 * ((K1 + 1 + 1) / 2 * 2) : (K1 + 3 + 3) / 4 * 4, BR = il ? K1 / 2 + 1 : K1;  // == TmaGeo
     for (int l0 = 0; l0 < pv.L; l0 += 4) {
         const int gi = plan.groups++;
         const int lg = pv.L - l0 < 4 ? pv.L - l0 : 4;
@@ -244,9 +269,11 @@ int lookup_plan_init(void* plan_blob, const PyramidView& pv, int radius) {
         for (int l = 0; l < lg; ++l) {
             const LevelView& lv = pv.lvl[l0 + l];
             // logical width = W_l (not the pitch): columns in the row padding read as zeros, like everything outside
-            cuuint64_t dims[3] = {(cuuint64_t)lv.w, (cuuint64_t)lv.h, (cuuint64_t)pv.B * pv.N};
-            cuuint64_t strides[2] = {(cuuint64_t)lv.pitch * 4, (cuuint64_t)lv.img_stride * 4};
-            cuuint32_t box[3] = {(cuuint32_t)BC, (cuuint32_t)K1, 1};
+            // interleaved: [2 * W_l floats][ceil(H_l / 2) pair rows]; the odd partner of a last odd row holds zeros
+            cuuint64_t dims[3] = {(cuuint64_t)(il ? 2 * lv.w : lv.w), (cuuint64_t)(il ? (lv.h + 1) / 2 : lv.h),
+                                  (cuuint64_t)pv.B * pv.N};
+            cuuint64_t strides[2] = {(cuuint64_t)lv.pitch * (il ? 8 : 4), (cuuint64_t)lv.img_stride * 4};
+            cuuint32_t box[3] = {(cuuint32_t)BC, (cuuint32_t)BR, 1};
             if (int rc = encode_f32_map(fn, &plan.maps[gi].m[l], (void*)lv.base, 3, dims, strides, box,
                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, "pyramid level"))
                 return rc;

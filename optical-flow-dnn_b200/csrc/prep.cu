@@ -123,9 +123,11 @@ __global__ void pool_level_kernel(const LevelView in, const LevelView out, int64
         int64_t t = idx / out.w;
         const int y = t % out.h;
         const int64_t img = t / out.h;
-        const float* s = in.base + img * in.img_stride + (int64_t)(2 * y) * in.pitch + 2 * x;
-        out.base[img * out.img_stride + (int64_t)y * out.pitch + x] =
-            (s[0] + s[1] + s[in.pitch] + s[in.pitch + 1]) * 0.25f;
+        const float* s = in.base + img * in.img_stride;
+        out.base[img * out.img_stride + out.at(y, x)] =
+            (s[in.at(2 * y, 2 * x)] + s[in.at(2 * y, 2 * x + 1)] + s[in.at(2 * y + 1, 2 * x)] + s[in.at(2 * y + 1, 2 * x + 1)]) * 0.25f;
+        // interleaved layout: the partner of an odd last row must read as zero
+        if (out.il && y == out.h - 1 && !(y & 1)) out.base[img * out.img_stride + out.at(y + 1, x)] = 0.f;
     }
 }
 

@@ -5,7 +5,7 @@ OUT=gpurun_out; TAG=${1:-p1}; mkdir -p $OUT
 timeout 1500 python -m pytest tests -m gpu -q > $OUT/${TAG}_pytest.log 2>&1; echo "pytest exit $?"; tail -5 $OUT/${TAG}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1; echo "smoke exit $?"; tail -4 $OUT/${TAG}_smoke.log
 timeout 600 python bench.py --steps 50 --warmup 5 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench exit $?"; cat $OUT/${TAG}_bench.json
-RAFTCORR_LOOKUP=cpasync timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > $OUT/${TAG}_bench_cpasync.json 2> $OUT/${TAG}_bench_cpasync.err; echo "bench(cpasync) exit $?"; cat $OUT/${TAG}_bench_cpasync.json
+RAFTCORR_PYRAMID_LAYOUT=rowmajor RAFTCORR_LOOKUP=cpasync timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > $OUT/${TAG}_bench_cpasync.json 2> $OUT/${TAG}_bench_cpasync.err; echo "bench(cpasync) exit $?"; cat $OUT/${TAG}_bench_cpasync.json
 timeout 300 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_plain.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu1.log 2>&1

@@ -322,14 +322,28 @@ def test_kernel_variants_agree(pkg, monkeypatch):
     coords = torch.from_numpy(O.coords_grid(B, H, W)).to(d) + 3.0 * torch.randn((B, 2, H, W), generator=g, device=d)
     coords[0, :, 0, :5] = torch.tensor([[-7.3, 0.0, 44.0, 100.5, 3.999], [2.0, -0.5, 29.0, 1.0, 29.999]], device=d)
 
+    # production: row-pair-interleaved pyramid, single-CTA build, TMA lookup
+    blk_il = pkg.CorrBlock(f1, f2, L, r)
+    assert blk_il._layout.interleaved == 1
+    o_il = blk_il(coords)
+    for pipe in ("322", "222", "242"):  # operand stages / store buffers / rows per buffer
+        monkeypatch.setenv("RAFTCORR_BUILD_PIPE", pipe)
+        for a, c in zip(blk_il.corr_pyramid, pkg.CorrBlock(f1, f2, L, r).corr_pyramid):
+            assert torch.equal(a, c), pipe
+    monkeypatch.delenv("RAFTCORR_BUILD_PIPE")
+    # the row-major layout (same arithmetic, different addresses) and the variants that only exist for it
+    monkeypatch.setenv("RAFTCORR_PYRAMID_LAYOUT", "rowmajor")
     monkeypatch.setenv("RAFTCORR_BUILD_CLUSTER", "1")
     blk = pkg.CorrBlock(f1, f2, L, r)
+    assert blk._layout.interleaved == 0
+    for a, c in zip(blk.corr_pyramid, blk_il.corr_pyramid):  # views exclude the (never written) row padding
+        assert torch.equal(a, c)
     monkeypatch.setenv("RAFTCORR_BUILD_CLUSTER", "2")
     blk2 = pkg.CorrBlock(f1, f2, L, r)
-    for a, c in zip(blk.corr_pyramid, blk2.corr_pyramid):  # views exclude the (never written) row padding
+    for a, c in zip(blk.corr_pyramid, blk2.corr_pyramid):
         assert torch.equal(a, c)
     monkeypatch.setenv("RAFTCORR_BUILD_CLUSTER", "1")
-    for pipe in ("322", "222", "242", "341", "421"):  # operand stages / store buffers / rows per buffer
+    for pipe in ("322", "222", "242", "341", "421"):
         monkeypatch.setenv("RAFTCORR_BUILD_PIPE", pipe)
         for a, c in zip(blk.corr_pyramid, pkg.CorrBlock(f1, f2, L, r).corr_pyramid):
             assert torch.equal(a, c), pipe
@@ -340,11 +354,14 @@ def test_kernel_variants_agree(pkg, monkeypatch):
     monkeypatch.setenv("RAFTCORR_LOOKUP", "tma")
     o_tma = blk(coords)
     o_tma2 = blk2(coords)
+    assert torch.equal(o_tma, o_il)
     monkeypatch.setenv("RAFTCORR_LOOKUP_BUFS", "2")  # 2-deep patch ring, 3 CTAs per SM
     assert torch.equal(blk(coords), o_tma)
     monkeypatch.delenv("RAFTCORR_LOOKUP_BUFS")
     monkeypatch.setenv("RAFTCORR_LOOKUP", "cpasync")
     o_cp = blk(coords)
+    with pytest.raises(pkg.RaftCorrError, match="row-major"):
+        blk_il(coords)
     assert torch.equal(o_tma, o_tma2)
     assert float((o_tma - o_cp).abs().max()) <= 1e-6 * float(o_tma.abs().max())
     # unplanned C entry point == planned one
