@@ -99,7 +99,7 @@ int raftcorr_lookup_fwd(const float* pyramid, const raftcorr_pyramid_layout* lay
 /* The same lookup with the per-pyramid setup (TMA tensor maps, launch geometry) done once: RAFT calls
  * the lookup 12-32 times per volume (raft.py:141-144).  The plan is a caller-owned HOST blob, valid as
  * long as `pyramid` and `layout` are; initialise it after raftcorr_build_fwd, reuse it for every call. */
-#define RAFTCORR_LOOKUP_PLAN_BYTES 2048
+#define RAFTCORR_LOOKUP_PLAN_BYTES 4096
 typedef struct raftcorr_lookup_plan {
     unsigned char opaque[RAFTCORR_LOOKUP_PLAN_BYTES];
 } raftcorr_lookup_plan;

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libraftcorr_b200.so")
 MAX_LEVELS = 8
 BUILD_FP32_SIMT = 0
 BUILD_TF32_TC = 1
-LOOKUP_PLAN_BYTES = 2048
+LOOKUP_PLAN_BYTES = 4096
 
 
 class RaftCorrError(RuntimeError):

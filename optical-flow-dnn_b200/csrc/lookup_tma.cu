@@ -43,6 +43,7 @@ struct TmaGeo {
 
 struct LookupMaps {
     CUtensorMap m[4];
+    CUtensorMap ms[4];  // interleaved layout: one pair row shorter, for windows that start on an even row
 };
 
 // kBufs = patch ring depth per warp.  3 (two pixels in flight while one is evaluated) fits two CTAs per SM
@@ -75,7 +76,10 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
         fence_mbar_init();
         if (warp == 0) {
 #pragma unroll
-            for (int l = 0; l < LG; ++l) prefetch_tensormap(&maps.m[l]);
+            for (int l = 0; l < LG; ++l) {
+                prefetch_tensormap(&maps.m[l]);
+                if (IL) prefetch_tensormap(&maps.ms[l]);
+            }
         }
     }
     __syncwarp();
@@ -116,15 +120,30 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
 
     auto issue = [&](int n, int buf) {  // lane 0 only
         const int img = b * N + p0 + warp + kWarps * n;
+        if (IL) {
+            // a window starting on an even row spans K1/2 pair rows, on an odd row K1/2 + 1: two boxes per level
+            int y0[LG], short_boxes = 0;
+#pragma unroll
+            for (int l = 0; l < LG; ++l) {
+                y0[l] = __float2int_rd(cys[n] * g.inv_scale[l]) - R;
+                short_boxes += !(y0[l] & 1);
+            }
+            mbar_expect_tx(my_bar + 8 * buf, LG * G::BOX_BYTES - short_boxes * (G::BC * 4));
+#pragma unroll
+            for (int l = 0; l < LG; ++l) {
+                const int x0 = __float2int_rd(cxs[n] * g.inv_scale[l]) - R;
+                // inner coordinate counts interleaved floats: 2 * column, 16-byte aligned at even columns
+                tma_load_3d(my_patch + (buf * LG + l) * G::SLOT, (y0[l] & 1) ? &maps.m[l] : &maps.ms[l], my_bar + 8 * buf,
+                            2 * (x0 & ~1), y0[l] >> 1, img);
+            }
+            return;
+        }
         mbar_expect_tx(my_bar + 8 * buf, LG * G::BOX_BYTES);
 #pragma unroll
         for (int l = 0; l < LG; ++l) {
             const int x0 = __float2int_rd(cxs[n] * g.inv_scale[l]) - R;
             const int y0 = __float2int_rd(cys[n] * g.inv_scale[l]) - R;
-            if (IL)  // inner coordinate counts interleaved floats: 2 * column, 16-byte aligned at even columns
-                tma_load_3d(my_patch + (buf * LG + l) * G::SLOT, &maps.m[l], my_bar + 8 * buf, 2 * (x0 & ~1), y0 >> 1, img);
-            else
-                tma_load_3d(my_patch + (buf * LG + l) * G::SLOT, &maps.m[l], my_bar + 8 * buf, x0 & ~3, y0, img);
+            tma_load_3d(my_patch + (buf * LG + l) * G::SLOT, &maps.m[l], my_bar + 8 * buf, x0 & ~3, y0, img);
         }
     };
 
@@ -277,8 +296,15 @@ int lookup_plan_init(void* plan_blob, const PyramidView& pv, int radius) {
             if (int rc = encode_f32_map(fn, &plan.maps[gi].m[l], (void*)lv.base, 3, dims, strides, box,
                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, "pyramid level"))
                 return rc;
+            if (il) box[1] = (cuuint32_t)(BR - 1);
+            if (int rc = encode_f32_map(fn, &plan.maps[gi].ms[l], (void*)lv.base, 3, dims, strides, box,
+                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, "pyramid level"))
+                return rc;
         }
-        for (int l = lg; l < 4; ++l) plan.maps[gi].m[l] = plan.maps[gi].m[0];
+        for (int l = lg; l < 4; ++l) {
+            plan.maps[gi].m[l] = plan.maps[gi].m[0];
+            plan.maps[gi].ms[l] = plan.maps[gi].ms[0];
+        }
     }
     std::memcpy(plan_blob, &plan, sizeof(plan));
     return 0;
