@@ -216,7 +216,11 @@ int run_fwd_tma_bufs(const LookupMaps& maps, const GroupView& g, const float* co
     using G = TmaGeo<R, IL>;
     const size_t smem = 128 + (size_t)kWarps * kBufs * LG * G::SLOT + kWarps * kBarBytes + sizeof(float) * LG * G::KK * kTilePitch;
     auto kern = lookup_fwd_tma_kernel<R, LG, kBufs, IL>;
-    RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr_done = false;  // per instantiation; the attribute is per function and device-independent here
+    if (!attr_done) {
+        RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(ceil_div(g.N, kPix), g.B);
     cfg.blockDim = dim3(kWarps * 32);
