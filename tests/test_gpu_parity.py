@@ -148,6 +148,7 @@ SEEDED = [
     (2, 256, 23, 47, 4, 4),
     (2, 64, 17, 16, 3, 2),
     (1, 32, 8, 9, 2, 1),
+    (1, 320, 12, 20, 2, 2),  # D > 256: ten k-blocks in the tensor-core kernels, CUDA-core backward GEMMs
 ]
 
 
@@ -434,3 +435,37 @@ def test_five_levels(pkg, mode):
     ref = O.lookup(O.corr_pyramid(f1, f2, L, np.float64), coords, r)
     blk = pkg.CorrBlock(torch.from_numpy(f1).to(dev()), torch.from_numpy(f2).to(dev()), L, r, build_mode=mode)
     assert rel_err(blk(torch.from_numpy(coords).to(dev())), ref) <= TOL[mode]
+
+
+def test_cuda_graph_capture_replays_bit_identically(pkg):
+    """Every entry point launches on the caller's stream without host synchronisation, so a whole refinement
+    loop (build + lookups, and the on-the-fly variant) captures into a CUDA graph and replays the same bits."""
+    d = dev()
+    g = torch.Generator(device=d).manual_seed(21)
+    B, D, H, W, L, r = 2, 128, 24, 40, 4, 4
+    f1 = torch.randn((B, D, H, W), generator=g, device=d)
+    f2 = torch.randn((B, D, H, W), generator=g, device=d)
+    coords = [torch.from_numpy(O.coords_grid(B, H, W)).to(d) + 2.0 * torch.randn((B, 2, H, W), generator=g, device=d)
+              for _ in range(3)]
+
+    def loop():
+        blk = pkg.CorrBlock(f1, f2, L, r)
+        alt = pkg.AlternateCorrBlock(f1, f2, L, r)
+        return [blk(c) for c in coords] + [alt(coords[0])]
+
+    with torch.no_grad():
+        eager = [o.clone() for o in loop()]
+        side = torch.cuda.Stream(d)
+        side.wait_stream(torch.cuda.current_stream(d))
+        with torch.cuda.stream(side):
+            loop()  # warm-up on the capture stream (lazy module loading is not capturable)
+        torch.cuda.current_stream(d).wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs = loop()
+        for _ in range(2):
+            graph.replay()
+        torch.cuda.synchronize()
+    for a, b in zip(eager, outs):
+        assert torch.equal(a, b)
