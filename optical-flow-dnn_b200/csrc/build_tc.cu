@@ -98,7 +98,9 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     // 1024-byte alignment: required by the 128B swizzle atoms of TMA and UMMA
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t stage_base = smem_base;                                  // kStages x (A | B)
-    const uint32_t store_base = smem_base + kStages * kStageBytes;          // kNumStoreBufs x 2 rows
+    // pair MMA: a CTA holds its A tile and HALF of the B tile per stage -> 32 KB stages, so more of them fit
+    constexpr int kStageStride = PAIR_MMA ? kABytes + kBBytes / 2 : kStageBytes;
+    const uint32_t store_base = smem_base + kStages * kStageStride;         // kNumStoreBufs x 2 rows
     const uint32_t bar_base = store_base + kNumStoreBufs * kStoreBufBytes;  // mbarriers (8 B each)
     const uint32_t full_bar = bar_base;                       // [kStages]
     const uint32_t empty_bar = bar_base + 8 * kStages;        // [kStages]
@@ -158,7 +160,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const int b = t / (tiles_per_m * P.m_groups);
                 for (int kb = 0; kb < P.k_blocks; ++kb) {
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-                    const uint32_t sa = stage_base + stage * kStageBytes;
+                    const uint32_t sa = stage_base + stage * kStageStride;
                     const uint32_t sb = sa + kABytes;
                     if (PAIR_MMA) {
                         // both CTAs' loads complete on the LEADER's barrier (peer bit cleared); it expects both halves
@@ -198,7 +200,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 for (int kb = 0; kb < P.k_blocks; ++kb) {
                     mbar_wait(full_bar + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t sa = stage_base + stage * kStageBytes;
+                    const uint32_t sa = stage_base + stage * kStageStride;
                     const uint64_t adesc = make_smem_desc(sa);
                     const uint64_t bdesc = make_smem_desc(sa + kABytes);
 #pragma unroll
@@ -545,8 +547,26 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (mode == 2) {
-        RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<2>, map_a, map_b, map_out, P));
+        // 32 KB stages: RAFTCORR_BUILD_PAIR_STAGES = 3..5 operand stages (default 5)
+        const char* se = std::getenv("RAFTCORR_BUILD_PAIR_STAGES");
+        const int ns = se ? atoi(se) : 5;
+        constexpr int kPairStage = kABytes + kBBytes / 2;
+#define RAFTCORR_PAIR_CASE(NS)                                                                                      \
+    case NS: {                                                                                                      \
+        constexpr int smem2 = NS * kPairStage + 2 * 2 * kRowTileBytes + 1024 + 256;                                 \
+        static_assert(smem2 <= 232448, "pair pipeline does not fit shared memory");                                 \
+        cfg.dynamicSmemBytes = smem2;                                                                               \
+        RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<2, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));   \
+        RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<2, NS>, map_a, map_b, map_out, P));                        \
+        break;                                                                                                      \
+    }
+        switch (ns) {
+            RAFTCORR_PAIR_CASE(3)
+            RAFTCORR_PAIR_CASE(4)
+            RAFTCORR_PAIR_CASE(5)
+            default: return fail("RAFTCORR_BUILD_PAIR_STAGES=%d not compiled (3..5)", ns);
+        }
+#undef RAFTCORR_PAIR_CASE
     } else if (mode == 1) {
         RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<1>, map_a, map_b, map_out, P));
