@@ -216,10 +216,13 @@ int run_fwd_tma_bufs(const LookupMaps& maps, const GroupView& g, const float* co
     using G = TmaGeo<R, IL>;
     const size_t smem = 128 + (size_t)kWarps * kBufs * LG * G::SLOT + kWarps * kBarBytes + sizeof(float) * LG * G::KK * kTilePitch;
     auto kern = lookup_fwd_tma_kernel<R, LG, kBufs, IL>;
-    static bool attr_done = false;  // per instantiation; the attribute is per function and device-independent here
-    if (!attr_done) {
+    // the opt-in is per function AND per device (nn.DataParallel drives several devices from one process)
+    static bool attr_done[64] = {};
+    int dev = 0;
+    RC_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(ceil_div(g.N, kPix), g.B);

@@ -469,3 +469,49 @@ def test_cuda_graph_capture_replays_bit_identically(pkg):
         torch.cuda.synchronize()
     for a, b in zip(eager, outs):
         assert torch.equal(a, b)
+
+
+def test_two_devices_from_one_process(pkg):
+    """nn.DataParallel (raft/train.py:71) drives several GPUs from threads of ONE process: every entry point takes the
+    device explicitly, per-device state (function attributes, tensor maps) must not leak between devices."""
+    import threading
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(3)
+    B, D, H, W, L, r = 2, 64, 24, 40, 4, 4
+    f1 = rng.normal(size=(B, D, H, W)).astype(np.float32)
+    f2 = rng.normal(size=(B, D, H, W)).astype(np.float32)
+    coords = O.coords_grid(B, H, W) + rng.normal(0, 2.0, (B, 2, H, W)).astype(np.float32)
+    results, errors = {}, []
+
+    def work(i):
+        try:
+            d = torch.device(f"cuda:{i}")
+            a = torch.from_numpy(f1).to(d).requires_grad_()
+            b = torch.from_numpy(f2).to(d)
+            c = torch.from_numpy(coords).to(d)
+            outs = []
+            for _ in range(3):
+                blk = pkg.CorrBlock(a, b, L, r)
+                o = blk(c)
+                alt = pkg.AlternateCorrBlock(a.detach(), b, L, r)(c)
+                outs.append((o.detach().cpu(), alt.cpu()))
+            o.sum().backward()
+            results[i] = (outs, a.grad.cpu())
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in (1, 0)]  # device 1 first: nothing may assume device 0
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    (o0, g0), (o1, g1) = results[0], results[1]
+    for (a0, b0), (a1, b1) in zip(o0, o1):
+        assert torch.equal(a0, a1) and torch.equal(b0, b1)
+    assert torch.equal(o0[0][0], o0[2][0])
+    ref = O.lookup(O.corr_pyramid(f1, f2, L, np.float64), coords, r)
+    assert rel_err(o1[0][0], ref) <= TOL["tf32"]
+    assert float((g0 - g1).abs().max()) <= 1e-5 * float(g0.abs().max())  # atomics: order differs between runs
