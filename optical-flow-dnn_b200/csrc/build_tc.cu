@@ -489,7 +489,7 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
             return rc;
     }
     const bool il = lay.interleaved != 0;
-    RC_REQUIRE(!il || mode == 0, "tf32 build: the interleaved pyramid layout needs the single-CTA kernel");
+    RC_REQUIRE(!il || mode != 1, "tf32 build: the multicast-pair experiment writes the row-major layout only");
     if (il) {  // level 0 as [2 * W interleaved floats][pair rows][N1][B]
         const int hp = (lay.h[0] + 1) / 2;
         const int64_t img = (int64_t)hp * 2 * lay.pitch[0];
@@ -556,8 +556,15 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
         constexpr int smem2 = NS * kPairStage + 2 * 2 * kRowTileBytes + 1024 + 256;                                 \
         static_assert(smem2 <= 232448, "pair pipeline does not fit shared memory");                                 \
         cfg.dynamicSmemBytes = smem2;                                                                               \
-        RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<2, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));   \
-        RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<2, NS>, map_a, map_b, map_out, P));                        \
+        if (il) {                                                                                                   \
+            RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<2, NS, 2, 2, true>,                                        \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));                      \
+            RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<2, NS, 2, 2, true>, map_a, map_b, map_out, P));        \
+        } else {                                                                                                    \
+            RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<2, NS, 2, 2, false>,                                       \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));                      \
+            RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<2, NS, 2, 2, false>, map_a, map_b, map_out, P));       \
+        }                                                                                                           \
         break;                                                                                                      \
     }
         switch (ns) {
