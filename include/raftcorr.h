@@ -108,6 +108,23 @@ int raftcorr_lookup_plan_init(raftcorr_lookup_plan* plan, const float* pyramid, 
 int raftcorr_lookup_fwd_planned(const raftcorr_lookup_plan* plan, const float* coords, float* out, int device,
                                 raftcorr_stream_t stream);
 
+/* SURVEY.md 8(f) rank 1 -- the lookup fused with its only consumer, the motion encoder's first 1x1 convolution:
+ *   out[B, Cout, H, W] = relu( bias + W * lookup(coords) )
+ * replaces `corr = corr_fn(coords1)` (raft/core/raft.py:144) followed by `F.relu(self.convc1(corr))`
+ * (raft/core/update.py:135 SmallMotionEncoder, :170 BasicMotionEncoder; convc1 = nn.Conv2d(L*K*K, Cout, 1), :116,:158).
+ * The [B, L*K*K, H, W] lookup result never reaches HBM: its K*K samples per level become rows of a TF32 operand tile
+ * in shared memory and the product runs on tcgen05 (fp32 accumulate), level by level, behind the gather.
+ *   weight [Cout][L*K*K] fp32 (conv weight [Cout, L*K*K, 1, 1], the reference's channel order); pack it once per
+ *   weight update with raftcorr_convc1_pack_weight into a caller-owned device buffer of raftcorr_convc1_weight_bytes.
+ *   bias [Cout] or NULL; relu != 0 applies max(., 0).  Cout: multiple of 16 up to 128, or of 32 up to 256
+ *   (RAFT: 96 and 256).  The plan must describe at most 4 levels. */
+size_t raftcorr_convc1_weight_bytes(int levels, int radius, int cout);
+int raftcorr_convc1_pack_weight(const float* weight, int levels, int radius, int cout, void* packed, int device,
+                                raftcorr_stream_t stream);
+int raftcorr_lookup_convc1_fwd(const raftcorr_lookup_plan* plan, const float* coords, const void* packed_weight,
+                               const float* bias, int cout, int relu, float* out, int device,
+                               raftcorr_stream_t stream);
+
 /* Adjoint of the lookup: dpyramid (same layout, ACCUMULATED into -- zero it once, then call once
  * per refinement iteration) += scatter of grad_out[B, L*(2r+1)^2, H, W].
  * dcoords [B,2,H,W] is optional (NULL to skip); when given, pyramid must be the forward pyramid. */

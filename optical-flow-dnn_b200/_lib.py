@@ -46,6 +46,10 @@ SIGNATURES = {
     "raftcorr_lookup_fwd": (_c_int, [_c_void_p, _LAYP, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p]),
     "raftcorr_lookup_plan_init": (_c_int, [_c_void_p, _c_void_p, _LAYP, _c_int, _c_int]),
     "raftcorr_lookup_fwd_planned": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),
+    "raftcorr_convc1_weight_bytes": (_c_size_t, [_c_int] * 3),
+    "raftcorr_convc1_pack_weight": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_void_p]),
+    "raftcorr_lookup_convc1_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int,
+                                             _c_void_p]),
     "raftcorr_lookup_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _LAYP, _c_int, _c_void_p, _c_int,
                                       _c_void_p]),
     "raftcorr_build_bwd_workspace_bytes": (_c_size_t, [_c_int] * 5),

@@ -193,13 +193,8 @@ class CorrBlock:
         K = 2 * self.radius + 1
         out = torch.empty((self._B, self.num_levels * K * K, self._H, self._W), dtype=torch.float32, device=dev)
         L = _lib.lib()
-        if self._plan is None or self._plan_ptr != pyr.data_ptr():
-            # per-pyramid setup (tensor maps, launch geometry) once; every refinement iteration reuses it
-            self._plan = ctypes.create_string_buffer(_lib.LOOKUP_PLAN_BYTES)
-            check(L.raftcorr_lookup_plan_init(self._plan, _ptr(pyr), ctypes.byref(lay), self.radius, dev.index),
-                  "raftcorr_lookup_plan_init")
-            self._plan_ptr = pyr.data_ptr()
-        check(L.raftcorr_lookup_fwd_planned(self._plan, _ptr(coords), _ptr(out), dev.index, _stream(dev)),
+        # per-pyramid setup (tensor maps, launch geometry) once; every refinement iteration reuses it
+        check(L.raftcorr_lookup_fwd_planned(self._ensure_plan(pyr), _ptr(coords), _ptr(out), dev.index, _stream(dev)),
               "raftcorr_lookup_fwd_planned")
         return out
 
@@ -210,6 +205,65 @@ class CorrBlock:
         if torch.is_grad_enabled() and (self._pyr.requires_grad or coords.requires_grad):
             return _LookupFn.apply(self._pyr, coords, self)
         return self._lookup(self._pyr, coords)
+
+    def _ensure_plan(self, pyr):
+        if self._plan is None or self._plan_ptr != pyr.data_ptr():
+            self._plan = ctypes.create_string_buffer(_lib.LOOKUP_PLAN_BYTES)
+            check(_lib.lib().raftcorr_lookup_plan_init(self._plan, _ptr(pyr), ctypes.byref(self._layout), self.radius,
+                                                       self._device.index), "raftcorr_lookup_plan_init")
+            self._plan_ptr = pyr.data_ptr()
+        return self._plan
+
+    def lookup_convc1(self, coords, weight, bias=None, relu=True):
+        """``relu(conv1x1(self(coords), weight, bias))`` in one kernel -- the lookup fused with its only consumer,
+        the motion encoder's first convolution (``F.relu(self.convc1(corr))``, raft/core/update.py:135,170; the
+        call it replaces in the refinement loop is raft/core/raft.py:144 + the first line of the encoder).
+
+        ``weight``: ``convc1.weight`` ``[Cout, L*(2r+1)^2, 1, 1]`` (or 2-D), ``bias``: ``convc1.bias`` or None.
+        Returns ``[B, Cout, H, W]`` fp32.  The ``[B, L*(2r+1)^2, H, W]`` lookup tensor is never written: its samples
+        become TF32 operand tiles in shared memory and the product runs on the tensor cores with fp32 accumulation
+        (the precision cuDNN uses for this convolution by default).  Inference path: no autograd through it (use
+        ``self(coords)`` + ``convc1`` when gradients are needed).  Cout: multiple of 16 up to 128 or of 32 up to 256
+        (RAFT-small 96, RAFT-basic 256); at most 4 pyramid levels.
+        """
+        _check_coords(coords, self._B, self._H, self._W, self._device, "CorrBlock.lookup_convc1")
+        K = 2 * self.radius + 1
+        cin = self.num_levels * K * K
+        if not (isinstance(weight, torch.Tensor) and weight.is_cuda and weight.dtype == torch.float32):
+            raise RuntimeError("CorrBlock.lookup_convc1: weight must be a float32 CUDA tensor")
+        if weight.dim() == 4 and tuple(weight.shape[2:]) != (1, 1):
+            raise RuntimeError("CorrBlock.lookup_convc1: weight must be a 1x1 convolution kernel")
+        if weight.dim() not in (2, 4) or weight.shape[1] != cin:
+            raise RuntimeError(f"CorrBlock.lookup_convc1: weight must be [Cout, {cin}(, 1, 1)], got {tuple(weight.shape)}")
+        if torch.is_grad_enabled() and (weight.requires_grad or self._pyr.requires_grad or
+                                        (bias is not None and bias.requires_grad)):
+            raise RuntimeError("CorrBlock.lookup_convc1 is an inference kernel (no autograd): call it under "
+                               "torch.no_grad(), or use self(coords) followed by convc1 for training")
+        if self.num_levels > 4:
+            raise RaftCorrError("CorrBlock.lookup_convc1: at most 4 pyramid levels")
+        cout = int(weight.shape[0])
+        if bias is not None:
+            if not (bias.is_cuda and bias.dtype == torch.float32 and tuple(bias.shape) == (cout,)):
+                raise RuntimeError("CorrBlock.lookup_convc1: bias must be a float32 CUDA tensor of shape [Cout]")
+            bias = bias.detach().contiguous()
+        dev = self._device
+        L = _lib.lib()
+        # packed (TF32-rounded, k-blocked) copy of the weight, redone only when the parameter changes
+        key = (weight.data_ptr(), weight._version, cout)
+        if getattr(self, "_convw_key", None) != key:
+            nbytes = int(L.raftcorr_convc1_weight_bytes(self.num_levels, self.radius, cout))
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            w2 = weight.detach().reshape(cout, cin).contiguous()
+            check(L.raftcorr_convc1_pack_weight(_ptr(w2), self.num_levels, self.radius, cout, _ptr(packed), dev.index,
+                                                _stream(dev)), "raftcorr_convc1_pack_weight")
+            self._convw_key, self._convw = key, packed
+        coords = coords.detach().contiguous()
+        out = torch.empty((self._B, cout, self._H, self._W), dtype=torch.float32, device=dev)
+        pyr = self._pyr.detach()
+        check(L.raftcorr_lookup_convc1_fwd(self._ensure_plan(pyr), _ptr(coords), _ptr(self._convw), _ptr(bias), cout,
+                                           1 if relu else 0, _ptr(out), dev.index, _stream(dev)),
+              "raftcorr_lookup_convc1_fwd")
+        return out
 
     @property
     def corr_pyramid(self):

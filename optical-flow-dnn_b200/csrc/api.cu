@@ -170,6 +170,34 @@ int raftcorr_lookup_fwd_planned(const raftcorr_lookup_plan* plan, const float* c
     return lookup_plan_run(plan->opaque, coords, out, (cudaStream_t)stream);
 }
 
+size_t raftcorr_convc1_weight_bytes(int levels, int radius, int cout) {
+    if (levels < 1 || levels > 4 || radius < 1 || radius > 4 || cout < 1) return 0;
+    return conv_weight_bytes(levels, radius, cout);
+}
+
+int raftcorr_convc1_pack_weight(const float* weight, int levels, int radius, int cout, void* packed, int device,
+                                raftcorr_stream_t stream) {
+    RC_REQUIRE(weight && packed, "convc1_pack_weight: NULL tensor");
+    RC_REQUIRE(levels >= 1 && levels <= 4 && radius >= 1 && radius <= 4 && cout >= 1, "convc1_pack_weight: bad sizes");
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "convc1_pack_weight: cannot select device %d", device);
+    return launch_pack_conv_weight(weight, levels, radius, cout, (float*)packed, (cudaStream_t)stream);
+}
+
+int raftcorr_lookup_convc1_fwd(const raftcorr_lookup_plan* plan, const float* coords, const void* packed_weight,
+                               const float* bias, int cout, int relu, float* out, int device,
+                               raftcorr_stream_t stream) {
+    RC_REQUIRE(plan != nullptr, "lookup_convc1_fwd: plan is NULL");
+    bool empty = true;
+    for (int i = 0; i < 16 && empty; ++i) empty = plan->opaque[i] == 0;
+    if (empty) return 0;  // plan of an empty batch
+    RC_REQUIRE(coords && packed_weight && out, "lookup_convc1_fwd: NULL tensor");
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "lookup_convc1_fwd: cannot select device %d", device);
+    return launch_lookup_conv(plan->opaque, coords, (const float*)packed_weight, bias, cout, relu, out, device,
+                              (cudaStream_t)stream);
+}
+
 int raftcorr_lookup_bwd(const float* grad_out, const float* coords, const float* pyramid, float* dpyramid,
                         const raftcorr_pyramid_layout* lay, int radius, float* dcoords, int device,
                         raftcorr_stream_t stream) {

@@ -104,6 +104,12 @@ int launch_lookup_fwd(const PyramidView& pv, const float* coords, int radius, fl
 int launch_lookup_bwd(const float* grad_out, const float* coords, const PyramidView* pv_fwd,
                       const PyramidView& dpv, int radius, float* dcoords, cudaStream_t s);
 
+// lookup fused with the motion encoder's first 1x1 convolution (lookup_conv.cu)
+size_t conv_weight_bytes(int levels, int radius, int cout);
+int launch_pack_conv_weight(const float* weight, int levels, int radius, int cout, float* packed, cudaStream_t s);
+int launch_lookup_conv(const void* plan_blob, const float* coords, const float* packed_w, const float* bias, int cout,
+                       int relu, float* out, int device, cudaStream_t s);
+
 struct AltLevels {
     const float* f2[RAFTCORR_MAX_LEVELS];  // NHWC [B][h][w][C]
     float* df2[RAFTCORR_MAX_LEVELS];       // gradients (bwd only)

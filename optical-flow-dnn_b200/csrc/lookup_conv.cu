@@ -1,0 +1,486 @@
+// Correlation lookup fused with the motion encoder's first 1x1 convolution (+ bias, ReLU)  -- SURVEY.md 8(f) rank 1.
+//
+//   out[b, co, p] = relu( bias[co] + sum_ch W[co, ch] * lookup(coords)[b, ch, p] )
+//   (raft/core/corr.py:45-91 followed by raft/core/update.py:116,135 (small) / :158,170 (basic): the lookup result has
+//   no other reader, so its [B, L*K^2, H, W] tensor never has to exist in HBM.)
+//
+// One persistent CTA per SM, tile = 128 source pixels, pipelined by pyramid LEVEL (the level's K^2 channels are one
+// K-slice of the product):
+//   warps 0-15  gather : the TMA lookup of lookup_tma.cu (one box per (pixel, level), zero padding by the TMA unit,
+//                        lane = (x offset, group of vertically adjacent outputs)); a warp owns 8 pixels of the tile and
+//                        a 6-deep ring of patch boxes that runs across levels AND tiles.  The K^2 bilinear samples of a
+//                        pixel are rounded to TF32 and written as row `pixel` of the level's A operand tile
+//                        ([128 px][<= 96 ch], K-major, 128B swizzle) instead of an output tensor; two such tiles, so the
+//                        gather of level l+1 overlaps the MMAs of level l.
+//   warp 16     MMA    : tcgen05.mma kind::tf32, M = 128 pixels, N = Cout (two halves of <= 128 when Cout > 128), K = 8;
+//                        fp32 accumulators in TMEM, two accumulator stages (epilogue of tile i overlaps tile i+1).
+//   warp 17     weights: TMA loads of the packed weight k-blocks ([<= 128 co][32 ch], 16 KB stages, 4-deep ring; every
+//                        CTA streams the whole matrix once per tile, all L2 hits).
+//   warps 18-21 epilogue: TMEM lane = pixel: + bias, ReLU, 128-byte coalesced stores per output channel.
+#include <cstdlib>
+#include <cstring>
+
+#include "lookup_tma_common.cuh"
+#include "tc_util.cuh"
+
+namespace raftcorr {
+
+namespace {
+
+constexpr int kGatherWarps = 16;
+constexpr int kConvTileM = 128;                          // source pixels per tile = TMEM lanes
+constexpr int kPixPerWarp = kConvTileM / kGatherWarps;   // 8
+constexpr int kSlots = 6;                                // patch boxes in flight per gather warp (96 per SM)
+constexpr int kWStages = 4;
+constexpr int kWStageBytes = 128 * 128;                  // [<= 128 co][32 ch] tf32
+constexpr int kKBlockBytes = kConvTileM * 128;           // one 32-channel k-block of the A tile: 16 KB
+constexpr int kConvThreads = (kGatherWarps + 2 + 4) * 32;  // 704
+constexpr int kMmaWarp = kGatherWarps, kWeightWarp = kGatherWarps + 1, kEpiWarp0 = kGatherWarps + 2;
+constexpr uint32_t kConvTmemCols = 512;
+
+template <int R>
+struct ConvGeo {
+    static constexpr int K = 2 * R + 1, KK = K * K;
+    static constexpr int KB = (KK + 31) / 32;      // 128-byte k-blocks per level
+    static constexpr int KSTEPS = (KK + 7) / 8;    // K = 8 MMA steps per level (channels beyond K^2 are zero on both sides)
+    static constexpr int A_BYTES = KB * kKBlockBytes;
+};
+
+struct ConvParams {
+    const float* coords;
+    const float* bias;  // may be null
+    float* out;
+    int B, N, tiles_per_img, total_tiles;
+    int cout, nh, halves;  // N of one MMA = nh = cout / halves
+    int relu;
+    float inv_scale[4];
+};
+
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+template <int R, int LG, bool IL>
+__global__ void __launch_bounds__(kConvThreads, 1)
+lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constant__ CUtensorMap map_w, const ConvParams P) {
+    using G = TmaGeo<R, IL>;
+    using C = ConvGeo<R>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    // [2 A tiles] [kWStages weight stages] [gather warps x kSlots patch boxes] [barriers]
+    const uint32_t a_base = base;
+    const uint32_t w_base = a_base + 2 * C::A_BYTES;
+    const uint32_t patch_base = w_base + kWStages * kWStageBytes;
+    const uint32_t bar_base = patch_base + kGatherWarps * kSlots * G::SLOT;
+    const uint32_t patch_bar = bar_base;                                  // [kGatherWarps][kSlots]
+    const uint32_t a_full = patch_bar + 8 * kGatherWarps * kSlots;        // [2]
+    const uint32_t a_empty = a_full + 16;                                 // [2]
+    const uint32_t w_full = a_empty + 16;                                 // [kWStages]
+    const uint32_t w_empty = w_full + 8 * kWStages;                       // [kWStages]
+    const uint32_t tfull = w_empty + 8 * kWStages;                        // [2]
+    const uint32_t tempty = tfull + 16;                                   // [2]
+    const uint32_t tmem_slot = tempty + 16;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int my_tiles = first < P.total_tiles ? (P.total_tiles - first + stride - 1) / stride : 0;
+
+    if (warp < kGatherWarps) {
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) mbar_init(patch_bar + 8 * (warp * kSlots + i), 1);
+        }
+    } else if (warp == kMmaWarp) {
+        if (lane == 0) {
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(a_full + 8 * i, kGatherWarps);
+                mbar_init(a_empty + 8 * i, 1);
+                mbar_init(tfull + 8 * i, 1);
+                mbar_init(tempty + 8 * i, 128);
+            }
+            for (int i = 0; i < kWStages; ++i) {
+                mbar_init(w_full + 8 * i, 1);
+                mbar_init(w_empty + 8 * i, 1);
+            }
+        }
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kConvTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else if (warp == kWeightWarp && lane == 0) {
+        prefetch_tensormap(&map_w);
+#pragma unroll
+        for (int l = 0; l < LG; ++l) {
+            prefetch_tensormap(&maps.m[l]);
+            if (IL) prefetch_tensormap(&maps.ms[l]);
+        }
+    }
+    // the channels a level does not have (K^2 .. 32 * KB) must read as zero, not as stale shared memory
+    {
+        float4* a4 = reinterpret_cast<float4*>(gen);
+        for (int i = threadIdx.x; i < 2 * C::A_BYTES / 16; i += kConvThreads) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_mbar_init();
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+    if (warp < kGatherWarps) {
+        // ===================== gather: patches -> bilinear samples -> A tile rows =====================
+        const uint32_t my_patch = patch_base + warp * (kSlots * G::SLOT);
+        const float* my_patch_gen = reinterpret_cast<const float*>(gen + (my_patch - base));
+        const uint32_t my_bar = patch_bar + 8 * warp * kSlots;
+        const int jg = lane / G::K, li = lane - jg * G::K;
+        const int j0 = jg * G::RPL;
+        const bool lane_on = jg < G::GROUPS;
+        const int lane_off = j0 * G::BC + li;
+        const int lane_ch = li * G::K + j0;  // channel inside the level: x offset major (corr.py:66-78)
+        int il_row[2][G::RPL + 1];
+        if (IL) {
+#pragma unroll
+            for (int sy = 0; sy < 2; ++sy)
+#pragma unroll
+                for (int rr = 0; rr <= G::RPL; ++rr) {
+                    const int Y = sy + j0 + rr;
+                    il_row[sy][rr] = (Y >> 1) * G::BC + (Y & 1);
+                }
+        }
+        // channel part of the A tile address: k-block, 16-byte chunk inside the 128-byte row, word inside the chunk
+        uint32_t ch_off[G::RPL], ch_chunk[G::RPL];
+#pragma unroll
+        for (int k = 0; k < G::RPL; ++k) {
+            const int ch = lane_ch + k;
+            ch_off[k] = (uint32_t)(ch >> 5) * kKBlockBytes + (uint32_t)(ch & 3) * 4;
+            ch_chunk[k] = (uint32_t)(ch & 31) >> 2;
+        }
+
+        // coordinates: lanes 0..7 hold the warp's pixels of the tile being consumed, lanes 16..23 those of the next tile
+        auto load_coords = [&](int tile_iter, float& cx, float& cy) {
+            cx = cy = 0.f;
+            if (tile_iter < my_tiles && (lane & 15) < kPixPerWarp) {
+                const int t = first + tile_iter * stride;
+                const int b = t / P.tiles_per_img;
+                const int p = (t - b * P.tiles_per_img) * kConvTileM + warp * kPixPerWarp + (lane & 15);
+                if (p < P.N) {
+                    cx = clamp_coord(__ldg(P.coords + ((int64_t)b * 2 + 0) * P.N + p));
+                    cy = clamp_coord(__ldg(P.coords + ((int64_t)b * 2 + 1) * P.N + p));
+                }
+            }
+        };
+        float cx, cy;
+        load_coords(lane < 16 ? 0 : 1, cx, cy);
+
+        // lane 0 issues the box of (tile_iter, level, pixel j); x/y are that pixel's coordinates (warp-uniform)
+        auto issue = [&](int tile_iter, int l, int j, float x, float y, int slot) {
+            const int t = first + tile_iter * stride;
+            const int b = t / P.tiles_per_img;
+            const int p = (t - b * P.tiles_per_img) * kConvTileM + warp * kPixPerWarp + j;
+            if (p >= P.N) return;
+            const int img = b * P.N + p;
+            const int x0 = __float2int_rd(x * P.inv_scale[l]) - R;
+            const int y0 = __float2int_rd(y * P.inv_scale[l]) - R;
+            const uint32_t bar = my_bar + 8 * slot;
+            const uint32_t dst = my_patch + slot * G::SLOT;
+            if (IL) {
+                const bool tall = y0 & 1;  // a window starting on an odd row spans one more pair row
+                mbar_expect_tx(bar, tall ? G::BOX_BYTES : G::BOX_BYTES - G::BC * 4);
+                tma_load_3d(dst, tall ? &maps.m[l] : &maps.ms[l], bar, 2 * (x0 & ~1), y0 >> 1, img);
+            } else {
+                mbar_expect_tx(bar, G::BOX_BYTES);
+                tma_load_3d(dst, &maps.m[l], bar, x0 & ~3, y0, img);
+            }
+        };
+
+        const int total_items = my_tiles * LG * kPixPerWarp;
+        // issue cursor (runs kSlots - 1 items ahead of the consume cursor)
+        int i_ti = 0, i_l = 0, i_j = 0, i_q = 0, i_slot = 0;
+        auto issue_next = [&](int c_ti) {
+            if (i_q >= total_items) return;
+            const int src = i_j + (i_ti != c_ti ? 16 : 0);
+            const float x = __shfl_sync(0xffffffffu, cx, src), y = __shfl_sync(0xffffffffu, cy, src);
+            if (lane == 0) {
+                fence_proxy_async();  // the slot was read through the generic proxy kSlots items ago
+                issue(i_ti, i_l, i_j, x, y, i_slot);
+            }
+            ++i_q;
+            if (++i_slot == kSlots) i_slot = 0;
+            if (++i_j == kPixPerWarp) {
+                i_j = 0;
+                if (++i_l == LG) { i_l = 0; ++i_ti; }
+            }
+        };
+        for (int n = 0; n < kSlots - 1; ++n) issue_next(0);
+
+        int slot = 0;  // consume cursor's ring slot
+        uint32_t slot_phase = 0;  // one parity bit per ring slot (pixels past the end of an image skip their slot's turn)
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int t = first + ti * stride;
+            const int b = t / P.tiles_per_img;
+            const int p_base = (t - b * P.tiles_per_img) * kConvTileM + warp * kPixPerWarp;
+#pragma unroll 1
+            for (int l = 0; l < LG; ++l) {
+                const int g = ti * LG + l;
+                const uint32_t abuf = a_base + (uint32_t)(g & 1) * C::A_BYTES;
+                if (l == LG - 1) {  // the issue cursor is about to run into the next tile: fetch its coordinates
+                    float nx, ny;
+                    load_coords(ti + 1, nx, ny);
+                    if (lane >= 16) { cx = nx; cy = ny; }
+                }
+                mbar_wait(a_empty + 8 * (g & 1), ((g >> 1) & 1) ^ 1);  // the MMAs that read this A tile have retired
+#pragma unroll 1
+                for (int j = 0; j < kPixPerWarp; ++j) {
+                    issue_next(ti);
+                    const int p = p_base + j;
+                    if (p < P.N) {  // warp-uniform
+                        mbar_wait(my_bar + 8 * slot, (slot_phase >> slot) & 1u);
+                        slot_phase ^= 1u << slot;
+                        const float* pbuf = my_patch_gen + slot * (G::SLOT / 4);
+                        const float px = __shfl_sync(0xffffffffu, cx, j), py = __shfl_sync(0xffffffffu, cy, j);
+                        const float x = px * P.inv_scale[l], y = py * P.inv_scale[l];
+                        const float xf = floorf(x);
+                        const float ax = x - xf, ay = y - floorf(y);
+                        const float* Pp = IL ? pbuf + 2 * ((((int)xf - R) & 1) + li) : pbuf + (((int)xf - R) & 3) + lane_off;
+                        const int sy = IL ? (((int)floorf(y) - R) & 1) : 0;
+                        if (lane_on) {
+                            float h[G::RPL + 1];
+#pragma unroll
+                            for (int rr = 0; rr <= G::RPL; ++rr) {
+                                if (j0 + rr <= G::K) {
+                                    const int o = IL ? (sy ? il_row[1][rr] : il_row[0][rr]) : rr * G::BC;
+                                    const float a = Pp[o], c = Pp[o + (IL ? 2 : 1)];
+                                    h[rr] = a + ax * (c - a);
+                                } else {
+                                    h[rr] = 0.f;
+                                }
+                            }
+                            const int m = warp * kPixPerWarp + j;  // A tile row
+                            const uint32_t row = abuf + (uint32_t)(m >> 3) * 1024 + (uint32_t)(m & 7) * 128;
+#pragma unroll
+                            for (int k = 0; k < G::RPL; ++k)
+                                if (j0 + k < G::K) {
+                                    const float v = to_tf32(h[k] + ay * (h[k + 1] - h[k]));
+                                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + ch_off[k] + ((ch_chunk[k] ^ (uint32_t)(m & 7)) << 4)),
+                                                 "f"(v)
+                                                 : "memory");
+                                }
+                        }
+                    }
+                    __syncwarp();  // all lanes are done with the slot before lane 0 refills it
+                    if (++slot == kSlots) slot = 0;
+                }
+                // this warp's 16 rows of the level are complete: publish them to the tensor core (async proxy)
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full + 8 * (g & 1));
+            }
+            // the next tile's coordinates move to the lower half-warp
+            cx = __shfl_sync(0xffffffffu, cx, (lane & 15) + 16);
+            cy = __shfl_sync(0xffffffffu, cy, (lane & 15) + 16);
+        }
+    } else if (warp == kMmaWarp) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(kConvTileM, P.nh, false, false);
+            int ws = 0;
+            uint32_t wph = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                const int acc = ti & 1;
+                mbar_wait(tempty + 8 * acc, ((ti >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int l = 0; l < LG; ++l) {
+                    const int g = ti * LG + l;
+                    mbar_wait(a_full + 8 * (g & 1), (g >> 1) & 1);
+                    tc_fence_after();
+                    const uint32_t abuf = a_base + (uint32_t)(g & 1) * C::A_BYTES;
+#pragma unroll 1
+                    for (int kb = 0; kb < C::KB; ++kb) {
+                        const int nk = C::KSTEPS - 4 * kb < 4 ? C::KSTEPS - 4 * kb : 4;
+                        const uint64_t adesc = make_smem_desc(abuf + kb * kKBlockBytes);
+                        for (int h = 0; h < P.halves; ++h) {
+                            mbar_wait(w_full + 8 * ws, wph);
+                            tc_fence_after();
+                            const uint64_t bdesc = make_smem_desc(w_base + ws * kWStageBytes);
+                            const uint32_t d_tmem = tmem_base + acc * 256 + h * P.nh;
+                            for (int k = 0; k < nk; ++k)
+                                tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                            (l | kb | k) != 0 ? 1u : 0u);
+                            tc_commit(w_empty + 8 * ws);
+                            if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                        }
+                    }
+                    tc_commit(a_empty + 8 * (g & 1));  // the gather may overwrite this A tile
+                }
+                tc_commit(tfull + 8 * acc);
+            }
+        }
+    } else if (warp == kWeightWarp) {
+        // ===================== weight loader =====================
+        if (lane == 0) {
+            int ws = 0;
+            uint32_t wph = 0;
+            for (int ti = 0; ti < my_tiles; ++ti)
+                for (int l = 0; l < LG; ++l)
+                    for (int kb = 0; kb < C::KB; ++kb)
+                        for (int h = 0; h < P.halves; ++h) {
+                            mbar_wait(w_empty + 8 * ws, wph ^ 1);
+                            mbar_expect_tx(w_full + 8 * ws, (uint32_t)P.nh * 128);
+                            tma_load_3d(w_base + ws * kWStageBytes, &map_w, w_full + 8 * ws, 0, h * P.nh, l * C::KB + kb);
+                            if (++ws == kWStages) { ws = 0; wph ^= 1; }
+                        }
+        }
+    } else {
+        // ===================== epilogue: + bias, ReLU, channel-major stores =====================
+        const int ew = warp & 3;  // TMEM lane quarter this warp may access
+        const int m = ew * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            const int t = first + ti * stride;
+            const int b = t / P.tiles_per_img;
+            const int p = (t - b * P.tiles_per_img) * kConvTileM + m;
+            const bool ok = p < P.N;
+            const int acc = ti & 1;
+            mbar_wait(tfull + 8 * acc, (ti >> 1) & 1);
+            tc_fence_after();
+            float* dst = P.out + (int64_t)b * P.cout * P.N + p;
+            for (int c0 = 0; c0 < P.cout; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + lane_addr + acc * 256 + c0, v);
+                tmem_ld_wait();
+                if (c0 + 16 >= P.cout) {  // the accumulator has been read completely
+                    tc_fence_before();
+                    mbar_arrive(tempty + 8 * acc);
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float o = v[i] + (P.bias ? __ldg(P.bias + c0 + i) : 0.f);
+                    if (P.relu) o = fmaxf(o, 0.f);
+                    if (ok) dst[(int64_t)(c0 + i) * P.N] = o;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kConvTmemCols) : "memory");
+    }
+}
+
+// weight [Cout][L * K^2] fp32 -> packed [L * KB][Cout][32] TF32 (round to nearest), channels beyond K^2 zero
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __restrict__ packed, int cout, int L, int KK, int KB) {
+    const int64_t total = (int64_t)L * KB * cout * 32;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i & 31);
+        const int co = (int)((i >> 5) % cout);
+        const int blk = (int)((i >> 5) / cout);
+        const int l = blk / KB, ch = (blk % KB) * 32 + c;
+        packed[i] = ch < KK ? to_tf32(w[(int64_t)co * L * KK + l * KK + ch]) : 0.f;
+    }
+}
+
+template <int R, int LG, bool IL>
+int run_lookup_conv(const LookupMaps& maps, const CUtensorMap& map_w, const ConvParams& P, int device, cudaStream_t s) {
+    using G = TmaGeo<R, IL>;
+    using C = ConvGeo<R>;
+    constexpr size_t smem = 1024 + 2 * (size_t)C::A_BYTES + kWStages * kWStageBytes + (size_t)kGatherWarps * kSlots * G::SLOT +
+                            8 * (kGatherWarps * kSlots + 2 * kWStages + 8) + 16;
+    static_assert(smem <= 232448, "lookup+conv pipeline does not fit shared memory");
+    auto kern = lookup_conv_kernel<R, LG, IL>;
+    static bool attr_done[64] = {};
+    if (device < 0 || device >= 64 || !attr_done[device]) {
+        RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (device >= 0 && device < 64) attr_done[device] = true;
+    }
+    int sms = 0;
+    RC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int grid = P.total_tiles < sms ? P.total_tiles : sms;
+    kern<<<grid, kConvThreads, smem, s>>>(maps, map_w, P);
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int R, bool IL>
+int dispatch_lookup_conv(int lg, const LookupMaps& maps, const CUtensorMap& map_w, const ConvParams& P, int device,
+                         cudaStream_t s) {
+    switch (lg) {
+        case 1: return run_lookup_conv<R, 1, IL>(maps, map_w, P, device, s);
+        case 2: return run_lookup_conv<R, 2, IL>(maps, map_w, P, device, s);
+        case 3: return run_lookup_conv<R, 3, IL>(maps, map_w, P, device, s);
+        default: return run_lookup_conv<R, 4, IL>(maps, map_w, P, device, s);
+    }
+}
+
+inline int conv_kblocks(int radius) { return ((2 * radius + 1) * (2 * radius + 1) + 31) / 32; }
+
+}  // namespace
+
+size_t conv_weight_bytes(int levels, int radius, int cout) {
+    return (size_t)levels * conv_kblocks(radius) * cout * 32 * sizeof(float);
+}
+
+int launch_pack_conv_weight(const float* weight, int levels, int radius, int cout, float* packed, cudaStream_t s) {
+    const int KK = (2 * radius + 1) * (2 * radius + 1);
+    const int64_t total = (int64_t)levels * conv_kblocks(radius) * cout * 32;
+    const int grid = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+    pack_conv_weight_kernel<<<grid, 256, 0, s>>>(weight, packed, cout, levels, KK, conv_kblocks(radius));
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_lookup_conv(const void* plan_blob, const float* coords, const float* packed_w, const float* bias, int cout,
+                       int relu, float* out, int device, cudaStream_t s) {
+    LookupPlanData plan;
+    std::memcpy(&plan, plan_blob, sizeof(plan));
+    RC_REQUIRE(plan.magic == kPlanMagic, "lookup_convc1: lookup plan is not initialised");
+    RC_REQUIRE(plan.groups == 1, "lookup_convc1: at most 4 pyramid levels");
+    RC_REQUIRE(cout >= 16 && cout <= 256 && cout % 16 == 0 && (cout <= 128 || cout % 32 == 0),
+               "lookup_convc1: Cout must be a multiple of 16 up to 128, or a multiple of 32 up to 256 (got %d)", cout);
+    const GroupView& g = plan.g[0];
+    const int lg = plan.lg[0];
+    EncodeTiledFn fn;
+    if (int rc = get_encode_fn(&fn)) return rc;
+    ConvParams P{};
+    P.coords = coords; P.bias = bias; P.out = out;
+    P.B = g.B; P.N = g.N;
+    P.tiles_per_img = ceil_div(g.N, kConvTileM);
+    const int64_t total = (int64_t)g.B * P.tiles_per_img;
+    RC_REQUIRE(total < (1LL << 31), "lookup_convc1: too many tiles");
+    P.total_tiles = (int)total;
+    P.cout = cout;
+    P.halves = cout > 128 ? 2 : 1;
+    P.nh = cout / P.halves;
+    P.relu = relu;
+    for (int l = 0; l < 4; ++l) P.inv_scale[l] = g.inv_scale[l];
+    CUtensorMap map_w;
+    {
+        const int KB = conv_kblocks(plan.radius);
+        cuuint64_t dims[3] = {32, (cuuint64_t)cout, (cuuint64_t)lg * KB};
+        cuuint64_t strides[2] = {128, (cuuint64_t)cout * 128};
+        cuuint32_t box[3] = {32, (cuuint32_t)P.nh, 1};
+        if (int rc = encode_f32_map(fn, &map_w, (void*)packed_w, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "packed convc1 weight"))
+            return rc;
+    }
+    const bool il = g.lvl[0].il != 0;
+    const LookupMaps& maps = plan.maps[0];
+#define RAFTCORR_LC_CASE(R_)                                                                    \
+    case R_:                                                                                    \
+        return il ? dispatch_lookup_conv<R_, true>(lg, maps, map_w, P, device, s)               \
+                  : dispatch_lookup_conv<R_, false>(lg, maps, map_w, P, device, s);
+    switch (plan.radius) {
+        RAFTCORR_LC_CASE(1)
+        RAFTCORR_LC_CASE(2)
+        RAFTCORR_LC_CASE(3)
+        RAFTCORR_LC_CASE(4)
+        default: return fail("lookup_convc1: radius %d not supported (1..4)", plan.radius);
+    }
+#undef RAFTCORR_LC_CASE
+}
+
+}  // namespace raftcorr

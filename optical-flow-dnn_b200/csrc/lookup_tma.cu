@@ -13,8 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 
-#include "lookup_common.cuh"
-#include "tma_util.cuh"
+#include "lookup_tma_common.cuh"
 
 namespace raftcorr {
 
@@ -22,29 +21,6 @@ namespace {
 
 constexpr int kDefaultRingDepth = 3;
 constexpr int kBarBytes = 32;  // per-warp mbarrier block: up to 3 barriers, padded
-
-// IL = row pairs interleaved (raftcorr_pyramid_layout::interleaved): the window is (K+1)/2 + 1 pair rows of
-// 2 * (K+1 + 1) floats -- half as many, longer DRAM runs (the box starts at an even column: 16-byte rule again).
-template <int R, bool IL>
-struct TmaGeo {
-    static constexpr int K = 2 * R + 1;
-    static constexpr int K1 = K + 1;
-    // row-major: box columns cover any 0..3 start shift, 16-byte multiple
-    static constexpr int BC = IL ? 2 * ((K1 + 1 + 1) / 2 * 2) : (K1 + 3 + 3) / 4 * 4;  // floats per box row
-    static constexpr int BR = IL ? K1 / 2 + 1 : K1;                                     // box rows
-    static constexpr int BOX_BYTES = BC * BR * 4;
-    static constexpr int SLOT = (BOX_BYTES + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
-    static constexpr int KK = K * K;
-    // evaluation: lane = (x offset i, row group jg); a lane produces RPL vertically adjacent outputs of column i
-    // from RPL+1 horizontal lerps, so every patch value is loaded once per two outputs instead of once per tap
-    static constexpr int GROUPS = (32 / K) < K ? (32 / K) : K;
-    static constexpr int RPL = (K + GROUPS - 1) / GROUPS;
-};
-
-struct LookupMaps {
-    CUtensorMap m[4];
-    CUtensorMap ms[4];  // interleaved layout: one pair row shorter, for windows that start on an even row
-};
 
 // kBufs = patch ring depth per warp.  3 (two pixels in flight while one is evaluated) fits two CTAs per SM
 // at r=4; 2 fits three CTAs (24 warps) with the same number of patches in flight per SM.
@@ -267,15 +243,7 @@ int dispatch_fwd_tma(int lg, const LookupMaps& maps, const GroupView& g, const f
 }  // namespace
 
 // ---- plans: tensor maps + launch geometry encoded once per pyramid, reused by every refinement iteration
-struct LookupPlanData {
-    uint32_t magic;
-    int radius, groups, lg[2];
-    GroupView g[2];
-    LookupMaps maps[2];
-};
-static_assert(sizeof(LookupPlanData) <= RAFTCORR_LOOKUP_PLAN_BYTES, "plan blob too small");
-constexpr uint32_t kPlanMagic = 0x52434c50u;  // "RCLP"
-
+// (LookupPlanData: lookup_tma_common.cuh)
 int lookup_plan_init(void* plan_blob, const PyramidView& pv, int radius) {
     RC_REQUIRE(radius >= 1 && radius <= 4, "lookup: radius %d not supported (1..4)", radius);
     EncodeTiledFn fn;

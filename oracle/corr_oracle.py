@@ -140,6 +140,22 @@ def lookup(pyramid, coords, radius=4):
     return np.ascontiguousarray(out.transpose(0, 2, 1)).reshape(B, len(pyramid) * K * K, H, W)
 
 
+def lookup_convc1(pyramid, coords, weight, bias=None, radius=4, relu=True):
+    """the lookup followed by its only consumer, the motion encoder's first 1x1
+    convolution and ReLU -- ``cor = F.relu(self.convc1(corr))`` (raft/core/update.py:135 SmallMotionEncoder,
+    :170 BasicMotionEncoder; ``convc1 = nn.Conv2d(cor_planes, 96 | 256, 1)``, :116 / :158).
+
+    weight ``[Cout, L*K*K(, 1, 1)]``, bias ``[Cout]`` or None.  Returns ``[B, Cout, H, W]``.
+    """
+    feat = lookup(pyramid, coords, radius)  # [B, Cin, H, W]
+    dt = feat.dtype
+    w = np.asarray(weight).reshape(weight.shape[0], -1).astype(dt)
+    out = np.einsum("oc,bchw->bohw", w, feat)
+    if bias is not None:
+        out = out + np.asarray(bias).astype(dt)[None, :, None, None]
+    return np.maximum(out, dt.type(0)) if relu else out
+
+
 def lookup_grad(pyramid, coords, grad_out, radius=4, want_coords=False):
     """Adjoint of :func:`lookup` w.r.t. the pyramid (and optionally the coordinates).
 

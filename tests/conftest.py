@@ -22,3 +22,12 @@ def golden(request):
 
     g = np.load(os.path.join(ROOT, "tests", "golden", f"corr_{request.param}.npz"))
     return {k: g[k] for k in g.files}
+
+
+@pytest.fixture(params=["small", "basic"])
+def golden_convc1(request):
+    """Reference CorrBlock + the reference motion encoder's convc1 + ReLU (tests/golden/make_golden_convc1.py)."""
+    import numpy as np
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"convc1_{request.param}.npz"))
+    return {k: g[k] for k in g.files}

@@ -105,3 +105,18 @@ def test_pool_adjoint_is_adjoint():
     x = rng.normal(size=(3, 7, 9))
     y = rng.normal(size=(3, 3, 4))
     assert abs((O.avg_pool2(x) * y).sum() - (x * O.avg_pool2_adjoint(y, 7, 9)).sum()) < 1e-12
+
+
+def test_numpy_lookup_convc1_matches_reference(golden_convc1):
+    """SURVEY 8(f) rank 1 oracle: lookup -> convc1 -> ReLU against the reference CorrBlock + the reference motion
+    encoder's own convc1 (raft/core/update.py:135,170), fp64 and fp32."""
+    g = golden_convc1
+    B, D, H, W, L, r, cout = [int(v) for v in g["meta"]]
+    for dt, tol in ((np.float64, TOL_F64), (np.float32, 1e-5)):
+        pyr = O.corr_pyramid(g["fmap1"], g["fmap2"], L, dt)
+        for k in range(3):
+            out = O.lookup_convc1(pyr, g[f"coords{k}"], g["weight"], g["bias"], r)
+            assert out.shape == (B, cout, H, W)
+            ref = g[f"cor64_{k}"].astype(np.float64)
+            assert np.abs(out - ref).max() <= tol * np.abs(ref).max(), (dt, k)
+            assert float(g[f"fp32_err{k}"]) <= 1e-5  # the reference's own fp32 run agrees with its fp64 run
