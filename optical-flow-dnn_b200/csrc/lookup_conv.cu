@@ -62,6 +62,22 @@ __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float(u);
 }
 
+// Waits of the hot loops: no clock reads inside the loop (the shared mbar_wait spends six instructions per poll on
+// its time-out), a poll counter instead; the suspend-time hint lets one poll sleep in hardware for up to that long.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    uint32_t ok, polls = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(2000u)
+            : "memory");
+        if (!ok && ++polls > (1u << 26)) __trap();  // protocol bug -> trapped launch instead of a hang
+    } while (!ok);
+}
+
 template <int R, int LG, bool IL>
 __global__ void __launch_bounds__(kConvThreads, 1)
 lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constant__ CUtensorMap map_w, const ConvParams P) {
@@ -159,92 +175,95 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
         }
 
         // coordinates: lanes 0..7 hold the warp's pixels of the tile being consumed, lanes 16..23 those of the next tile
-        auto load_coords = [&](int tile_iter, float& cx, float& cy) {
-            cx = cy = 0.f;
+        auto tile_origin = [&](int tile_iter, int& b, int& p_base) {  // batch item and first pixel of this warp's rows
+            const int t = first + tile_iter * stride;
+            b = t / P.tiles_per_img;
+            p_base = (t - b * P.tiles_per_img) * kConvTileM + warp * kPixPerWarp;
+        };
+        auto load_coords = [&](int tile_iter, float& x, float& y) {
+            x = y = 0.f;
             if (tile_iter < my_tiles && (lane & 15) < kPixPerWarp) {
-                const int t = first + tile_iter * stride;
-                const int b = t / P.tiles_per_img;
-                const int p = (t - b * P.tiles_per_img) * kConvTileM + warp * kPixPerWarp + (lane & 15);
+                int b, p_base;
+                tile_origin(tile_iter, b, p_base);
+                const int p = p_base + (lane & 15);
                 if (p < P.N) {
-                    cx = clamp_coord(__ldg(P.coords + ((int64_t)b * 2 + 0) * P.N + p));
-                    cy = clamp_coord(__ldg(P.coords + ((int64_t)b * 2 + 1) * P.N + p));
+                    x = clamp_coord(__ldg(P.coords + ((int64_t)b * 2 + 0) * P.N + p));
+                    y = clamp_coord(__ldg(P.coords + ((int64_t)b * 2 + 1) * P.N + p));
                 }
             }
         };
         float cx, cy;
         load_coords(lane < 16 ? 0 : 1, cx, cy);
 
-        // lane 0 issues the box of (tile_iter, level, pixel j); x/y are that pixel's coordinates (warp-uniform)
-        auto issue = [&](int tile_iter, int l, int j, float x, float y, int slot) {
-            const int t = first + tile_iter * stride;
-            const int b = t / P.tiles_per_img;
-            const int p = (t - b * P.tiles_per_img) * kConvTileM + warp * kPixPerWarp + j;
-            if (p >= P.N) return;
-            const int img = b * P.N + p;
-            const int x0 = __float2int_rd(x * P.inv_scale[l]) - R;
-            const int y0 = __float2int_rd(y * P.inv_scale[l]) - R;
-            const uint32_t bar = my_bar + 8 * slot;
-            const uint32_t dst = my_patch + slot * G::SLOT;
-            if (IL) {
-                const bool tall = y0 & 1;  // a window starting on an odd row spans one more pair row
-                mbar_expect_tx(bar, tall ? G::BOX_BYTES : G::BOX_BYTES - G::BC * 4);
-                tma_load_3d(dst, tall ? &maps.m[l] : &maps.ms[l], bar, 2 * (x0 & ~1), y0 >> 1, img);
-            } else {
-                mbar_expect_tx(bar, G::BOX_BYTES);
-                tma_load_3d(dst, &maps.m[l], bar, x0 & ~3, y0, img);
-            }
-        };
-
+        // issue cursor: runs kSlots - 1 (pixel, level) items ahead of the consume cursor, across levels and tiles
+        const char* map_base = reinterpret_cast<const char*>(&maps);  // m[l] at 128 * l, ms[l] at 512 + 128 * l
         const int total_items = my_tiles * LG * kPixPerWarp;
-        // issue cursor (runs kSlots - 1 items ahead of the consume cursor)
-        int i_ti = 0, i_l = 0, i_j = 0, i_q = 0, i_slot = 0;
+        int i_ti = 0, i_l = 0, i_j = 0, i_q = 0, i_slot = 0, i_b = 0, i_pbase = 0;
+        if (my_tiles > 0) tile_origin(0, i_b, i_pbase);
         auto issue_next = [&](int c_ti) {
             if (i_q >= total_items) return;
             const int src = i_j + (i_ti != c_ti ? 16 : 0);
             const float x = __shfl_sync(0xffffffffu, cx, src), y = __shfl_sync(0xffffffffu, cy, src);
-            if (lane == 0) {
+            const int p = i_pbase + i_j;
+            if (lane == 0 && p < P.N) {
+                const float inv = __int_as_float((127 - i_l) << 23);  // 2^-level, exact (the plan has one level group)
+                const int x0 = __float2int_rd(x * inv) - R;
+                const int y0 = __float2int_rd(y * inv) - R;
+                const uint32_t bar = my_bar + 8 * i_slot;
+                const uint32_t dst = my_patch + i_slot * G::SLOT;
                 fence_proxy_async();  // the slot was read through the generic proxy kSlots items ago
-                issue(i_ti, i_l, i_j, x, y, i_slot);
+                if (IL) {
+                    const bool tall = y0 & 1;  // a window starting on an odd row spans one more pair row
+                    mbar_expect_tx(bar, tall ? G::BOX_BYTES : G::BOX_BYTES - G::BC * 4);
+                    tma_load_3d(dst, reinterpret_cast<const CUtensorMap*>(map_base + (tall ? 0 : 512) + 128 * i_l), bar,
+                                2 * (x0 & ~1), y0 >> 1, i_b * P.N + p);
+                } else {
+                    mbar_expect_tx(bar, G::BOX_BYTES);
+                    tma_load_3d(dst, reinterpret_cast<const CUtensorMap*>(map_base + 128 * i_l), bar, x0 & ~3, y0,
+                                i_b * P.N + p);
+                }
             }
             ++i_q;
             if (++i_slot == kSlots) i_slot = 0;
             if (++i_j == kPixPerWarp) {
                 i_j = 0;
-                if (++i_l == LG) { i_l = 0; ++i_ti; }
+                if (++i_l == LG) {
+                    i_l = 0;
+                    if (++i_ti < my_tiles) tile_origin(i_ti, i_b, i_pbase);
+                }
             }
         };
         for (int n = 0; n < kSlots - 1; ++n) issue_next(0);
 
         int slot = 0;  // consume cursor's ring slot
         uint32_t slot_phase = 0;  // one parity bit per ring slot (pixels past the end of an image skip their slot's turn)
+        const uint32_t a_row0 = (uint32_t)warp * 1024;  // rows warp * 8 + j of an A tile: one 8-row swizzle group per warp
         for (int ti = 0; ti < my_tiles; ++ti) {
-            const int t = first + ti * stride;
-            const int b = t / P.tiles_per_img;
-            const int p_base = (t - b * P.tiles_per_img) * kConvTileM + warp * kPixPerWarp;
-#pragma unroll 1
+            int b, p_base;
+            tile_origin(ti, b, p_base);
+#pragma unroll
             for (int l = 0; l < LG; ++l) {
                 const int g = ti * LG + l;
-                const uint32_t abuf = a_base + (uint32_t)(g & 1) * C::A_BYTES;
+                const uint32_t abuf = a_base + (uint32_t)(g & 1) * C::A_BYTES + a_row0;
+                const float inv = 1.0f / (float)(1 << l);
                 if (l == LG - 1) {  // the issue cursor is about to run into the next tile: fetch its coordinates
                     float nx, ny;
                     load_coords(ti + 1, nx, ny);
                     if (lane >= 16) { cx = nx; cy = ny; }
                 }
-                mbar_wait(a_empty + 8 * (g & 1), ((g >> 1) & 1) ^ 1);  // the MMAs that read this A tile have retired
+                mbar_wait_spin(a_empty + 8 * (g & 1), ((g >> 1) & 1) ^ 1);  // the MMAs that read this A tile have retired
 #pragma unroll 1
                 for (int j = 0; j < kPixPerWarp; ++j) {
                     issue_next(ti);
-                    const int p = p_base + j;
-                    if (p < P.N) {  // warp-uniform
-                        mbar_wait(my_bar + 8 * slot, (slot_phase >> slot) & 1u);
+                    if (p_base + j < P.N) {  // warp-uniform
+                        mbar_wait_spin(my_bar + 8 * slot, (slot_phase >> slot) & 1u);
                         slot_phase ^= 1u << slot;
                         const float* pbuf = my_patch_gen + slot * (G::SLOT / 4);
-                        const float px = __shfl_sync(0xffffffffu, cx, j), py = __shfl_sync(0xffffffffu, cy, j);
-                        const float x = px * P.inv_scale[l], y = py * P.inv_scale[l];
-                        const float xf = floorf(x);
-                        const float ax = x - xf, ay = y - floorf(y);
+                        const float x = __shfl_sync(0xffffffffu, cx, j) * inv, y = __shfl_sync(0xffffffffu, cy, j) * inv;
+                        const float xf = floorf(x), yf = floorf(y);
+                        const float ax = x - xf, ay = y - yf;
                         const float* Pp = IL ? pbuf + 2 * ((((int)xf - R) & 1) + li) : pbuf + (((int)xf - R) & 3) + lane_off;
-                        const int sy = IL ? (((int)floorf(y) - R) & 1) : 0;
+                        const int sy = IL ? (((int)yf - R) & 1) : 0;
                         if (lane_on) {
                             float h[G::RPL + 1];
 #pragma unroll
@@ -257,13 +276,12 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                                     h[rr] = 0.f;
                                 }
                             }
-                            const int m = warp * kPixPerWarp + j;  // A tile row
-                            const uint32_t row = abuf + (uint32_t)(m >> 3) * 1024 + (uint32_t)(m & 7) * 128;
+                            const uint32_t row = abuf + (uint32_t)j * 128;  // A tile row warp * 8 + j, swizzled by j
 #pragma unroll
                             for (int k = 0; k < G::RPL; ++k)
                                 if (j0 + k < G::K) {
                                     const float v = to_tf32(h[k] + ay * (h[k + 1] - h[k]));
-                                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + ch_off[k] + ((ch_chunk[k] ^ (uint32_t)(m & 7)) << 4)),
+                                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + ch_off[k] + ((ch_chunk[k] ^ (uint32_t)j) << 4)),
                                                  "f"(v)
                                                  : "memory");
                                 }
@@ -272,7 +290,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                     __syncwarp();  // all lanes are done with the slot before lane 0 refills it
                     if (++slot == kSlots) slot = 0;
                 }
-                // this warp's 16 rows of the level are complete: publish them to the tensor core (async proxy)
+                // this warp's 8 rows of the level are complete: publish them to the tensor core (async proxy)
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_full + 8 * (g & 1));
@@ -289,11 +307,11 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
             uint32_t wph = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int acc = ti & 1;
-                mbar_wait(tempty + 8 * acc, ((ti >> 1) & 1) ^ 1);
+                mbar_wait_spin(tempty + 8 * acc, ((ti >> 1) & 1) ^ 1);
                 tc_fence_after();
                 for (int l = 0; l < LG; ++l) {
                     const int g = ti * LG + l;
-                    mbar_wait(a_full + 8 * (g & 1), (g >> 1) & 1);
+                    mbar_wait_spin(a_full + 8 * (g & 1), (g >> 1) & 1);
                     tc_fence_after();
                     const uint32_t abuf = a_base + (uint32_t)(g & 1) * C::A_BYTES;
 #pragma unroll 1
@@ -301,7 +319,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                         const int nk = C::KSTEPS - 4 * kb < 4 ? C::KSTEPS - 4 * kb : 4;
                         const uint64_t adesc = make_smem_desc(abuf + kb * kKBlockBytes);
                         for (int h = 0; h < P.halves; ++h) {
-                            mbar_wait(w_full + 8 * ws, wph);
+                            mbar_wait_spin(w_full + 8 * ws, wph);
                             tc_fence_after();
                             const uint64_t bdesc = make_smem_desc(w_base + ws * kWStageBytes);
                             const uint32_t d_tmem = tmem_base + acc * 256 + h * P.nh;
@@ -326,7 +344,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                 for (int l = 0; l < LG; ++l)
                     for (int kb = 0; kb < C::KB; ++kb)
                         for (int h = 0; h < P.halves; ++h) {
-                            mbar_wait(w_empty + 8 * ws, wph ^ 1);
+                            mbar_wait_spin(w_empty + 8 * ws, wph ^ 1);
                             mbar_expect_tx(w_full + 8 * ws, (uint32_t)P.nh * 128);
                             tma_load_3d(w_base + ws * kWStageBytes, &map_w, w_full + 8 * ws, 0, h * P.nh, l * C::KB + kb);
                             if (++ws == kWStages) { ws = 0; wph ^= 1; }
@@ -343,7 +361,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
             const int p = (t - b * P.tiles_per_img) * kConvTileM + m;
             const bool ok = p < P.N;
             const int acc = ti & 1;
-            mbar_wait(tfull + 8 * acc, (ti >> 1) & 1);
+            mbar_wait_spin(tfull + 8 * acc, (ti >> 1) & 1);
             tc_fence_after();
             float* dst = P.out + (int64_t)b * P.cout * P.N + p;
             for (int c0 = 0; c0 < P.cout; c0 += 16) {
