@@ -8,13 +8,13 @@
 // K-slice of the product):
 //   warps 0-15  gather : the TMA lookup of lookup_tma.cu (one box per (pixel, level), zero padding by the TMA unit,
 //                        lane = (x offset, group of vertically adjacent outputs)); a warp owns 8 pixels of the tile and
-//                        a 6-deep ring of patch boxes that runs across levels AND tiles.  The K^2 bilinear samples of a
+//                        a ring of two 4-box batches (issued by four lanes at once) that runs across levels AND tiles.  The K^2 bilinear samples of a
 //                        pixel are rounded to TF32 and written as row `pixel` of the level's A operand tile
 //                        ([128 px][<= 96 ch], K-major, 128B swizzle) instead of an output tensor; two such tiles, so the
 //                        gather of level l+1 overlaps the MMAs of level l.
 //   warp 16     MMA    : tcgen05.mma kind::tf32, M = 128 pixels, N = Cout (two halves of <= 128 when Cout > 128), K = 8;
 //                        fp32 accumulators in TMEM, two accumulator stages (epilogue of tile i overlaps tile i+1).
-//   warp 17     weights: TMA loads of the packed weight k-blocks ([<= 128 co][32 ch], 16 KB stages, 4-deep ring; every
+//   warp 17     weights: TMA loads of the packed weight k-blocks ([<= 128 co][32 ch], 16 KB stages, 3-deep ring; every
 //                        CTA streams the whole matrix once per tile, all L2 hits).
 //   warps 18-21 epilogue: TMEM lane = pixel: + bias, ReLU, 128-byte coalesced stores per output channel.
 #include <cstdlib>
@@ -30,8 +30,9 @@ namespace {
 constexpr int kGatherWarps = 16;
 constexpr int kConvTileM = 128;                          // source pixels per tile = TMEM lanes
 constexpr int kPixPerWarp = kConvTileM / kGatherWarps;   // 8
-constexpr int kSlots = 6;                                // patch boxes in flight per gather warp (96 per SM)
-constexpr int kWStages = 4;
+constexpr int kBatch = 4;                                // patch boxes issued together (by kBatch lanes)
+constexpr int kSlots = 2 * kBatch;                       // ring: the batch being evaluated + the batch in flight
+constexpr int kWStages = 3;
 constexpr int kWStageBytes = 128 * 128;                  // [<= 128 co][32 ch] tf32
 constexpr int kKBlockBytes = kConvTileM * 128;           // one 32-channel k-block of the A tile: 16 KB
 constexpr int kConvThreads = (kGatherWarps + 2 + 4) * 32;  // 704
@@ -56,7 +57,10 @@ struct ConvParams {
     float inv_scale[4];
 };
 
-__device__ __forceinline__ float to_tf32(float x) {
+__device__ __forceinline__ float to_tf32(float x) {  // round to nearest (ties away), finite inputs: what cvt.rna does
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ float to_tf32_exact(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
@@ -76,6 +80,16 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
             : "memory");
         if (!ok && ++polls > (1u << 26)) __trap();  // protocol bug -> trapped launch instead of a hang
     } while (!ok);
+}
+
+// Long waits (accumulator / operand tile hand-overs): sleep between polls so that waiting warps do not take issue
+// slots from the gather warps.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t ns) {
+    uint32_t polls = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(ns);
+        if (++polls > (1u << 24)) __trap();
+    }
 }
 
 template <int R, int LG, bool IL>
@@ -195,23 +209,28 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
         float cx, cy;
         load_coords(lane < 16 ? 0 : 1, cx, cy);
 
-        // issue cursor: runs kSlots - 1 (pixel, level) items ahead of the consume cursor, across levels and tiles
+        // Patch boxes are issued in BATCHES of kBatch consecutive pixels of one level, by kBatch lanes at once (the
+        // address arithmetic runs once for the batch; only the TMA instruction itself is serialised per lane), one
+        // batch ahead of the batch being evaluated: the ring holds two batches.
         const char* map_base = reinterpret_cast<const char*>(&maps);  // m[l] at 128 * l, ms[l] at 512 + 128 * l
-        const int total_items = my_tiles * LG * kPixPerWarp;
-        int i_ti = 0, i_l = 0, i_j = 0, i_q = 0, i_slot = 0, i_b = 0, i_pbase = 0;
+        constexpr int kBatchesPerTile = LG * (kPixPerWarp / kBatch);
+        const int total_batches = my_tiles * kBatchesPerTile;
+        int i_n = 0, i_ti = 0, i_l = 0, i_jb = 0, i_b = 0, i_pbase = 0;  // issue cursor
         if (my_tiles > 0) tile_origin(0, i_b, i_pbase);
-        auto issue_next = [&](int c_ti) {
-            if (i_q >= total_items) return;
-            const int src = i_j + (i_ti != c_ti ? 16 : 0);
+        auto issue_batch = [&](int c_ti) {
+            if (i_n >= total_batches) return;
+            const int j = i_jb + (lane & (kBatch - 1));
+            const int src = j + (i_ti != c_ti ? 16 : 0);
             const float x = __shfl_sync(0xffffffffu, cx, src), y = __shfl_sync(0xffffffffu, cy, src);
-            const int p = i_pbase + i_j;
-            if (lane == 0 && p < P.N) {
+            const int p = i_pbase + j;
+            if (lane < kBatch && p < P.N) {
                 const float inv = __int_as_float((127 - i_l) << 23);  // 2^-level, exact (the plan has one level group)
                 const int x0 = __float2int_rd(x * inv) - R;
                 const int y0 = __float2int_rd(y * inv) - R;
-                const uint32_t bar = my_bar + 8 * i_slot;
-                const uint32_t dst = my_patch + i_slot * G::SLOT;
-                fence_proxy_async();  // the slot was read through the generic proxy kSlots items ago
+                const int slot = (i_n & 1) * kBatch + lane;
+                const uint32_t bar = my_bar + 8 * slot;
+                const uint32_t dst = my_patch + slot * G::SLOT;
+                fence_proxy_async();  // the slot was read through the generic proxy two batches ago
                 if (IL) {
                     const bool tall = y0 & 1;  // a window starting on an odd row spans one more pair row
                     mbar_expect_tx(bar, tall ? G::BOX_BYTES : G::BOX_BYTES - G::BC * 4);
@@ -223,19 +242,19 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                                 i_b * P.N + p);
                 }
             }
-            ++i_q;
-            if (++i_slot == kSlots) i_slot = 0;
-            if (++i_j == kPixPerWarp) {
-                i_j = 0;
+            ++i_n;
+            i_jb += kBatch;
+            if (i_jb == kPixPerWarp) {
+                i_jb = 0;
                 if (++i_l == LG) {
                     i_l = 0;
                     if (++i_ti < my_tiles) tile_origin(i_ti, i_b, i_pbase);
                 }
             }
         };
-        for (int n = 0; n < kSlots - 1; ++n) issue_next(0);
+        issue_batch(0);
 
-        int slot = 0;  // consume cursor's ring slot
+        int c_n = 0;              // consume cursor (batch index)
         uint32_t slot_phase = 0;  // one parity bit per ring slot (pixels past the end of an image skip their slot's turn)
         const uint32_t a_row0 = (uint32_t)warp * 1024;  // rows warp * 8 + j of an A tile: one 8-row swizzle group per warp
         for (int ti = 0; ti < my_tiles; ++ti) {
@@ -251,44 +270,48 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                     load_coords(ti + 1, nx, ny);
                     if (lane >= 16) { cx = nx; cy = ny; }
                 }
-                mbar_wait_spin(a_empty + 8 * (g & 1), ((g >> 1) & 1) ^ 1);  // the MMAs that read this A tile have retired
+                mbar_wait_sleep(a_empty + 8 * (g & 1), ((g >> 1) & 1) ^ 1, 64);  // the MMAs that read this A tile have retired
 #pragma unroll 1
-                for (int j = 0; j < kPixPerWarp; ++j) {
-                    issue_next(ti);
-                    if (p_base + j < P.N) {  // warp-uniform
-                        mbar_wait_spin(my_bar + 8 * slot, (slot_phase >> slot) & 1u);
-                        slot_phase ^= 1u << slot;
-                        const float* pbuf = my_patch_gen + slot * (G::SLOT / 4);
-                        const float x = __shfl_sync(0xffffffffu, cx, j) * inv, y = __shfl_sync(0xffffffffu, cy, j) * inv;
-                        const float xf = floorf(x), yf = floorf(y);
-                        const float ax = x - xf, ay = y - yf;
-                        const float* Pp = IL ? pbuf + 2 * ((((int)xf - R) & 1) + li) : pbuf + (((int)xf - R) & 3) + lane_off;
-                        const int sy = IL ? (((int)yf - R) & 1) : 0;
-                        if (lane_on) {
-                            float h[G::RPL + 1];
+                for (int jb = 0; jb < kPixPerWarp; jb += kBatch, ++c_n) {
+                    issue_batch(ti);
+#pragma unroll 1
+                    for (int k = 0; k < kBatch; ++k) {
+                        const int j = jb + k;
+                        if (p_base + j < P.N) {  // warp-uniform
+                            const int slot = (c_n & 1) * kBatch + k;
+                            mbar_wait_spin(my_bar + 8 * slot, (slot_phase >> slot) & 1u);
+                            slot_phase ^= 1u << slot;
+                            const float* pbuf = my_patch_gen + slot * (G::SLOT / 4);
+                            const float x = __shfl_sync(0xffffffffu, cx, j) * inv, y = __shfl_sync(0xffffffffu, cy, j) * inv;
+                            const float xf = floorf(x), yf = floorf(y);
+                            const float ax = x - xf, ay = y - yf;
+                            const float* Pp = IL ? pbuf + 2 * ((((int)xf - R) & 1) + li) : pbuf + (((int)xf - R) & 3) + lane_off;
+                            const int sy = IL ? (((int)yf - R) & 1) : 0;
+                            if (lane_on) {
+                                float h[G::RPL + 1];
 #pragma unroll
-                            for (int rr = 0; rr <= G::RPL; ++rr) {
-                                if (j0 + rr <= G::K) {
-                                    const int o = IL ? (sy ? il_row[1][rr] : il_row[0][rr]) : rr * G::BC;
-                                    const float a = Pp[o], c = Pp[o + (IL ? 2 : 1)];
-                                    h[rr] = a + ax * (c - a);
-                                } else {
-                                    h[rr] = 0.f;
+                                for (int rr = 0; rr <= G::RPL; ++rr) {
+                                    if (j0 + rr <= G::K) {
+                                        const int o = IL ? (sy ? il_row[1][rr] : il_row[0][rr]) : rr * G::BC;
+                                        const float a = Pp[o], c = Pp[o + (IL ? 2 : 1)];
+                                        h[rr] = a + ax * (c - a);
+                                    } else {
+                                        h[rr] = 0.f;
+                                    }
                                 }
+                                const uint32_t row = abuf + (uint32_t)j * 128;  // A tile row warp * 8 + j, swizzled by j
+#pragma unroll
+                                for (int kk = 0; kk < G::RPL; ++kk)
+                                    if (j0 + kk < G::K) {
+                                        const float v = to_tf32(h[kk] + ay * (h[kk + 1] - h[kk]));
+                                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + ch_off[kk] + ((ch_chunk[kk] ^ (uint32_t)j) << 4)),
+                                                     "f"(v)
+                                                     : "memory");
+                                    }
                             }
-                            const uint32_t row = abuf + (uint32_t)j * 128;  // A tile row warp * 8 + j, swizzled by j
-#pragma unroll
-                            for (int k = 0; k < G::RPL; ++k)
-                                if (j0 + k < G::K) {
-                                    const float v = to_tf32(h[k] + ay * (h[k + 1] - h[k]));
-                                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + ch_off[k] + ((ch_chunk[k] ^ (uint32_t)j) << 4)),
-                                                 "f"(v)
-                                                 : "memory");
-                                }
                         }
                     }
-                    __syncwarp();  // all lanes are done with the slot before lane 0 refills it
-                    if (++slot == kSlots) slot = 0;
+                    __syncwarp();  // all lanes are done with this half of the ring before it is refilled
                 }
                 // this warp's 8 rows of the level are complete: publish them to the tensor core (async proxy)
                 fence_proxy_async();
@@ -307,11 +330,11 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
             uint32_t wph = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int acc = ti & 1;
-                mbar_wait_spin(tempty + 8 * acc, ((ti >> 1) & 1) ^ 1);
+                mbar_wait_sleep(tempty + 8 * acc, ((ti >> 1) & 1) ^ 1, 256);
                 tc_fence_after();
                 for (int l = 0; l < LG; ++l) {
                     const int g = ti * LG + l;
-                    mbar_wait_spin(a_full + 8 * (g & 1), (g >> 1) & 1);
+                    mbar_wait_sleep(a_full + 8 * (g & 1), (g >> 1) & 1, 128);
                     tc_fence_after();
                     const uint32_t abuf = a_base + (uint32_t)(g & 1) * C::A_BYTES;
 #pragma unroll 1
@@ -344,7 +367,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                 for (int l = 0; l < LG; ++l)
                     for (int kb = 0; kb < C::KB; ++kb)
                         for (int h = 0; h < P.halves; ++h) {
-                            mbar_wait_spin(w_empty + 8 * ws, wph ^ 1);
+                            mbar_wait_sleep(w_empty + 8 * ws, wph ^ 1, 128);
                             mbar_expect_tx(w_full + 8 * ws, (uint32_t)P.nh * 128);
                             tma_load_3d(w_base + ws * kWStageBytes, &map_w, w_full + 8 * ws, 0, h * P.nh, l * C::KB + kb);
                             if (++ws == kWStages) { ws = 0; wph ^= 1; }
@@ -361,9 +384,10 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
             const int p = (t - b * P.tiles_per_img) * kConvTileM + m;
             const bool ok = p < P.N;
             const int acc = ti & 1;
-            mbar_wait_spin(tfull + 8 * acc, (ti >> 1) & 1);
+            mbar_wait_sleep(tfull + 8 * acc, (ti >> 1) & 1, 512);
             tc_fence_after();
             float* dst = P.out + (int64_t)b * P.cout * P.N + p;
+            const float* bias = P.bias;
             for (int c0 = 0; c0 < P.cout; c0 += 16) {
                 float v[16];
                 tmem_ld16(tmem_base + lane_addr + acc * 256 + c0, v);
@@ -372,12 +396,20 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                     tc_fence_before();
                     mbar_arrive(tempty + 8 * acc);
                 }
+                if (bias) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float o = v[i] + (P.bias ? __ldg(P.bias + c0 + i) : 0.f);
-                    if (P.relu) o = fmaxf(o, 0.f);
-                    if (ok) dst[(int64_t)(c0 + i) * P.N] = o;
+                    for (int i = 0; i < 16; ++i) v[i] += __ldg(bias + i);
+                    bias += 16;
                 }
+                if (P.relu) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (ok) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) dst[(int64_t)i * P.N] = v[i];
+                }
+                dst += (int64_t)16 * P.N;
             }
         }
     }
@@ -398,7 +430,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __re
         const int co = (int)((i >> 5) % cout);
         const int blk = (int)((i >> 5) / cout);
         const int l = blk / KB, ch = (blk % KB) * 32 + c;
-        packed[i] = ch < KK ? to_tf32(w[(int64_t)co * L * KK + l * KK + ch]) : 0.f;
+        packed[i] = ch < KK ? to_tf32_exact(w[(int64_t)co * L * KK + l * KK + ch]) : 0.f;
     }
 }
 
