@@ -158,6 +158,10 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+    // Programmatic dependent launch: everything above (96 KB of zero fill, barrier init, TMEM allocation) overlaps the
+    // tail of the previous kernel in the stream; its results (the coordinates) are visible from here on.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     if (warp < kGatherWarps) {
         // ===================== gather: patches -> bilinear samples -> A tile rows =====================
@@ -270,7 +274,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                     load_coords(ti + 1, nx, ny);
                     if (lane >= 16) { cx = nx; cy = ny; }
                 }
-                mbar_wait_sleep(a_empty + 8 * (g & 1), ((g >> 1) & 1) ^ 1, 64);  // the MMAs that read this A tile have retired
+                mbar_wait_sleep(a_empty + 8 * (g & 1), ((g >> 1) & 1) ^ 1, 500);  // the MMAs that read this A tile have retired
 #pragma unroll 1
                 for (int jb = 0; jb < kPixPerWarp; jb += kBatch, ++c_n) {
                     issue_batch(ti);
@@ -330,11 +334,11 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
             uint32_t wph = 0;
             for (int ti = 0; ti < my_tiles; ++ti) {
                 const int acc = ti & 1;
-                mbar_wait_sleep(tempty + 8 * acc, ((ti >> 1) & 1) ^ 1, 256);
+                mbar_wait_sleep(tempty + 8 * acc, ((ti >> 1) & 1) ^ 1, 2000);
                 tc_fence_after();
                 for (int l = 0; l < LG; ++l) {
                     const int g = ti * LG + l;
-                    mbar_wait_sleep(a_full + 8 * (g & 1), (g >> 1) & 1, 128);
+                    mbar_wait_sleep(a_full + 8 * (g & 1), (g >> 1) & 1, 1000);
                     tc_fence_after();
                     const uint32_t abuf = a_base + (uint32_t)(g & 1) * C::A_BYTES;
 #pragma unroll 1
@@ -367,7 +371,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                 for (int l = 0; l < LG; ++l)
                     for (int kb = 0; kb < C::KB; ++kb)
                         for (int h = 0; h < P.halves; ++h) {
-                            mbar_wait_sleep(w_empty + 8 * ws, wph ^ 1, 128);
+                            mbar_wait_sleep(w_empty + 8 * ws, wph ^ 1, 1000);
                             mbar_expect_tx(w_full + 8 * ws, (uint32_t)P.nh * 128);
                             tma_load_3d(w_base + ws * kWStageBytes, &map_w, w_full + 8 * ws, 0, h * P.nh, l * C::KB + kb);
                             if (++ws == kWStages) { ws = 0; wph ^= 1; }
@@ -384,7 +388,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
             const int p = (t - b * P.tiles_per_img) * kConvTileM + m;
             const bool ok = p < P.N;
             const int acc = ti & 1;
-            mbar_wait_sleep(tfull + 8 * acc, (ti >> 1) & 1, 512);
+            mbar_wait_sleep(tfull + 8 * acc, (ti >> 1) & 1, 8000);
             tc_fence_after();
             float* dst = P.out + (int64_t)b * P.cout * P.N + p;
             const float* bias = P.bias;
@@ -450,8 +454,17 @@ int run_lookup_conv(const LookupMaps& maps, const CUtensorMap& map_w, const Conv
     int sms = 0;
     RC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const int grid = P.total_tiles < sms ? P.total_tiles : sms;
-    kern<<<grid, kConvThreads, smem, s>>>(maps, map_w, P);
-    RC_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RC_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, map_w, P));
     return 0;
 }
 
