@@ -256,6 +256,35 @@ def run_ours(args):
             build_ms.append(kb0.elapsed_time(kb1))
             look_ms.append(kl0.elapsed_time(kl1) / iters)
             del blk
+        # SURVEY.md 8(f) rank 1, reported beside the headline (not part of it): the lookup fused with the motion
+        # encoder's first 1x1 convolution + ReLU (update.py:158,170: 324 -> 256) against the unfused pair
+        # (our lookup followed by cuDNN's convolution), per refinement iteration, same coordinates
+        fused = None
+        if rank == 0 and mode == "tf32" and not args.no_fused:
+            cw = torch.randn((256, L * K * K, 1, 1), generator=g, device=dev) / math.sqrt(L * K * K)
+            cb = torch.randn((256,), generator=g, device=dev)
+            blk = rc.CorrBlock(f1, f2, num_levels=L, radius=r, build_mode=mode)
+
+            def per_iter(fn):
+                for c in coords:
+                    fn(c)
+                torch.cuda.synchronize(dev)
+                ts = []
+                for _ in range(5):
+                    kl0.record()
+                    for c in coords:
+                        fn(c)
+                    kl1.record()
+                    torch.cuda.synchronize(dev)
+                    ts.append(kl0.elapsed_time(kl1) / iters)
+                return sorted(ts)[len(ts) // 2]
+
+            f_ms = per_iter(lambda c: blk.lookup_convc1(c, cw, cb))
+            u_ms = per_iter(lambda c: torch.relu_(torch.nn.functional.conv2d(blk(c), cw, cb)))
+            fused = {"ms_per_launch": f_ms, "unfused_lookup_plus_cudnn_conv1x1_relu_ms": u_ms, "cout": 256,
+                     "what": "CorrBlock.lookup_convc1 (lookup -> TF32 tcgen05 product with convc1's weight -> bias, ReLU); "
+                             "SURVEY 8(f) rank 1, not part of the headline step"}
+            del blk
         clocks = sampler.stop() if rank == 0 else None
 
         # ---- e2e: public API from pinned host buffers, copies inside the timed region.
@@ -326,6 +355,8 @@ def run_ours(args):
             "lookup": {"ms_per_launch": l_ms, "achieved_gbs": B * lb / (l_ms * 1e-3) / 1e9,
                        "share_of_step": 1.0 - build_share},
         }
+        if fused:
+            kern["lookup_convc1"] = fused
         lookup_name = "lookup_fwd_kernel<4,4>" if os.environ.get("RAFTCORR_LOOKUP") == "cpasync" else "lookup_fwd_tma_kernel<4,4>"
         if build_share >= 0.5:
             dom, ach, alg = ("build_tc_kernel" if mode == "tf32" else "sgemm_kernel"), kern["build"]["achieved_gbs"], B * bb
@@ -393,6 +424,7 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("RAFTCORR_BUILD_MODE", "tf32"), choices=["tf32", "fp32"])
     ap.add_argument("--batch", type=int, default=0, help="frame pairs per GPU (default 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="skip the lookup+convc1 side measurement")
     ap.add_argument("--l2-fetch", type=int, default=0, help="set cudaLimitMaxL2FetchGranularity (32/64/128) first")
     args = ap.parse_args()
     line = None
