@@ -36,7 +36,11 @@ class UpdateOperator(nn.Module):
         self.fh2 = nn.Conv2d(128, 2, 3, padding=1)
 
     def forward(self, net, inp, corr, flow):
-        cor = F.relu(self.convc1(corr))
+        if isinstance(corr, tuple):  # (corr_fn, coords): the INTEGRATION.md 2c patch -- lookup fused with convc1 + ReLU
+            corr_fn, coords = corr
+            cor = corr_fn.lookup_convc1(coords, self.convc1.weight, self.convc1.bias)
+        else:
+            cor = F.relu(self.convc1(corr))
         flo = F.relu(self.convf2(F.relu(self.convf1(flow))))
         mot = torch.cat([F.relu(self.conv(torch.cat([cor, flo], 1))), flow], 1)
         x = torch.cat([inp, mot], 1)
@@ -83,8 +87,9 @@ def coords_grid(B, H, W, device):
     return torch.stack([xs, ys]).float()[None].repeat(B, 1, 1, 1)
 
 
-def refine(corr_cls, op, f1, f2, net, inp, iters=12, **corr_kw):
-    """raft.py:116-176 without the encoders / upsampling: returns the list of 1/8-resolution flows."""
+def refine(corr_cls, op, f1, f2, net, inp, iters=12, fused_convc1=False, **corr_kw):
+    """raft.py:116-176 without the encoders / upsampling: returns the list of 1/8-resolution flows.
+    ``fused_convc1``: hand the update operator (corr_fn, coords) instead of the looked-up features."""
     B, _, H, W = f1.shape
     corr_fn = corr_cls(f1, f2, num_levels=LEVELS, radius=RADIUS, **corr_kw)
     c0 = coords_grid(B, H, W, f1.device).to(f1.dtype)
@@ -92,7 +97,7 @@ def refine(corr_cls, op, f1, f2, net, inp, iters=12, **corr_kw):
     flows = []
     for _ in range(iters):
         c1 = c1.detach()
-        corr = corr_fn(c1).to(net.dtype)  # the reference ends in .float() (corr.py:91)
+        corr = (corr_fn, c1) if fused_convc1 else corr_fn(c1).to(net.dtype)  # the reference ends in .float() (corr.py:91)
         net, delta = op(net, inp, corr, c1 - c0)
         c1 = c1 + delta
         flows.append(c1 - c0)

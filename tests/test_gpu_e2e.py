@@ -20,7 +20,7 @@ def _epe(a, b):
     return float(np.sqrt(((a - b) ** 2).sum(1)).mean())
 
 
-@pytest.mark.parametrize("variant", ["corr_tf32", "corr_fp32", "alternate"])
+@pytest.mark.parametrize("variant", ["corr_tf32", "corr_fp32", "alternate", "corr_tf32_fusedconvc1", "corr_fp32_fusedconvc1"])
 def test_flow_after_12_iterations_matches_reference(variant):
     import optical_flow_dnn_b200 as rc
 
@@ -34,7 +34,8 @@ def test_flow_after_12_iterations_matches_reference(variant):
         if variant == "alternate":
             flows = RH.refine(rc.AlternateCorrBlock, op, f1, f2, net, inp)
         else:
-            flows = RH.refine(rc.CorrBlock, op, f1, f2, net, inp, build_mode=variant.split("_")[1])
+            flows = RH.refine(rc.CorrBlock, op, f1, f2, net, inp, build_mode=variant.split("_")[1],
+                              fused_convc1=variant.endswith("fusedconvc1"))
     got = torch.stack(flows).cpu().numpy()
     assert got.shape == gold.shape
     per_iter = [_epe(got[i], gold[i]) for i in range(len(gold))]
