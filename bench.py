@@ -327,15 +327,21 @@ def run_ours(args):
                     ev_out[k].record(s_out)
 
         e2e_run(4)
-        barrier()
-        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        x0.record(s_in)
-        e2e_run(args.steps)
-        for st in (s_in, s_cmp):
-            s_out.wait_stream(st)
-        x1.record(s_out)
-        barrier()
-        e2e_ms = x0.elapsed_time(x1)
+        # The copies cross a PCIe link / host memory system shared with whatever else runs on the box: the same code
+        # measures 2.5 ms and 4.8 ms per step minutes apart.  Three trials of K steps each, the MEDIAN is reported
+        # (all three are in the JSON line).
+        e2e_trials = []
+        for _ in range(3):
+            barrier()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record(s_in)
+            e2e_run(args.steps)
+            for st in (s_in, s_cmp):
+                s_out.wait_stream(st)
+            x1.record(s_out)
+            barrier()
+            e2e_trials.append(x0.elapsed_time(x1))
+        e2e_ms = sorted(e2e_trials)[1]
 
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -382,6 +388,7 @@ def run_ours(args):
                        "l2": f"pyramid {B * 4 * H * W * (H * W) * 1.33 / 1e9:.2f} GB per GPU >> 126 MB L2 (inputs larger than L2)"},
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "trials_ms_per_step": [t_ / args.steps for t_ in e2e_trials], "reported": "median of 3 trials of K steps (rank 0's trials listed)",
                     "result": "last lookup's [B,324,H,W] features copied to pinned host memory each step; "
                               "steps pipelined over H2D | compute | D2H streams (2 buffer sets)"},
             "gpu_launches": launches_per_step * args.steps,
