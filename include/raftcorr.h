@@ -125,6 +125,17 @@ int raftcorr_lookup_convc1_fwd(const raftcorr_lookup_plan* plan, const float* co
                                const float* bias, int cout, int relu, float* out, int device,
                                raftcorr_stream_t stream);
 
+/* SURVEY.md 8(f) rank 4 -- RAFT.upsample_flow (raft/core/raft.py:70-81), called after every refinement iteration
+ * (raft.py:161-176; twice per iteration by the uncertainty model, with the same mask):
+ *   out[b, c, 8h+i, 8w+j] = sum_{k<9} softmax_k(mask[b, 64k + 8i + j, h, w]) * 8 * flow[b, c, h + k/3 - 1, w + k%3 - 1]
+ * flow [B,C,H,W], mask [B,576,H,W], out [B,C,8H,8W], all fp32 contiguous; C in 1..4 (flow and flow variance can
+ * share one pass over the mask: concatenate them along C).  One read of the mask, one write of the result.
+ * _bwd: grad_out [B,C,8H,8W] -> dmask [B,576,H,W] (overwritten) and dflow [B,C,H,W] (overwritten). */
+int raftcorr_upsample_flow_fwd(const float* flow, const float* mask, int B, int C, int H, int W, float* out, int device,
+                               raftcorr_stream_t stream);
+int raftcorr_upsample_flow_bwd(const float* flow, const float* mask, const float* grad_out, int B, int C, int H, int W,
+                               float* dmask, float* dflow, int device, raftcorr_stream_t stream);
+
 /* Adjoint of the lookup: dpyramid (same layout, ACCUMULATED into -- zero it once, then call once
  * per refinement iteration) += scatter of grad_out[B, L*(2r+1)^2, H, W].
  * dcoords [B,2,H,W] is optional (NULL to skip); when given, pyramid must be the forward pyramid. */

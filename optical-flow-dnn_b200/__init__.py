@@ -9,5 +9,6 @@ hand-written CUDA behind the C ABI of ``include/raftcorr.h`` (``libraftcorr_b200
 """
 from .corr import AlternateCorrBlock, CorrBlock, set_default_build_mode  # noqa: F401
 from ._lib import RaftCorrError  # noqa: F401
+from .upsample import upsample_flow  # noqa: F401
 
-__all__ = ["CorrBlock", "AlternateCorrBlock", "RaftCorrError", "set_default_build_mode"]
+__all__ = ["CorrBlock", "AlternateCorrBlock", "RaftCorrError", "set_default_build_mode", "upsample_flow"]

@@ -50,6 +50,9 @@ SIGNATURES = {
     "raftcorr_convc1_pack_weight": (_c_int, [_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_void_p]),
     "raftcorr_lookup_convc1_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_int,
                                              _c_void_p]),
+    "raftcorr_upsample_flow_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_int, _c_void_p]),
+    "raftcorr_upsample_flow_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
+                                             _c_void_p, _c_int, _c_void_p]),
     "raftcorr_lookup_bwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _LAYP, _c_int, _c_void_p, _c_int,
                                       _c_void_p]),
     "raftcorr_build_bwd_workspace_bytes": (_c_size_t, [_c_int] * 5),

@@ -198,6 +198,28 @@ int raftcorr_lookup_convc1_fwd(const raftcorr_lookup_plan* plan, const float* co
                               (cudaStream_t)stream);
 }
 
+int raftcorr_upsample_flow_fwd(const float* flow, const float* mask, int B, int C, int H, int W, float* out, int device,
+                               raftcorr_stream_t stream) {
+    RC_REQUIRE(B >= 0 && H >= 1 && W >= 1, "upsample_flow: bad sizes B=%d H=%d W=%d", B, H, W);
+    if (B == 0) return 0;
+    RC_REQUIRE(flow && mask && out, "upsample_flow: NULL tensor");
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "upsample_flow: cannot select device %d", device);
+    return launch_upsample_fwd(flow, mask, B, C, H, W, out, (cudaStream_t)stream);
+}
+
+int raftcorr_upsample_flow_bwd(const float* flow, const float* mask, const float* grad_out, int B, int C, int H, int W,
+                               float* dmask, float* dflow, int device, raftcorr_stream_t stream) {
+    RC_REQUIRE(B >= 0 && H >= 1 && W >= 1, "upsample_flow_bwd: bad sizes B=%d H=%d W=%d", B, H, W);
+    if (B == 0) return 0;
+    RC_REQUIRE(flow && mask && grad_out && dmask && dflow, "upsample_flow_bwd: NULL tensor");
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "upsample_flow_bwd: cannot select device %d", device);
+    cudaStream_t s = (cudaStream_t)stream;
+    RC_CUDA(cudaMemsetAsync(dflow, 0, sizeof(float) * (size_t)B * C * H * W, s));
+    return launch_upsample_bwd(flow, mask, grad_out, B, C, H, W, dmask, dflow, s);
+}
+
 int raftcorr_lookup_bwd(const float* grad_out, const float* coords, const float* pyramid, float* dpyramid,
                         const raftcorr_pyramid_layout* lay, int radius, float* dcoords, int device,
                         raftcorr_stream_t stream) {

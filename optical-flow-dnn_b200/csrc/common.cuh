@@ -110,6 +110,11 @@ int launch_pack_conv_weight(const float* weight, int levels, int radius, int cou
 int launch_lookup_conv(const void* plan_blob, const float* coords, const float* packed_w, const float* bias, int cout,
                        int relu, float* out, int device, cudaStream_t s);
 
+// convex 8x flow upsampling (upsample.cu)
+int launch_upsample_fwd(const float* flow, const float* mask, int B, int C, int H, int W, float* out, cudaStream_t s);
+int launch_upsample_bwd(const float* flow, const float* mask, const float* gout, int B, int C, int H, int W, float* dmask,
+                        float* dflow, cudaStream_t s);
+
 struct AltLevels {
     const float* f2[RAFTCORR_MAX_LEVELS];  // NHWC [B][h][w][C]
     float* df2[RAFTCORR_MAX_LEVELS];       // gradients (bwd only)

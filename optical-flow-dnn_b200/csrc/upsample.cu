@@ -1,0 +1,210 @@
+// Convex 8x upsampling of the flow: RAFT.upsample_flow, raft/core/raft.py:70-81, called after
+// EVERY refinement iteration (raft.py:161-176; twice per iteration by the uncertainty model, with the same mask).
+//
+//   out[b, c, 8h+i, 8w+j] = sum_k softmax_k(mask[b, k*64 + i*8 + j, h, w]) * 8 * flow[b, c, h + k/3 - 1, w + k%3 - 1]
+//   (k = 0..8 over the 3x3 neighbourhood in F.unfold's order, zeros outside the image)
+//
+// The reference materialises softmax(mask), unfold(8*flow), their product and the permuted result: ~5 passes over a
+// [B, 576, H, W] tensor (16 MB per frame pair at 55x128 -- as many bytes per iteration as the correlation lookup).
+// Here the mask is read exactly once: one CTA owns 32 consecutive pixels of one feature row; warp i handles sub-row
+// i, lanes run along the pixels (every mask load is one 128-byte line), the 9-way softmax and the weighted sum stay
+// in registers, and the [C][8][256] output tile is transposed through shared memory so that the eight output rows
+// leave as contiguous 1 KB runs.  Up to 4 channels share the pass (flow + variance of the uncertainty model).
+// The backward recomputes the softmax from the mask (one read) and writes d_mask once; d_flow is accumulated in
+// shared memory and leaves with one red.global.add per neighbourhood element.
+#include "common.cuh"
+
+namespace raftcorr {
+
+namespace {
+
+constexpr int kUpPix = 32;      // pixels per CTA (one warp lane each)
+constexpr int kUpMaxC = 4;     // flow (2) + flow variance (2) of the uncertainty model share one pass
+
+__device__ __forceinline__ float ld_stream(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// flow neighbourhood of the CTA's pixels: rows h-1..h+1, columns w0-1..w0+32, times 8, zero outside the image
+template <int C>
+__device__ __forceinline__ void load_flow_tile(float (*fs)[3][kUpPix + 2], const float* __restrict__ flow, int b, int h, int w0,
+                                               int H, int W) {
+    for (int idx = threadIdx.x; idx < C * 3 * (kUpPix + 2); idx += blockDim.x) {
+        const int x = idx % (kUpPix + 2);
+        const int r = (idx / (kUpPix + 2)) % 3;
+        const int c = idx / (3 * (kUpPix + 2));
+        const int yy = h + r - 1, xx = w0 + x - 1;
+        fs[c][r][x] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? 8.0f * __ldg(flow + (((int64_t)b * C + c) * H + yy) * W + xx) : 0.f;
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+upsample_fwd_kernel(const float* __restrict__ flow, const float* __restrict__ mask, float* __restrict__ out, int H, int W) {
+    __shared__ float fs[C][3][kUpPix + 2];
+    __shared__ float os[C][8][8 * kUpPix + 4];  // [c][i][8 * pixel + j]
+    const int b = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * kUpPix;
+    const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
+    const int w = w0 + lane;
+    const int64_t HW = (int64_t)H * W;
+    load_flow_tile<C>(fs, flow, b, h, w0, H, W);
+    __syncthreads();
+    if (w < W) {
+        const float* mp = mask + ((int64_t)b * 576 + i * 8) * HW + (int64_t)h * W + w;  // channel k*64 + i*8 + j
+        float nb[C][9];
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) nb[c][k] = fs[c][k / 3][lane + k % 3];
+#pragma unroll 2
+        for (int j = 0; j < 8; ++j) {
+            float m[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) m[k] = ld_stream(mp + ((int64_t)k * 64 + j) * HW);
+            float mx = m[0];
+#pragma unroll
+            for (int k = 1; k < 9; ++k) mx = fmaxf(mx, m[k]);
+            float den = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                m[k] = expf(m[k] - mx);
+                den += m[k];
+            }
+            const float inv = 1.0f / den;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc += m[k] * nb[c][k];
+                os[c][i][8 * lane + j] = acc * inv;
+            }
+        }
+    }
+    __syncthreads();
+    // eight output rows per channel, each 8 * (pixels of this CTA) contiguous floats
+    const int npx = min(kUpPix, W - w0);
+    const int row_len = 8 * npx;
+    for (int idx = threadIdx.x; idx < C * 8 * (row_len / 4); idx += blockDim.x) {
+        const int q = idx % (row_len / 4);
+        const int ii = (idx / (row_len / 4)) % 8;
+        const int c = idx / ((row_len / 4) * 8);
+        const float4 v = *reinterpret_cast<const float4*>(&os[c][ii][4 * q]);
+        *reinterpret_cast<float4*>(out + (((int64_t)b * C + c) * 8 * H + 8 * h + ii) * (8 * (int64_t)W) + 8 * w0 + 4 * q) = v;
+    }
+}
+
+// gout [B, C, 8H, 8W] -> dmask [B, 576, H, W] (overwritten), dflow [B, C, H, W] (ACCUMULATED into: zero it first)
+template <int C>
+__global__ void __launch_bounds__(256)
+upsample_bwd_kernel(const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ gout,
+                    float* __restrict__ dmask, float* __restrict__ dflow, int H, int W) {
+    __shared__ float fs[C][3][kUpPix + 2];
+    __shared__ float gs[C][8][8 * kUpPix + 4];
+    __shared__ float dfs[C][3][kUpPix + 2];
+    const int b = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * kUpPix;
+    const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
+    const int w = w0 + lane;
+    const int64_t HW = (int64_t)H * W;
+    load_flow_tile<C>(fs, flow, b, h, w0, H, W);
+    for (int idx = threadIdx.x; idx < C * 3 * (kUpPix + 2); idx += blockDim.x) (&dfs[0][0][0])[idx] = 0.f;
+    const int npx = min(kUpPix, W - w0);
+    const int row_len = 8 * npx;
+    for (int idx = threadIdx.x; idx < C * 8 * (row_len / 4); idx += blockDim.x) {
+        const int q = idx % (row_len / 4);
+        const int ii = (idx / (row_len / 4)) % 8;
+        const int c = idx / ((row_len / 4) * 8);
+        *reinterpret_cast<float4*>(&gs[c][ii][4 * q]) =
+            *reinterpret_cast<const float4*>(gout + (((int64_t)b * C + c) * 8 * H + 8 * h + ii) * (8 * (int64_t)W) + 8 * w0 + 4 * q);
+    }
+    __syncthreads();
+    if (w < W) {
+        const int64_t moff = ((int64_t)b * 576 + i * 8) * HW + (int64_t)h * W + w;
+        float nb[C][9], dn[C][9];
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                nb[c][k] = fs[c][k / 3][lane + k % 3];
+                dn[c][k] = 0.f;
+            }
+#pragma unroll 2
+        for (int j = 0; j < 8; ++j) {
+            float m[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) m[k] = ld_stream(mask + moff + ((int64_t)k * 64 + j) * HW);
+            float mx = m[0];
+#pragma unroll
+            for (int k = 1; k < 9; ++k) mx = fmaxf(mx, m[k]);
+            float den = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                m[k] = expf(m[k] - mx);
+                den += m[k];
+            }
+            const float inv = 1.0f / den;
+            float g[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) g[c] = gs[c][i][8 * lane + j];
+            // s_k = d out / d p_k;  d mask_k = p_k (s_k - sum_k' p_k' s_k')
+            float s[9], dot = 0.f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                m[k] *= inv;
+                float a = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    a += g[c] * nb[c][k];
+                    dn[c][k] += m[k] * g[c];
+                }
+                s[k] = a;
+                dot += m[k] * a;
+            }
+#pragma unroll
+            for (int k = 0; k < 9; ++k) dmask[moff + ((int64_t)k * 64 + j) * HW] = m[k] * (s[k] - dot);
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) atomicAdd(&dfs[c][k / 3][lane + k % 3], 8.0f * dn[c][k]);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < C * 3 * (kUpPix + 2); idx += blockDim.x) {
+        const int x = idx % (kUpPix + 2);
+        const int r = (idx / (kUpPix + 2)) % 3;
+        const int c = idx / (3 * (kUpPix + 2));
+        const int yy = h + r - 1, xx = w0 + x - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W && xx <= w0 + npx)
+            atomicAdd(dflow + (((int64_t)b * C + c) * H + yy) * W + xx, dfs[c][r][x]);
+    }
+}
+
+}  // namespace
+
+int launch_upsample_fwd(const float* flow, const float* mask, int B, int C, int H, int W, float* out, cudaStream_t s) {
+    RC_REQUIRE(C >= 1 && C <= kUpMaxC, "upsample_flow: 1..%d channels (got %d)", kUpMaxC, C);
+    RC_REQUIRE(B <= 65535 && H <= 65535, "upsample_flow: batch / height too large for one launch");
+    dim3 grid(ceil_div(W, kUpPix), H, B);
+#define RAFTCORR_UP_CASE(C_) case C_: upsample_fwd_kernel<C_><<<grid, 256, 0, s>>>(flow, mask, out, H, W); break;
+    switch (C) {
+        RAFTCORR_UP_CASE(1) RAFTCORR_UP_CASE(2) RAFTCORR_UP_CASE(3) RAFTCORR_UP_CASE(4)
+    }
+#undef RAFTCORR_UP_CASE
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_upsample_bwd(const float* flow, const float* mask, const float* gout, int B, int C, int H, int W, float* dmask,
+                        float* dflow, cudaStream_t s) {
+    RC_REQUIRE(C >= 1 && C <= 4, "upsample_flow backward: 1..4 channels (got %d)", C);
+    RC_REQUIRE(B <= 65535 && H <= 65535, "upsample_flow: batch / height too large for one launch");
+    dim3 grid(ceil_div(W, kUpPix), H, B);
+#define RAFTCORR_UP_CASE(C_) case C_: upsample_bwd_kernel<C_><<<grid, 256, 0, s>>>(flow, mask, gout, dmask, dflow, H, W); break;
+    switch (C) { RAFTCORR_UP_CASE(1) RAFTCORR_UP_CASE(2) RAFTCORR_UP_CASE(3) RAFTCORR_UP_CASE(4) }
+#undef RAFTCORR_UP_CASE
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace raftcorr

@@ -358,6 +358,47 @@ def alt_grad(fmap1, fmap2, coords, grad_out, num_levels=4, radius=4, dtype=np.fl
     return df1.transpose(0, 2, 1).reshape(B, D, H, W), g
 
 
+# --------------------------------------------------------------------------- convex upsampling
+def _neighbours(flow):
+    """``F.unfold(8 * flow, [3, 3], padding=1)`` as ``[B, C, 9, H, W]`` (k = ky*3 + kx, zero padding)."""
+    B, C, H, W = flow.shape
+    pad = np.zeros((B, C, H + 2, W + 2), flow.dtype)
+    pad[:, :, 1:-1, 1:-1] = flow.dtype.type(8) * flow
+    return np.stack([pad[:, :, ky:ky + H, kx:kx + W] for ky in range(3) for kx in range(3)], axis=2)
+
+
+def upsample_flow(flow, mask):
+    """``RAFT.upsample_flow`` (raft/core/raft.py:70-81): convex combination of the 3x3 neighbourhood of ``8 * flow``
+    with ``softmax`` weights, 8x8 sub-pixels per feature pixel.  flow ``[B,C,H,W]``, mask ``[B,576,H,W]`` ->
+    ``[B,C,8H,8W]``."""
+    B, C, H, W = flow.shape
+    m = mask.reshape(B, 1, 9, 8, 8, H, W).astype(flow.dtype)       # raft.py:73
+    m = np.exp(m - m.max(axis=2, keepdims=True))
+    m = m / m.sum(axis=2, keepdims=True)                           # raft.py:74
+    nb = _neighbours(flow).reshape(B, C, 9, 1, 1, H, W)            # raft.py:76-77
+    up = (m * nb).sum(axis=2)                                      # raft.py:79  [B,C,8,8,H,W]
+    return np.ascontiguousarray(up.transpose(0, 1, 4, 2, 5, 3)).reshape(B, C, 8 * H, 8 * W)  # raft.py:80-81
+
+
+def upsample_flow_grad(flow, mask, grad_out):
+    """Adjoint of :func:`upsample_flow`: returns ``(dflow [B,C,H,W], dmask [B,576,H,W])``."""
+    B, C, H, W = flow.shape
+    dt = flow.dtype
+    m = mask.reshape(B, 1, 9, 8, 8, H, W).astype(dt)
+    p = np.exp(m - m.max(axis=2, keepdims=True))
+    p = p / p.sum(axis=2, keepdims=True)
+    nb = _neighbours(flow).reshape(B, C, 9, 1, 1, H, W)
+    g = grad_out.reshape(B, C, H, 8, W, 8).transpose(0, 1, 3, 5, 2, 4)[:, :, None]  # [B,C,1,8,8,H,W]
+    s = (g * nb).sum(axis=1, keepdims=True)                        # d out / d p_k   [B,1,9,8,8,H,W]
+    dmask = p * (s - (p * s).sum(axis=2, keepdims=True))
+    dnb = (g * p).sum(axis=(3, 4))                                 # [B,C,9,H,W]
+    dpad = np.zeros((B, C, H + 2, W + 2), dt)
+    for k in range(9):
+        ky, kx = divmod(k, 3)
+        dpad[:, :, ky:ky + H, kx:kx + W] += dnb[:, :, k]
+    return dt.type(8) * dpad[:, :, 1:-1, 1:-1], dmask.reshape(B, 576, H, W)
+
+
 # --------------------------------------------------------------------------- helpers
 def coords_grid(B, H, W, dtype=np.float32):
     """``coords_grid`` (raft/core/utils/utils.py:88-102): channel 0 = x, channel 1 = y."""

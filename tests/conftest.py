@@ -31,3 +31,12 @@ def golden_convc1(request):
 
     g = np.load(os.path.join(ROOT, "tests", "golden", f"convc1_{request.param}.npz"))
     return {k: g[k] for k in g.files}
+
+
+@pytest.fixture(params=["flow", "flow_var"])
+def golden_upsample(request):
+    """The reference's own RAFT.upsample_flow and its autograd gradients (tests/golden/make_golden_upsample.py)."""
+    import numpy as np
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"upsample_{request.param}.npz"))
+    return {k: g[k] for k in g.files}

@@ -120,3 +120,19 @@ def test_numpy_lookup_convc1_matches_reference(golden_convc1):
             ref = g[f"cor64_{k}"].astype(np.float64)
             assert np.abs(out - ref).max() <= tol * np.abs(ref).max(), (dt, k)
             assert float(g[f"fp32_err{k}"]) <= 1e-5  # the reference's own fp32 run agrees with its fp64 run
+
+
+def test_numpy_upsample_flow_matches_reference(golden_upsample):
+    """SURVEY 8(f) rank 4 oracle: convex upsampling and its adjoint against the reference's RAFT.upsample_flow
+    (raft/core/raft.py:70-81) and torch autograd, fp64."""
+    g = golden_upsample
+    flow, mask = g["flow"].astype(np.float64), g["mask"].astype(np.float64)
+    up = O.upsample_flow(flow, mask)
+    assert up.shape == g["up64"].shape
+    assert np.abs(up - g["up64"]).max() <= TOL_F64 * np.abs(g["up64"]).max()
+    from make_golden import grad_weights
+    dflow, dmask = O.upsample_flow_grad(flow, mask, grad_weights(up.shape, 0))
+    assert np.abs(dflow - g["dflow64"]).max() <= TOL_F64 * np.abs(g["dflow64"]).max()
+    assert np.abs(dmask - g["dmask64"]).max() <= TOL_F64 * np.abs(g["dmask64"]).max()
+    up32 = O.upsample_flow(g["flow"], g["mask"])
+    assert up32.dtype == np.float32 and np.abs(up32 - g["up64"]).max() <= 1e-5 * np.abs(g["up64"]).max()
