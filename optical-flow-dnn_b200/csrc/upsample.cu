@@ -41,28 +41,35 @@ __device__ __forceinline__ void load_flow_tile(float (*fs)[3][kUpPix + 2], const
 }
 
 template <int C>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 upsample_fwd_kernel(const float* __restrict__ flow, const float* __restrict__ mask, float* __restrict__ out, int H, int W) {
     __shared__ float fs[C][3][kUpPix + 2];
-    __shared__ float os[C][8][8 * kUpPix + 4];  // [c][i][8 * pixel + j]
+    __shared__ __align__(16) float os[C][8][8 * kUpPix + 4];  // [c][i][8 * pixel + j]; rows are read back as float4
     const int b = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * kUpPix;
     const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
     const int w = w0 + lane;
     const int64_t HW = (int64_t)H * W;
+    // all 72 mask values of this thread are requested first (they do not depend on the flow tile): one DRAM round
+    // trip per CTA, overlapped with the flow-tile load
+    float mm[8][9];
+    if (w < W) {
+        const float* mp = mask + ((int64_t)b * 576 + i * 8) * HW + (int64_t)h * W + w;  // channel k*64 + i*8 + j
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int k = 0; k < 9; ++k) mm[j][k] = ld_stream(mp + ((int64_t)k * 64 + j) * HW);
+    }
     load_flow_tile<C>(fs, flow, b, h, w0, H, W);
     __syncthreads();
     if (w < W) {
-        const float* mp = mask + ((int64_t)b * 576 + i * 8) * HW + (int64_t)h * W + w;  // channel k*64 + i*8 + j
         float nb[C][9];
 #pragma unroll
         for (int c = 0; c < C; ++c)
 #pragma unroll
             for (int k = 0; k < 9; ++k) nb[c][k] = fs[c][k / 3][lane + k % 3];
-#pragma unroll 2
-        for (int j = 0; j < 8; ++j) {
-            float m[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) m[k] = ld_stream(mp + ((int64_t)k * 64 + j) * HW);
+        for (int j = 0; j < 8; ++j) {
+            float* m = mm[j];
             float mx = m[0];
 #pragma unroll
             for (int k = 1; k < 9; ++k) mx = fmaxf(mx, m[k]);
@@ -101,7 +108,7 @@ __global__ void __launch_bounds__(256)
 upsample_bwd_kernel(const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ gout,
                     float* __restrict__ dmask, float* __restrict__ dflow, int H, int W) {
     __shared__ float fs[C][3][kUpPix + 2];
-    __shared__ float gs[C][8][8 * kUpPix + 4];
+    __shared__ __align__(16) float gs[C][8][8 * kUpPix + 4];
     __shared__ float dfs[C][3][kUpPix + 2];
     const int b = blockIdx.z, h = blockIdx.y, w0 = blockIdx.x * kUpPix;
     const int lane = threadIdx.x & 31, i = threadIdx.x >> 5;
