@@ -6,6 +6,7 @@
  *
  *   raft/core/corr.py:18-43      CorrBlock.__init__  (volume + pyramid)      -> raftcorr_build_fwd
  *   raft/core/corr.py:45-91      CorrBlock.__call__  (lookup)                -> raftcorr_lookup_fwd
+ *   raft/core/extractor.py:231,239 + raft.py:114-119  conv2 head + CorrBlock  -> raftcorr_fnet_head_build_fwd
  *   autograd of corr.py:81       grid_sampler_2d_backward x L x iters        -> raftcorr_lookup_bwd
  *   autograd of corr.py:31-43    avg_pool2d_backward, mul, 2 x matmul bwd    -> raftcorr_build_bwd
  *   raft/alt_cuda_corr/correlation.cpp:23-33  alt_cuda_corr.forward          -> raftcorr_alt_forward
@@ -91,6 +92,24 @@ size_t raftcorr_build_fwd_workspace_bytes(int B, int D, int H, int W, int mode);
 int raftcorr_build_fwd(const float* fmap1, const float* fmap2, int D, float* pyramid,
                        const raftcorr_pyramid_layout* layout, int mode, void* workspace,
                        size_t workspace_bytes, int device, raftcorr_stream_t stream);
+
+/* SURVEY.md 8(f) rank 2 -- the feature encoder's output head fused into the build's prologue:
+ *   fmap = conv2(x) (1x1, raft/core/extractor.py:172,231 BasicEncoder 128 -> 256; :287,341 SmallEncoder 96 -> 128),
+ *   fmap1, fmap2 = split(fmap) (:239), .float() (raft/core/raft.py:114-115), CorrBlock(fmap1, fmap2) (raft.py:116-119)
+ * as ONE call: x [2B][Cin][H][W] is the head's input (output of layer3; images 0..B-1 are frame 1, B..2B-1 frame 2,
+ * the order of extractor.py:215-217), weight [D][Cin] (conv2.weight [D, Cin, 1, 1]), bias [D] or NULL.  A tcgen05
+ * TF32 product (fp32 accumulate; x and W rounded to nearest, the precision cuDNN's default gives this convolution)
+ * writes the build's pixel-major, TF32-rounded operand buffers directly -- the NCHW feature maps never exist --
+ * and the tensor-core build follows on the same stream.  TF32 build only; `layout` describes B pairs.
+ * Needs Cin % 4 == 0, (H*W) % 4 == 0, D <= 256 and ceil(Cin/32)*roundup(D,32) <= 1024 (the weight stays resident in
+ * shared memory): raftcorr_fnet_head_supported() returns 1 when the shapes qualify, else call conv2 yourself and
+ * use raftcorr_build_fwd.  Work space: raftcorr_fnet_head_build_workspace_bytes(); after the call its first
+ * raftcorr_build_fwd_workspace_bytes() bytes hold the two operand buffers [B][H*W][roundup(D,32)]. */
+int raftcorr_fnet_head_supported(int Cin, int D, int H, int W);
+size_t raftcorr_fnet_head_build_workspace_bytes(int B, int Cin, int D, int H, int W);
+int raftcorr_fnet_head_build_fwd(const float* x, const float* weight, const float* bias, int Cin, int D, float* pyramid,
+                                 const raftcorr_pyramid_layout* layout, void* workspace, size_t workspace_bytes,
+                                 int device, raftcorr_stream_t stream);
 
 /* CorrBlock.__call__ (corr.py:45-91): out[B, L*(2r+1)^2, H, W]. */
 int raftcorr_lookup_fwd(const float* pyramid, const raftcorr_pyramid_layout* layout, const float* coords,

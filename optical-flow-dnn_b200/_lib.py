@@ -43,6 +43,10 @@ SIGNATURES = {
     "raftcorr_build_fwd_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "raftcorr_build_fwd": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _LAYP, _c_int, _c_void_p, _c_size_t,
                                      _c_int, _c_void_p]),
+    "raftcorr_fnet_head_supported": (_c_int, [_c_int] * 4),
+    "raftcorr_fnet_head_build_workspace_bytes": (_c_size_t, [_c_int] * 5),
+    "raftcorr_fnet_head_build_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _LAYP, _c_void_p,
+                                               _c_size_t, _c_int, _c_void_p]),
     "raftcorr_lookup_fwd": (_c_int, [_c_void_p, _LAYP, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p]),
     "raftcorr_lookup_plan_init": (_c_int, [_c_void_p, _c_void_p, _LAYP, _c_int, _c_int]),
     "raftcorr_lookup_fwd_planned": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),

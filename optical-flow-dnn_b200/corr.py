@@ -100,6 +100,48 @@ class _BuildFn(torch.autograd.Function):
         return df1, df2, None
 
 
+class _HeadBuildFn(torch.autograd.Function):
+    """(x, conv2.weight, conv2.bias) -> flat pyramid buffer: extractor.py:231,239 + raft.py:114-119 in one kernel pair.
+    Backward: recompute fmap = conv2(x) (the forward never stored it), volume adjoint -> dfmap, then conv2's own
+    adjoint through torch autograd."""
+
+    @staticmethod
+    def forward(ctx, x, w2, bias, block):
+        ctx.block = block
+        ctx.save_for_backward(x, w2, bias)
+        return block._head_build(x, w2.contiguous(), bias)
+
+    @staticmethod
+    def backward(ctx, dpyr):
+        x, w2, bias = ctx.saved_tensors
+        block = ctx.block
+        acc = block._grad_acc
+        block._grad_acc = None
+        if dpyr is None:
+            return None, None, None, None
+        if acc is None or dpyr.data_ptr() != acc.data_ptr():
+            dpyr = dpyr.contiguous().clone()  # build_bwd folds levels in place
+        B, D = block._B, block._D
+        dev = x.device
+        with torch.enable_grad():
+            xg = x.detach().requires_grad_(ctx.needs_input_grad[0])
+            wg = w2.detach().requires_grad_(ctx.needs_input_grad[1])
+            bg = bias.detach().requires_grad_(ctx.needs_input_grad[2]) if bias is not None else None
+            f = torch.nn.functional.conv2d(xg, wg.reshape(D, -1, 1, 1), bg)
+        fd = f.detach()
+        df = torch.empty_like(fd)
+        L = _lib.lib()
+        ws_bytes = L.raftcorr_build_bwd_workspace_bytes(B, D, block._H, block._W, block._mode)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+        check(L.raftcorr_build_bwd(_ptr(dpyr), ctypes.byref(block._layout), _ptr(fd[:B]), _ptr(fd[B:]), D, _ptr(df[:B]),
+                                   _ptr(df[B:]), block._mode, _ptr(ws), ws_bytes, dev.index, _stream(dev)),
+              "raftcorr_build_bwd")
+        wanted = [t for t in (xg, wg, bg) if t is not None and t.requires_grad]
+        grads = list(torch.autograd.grad(f, wanted, df)) if wanted else []
+        out = [grads.pop(0) if (t is not None and t.requires_grad) else None for t in (xg, wg, bg)]
+        return out[0], out[1], out[2], None
+
+
 class _LookupFn(torch.autograd.Function):
     """(pyramid, coords) -> motion features (raft/core/corr.py:45-91)."""
 
@@ -150,6 +192,16 @@ class CorrBlock:
 
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4, build_mode=None):
         _check_fmaps(fmap1, fmap2, "CorrBlock")
+        B, D, H, W = fmap1.shape
+        self._setup(B, D, H, W, fmap1.device, num_levels, radius, build_mode)
+        fmap1 = fmap1.contiguous()
+        fmap2 = fmap2.contiguous()
+        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+            self._pyr = _BuildFn.apply(fmap1, fmap2, self)
+        else:
+            self._pyr = self._build(fmap1, fmap2)
+
+    def _setup(self, B, D, H, W, device, num_levels, radius, build_mode):
         self.num_levels = int(num_levels)
         self.radius = int(radius)
         if not 1 <= self.radius <= 4:
@@ -158,9 +210,8 @@ class CorrBlock:
         if mode not in _MODES:
             raise ValueError(f"unknown build mode {mode!r}")
         self._mode = _MODES[mode]
-        B, D, H, W = fmap1.shape
         self._B, self._D, self._H, self._W = B, D, H, W
-        self._device = fmap1.device
+        self._device = device
         # the tensor-core build writes row pairs interleaved (fewer, longer DRAM runs per lookup window);
         # gradient pyramids are row-major inside the library whatever this says, and never larger
         # (RAFTCORR_PYRAMID_LAYOUT=rowmajor keeps the old layout: A/B switch, needed by the cp.async lookup and the
@@ -170,12 +221,60 @@ class CorrBlock:
         self._grad_acc = None
         self._plan = None
         self._plan_ptr = 0
-        fmap1 = fmap1.contiguous()
-        fmap2 = fmap2.contiguous()
-        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
-            self._pyr = _BuildFn.apply(fmap1, fmap2, self)
+
+    @classmethod
+    def from_encoder_head(cls, x, weight, bias=None, num_levels=4, radius=4):
+        """``CorrBlock(*split(conv2(x)))`` in one call -- the feature encoder's output head fused into the build.
+
+        Replaces the tail of the reference encoders, ``x = self.conv2(x)`` + ``torch.split`` (raft/core/extractor.py:
+        231,239 BasicEncoder; :341,349 SmallEncoder), the ``.float()`` casts and the ``CorrBlock(fmap1, fmap2)``
+        constructor (raft/core/raft.py:114-119): ``x`` is the head's INPUT ``[2B, Cin, H, W]`` (the output of
+        ``layer3`` for the concatenated frames, frame-1 images first), ``weight``/``bias`` are ``conv2``'s parameters
+        (``[D, Cin, 1, 1]`` or ``[D, Cin]``; ``[D]``).  The 1x1 convolution runs as a tcgen05 TF32 product (fp32
+        accumulate -- the precision cuDNN uses for it by default) that writes the build's pixel-major operand buffers
+        directly; the NCHW feature maps are never materialised.  TF32 build only.  Differentiable w.r.t. ``x``,
+        ``weight`` and ``bias`` (the backward recomputes ``conv2(x)`` and chains the volume's adjoint through it).
+        Valid when the encoder's dropout is inactive (eval mode or ``dropout=0``, extractor.py:234-235).
+        Shapes the fused kernel does not take (``Cin % 4``, ``H*W % 4``, ``D > 256``) go through ``conv2`` + the
+        ordinary constructor -- still this library's kernels, never a CPU path.
+        """
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4 and x.shape[0] % 2 == 0):
+            raise RuntimeError("CorrBlock.from_encoder_head: x must be a CUDA tensor [2B, Cin, H, W]")
+        if not (isinstance(weight, torch.Tensor) and weight.is_cuda and weight.dtype == torch.float32):
+            raise RuntimeError("CorrBlock.from_encoder_head: weight must be a float32 CUDA tensor")
+        if weight.dim() == 4 and tuple(weight.shape[2:]) != (1, 1):
+            raise RuntimeError("CorrBlock.from_encoder_head: weight must be a 1x1 convolution kernel")
+        B2, Cin, H, W = x.shape
+        if weight.dim() not in (2, 4) or weight.shape[1] != Cin:
+            raise RuntimeError(f"CorrBlock.from_encoder_head: weight must be [D, {Cin}(, 1, 1)], got {tuple(weight.shape)}")
+        D = int(weight.shape[0])
+        if bias is not None and not (bias.is_cuda and bias.dtype == torch.float32 and tuple(bias.shape) == (D,)):
+            raise RuntimeError("CorrBlock.from_encoder_head: bias must be a float32 CUDA tensor of shape [D]")
+        x = x.float().contiguous()  # raft.py:114-115 casts after the head; the fused product wants fp32 input
+        w2 = weight.reshape(D, Cin)
+        if not _lib.lib().raftcorr_fnet_head_supported(Cin, D, H, W):
+            f = torch.nn.functional.conv2d(x, w2.reshape(D, Cin, 1, 1), bias)
+            return cls(f[: B2 // 2], f[B2 // 2:], num_levels=num_levels, radius=radius, build_mode="tf32")
+        self = cls.__new__(cls)
+        self._setup(B2 // 2, D, H, W, x.device, num_levels, radius, "tf32")
+        needs_grad = x.requires_grad or w2.requires_grad or (bias is not None and bias.requires_grad)
+        if torch.is_grad_enabled() and needs_grad:
+            self._pyr = _HeadBuildFn.apply(x, w2, bias, self)
         else:
-            self._pyr = self._build(fmap1, fmap2)
+            self._pyr = self._head_build(x, w2.contiguous(), bias)
+        return self
+
+    def _head_build(self, x, w2, bias):
+        lay, dev = self._layout, self._device
+        L = _lib.lib()
+        Cin = x.shape[1]
+        pyr = torch.empty(lay.total_floats, dtype=torch.float32, device=dev)
+        ws_bytes = L.raftcorr_fnet_head_build_workspace_bytes(self._B, Cin, self._D, self._H, self._W)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(L.raftcorr_fnet_head_build_fwd(_ptr(x), _ptr(w2), _ptr(bias.contiguous() if bias is not None else None),
+                                             Cin, self._D, _ptr(pyr), ctypes.byref(lay), _ptr(ws), ws_bytes, dev.index,
+                                             _stream(dev)), "raftcorr_fnet_head_build_fwd")
+        return pyr
 
     # -- kernels ------------------------------------------------------------------------------
     def _build(self, fmap1, fmap2):

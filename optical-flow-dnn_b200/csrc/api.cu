@@ -134,6 +134,36 @@ int raftcorr_build_fwd(const float* fmap1, const float* fmap2, int D, float* pyr
     return fail("build_fwd: unknown mode %d", mode);
 }
 
+int raftcorr_fnet_head_supported(int Cin, int D, int H, int W) {
+    return (H >= 1 && W >= 1 && fnet_head_supported(Cin, D, H * W)) ? 1 : 0;
+}
+
+size_t raftcorr_fnet_head_build_workspace_bytes(int B, int Cin, int D, int H, int W) {
+    if (B < 0 || Cin < 1 || D < 1 || H < 1 || W < 1) return 0;
+    return raftcorr_build_fwd_workspace_bytes(B, D, H, W, RAFTCORR_BUILD_TF32_TC) + fnet_head_weight_bytes(Cin, D);
+}
+
+int raftcorr_fnet_head_build_fwd(const float* x, const float* weight, const float* bias, int Cin, int D, float* pyramid,
+                                 const raftcorr_pyramid_layout* lay, void* workspace, size_t workspace_bytes, int device,
+                                 raftcorr_stream_t stream) {
+    if (int rc = check_layout(lay)) return rc;
+    if (lay->B == 0) return 0;
+    RC_REQUIRE(x && weight && pyramid, "fnet_head_build_fwd: NULL tensor");
+    RC_REQUIRE(Cin >= 1 && D >= 1, "fnet_head_build_fwd: bad sizes Cin=%d D=%d", Cin, D);
+    const size_t ops = raftcorr_build_fwd_workspace_bytes(lay->B, D, lay->H, lay->W, RAFTCORR_BUILD_TF32_TC);
+    const size_t need = ops + fnet_head_weight_bytes(Cin, D);
+    RC_REQUIRE(workspace && workspace_bytes >= need, "fnet_head_build_fwd: workspace too small (%zu < %zu)", workspace_bytes,
+               need);
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "fnet_head_build_fwd: cannot select device %d", device);
+    cudaStream_t s = (cudaStream_t)stream;
+    float* f1n = (float*)workspace;
+    float* f2n = (float*)((char*)workspace + ops / 2);
+    float* wr = (float*)((char*)workspace + ops);
+    if (int rc = launch_fnet_head(x, weight, bias, lay->B, Cin, D, lay->H * lay->W, f1n, f2n, wr, device, s)) return rc;
+    return launch_build_tc(f1n, f2n, D, pyramid, *lay, device, s);
+}
+
 int raftcorr_lookup_fwd(const float* pyramid, const raftcorr_pyramid_layout* lay, const float* coords, int radius,
                         float* out, int device, raftcorr_stream_t stream) {
     if (int rc = check_layout(lay)) return rc;

@@ -110,6 +110,12 @@ int launch_pack_conv_weight(const float* weight, int levels, int radius, int cou
 int launch_lookup_conv(const void* plan_blob, const float* coords, const float* packed_w, const float* bias, int cout,
                        int relu, float* out, int device, cudaStream_t s);
 
+// encoder output head -> build operands (fnet_head.cu)
+bool fnet_head_supported(int Cin, int D, int HW);
+size_t fnet_head_weight_bytes(int Cin, int D);
+int launch_fnet_head(const float* x, const float* weight, const float* bias, int B, int Cin, int D, int HW, float* f1n,
+                     float* f2n, float* w_rounded, int device, cudaStream_t s);
+
 // convex 8x flow upsampling (upsample.cu)
 int launch_upsample_fwd(const float* flow, const float* mask, int B, int C, int H, int W, float* out, cudaStream_t s);
 int launch_upsample_bwd(const float* flow, const float* mask, const float* gout, int B, int C, int H, int W, float* dmask,

@@ -40,6 +40,23 @@ def level_shapes(H: int, W: int, num_levels: int):
     return out
 
 
+# --------------------------------------------------------------------------- encoder head
+def fnet_head(x, weight, bias=None, dtype=np.float32):
+    """The feature encoders' output head: ``fmap = conv2(x)`` with a 1x1 kernel (raft/core/extractor.py:231
+    BasicEncoder, :341 SmallEncoder; ``conv2 = nn.Conv2d(Cin, D, kernel_size=1)``, :172/:287), split per frame
+    (``torch.split(x, [B, B], dim=0)``, :239/:349) and cast to fp32 (raft/core/raft.py:114-115).
+
+    ``x``: ``[2B, Cin, H, W]``, ``weight``: ``[D, Cin(, 1, 1)]``, ``bias``: ``[D]`` or None.
+    Returns ``(fmap1, fmap2)``, each ``[B, D, H, W]``.
+    """
+    B2, Cin, H, W = x.shape
+    w = np.asarray(weight).reshape(weight.shape[0], Cin).astype(dtype)
+    f = np.einsum("dc,bchw->bdhw", w, np.asarray(x).astype(dtype), optimize=True)
+    if bias is not None:
+        f = f + np.asarray(bias).astype(dtype)[None, :, None, None]
+    return f[: B2 // 2], f[B2 // 2:]
+
+
 # --------------------------------------------------------------------------- build
 def corr_volume(fmap1, fmap2, dtype=np.float32):
     """All-pairs volume ``V0[b,h1,w1,0,h2,w2] = <f1[b,:,h1,w1], f2[b,:,h2,w2]> / sqrt(D)``.

@@ -40,3 +40,12 @@ def golden_upsample(request):
 
     g = np.load(os.path.join(ROOT, "tests", "golden", f"upsample_{request.param}.npz"))
     return {k: g[k] for k in g.files}
+
+
+@pytest.fixture(params=["basic", "small"])
+def golden_fnet_head(request):
+    """The reference encoders' own conv2 head + the reference CorrBlock on its output (tests/golden/make_golden_fnet_head.py)."""
+    import numpy as np
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"fnet_head_{request.param}.npz"))
+    return {k: g[k] for k in g.files}

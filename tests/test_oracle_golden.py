@@ -122,6 +122,27 @@ def test_numpy_lookup_convc1_matches_reference(golden_convc1):
             assert float(g[f"fp32_err{k}"]) <= 1e-5  # the reference's own fp32 run agrees with its fp64 run
 
 
+def test_numpy_fnet_head_matches_reference(golden_fnet_head):
+    """SURVEY 8(f) rank 2 oracle: conv2 head + split against the reference encoders' own ``conv2`` on the input a
+    forward hook captured inside ``self.fnet([image_1, image_2])`` (raft/core/extractor.py:231,239 / :341,349), then
+    the volume and lookups of the reference CorrBlock on those maps."""
+    g = golden_fnet_head
+    B, Cin, D, H, W, L, r = [int(v) for v in g["meta"]]
+    assert float(g["fp32_err_head"]) <= 1e-5
+    for dt, tol in ((np.float64, 1e-6), (np.float32, 1e-5)):  # goldens are fp64 answers stored as fp32
+        f1, f2 = O.fnet_head(g["x"], g["weight"], g["bias"], dt)
+        assert f1.shape == (B, D, H, W) and f2.shape == (B, D, H, W)
+        for f, ref in ((f1, g["fmap1"]), (f2, g["fmap2"])):
+            assert np.abs(f - ref.astype(np.float64)).max() <= tol * np.abs(ref).max(), dt
+        pyr = O.corr_pyramid(f1, f2, L, dt)
+        assert np.abs(pyr[0] - g["pyr0"].astype(np.float64)).max() <= tol * np.abs(g["pyr0"]).max()
+        for k in range(3):
+            out = O.lookup(pyr, g[f"coords{k}"], r)
+            ref = g[f"out64_{k}"].astype(np.float64)
+            assert np.abs(out - ref).max() <= tol * np.abs(ref).max(), (dt, k)
+            assert float(g[f"fp32_err{k}"]) <= 1e-5
+
+
 def test_numpy_upsample_flow_matches_reference(golden_upsample):
     """SURVEY 8(f) rank 4 oracle: convex upsampling and its adjoint against the reference's RAFT.upsample_flow
     (raft/core/raft.py:70-81) and torch autograd, fp64."""
