@@ -16,6 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 import optical_flow_dnn_b200 as rc
+from optical_flow_dnn_b200.ddp import GradBucket
 
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); lr = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(lr)
@@ -36,24 +37,31 @@ coords = [(grid + flow).contiguous()]
 for _ in range(iters - 1): coords.append((coords[-1] + 0.5 * torch.randn((B, 2, H, W), generator=g, device=dev)).contiguous())
 ws = [torch.randn((B, L * (2 * r + 1) ** 2, H, W), generator=g, device=dev) for _ in range(iters)]
 BUCKET = 21_000_000 // 4                                       # RAFT-basic: 5.25 M fp32 parameters
-bucket = torch.zeros(BUCKET, device=dev)
 n_head = head_w.numel() + head_b.numel()
+rest = torch.zeros(BUCKET - n_head, device=dev, requires_grad=True)   # stands in for the other parameters' gradients
+gb = GradBucket([head_w, head_b, rest])                        # .grad tensors are views of ONE flat buffer
+bucket = gb.flat
+FUSED_HEAD = os.environ.get("TRAIN_FUSED_HEAD", "1") != "0"    # CorrBlock.from_encoder_head vs einsum head + CorrBlock
+x12 = torch.cat([x1, x2]).contiguous()
 
 def step(allreduce):
-    head_w.grad = head_b.grad = None
-    w2 = head_w.view(D, Cin)  # the 1x1 convolution as a plain product (cuBLAS), + bias
-    f1 = torch.einsum("oc,bchw->bohw", w2, x1) + head_b.view(1, D, 1, 1)
-    f2 = torch.einsum("oc,bchw->bohw", w2, x2) + head_b.view(1, D, 1, 1)
-    blk = rc.CorrBlock(f1, f2, L, r)
+    gb.zero()
+    if FUSED_HEAD:   # conv2 head fused into the build; gradients flow back through it
+        blk = rc.CorrBlock.from_encoder_head(x12, head_w, head_b, num_levels=L, radius=r)
+    else:
+        w2 = head_w.view(D, Cin)  # the 1x1 convolution as a plain product (cuBLAS), + bias
+        f1 = torch.einsum("oc,bchw->bohw", w2, x1) + head_b.view(1, D, 1, 1)
+        f2 = torch.einsum("oc,bchw->bohw", w2, x2) + head_b.view(1, D, 1, 1)
+        blk = rc.CorrBlock(f1, f2, L, r)
     loss = 0
     for c, w in zip(coords, ws): loss = loss + (blk(c) * w).sum()
-    loss.backward()
-    bucket[: head_w.numel()].copy_(head_w.grad.flatten()); bucket[head_w.numel(): n_head].copy_(head_b.grad)
-    if allreduce and world > 1:
-        dist.all_reduce(bucket, op=dist.ReduceOp.SUM)
+    loss.backward()          # accumulates straight into the bucket
+    if allreduce:
+        gb.all_reduce_async()   # side stream, averaged over ranks
+        gb.wait()
 
 def timed(allreduce, n=10):
-    for _ in range(3): step(allreduce)
+    for _ in range(6): step(allreduce)
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -89,7 +97,7 @@ if world > 1:
     dist.all_gather(gathered, summed)
     ok = all(torch.equal(gathered[0], t_) for t_ in gathered) and bool(torch.isfinite(summed).all())
 if rank == 0:
-    print(json.dumps({"config": "3 training step, B=10 pairs/GPU, 46x62, D=256, r=4, 12 it, fwd+bwd (eager autograd)", "n_gpus": world,
+    print(json.dumps({"fused_head": FUSED_HEAD, "config": "3 training step, B=10 pairs/GPU, 46x62, D=256, r=4, 12 it, fwd+bwd (eager autograd)", "n_gpus": world,
                       "ms_per_step_no_allreduce": ms_local, "ms_per_step_with_allreduce": ms_ar,
                       "pairs_per_s": world * B / (ms_ar * 1e-3), "allreduce_21MB_us": ar_us, "grads_identical_across_ranks": ok}))
 if world > 1: dist.destroy_process_group()
