@@ -285,6 +285,36 @@ def run_ours(args):
                      "what": "CorrBlock.lookup_convc1 (lookup -> TF32 tcgen05 product with convc1's weight -> bias, ReLU); "
                              "SURVEY 8(f) rank 1, not part of the headline step"}
             del blk
+        # SURVEY.md 8(f) rank 2, also beside the headline: the encoders' 1x1 conv2 head (128 -> 256) fused in front of
+        # the build (CorrBlock.from_encoder_head) against cuDNN's conv2 + split + CorrBlock(fmap1, fmap2)
+        head = None
+        if rank == 0 and mode == "tf32" and not args.no_fused:
+            hx = [torch.randn((2 * B, 128, H, W), generator=g, device=dev) for _ in range(2)]
+            hw = torch.randn((D, 128, 1, 1), generator=g, device=dev) / math.sqrt(128.0)
+            hb = 0.1 * torch.randn((D,), generator=g, device=dev)
+
+            def per_call(fn):
+                for i in range(3):
+                    fn(hx[i & 1])
+                torch.cuda.synchronize(dev)
+                ts = []
+                for _ in range(5):
+                    kl0.record()
+                    for i in range(4):
+                        fn(hx[i & 1])
+                    kl1.record()
+                    torch.cuda.synchronize(dev)
+                    ts.append(kl0.elapsed_time(kl1) / 4)
+                return sorted(ts)[len(ts) // 2]
+
+            def unfused_head(x_):
+                f_ = torch.nn.functional.conv2d(x_, hw, hb)
+                return rc.CorrBlock(f_[:B], f_[B:], num_levels=L, radius=r, build_mode=mode)
+
+            head = {"ms_per_call": per_call(lambda x_: rc.CorrBlock.from_encoder_head(x_, hw, hb, num_levels=L, radius=r)),
+                    "cudnn_conv2_plus_build_ms": per_call(unfused_head), "cin": 128,
+                    "what": "CorrBlock.from_encoder_head (tcgen05 TF32 1x1 conv writing the build's operand buffers, then the "
+                            "build); SURVEY 8(f) rank 2, not part of the headline step"}
         clocks = sampler.stop() if rank == 0 else None
 
         # ---- e2e: public API from pinned host buffers, copies inside the timed region.
@@ -327,6 +357,18 @@ def run_ours(args):
                     ev_out[k].record(s_out)
 
         e2e_run(4)
+        # what the link gives a lone pinned copy on this box, to read the e2e number against (rank 0's link)
+        for st in (s_in, s_cmp, s_out):
+            st.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(s_in):
+            dbuf[0][0].copy_(hf1, non_blocking=True)
+            p0.record(s_in)
+            for _ in range(4):
+                dbuf[0][0].copy_(hf1, non_blocking=True)
+            p1.record(s_in)
+        s_in.synchronize()
+        h2d_alone_gbs = 4 * hf1.numel() * 4 / (p0.elapsed_time(p1) * 1e-3) / 1e9
         # The copies cross a PCIe link / host memory system shared with whatever else runs on the box: the same code
         # measures 2.5 ms and 4.8 ms per step minutes apart.  Three trials of K steps each, the MEDIAN is reported
         # (all three are in the JSON line).
@@ -363,6 +405,8 @@ def run_ours(args):
         }
         if fused:
             kern["lookup_convc1"] = fused
+        if head:
+            kern["fnet_head_build"] = head
         lookup_name = "lookup_fwd_kernel<4,4>" if os.environ.get("RAFTCORR_LOOKUP") == "cpasync" else "lookup_fwd_tma_kernel<4,4>"
         if build_share >= 0.5:
             dom, ach, alg = ("build_tc_kernel" if mode == "tf32" else "sgemm_kernel"), kern["build"]["achieved_gbs"], B * bb
@@ -388,6 +432,7 @@ def run_ours(args):
                        "l2": f"pyramid {B * 4 * H * W * (H * W) * 1.33 / 1e9:.2f} GB per GPU >> 126 MB L2 (inputs larger than L2)"},
             "e2e": {"value": world * B * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_gbs_in_step": h2d / (e2e_ms / args.steps * 1e-3) / 1e9, "h2d_gbs_lone_pinned_copy": h2d_alone_gbs,
                     "trials_ms_per_step": [t_ / args.steps for t_ in e2e_trials], "reported": "median of 3 trials of K steps (rank 0's trials listed)",
                     "result": "last lookup's [B,324,H,W] features copied to pinned host memory each step; "
                               "steps pipelined over H2D | compute | D2H streams (2 buffer sets)"},

@@ -111,6 +111,16 @@ int raftcorr_fnet_head_build_fwd(const float* x, const float* weight, const floa
                                  const raftcorr_pyramid_layout* layout, void* workspace, size_t workspace_bytes,
                                  int device, raftcorr_stream_t stream);
 
+/* The same head in front of the on-the-fly path: conv2 + split + .float() + AlternateCorrBlock.__init__
+ * (extractor.py:231,239, raft.py:114-117, corr.py:124-140) -- frame-1 maps land in f1_nhwc, frame-2 maps in level 0 of
+ * the NHWC feature pyramid (both TF32-rounded, as raftcorr_alt_pyramid writes them in mode RAFTCORR_BUILD_TF32_TC),
+ * the pooled levels follow.  Needs D % 32 == 0 and raftcorr_fnet_head_supported(); work space (the rounded weight):
+ * raftcorr_fnet_head_alt_workspace_bytes(). */
+size_t raftcorr_fnet_head_alt_workspace_bytes(int Cin, int D);
+int raftcorr_fnet_head_alt_pyramid(const float* x, const float* weight, const float* bias, int B, int Cin, int D, int H,
+                                   int W, int L, float* f1_nhwc, float* f2_pyramid_nhwc, void* workspace,
+                                   size_t workspace_bytes, int device, raftcorr_stream_t stream);
+
 /* CorrBlock.__call__ (corr.py:45-91): out[B, L*(2r+1)^2, H, W]. */
 int raftcorr_lookup_fwd(const float* pyramid, const raftcorr_pyramid_layout* layout, const float* coords,
                         int radius, float* out, int device, raftcorr_stream_t stream);

@@ -47,6 +47,9 @@ SIGNATURES = {
     "raftcorr_fnet_head_build_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "raftcorr_fnet_head_build_fwd": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _LAYP, _c_void_p,
                                                _c_size_t, _c_int, _c_void_p]),
+    "raftcorr_fnet_head_alt_workspace_bytes": (_c_size_t, [_c_int] * 2),
+    "raftcorr_fnet_head_alt_pyramid": (_c_int, [_c_void_p] * 3 + [_c_int] * 6 + [_c_void_p, _c_void_p, _c_void_p, _c_size_t,
+                                                                                   _c_int, _c_void_p]),
     "raftcorr_lookup_fwd": (_c_int, [_c_void_p, _LAYP, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p]),
     "raftcorr_lookup_plan_init": (_c_int, [_c_void_p, _c_void_p, _LAYP, _c_int, _c_int]),
     "raftcorr_lookup_fwd_planned": (_c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p]),

@@ -155,32 +155,72 @@ class _LookupFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         coords, pyr = ctx.saved_tensors
+        dpyr_ret, dcoords = _lookup_backward(ctx.block, gout, coords, pyr, ctx.needs_input_grad[0],
+                                             ctx.need_dcoords and ctx.needs_input_grad[1])
+        return dpyr_ret, dcoords, None
+
+
+def _lookup_backward(block, gout, coords, pyr, want_pyr, want_dcoords):
+    """Adjoint of one lookup: scatter ``gout`` into the block's gradient pyramid (and optionally d/dcoords)."""
+    lay = block._layout
+    dev = coords.device
+    dpyr_ret = None
+    if want_pyr:
+        # One persistent gradient pyramid for ALL refinement iterations: every lookup backward
+        # scatter-adds into it; it is handed to autograd exactly once (by the first lookup whose
+        # backward runs) and the build backward -- which depends on every lookup -- only runs after
+        # the last one has added its share.  The reference instead materialises iters x L dense,
+        # zero-filled level-sized tensors (grid_sampler_2d_backward) and sums them.
+        first = block._grad_acc is None
+        if first:
+            block._grad_acc = torch.zeros(lay.total_floats, dtype=torch.float32, device=dev)
+            dpyr_ret = block._grad_acc
+        acc = block._grad_acc
+    else:
+        acc = None
+    dcoords = torch.empty_like(coords) if want_dcoords else None
+    if acc is None and dcoords is None:
+        return None, None
+    if acc is None:  # coords gradient only: scatter into a scratch pyramid
+        acc = torch.zeros(lay.total_floats, dtype=torch.float32, device=dev)
+    check(_lib.lib().raftcorr_lookup_bwd(_ptr(gout.contiguous()), _ptr(coords), _ptr(pyr), _ptr(acc),
+                                         ctypes.byref(lay), block.radius, _ptr(dcoords), dev.index, _stream(dev)),
+          "raftcorr_lookup_bwd")
+    return dpyr_ret, dcoords
+
+
+class _LookupConvFn(torch.autograd.Function):
+    """``relu(conv1x1(lookup(coords)))`` with autograd: the forward is the fused kernel; the backward RECOMPUTES the
+    lookup (50 us) instead of keeping the ``[B, L*K*K, H, W]`` tensor alive per refinement iteration (73 MB each at
+    config 2 -- the reference's autograd graph holds 12 of them), forms the weight / bias gradients with cuBLAS and
+    scatters ``W^T g`` into the block's gradient pyramid with the ordinary lookup adjoint."""
+
+    @staticmethod
+    def forward(ctx, pyr, coords, w2, bias, block, relu):
+        out = block._lookup_convc1(pyr.detach(), coords, w2.detach(), bias.detach() if bias is not None else None, relu)
+        ctx.block, ctx.relu = block, relu
+        ctx.save_for_backward(pyr, coords, w2, out if relu else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pyr, coords, w2, out = ctx.saved_tensors
         block = ctx.block
-        lay = block._layout
-        dev = coords.device
+        g = g.contiguous()
+        if ctx.relu:
+            g = g * (out > 0)
+        dw = db = None
+        if ctx.needs_input_grad[2]:
+            feat = block._lookup(pyr.detach(), coords)
+            dw = torch.einsum("bohw,bchw->oc", g, feat)
+            del feat
+        if ctx.needs_input_grad[3]:
+            db = g.sum(dim=(0, 2, 3))
         dpyr_ret = None
         if ctx.needs_input_grad[0]:
-            # One persistent gradient pyramid for ALL refinement iterations: every lookup backward
-            # scatter-adds into it; it is handed to autograd exactly once (by the first lookup whose
-            # backward runs) and the build backward -- which depends on every lookup -- only runs after
-            # the last one has added its share.  The reference instead materialises iters x L dense,
-            # zero-filled level-sized tensors (grid_sampler_2d_backward) and sums them.
-            first = block._grad_acc is None
-            if first:
-                block._grad_acc = torch.zeros(lay.total_floats, dtype=torch.float32, device=dev)
-                dpyr_ret = block._grad_acc
-            acc = block._grad_acc
-        else:
-            acc = None
-        dcoords = torch.empty_like(coords) if ctx.need_dcoords and ctx.needs_input_grad[1] else None
-        if acc is None and dcoords is None:
-            return None, None, None
-        if acc is None:  # coords gradient only: scatter into a scratch pyramid
-            acc = torch.zeros(lay.total_floats, dtype=torch.float32, device=dev)
-        check(_lib.lib().raftcorr_lookup_bwd(_ptr(gout.contiguous()), _ptr(coords), _ptr(pyr), _ptr(acc),
-                                             ctypes.byref(lay), block.radius, _ptr(dcoords), dev.index, _stream(dev)),
-              "raftcorr_lookup_bwd")
-        return dpyr_ret, dcoords, None
+            dfeat = torch.einsum("oc,bohw->bchw", w2, g)
+            dpyr_ret, _ = _lookup_backward(block, dfeat, coords, pyr, True, False)
+        return dpyr_ret, None, dw, db, None, None
 
 
 class CorrBlock:
@@ -321,9 +361,10 @@ class CorrBlock:
         ``weight``: ``convc1.weight`` ``[Cout, L*(2r+1)^2, 1, 1]`` (or 2-D), ``bias``: ``convc1.bias`` or None.
         Returns ``[B, Cout, H, W]`` fp32.  The ``[B, L*(2r+1)^2, H, W]`` lookup tensor is never written: its samples
         become TF32 operand tiles in shared memory and the product runs on the tensor cores with fp32 accumulation
-        (the precision cuDNN uses for this convolution by default).  Inference path: no autograd through it (use
-        ``self(coords)`` + ``convc1`` when gradients are needed).  Cout: multiple of 16 up to 128 or of 32 up to 256
-        (RAFT-small 96, RAFT-basic 256); at most 4 pyramid levels.
+        (the precision cuDNN uses for this convolution by default).  Differentiable w.r.t. the feature maps (through
+        the pyramid), ``weight`` and ``bias``; the backward recomputes the lookup instead of saving it (coords get no
+        gradient: raft.py:143 detaches them).  Cout: multiple of 16 up to 128 or of 32 up to 256 (RAFT-small 96,
+        RAFT-basic 256); at most 4 pyramid levels.
         """
         _check_coords(coords, self._B, self._H, self._W, self._device, "CorrBlock.lookup_convc1")
         K = 2 * self.radius + 1
@@ -334,31 +375,35 @@ class CorrBlock:
             raise RuntimeError("CorrBlock.lookup_convc1: weight must be a 1x1 convolution kernel")
         if weight.dim() not in (2, 4) or weight.shape[1] != cin:
             raise RuntimeError(f"CorrBlock.lookup_convc1: weight must be [Cout, {cin}(, 1, 1)], got {tuple(weight.shape)}")
-        if torch.is_grad_enabled() and (weight.requires_grad or self._pyr.requires_grad or
-                                        (bias is not None and bias.requires_grad)):
-            raise RuntimeError("CorrBlock.lookup_convc1 is an inference kernel (no autograd): call it under "
-                               "torch.no_grad(), or use self(coords) followed by convc1 for training")
         if self.num_levels > 4:
             raise RaftCorrError("CorrBlock.lookup_convc1: at most 4 pyramid levels")
         cout = int(weight.shape[0])
         if bias is not None:
             if not (bias.is_cuda and bias.dtype == torch.float32 and tuple(bias.shape) == (cout,)):
                 raise RuntimeError("CorrBlock.lookup_convc1: bias must be a float32 CUDA tensor of shape [Cout]")
-            bias = bias.detach().contiguous()
+        coords = coords.detach().contiguous()
+        w2 = weight.reshape(cout, cin)
+        if torch.is_grad_enabled() and (weight.requires_grad or self._pyr.requires_grad or
+                                        (bias is not None and bias.requires_grad)):
+            return _LookupConvFn.apply(self._pyr, coords, w2, bias, self, bool(relu))
+        return self._lookup_convc1(self._pyr.detach(), coords, w2.detach(), bias.detach() if bias is not None else None, relu)
+
+    def _lookup_convc1(self, pyr, coords, w2, bias, relu):
+        cout, cin = w2.shape
         dev = self._device
         L = _lib.lib()
+        if bias is not None:
+            bias = bias.contiguous()
         # packed (TF32-rounded, k-blocked) copy of the weight, redone only when the parameter changes
-        key = (weight.data_ptr(), weight._version, cout)
+        key = (w2.data_ptr(), w2._version, cout)
         if getattr(self, "_convw_key", None) != key:
             nbytes = int(L.raftcorr_convc1_weight_bytes(self.num_levels, self.radius, cout))
             packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            w2 = weight.detach().reshape(cout, cin).contiguous()
-            check(L.raftcorr_convc1_pack_weight(_ptr(w2), self.num_levels, self.radius, cout, _ptr(packed), dev.index,
+            wc = w2.contiguous()
+            check(L.raftcorr_convc1_pack_weight(_ptr(wc), self.num_levels, self.radius, cout, _ptr(packed), dev.index,
                                                 _stream(dev)), "raftcorr_convc1_pack_weight")
             self._convw_key, self._convw = key, packed
-        coords = coords.detach().contiguous()
         out = torch.empty((self._B, cout, self._H, self._W), dtype=torch.float32, device=dev)
-        pyr = self._pyr.detach()
         check(L.raftcorr_lookup_convc1_fwd(self._ensure_plan(pyr), _ptr(coords), _ptr(self._convw), _ptr(bias), cout,
                                            1 if relu else 0, _ptr(out), dev.index, _stream(dev)),
               "raftcorr_lookup_convc1_fwd")
@@ -429,6 +474,33 @@ class _AltPrepFn(torch.autograd.Function):
         return df1, df2, None
 
 
+class _AltHeadPrepFn(torch.autograd.Function):
+    """(x, conv2.weight, conv2.bias) -> (fmap1 NHWC, pooled fmap2 pyramid NHWC): the encoder head fused in front of
+    AlternateCorrBlock.__init__.  Backward: fold + transpose the NHWC gradients (raftcorr_alt_grad_finish), then
+    conv2's own adjoint through torch autograd."""
+
+    @staticmethod
+    def forward(ctx, x, w2, bias, block):
+        ctx.block = block
+        ctx.save_for_backward(x, w2, bias)
+        return block._head_prep(x, w2.contiguous(), bias)
+
+    @staticmethod
+    def backward(ctx, df1n, df2p):
+        x, w2, bias = ctx.saved_tensors
+        df1, df2, _ = _AltPrepFn.backward(ctx, df1n, df2p)
+        D = ctx.block._D
+        with torch.enable_grad():
+            xg = x.detach().requires_grad_(ctx.needs_input_grad[0])
+            wg = w2.detach().requires_grad_(ctx.needs_input_grad[1])
+            bg = bias.detach().requires_grad_(ctx.needs_input_grad[2]) if bias is not None else None
+            f = torch.nn.functional.conv2d(xg, wg.reshape(D, -1, 1, 1), bg)
+        wanted = [t for t in (xg, wg, bg) if t is not None and t.requires_grad]
+        grads = list(torch.autograd.grad(f, wanted, torch.cat([df1, df2]))) if wanted else []
+        out = [grads.pop(0) if (t is not None and t.requires_grad) else None for t in (xg, wg, bg)]
+        return out[0], out[1], out[2], None
+
+
 class _AltLookupFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, f1n, f2p, coords, block):
@@ -496,6 +568,60 @@ class AlternateCorrBlock:
         else:
             self._f1n, self._f2p = self._prep(fmap1, fmap2)
 
+    @classmethod
+    def from_encoder_head(cls, x, weight, bias=None, num_levels=4, radius=4):
+        """``AlternateCorrBlock(*split(conv2(x)))`` in one call: the encoders' 1x1 output convolution (raft/core/
+        extractor.py:231,239 / :341,349) writes the NHWC, TF32-rounded feature tensors of the on-the-fly path directly
+        (see :meth:`CorrBlock.from_encoder_head`).  TF32 mode, ``D % 32 == 0``; other shapes run ``conv2`` + the
+        ordinary constructor.  Differentiable w.r.t. ``x``, ``weight``, ``bias``."""
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4 and x.shape[0] % 2 == 0):
+            raise RuntimeError("AlternateCorrBlock.from_encoder_head: x must be a CUDA tensor [2B, Cin, H, W]")
+        if not (isinstance(weight, torch.Tensor) and weight.is_cuda and weight.dtype == torch.float32 and
+                weight.dim() in (2, 4) and weight.shape[1] == x.shape[1] and tuple(weight.shape[2:]) in ((), (1, 1))):
+            raise RuntimeError("AlternateCorrBlock.from_encoder_head: weight must be a float32 CUDA tensor [D, Cin(, 1, 1)]")
+        B2, Cin, H, W = x.shape
+        D = int(weight.shape[0])
+        if bias is not None and not (bias.is_cuda and bias.dtype == torch.float32 and tuple(bias.shape) == (D,)):
+            raise RuntimeError("AlternateCorrBlock.from_encoder_head: bias must be a float32 CUDA tensor of shape [D]")
+        x = x.float().contiguous()
+        w2 = weight.reshape(D, Cin)
+        if D % 32 != 0 or not _lib.lib().raftcorr_fnet_head_supported(Cin, D, H, W):
+            f = torch.nn.functional.conv2d(x, w2.reshape(D, Cin, 1, 1), bias)
+            return cls(f[: B2 // 2], f[B2 // 2:], num_levels=num_levels, radius=radius)
+        self = cls.__new__(cls)
+        self._mode = _MODES["tf32"]
+        self.num_levels, self.radius = int(num_levels), int(radius)
+        if not 1 <= self.radius <= 4 or not 1 <= self.num_levels <= 4:
+            raise RaftCorrError("AlternateCorrBlock: radius and num_levels must be in [1, 4]")
+        if (H >> (self.num_levels - 1)) < 1 or (W >> (self.num_levels - 1)) < 1:
+            raise RaftCorrError("AlternateCorrBlock: feature maps too small for the number of levels")
+        self._B, self._D, self._H, self._W = B2 // 2, D, H, W
+        self._device = x.device
+        self._fmaps = None
+        self._head = (x, w2, bias)
+        self._grad_acc = (None, None)
+        needs_grad = x.requires_grad or w2.requires_grad or (bias is not None and bias.requires_grad)
+        if torch.is_grad_enabled() and needs_grad:
+            self._f1n, self._f2p = _AltHeadPrepFn.apply(x, w2, bias, self)
+        else:
+            self._f1n, self._f2p = self._head_prep(x, w2.contiguous(), bias)
+        return self
+
+    def _head_prep(self, x, w2, bias):
+        B, D, H, W, L = self._B, self._D, self._H, self._W, self.num_levels
+        dev = self._device
+        lib = _lib.lib()
+        f1n = torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
+        f2p = torch.empty(_alt_sizes(B, D, H, W, L), dtype=torch.float32, device=dev)
+        wsb = int(lib.raftcorr_fnet_head_alt_workspace_bytes(x.shape[1], D))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        check(lib.raftcorr_fnet_head_alt_pyramid(_ptr(x), _ptr(w2), _ptr(bias.contiguous() if bias is not None else None), B,
+                                                 x.shape[1], D, H, W, L, _ptr(f1n), _ptr(f2p), _ptr(ws), wsb, dev.index,
+                                                 _stream(dev)), "raftcorr_fnet_head_alt_pyramid")
+        ws_bytes = int(lib.raftcorr_alt_lookup_workspace_bytes(B, H, W, L, self._mode))
+        self._ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        return f1n, f2p
+
     def _prep(self, fmap1, fmap2):
         B, D, H, W, L = self._B, self._D, self._H, self._W, self.num_levels
         dev = self._device
@@ -530,6 +656,10 @@ class AlternateCorrBlock:
         (corr.py:136-140).  Nothing in RAFT reads it; materialised on demand from the inputs."""
         import torch.nn.functional as F
 
+        if self._fmaps is None:  # built from the encoder head: the NCHW maps were never materialised
+            x, w2, bias = self._head
+            f = F.conv2d(x, w2.reshape(self._D, -1, 1, 1), bias)
+            self._fmaps = (f[: self._B], f[self._B:])
         f1, f2 = self._fmaps
         out = [(f1, f2)]
         for _ in range(self.num_levels):

@@ -164,6 +164,35 @@ int raftcorr_fnet_head_build_fwd(const float* x, const float* weight, const floa
     return launch_build_tc(f1n, f2n, D, pyramid, *lay, device, s);
 }
 
+size_t raftcorr_fnet_head_alt_workspace_bytes(int Cin, int D) {
+    if (Cin < 1 || D < 1) return 0;
+    return fnet_head_weight_bytes(Cin, D);
+}
+
+int raftcorr_fnet_head_alt_pyramid(const float* x, const float* weight, const float* bias, int B, int Cin, int D, int H,
+                                   int W, int L, float* f1_nhwc, float* f2_pyr, void* workspace, size_t workspace_bytes,
+                                   int device, raftcorr_stream_t stream) {
+    RC_REQUIRE(B == 0 || (x && weight && f1_nhwc && f2_pyr), "fnet_head_alt_pyramid: NULL tensor");
+    RC_REQUIRE(D % 32 == 0, "fnet_head_alt_pyramid: the TF32 on-the-fly path needs D %% 32 == 0 (got %d)", D);
+    AltLevels lv{};
+    if (int rc = alt_levels(f2_pyr, nullptr, B, D, H, W, L, &lv)) return rc;
+    if (B == 0) return 0;
+    const size_t need = fnet_head_weight_bytes(Cin, D);
+    RC_REQUIRE(workspace && workspace_bytes >= need, "fnet_head_alt_pyramid: workspace too small (%zu < %zu)", workspace_bytes,
+               need);
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "fnet_head_alt_pyramid: cannot select device %d", device);
+    cudaStream_t s = (cudaStream_t)stream;
+    // frame-1 maps -> f1_nhwc, frame-2 maps -> level 0 of the feature pyramid, both NHWC and TF32-rounded (D == Dp)
+    if (int rc = launch_fnet_head(x, weight, bias, B, Cin, D, H * W, f1_nhwc, const_cast<float*>(lv.f2[0]), (float*)workspace,
+                                  device, s))
+        return rc;
+    for (int l = 1; l < L; ++l)  // corr.py:138-139
+        if (int rc = launch_pool_nhwc(lv.f2[l - 1], const_cast<float*>(lv.f2[l]), B, lv.h[l - 1], lv.w[l - 1], D, true, s))
+            return rc;
+    return 0;
+}
+
 int raftcorr_lookup_fwd(const float* pyramid, const raftcorr_pyramid_layout* lay, const float* coords, int radius,
                         float* out, int device, raftcorr_stream_t stream) {
     if (int rc = check_layout(lay)) return rc;

@@ -106,6 +106,45 @@ def test_full_size_against_unfused(pkg):
         assert float((out2.double() - ref2).abs().max() / ref2.abs().max()) <= 1e-3
 
 
+@pytest.mark.parametrize("relu", [True, False])
+def test_autograd_matches_unfused_path(pkg, relu):
+    """Training use: gradients w.r.t. the feature maps, convc1's weight and bias through the fused call (backward
+    recomputes the lookup, nothing of size [B, 324, H, W] is kept) against torch autograd through lookup + conv2d."""
+    B, D, H, W, L, r, cout = 2, 64, 20, 28, 4, 3, 96
+    g = torch.Generator(device=dev()).manual_seed(17)
+    f1 = torch.randn((B, D, H, W), generator=g, device=dev())
+    f2 = torch.randn((B, D, H, W), generator=g, device=dev())
+    cin = L * (2 * r + 1) ** 2
+    w = torch.randn((cout, cin, 1, 1), generator=g, device=dev()) / cin ** 0.5
+    b = torch.randn((cout,), generator=g, device=dev())
+    coords = [torch.from_numpy(O.coords_grid(B, H, W)).to(dev()) + s * torch.randn((B, 2, H, W), generator=g, device=dev())
+              for s in (0.0, 3.0)]
+    gout = [torch.randn((B, cout, H, W), generator=g, device=dev()) for _ in coords]
+
+    def run(fused):
+        a1, a2, ww, bb = (z.detach().clone().requires_grad_(True) for z in (f1, f2, w, b))
+        blk = pkg.CorrBlock(a1, a2, L, r, build_mode="fp32")
+        loss = 0
+        for c, go in zip(coords, gout):
+            if fused:
+                o = blk.lookup_convc1(c, ww, bb, relu=relu)
+            else:
+                o = torch.nn.functional.conv2d(blk(c).double(), ww.double(), bb.double())
+                if relu:  # same ReLU mask in both arms: an activation within TF32 rounding of zero may flip otherwise,
+                    with torch.no_grad():  # and one flipped unit moves a whole pixel's gradient by O(1)
+                        mask = blk.lookup_convc1(c, ww.detach(), bb.detach(), relu=True) > 0
+                    o = o * mask
+                o = o.float()
+            loss = loss + (o * go).sum()
+        loss.backward()
+        return a1.grad, a2.grad, ww.grad, bb.grad
+
+    got, want = run(True), run(False)
+    for name, a, ref in zip(("dfmap1", "dfmap2", "dweight", "dbias"), got, want):
+        assert a is not None and a.shape == ref.shape, name
+        assert float((a - ref).abs().max() / ref.abs().max()) <= 2e-3, name
+
+
 def test_errors(pkg):
     d = dev()
     f = torch.randn(1, 32, 16, 16, device=d)
@@ -116,8 +155,6 @@ def test_errors(pkg):
     with pytest.raises(pkg.RaftCorrError):
         with torch.no_grad():
             blk.lookup_convc1(c, torch.randn(40, 98, device=d))      # Cout not a multiple of 16
-    with pytest.raises(RuntimeError):
-        blk.lookup_convc1(c, torch.randn(96, 98, device=d, requires_grad=True))  # inference kernel: no autograd
     with pytest.raises(RuntimeError):
         with torch.no_grad():
             blk.lookup_convc1(c, torch.randn(96, 98))                # CPU weight

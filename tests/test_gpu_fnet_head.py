@@ -202,3 +202,46 @@ def test_errors(pkg):
         pkg.CorrBlock.from_encoder_head(x.cpu(), torch.randn(64, 32, device=d))      # CPU input: no CPU path
     with pytest.raises(RuntimeError):
         pkg.CorrBlock.from_encoder_head(x, torch.randn(64, 32, device=d), torch.randn(63, device=d))
+
+
+def test_alternate_block_from_encoder_head(pkg, golden_fnet_head):
+    """The on-the-fly class built from the head: same goldens (AlternateCorrBlock == CorrBlock)."""
+    g = golden_fnet_head
+    B, Cin, D, H, W, L, r = [int(v) for v in g["meta"]]
+    with torch.no_grad():
+        blk = pkg.AlternateCorrBlock.from_encoder_head(t(g["x"]), t(g["weight"]), t(g["bias"]), num_levels=L, radius=r)
+        for k in range(3):
+            out = blk(t(g[f"coords{k}"]))
+            assert tuple(out.shape) == (B, L * (2 * r + 1) ** 2, H, W)
+            assert rel_err(out, g[f"out64_{k}"]) <= TOL, f"coords set {k}"
+        f1, f2 = blk.pyramid[0]
+        assert rel_err(f1, g["fmap1"]) <= 1e-3 and rel_err(f2, g["fmap2"]) <= 1e-3
+
+
+def test_alternate_block_head_autograd(pkg):
+    B, Cin, D, H, W, L, r = 1, 96, 128, 16, 20, 3, 3
+    g = torch.Generator(device=dev()).manual_seed(47)
+    x = torch.randn((2 * B, Cin, H, W), generator=g, device=dev())
+    w = torch.randn((D, Cin, 1, 1), generator=g, device=dev()) / Cin ** 0.5
+    b = 0.1 * torch.randn((D,), generator=g, device=dev())
+    coords = [torch.from_numpy(O.coords_grid(B, H, W)).to(dev()) + s * torch.randn((B, 2, H, W), generator=g, device=dev())
+              for s in (0.0, 3.0)]
+    gout = [torch.randn((B, L * (2 * r + 1) ** 2, H, W), generator=g, device=dev()) for _ in coords]
+
+    def run(fused):
+        xs, ws, bs = (z.detach().clone().requires_grad_(True) for z in (x, w, b))
+        if fused:
+            blk = pkg.AlternateCorrBlock.from_encoder_head(xs, ws, bs, num_levels=L, radius=r)
+        else:
+            old = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = False
+            f = torch.nn.functional.conv2d(xs, ws, bs)
+            torch.backends.cudnn.allow_tf32 = old
+            blk = pkg.CorrBlock(f[:B], f[B:], L, r, build_mode="fp32")
+        sum((blk(c) * go).sum() for c, go in zip(coords, gout)).backward()
+        return xs.grad, ws.grad, bs.grad
+
+    got, want = run(True), run(False)
+    for name, a, ref in zip(("dx", "dweight", "dbias"), got, want):
+        assert a is not None and a.shape == ref.shape
+        assert rel_err(a, ref) <= 2e-3, name
