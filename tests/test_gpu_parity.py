@@ -246,6 +246,43 @@ def test_full_size_properties(pkg, mode):
     assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs), 1.0)
 
 
+# ------------------------------------------------------------------ pyramids beyond 4 GiB (configs 4 and 5a)
+@pytest.mark.parametrize("shape", [(16, 256, 47, 156), (1, 256, 135, 240)], ids=["config4_B16_kitti", "config5a_B1_1080p"])
+def test_pyramid_larger_than_4GiB(pkg, shape):
+    """BASELINE.json configs[3] (raft_uncertainty on KITTI, 375x1242 -> 47x156, B=16: 4.5 GB pyramid) and the 1080p
+    shape of configs[4] as a volume (135x240, one pair: 5.6 GB): every offset past 2^32 bytes must be right.  Checked on
+    the LAST source pixels of the LAST pair, which live at the far end of each level: volume rows against fp64 dot
+    products, each level against the 2x2 mean of the previous one, lookup against the on-the-fly class."""
+    B, D, H, W = shape
+    L, r = 4, 4
+    N = H * W
+    g = torch.Generator(device=dev()).manual_seed(77)
+    f1 = torch.randn((B, D, H, W), generator=g, device=dev())
+    f2 = torch.randn((B, D, H, W), generator=g, device=dev())
+    with torch.no_grad():
+        blk = pkg.CorrBlock(f1, f2, L, r)
+        assert blk._layout.total_floats * 4 > 2 ** 32
+        b = B - 1
+        ms = torch.tensor([0, N // 2, N - 130, N - 2, N - 1], device=dev())
+        rows = torch.einsum("dm,dn->mn", f1[b].reshape(D, N)[:, ms].double(), f2[b].reshape(D, N).double()) / np.sqrt(D)
+        pyr = blk.corr_pyramid
+        got = pyr[0].reshape(B, N, H, W)[b, ms].reshape(len(ms), N)
+        scale = float(rows.abs().max())
+        assert float((got.double() - rows).abs().max()) <= TOL["tf32"] * scale
+        for l in range(1, L):
+            prev = pyr[l - 1].reshape(B, N, *pyr[l - 1].shape[-2:])[b, ms]
+            want = torch.nn.functional.avg_pool2d(prev.contiguous(), 2, stride=2)
+            assert float((want - pyr[l].reshape(B, N, *pyr[l].shape[-2:])[b, ms]).abs().max()) <= 1e-5 * scale
+        del pyr, got, rows
+        coords = torch.from_numpy(O.coords_grid(B, H, W)).to(dev()) + 3.0 * torch.randn((B, 2, H, W), generator=g, device=dev())
+        out = blk(coords)
+        alt = pkg.AlternateCorrBlock(f1, f2, L, r)(coords)
+        assert float((alt - out).abs().max()) <= TOL["tf32"] * float(out.abs().max())
+        # and the last pair alone gives the same bits as inside the big batch
+        solo = pkg.CorrBlock(f1[b:], f2[b:], L, r)(coords[b:])
+        assert torch.equal(solo[0], out[b])
+
+
 # ------------------------------------------------------------------ edge cases / error behaviour
 def test_edge_cases_and_errors(pkg):
     d = dev()
