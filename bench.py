@@ -260,7 +260,7 @@ def run_ours(args):
         # encoder's first 1x1 convolution + ReLU (update.py:158,170: 324 -> 256) against the unfused pair
         # (our lookup followed by cuDNN's convolution), per refinement iteration, same coordinates
         fused = None
-        if rank == 0 and mode == "tf32" and not args.no_fused:
+        if rank == 0 and mode != "fp32" and not args.no_fused:
             cw = torch.randn((256, L * K * K, 1, 1), generator=g, device=dev) / math.sqrt(L * K * K)
             cb = torch.randn((256,), generator=g, device=dev)
             blk = rc.CorrBlock(f1, f2, num_levels=L, radius=r, build_mode=mode)
@@ -288,7 +288,7 @@ def run_ours(args):
         # SURVEY.md 8(f) rank 2, also beside the headline: the encoders' 1x1 conv2 head (128 -> 256) fused in front of
         # the build (CorrBlock.from_encoder_head) against cuDNN's conv2 + split + CorrBlock(fmap1, fmap2)
         head = None
-        if rank == 0 and mode == "tf32" and not args.no_fused:
+        if rank == 0 and mode != "fp32" and not args.no_fused:
             hx = [torch.randn((2 * B, 128, H, W), generator=g, device=dev) for _ in range(2)]
             hw = torch.randn((D, 128, 1, 1), generator=g, device=dev) / math.sqrt(128.0)
             hb = 0.1 * torch.randn((D,), generator=g, device=dev)
@@ -309,7 +309,7 @@ def run_ours(args):
 
             def unfused_head(x_):
                 f_ = torch.nn.functional.conv2d(x_, hw, hb)
-                return rc.CorrBlock(f_[:B], f_[B:], num_levels=L, radius=r, build_mode=mode)
+                return rc.CorrBlock(f_[:B], f_[B:], num_levels=L, radius=r, build_mode="tf32")
 
             head = {"ms_per_call": per_call(lambda x_: rc.CorrBlock.from_encoder_head(x_, hw, hb, num_levels=L, radius=r)),
                     "cudnn_conv2_plus_build_ms": per_call(unfused_head), "cin": 128,
@@ -409,7 +409,7 @@ def run_ours(args):
             kern["fnet_head_build"] = head
         lookup_name = "lookup_fwd_kernel<4,4>" if os.environ.get("RAFTCORR_LOOKUP") == "cpasync" else "lookup_fwd_tma_kernel<4,4>"
         if build_share >= 0.5:
-            dom, ach, alg = ("build_tc_kernel" if mode == "tf32" else "sgemm_kernel"), kern["build"]["achieved_gbs"], B * bb
+            dom, ach, alg = ("build_tc_kernel" if mode != "fp32" else "sgemm_kernel"), kern["build"]["achieved_gbs"], B * bb
         else:
             dom, ach, alg = lookup_name, kern["lookup"]["achieved_gbs"], B * lb
         traffic = None
@@ -419,13 +419,16 @@ def run_ours(args):
         except Exception:
             traffic = None
         # tf32: 1 paired NCHW->NHWC transpose + build_tc; fp32: sgemm + (L-1) pooling passes; + one lookup per iteration
-        launches_per_step = (2 if mode == "tf32" else 1 + (L - 1)) + iters
+        launches_per_step = (2 if mode != "fp32" else 1 + (L - 1)) + iters
         cpu = cpu_port_run(3, 1, iters, SHAPE) if world == 1 and not args.no_cpu_baseline else None
         line = {
             "metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if mode == "tf32" else "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"tf32": "tf32", "f16": "f16 operands (block-scaled, 11-bit significands like tf32), f32 accumulate", "fp32": "f32"}[mode],
             "data": "synthetic",
+            "precision": ("volume and lookups within 1e-3 of max|ref| (north_star); measured 3.07e-4 for f16 and for tf32 alike "
+                          "(profiles/r01_f16_parity_b8.json): block-scaled fp16 operands carry TF32's 11 significant bits, "
+                          "accumulation is fp32, the stored pyramid is fp32") if mode != "fp32" else "fp32 FFMA",
             "config": {"workload": f"RAFT-basic CorrBlock build + {iters} lookups @436x1024 (fmap {H}x{W}, D={D}, r={r}, L={L}), "
                                    f"B={B} frame pairs per GPU (BASELINE.json configs[1] shape)",
                        "pairs_per_gpu": B, "iters": iters, "build_mode": mode, "parallelism": f"pair-sharded x{world}, no collective",
@@ -473,7 +476,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--iters", type=int, default=12, help="lookups per build (metric: 12)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("RAFTCORR_BUILD_MODE", "tf32"), choices=["tf32", "fp32"])
+    ap.add_argument("--mode", default=os.environ.get("RAFTCORR_BUILD_MODE", "f16"), choices=["tf32", "f16", "fp32"])
     ap.add_argument("--batch", type=int, default=0, help="frame pairs per GPU (default 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="skip the lookup+convc1 side measurement")

@@ -69,8 +69,16 @@ typedef struct raftcorr_pyramid_layout {
 /* Build precision modes for raftcorr_build_fwd. */
 enum {
     RAFTCORR_BUILD_FP32_SIMT = 0, /* exact fp32 FFMA accumulation (CUDA cores) */
-    RAFTCORR_BUILD_TF32_TC = 1    /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM, TMA fed,
+    RAFTCORR_BUILD_TF32_TC = 1,   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM, TMA fed,
                                      pooling fused into the epilogue */
+    RAFTCORR_BUILD_F16_TC = 2     /* the same kernel on BLOCK-SCALED fp16 operands (kind::f16): fp16 has TF32's 11
+                                     significant bits; one power-of-two scale per 64-pixel operand block (64 consecutive
+                                     source pixels / one row pair of an 8x32 target tile) keeps everything down to 2^-29
+                                     of the block maximum at full precision and is undone by two scalars in the epilogue.
+                                     fp32 accumulate; half the operand bytes, MMA instructions and accumulator
+                                     updates of the TF32 build (which the 1 kW power cap turns into time).
+                                     raftcorr_build_fwd only; the backward and the on-the-fly entry points treat it
+                                     as RAFTCORR_BUILD_TF32_TC. */
 };
 
 int raftcorr_abi_version(void);

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libraftcorr_b200.so")
 MAX_LEVELS = 8
 BUILD_FP32_SIMT = 0
 BUILD_TF32_TC = 1
+BUILD_F16_TC = 2
 LOOKUP_PLAN_BYTES = 4096
 
 

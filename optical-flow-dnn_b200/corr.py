@@ -20,12 +20,15 @@ import torch
 from . import _lib
 from ._lib import RaftCorrError, check
 
-_MODES = {"fp32": _lib.BUILD_FP32_SIMT, "tf32": _lib.BUILD_TF32_TC}
-_default_mode = os.environ.get("RAFTCORR_BUILD_MODE", "tf32")
+_MODES = {"fp32": _lib.BUILD_FP32_SIMT, "tf32": _lib.BUILD_TF32_TC, "f16": _lib.BUILD_F16_TC}
+_default_mode = os.environ.get("RAFTCORR_BUILD_MODE", "f16")
 
 
 def set_default_build_mode(mode: str) -> None:
     """``"tf32"``: tcgen05 tensor-core build (TF32 operands, fp32 accumulate; <=1e-3 of max|V|).
+    ``"f16"``: the same kernel on block-scaled fp16 operands (TF32's 11 significant bits, one power-of-two scale per
+    operand tile, fp32 accumulate; same error, half the operand traffic) -- volume build only, everything else
+    (backward, on-the-fly class, fused encoder head) runs as ``"tf32"``.
     ``"fp32"``: exact fp32 FFMA build on CUDA cores."""
     global _default_mode
     if mode not in _MODES:
@@ -226,8 +229,9 @@ class _LookupConvFn(torch.autograd.Function):
 class CorrBlock:
     """All-pairs correlation volume + pyramid + lookup; drop-in for raft/core/corr.py:13-116.
 
-    ``build_mode`` (extension; RAFT never passes it): ``"tf32"`` | ``"fp32"``, default from
-    :func:`set_default_build_mode` / ``RAFTCORR_BUILD_MODE``.
+    ``build_mode`` (extension; RAFT never passes it): ``"f16"`` (default: block-scaled fp16 operands, TF32's 11
+    significant bits, fp32 accumulate) | ``"tf32"`` | ``"fp32"``; default from :func:`set_default_build_mode` /
+    ``RAFTCORR_BUILD_MODE``.
     """
 
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4, build_mode=None):
@@ -249,6 +253,8 @@ class CorrBlock:
         mode = build_mode or _default_mode
         if mode not in _MODES:
             raise ValueError(f"unknown build mode {mode!r}")
+        if mode == "f16" and D > 256:  # the fp16 operand pass keeps a 64-pixel x D block in registers: D <= 256
+            mode = "tf32"
         self._mode = _MODES[mode]
         self._B, self._D, self._H, self._W = B, D, H, W
         self._device = device
@@ -256,7 +262,7 @@ class CorrBlock:
         # gradient pyramids are row-major inside the library whatever this says, and never larger
         # (RAFTCORR_PYRAMID_LAYOUT=rowmajor keeps the old layout: A/B switch, needed by the cp.async lookup and the
         # CTA-pair build experiments)
-        il = mode == "tf32" and os.environ.get("RAFTCORR_PYRAMID_LAYOUT", "interleaved") != "rowmajor"
+        il = mode in ("tf32", "f16") and os.environ.get("RAFTCORR_PYRAMID_LAYOUT", "interleaved") != "rowmajor"
         self._layout = _lib.make_layout(B, H, W, self.num_levels, interleaved=il)
         self._grad_acc = None
         self._plan = None
@@ -545,6 +551,8 @@ class AlternateCorrBlock:
         mode = build_mode or (_default_mode if fmap1.shape[1] % 32 == 0 else "fp32")
         if mode not in _MODES:
             raise ValueError(f"unknown build mode {mode!r} (expected one of {sorted(_MODES)})")
+        if mode == "f16":  # block-scaled fp16 operands exist for the volume build only
+            mode = "tf32" if fmap1.shape[1] % 32 == 0 else "fp32"
         if mode == "tf32" and fmap1.shape[1] % 32 != 0:
             raise RaftCorrError("AlternateCorrBlock: build_mode='tf32' needs a feature dim that is a multiple of 32")
         self._mode = _MODES[mode]

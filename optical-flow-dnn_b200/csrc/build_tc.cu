@@ -77,7 +77,25 @@ struct BuildParams {
     int total_tiles;
     int lsu_store;  // A/B: level-0 rows leave through LSU stores instead of TMA
     float scale;
+    // RAFTCORR_BUILD_F16_TC: operands are fp16 with one power-of-two scale per 64-pixel operand BLOCK (fmap1: half an
+    // m-tile = 64 TMEM lanes; fmap2: one row pair of the 8x32 target tile = one epilogue phase) -- the same 11
+    // significant bits as TF32 at half the operand bytes, half the MMA instructions (K = 16) and half the accumulator
+    // read-modify-writes; undoing the scales is one scalar per thread times one per phase
+    int f16, k_elems;            // k_elems: operand elements per 128-byte k-block (32 tf32 / 64 fp16)
+    const float* inv_a;          // [B][2 * m_tiles]
+    const float* inv_b;          // [B][4 * bands][w_tiles]
 };
+
+// kind::f16 twin of tc_mma_tf32 (A = B = fp16, D = fp32): format fields 0, same shape fields
+constexpr uint32_t kInstrDescF16 = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 
 // MODE 0: one CTA per tile.  MODE 1: CTA pair, each loads half of the B tile and TMA-multicasts it to both
 // (every CTA still ingests the whole tile).  MODE 2: CTA pair issuing ONE tcgen05.mma.cta_group::2 (M = 256):
@@ -166,19 +184,19 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         // both CTAs' loads complete on the LEADER's barrier (peer bit cleared); it expects both halves
                         const uint32_t lead_bar = (full_bar + 8 * stage) & kPeerBitMask;
                         if (crank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * (kABytes + kBBytes / 2));
-                        tma_load_3d_2sm(sa, &map_a, lead_bar, kb * kBlockK, mt * kTileM, b);
-                        tma_load_4d_2sm(sb, &map_b, lead_bar, kb * kBlockK, wt * kTileW, band * kTileH + crank * (kTileH / 2), b);
+                        tma_load_3d_2sm(sa, &map_a, lead_bar, kb * P.k_elems, mt * kTileM, b);
+                        tma_load_4d_2sm(sb, &map_b, lead_bar, kb * P.k_elems, wt * kTileW, band * kTileH + crank * (kTileH / 2), b);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                         continue;
                     }
                     mbar_expect_tx(full_bar + 8 * stage, kStageBytes);
-                    tma_load_3d(sa, &map_a, full_bar + 8 * stage, kb * kBlockK, mt * kTileM, b);
+                    tma_load_3d(sa, &map_a, full_bar + 8 * stage, kb * P.k_elems, mt * kTileM, b);
                     if (CL == 1) {
-                        tma_load_4d(sb, &map_b, full_bar + 8 * stage, kb * kBlockK, wt * kTileW, band * kTileH, b);
+                        tma_load_4d(sb, &map_b, full_bar + 8 * stage, kb * P.k_elems, wt * kTileW, band * kTileH, b);
                     } else {
                         // this CTA fetches 1/CL of the B tile (kTileH/CL target rows) and multicasts it into the
                         // same smem offset of every CTA of the cluster; each full barrier collects all CL parts
-                        tma_load_4d_mcast(sb + crank * (kBBytes / CL), &map_b, full_bar + 8 * stage, kb * kBlockK,
+                        tma_load_4d_mcast(sb + crank * (kBBytes / CL), &map_b, full_bar + 8 * stage, kb * P.k_elems,
                                           wt * kTileW, band * kTileH + crank * (kTileH / CL), b, (uint16_t)((1u << CL) - 1));
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -209,6 +227,9 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         if (PAIR_MMA)
                             tc_mma_tf32_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc2,
                                             (kb | k) != 0 ? 1u : 0u);
+                        else if (P.f16)  // K = 16 halves = the same 32 bytes per instruction
+                            tc_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDescF16,
+                                       (kb | k) != 0 ? 1u : 0u);
                         else
                             tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
                                         (kb | k) != 0 ? 1u : 0u);
@@ -239,12 +260,22 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int mt = ((t / tiles_per_m) % P.m_groups) * CL + crank;
             const int b = t / (tiles_per_m * P.m_groups);
             const int acc = it & 1;
+            // block-scaled fp16 operands: undo the power-of-two block scales together with 1/sqrt(D); all five scalars
+            // are fetched before the accumulator wait so that their latency never sits on the store chain
+            float sc4[4] = {P.scale, P.scale, P.scale, P.scale};
+            if (P.f16) {
+                const float sa = P.scale * __ldg(P.inv_a + (b * P.m_tiles + mt) * 2 + (ml >> 6));
+                const float* sb = P.inv_b + (int64_t)(b * P.bands + band) * 4 * P.w_tiles + wt;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) sc4[p] = sa * __ldg(sb + p * P.w_tiles);
+            }
             mbar_wait(tfull_bar + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + lane_addr + acc * kTileN;
 #pragma unroll
             for (int p = 0; p < kTileH / RP; ++p) {
                 float ra[32], rb[32];
+                const float tsc = sc4[RP == 2 ? p : p >> 1];
                 tmem_ld32(t_acc + (RP * p) * kTileW, ra);
                 if (RP == 2) tmem_ld32(t_acc + (2 * p + 1) * kTileW, rb);
                 tmem_ld_wait();
@@ -259,20 +290,20 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const uint32_t off = ((uint32_t)j ^ swz) << 4;
                     if (IL) {
                         // the two rows leave as ONE run (a0 b0 a1 b1 ...): first box = target columns 0..15, second = 16..31
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(ra[2 * j] * P.scale),
-                                     "f"(rb[2 * j] * P.scale), "f"(ra[2 * j + 1] * P.scale), "f"(rb[2 * j + 1] * P.scale)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(ra[2 * j] * tsc),
+                                     "f"(rb[2 * j] * tsc), "f"(ra[2 * j + 1] * tsc), "f"(rb[2 * j + 1] * tsc)
                                      : "memory");
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + off), "f"(ra[16 + 2 * j] * P.scale),
-                                     "f"(rb[16 + 2 * j] * P.scale), "f"(ra[17 + 2 * j] * P.scale), "f"(rb[17 + 2 * j] * P.scale)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + off), "f"(ra[16 + 2 * j] * tsc),
+                                     "f"(rb[16 + 2 * j] * tsc), "f"(ra[17 + 2 * j] * tsc), "f"(rb[17 + 2 * j] * tsc)
                                      : "memory");
                         continue;
                     }
-                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(ra[4 * j] * P.scale),
-                                 "f"(ra[4 * j + 1] * P.scale), "f"(ra[4 * j + 2] * P.scale), "f"(ra[4 * j + 3] * P.scale)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(ra[4 * j] * tsc),
+                                 "f"(ra[4 * j + 1] * tsc), "f"(ra[4 * j + 2] * tsc), "f"(ra[4 * j + 3] * tsc)
                                  : "memory");
                     if (RP == 2)
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + off), "f"(rb[4 * j] * P.scale),
-                                     "f"(rb[4 * j + 1] * P.scale), "f"(rb[4 * j + 2] * P.scale), "f"(rb[4 * j + 3] * P.scale)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + off), "f"(rb[4 * j] * tsc),
+                                     "f"(rb[4 * j + 1] * tsc), "f"(rb[4 * j + 2] * tsc), "f"(rb[4 * j + 3] * tsc)
                                      : "memory");
                 }
                 if (P.lsu_store && RP == 2 && !IL) {
@@ -326,7 +357,6 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int ew = warp & 3;
         const int ml = ew * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
-        const float q = 0.25f * P.scale;
         int it = 0;
         for (int t = first; t < P.total_tiles; t += stride, ++it) {
             const int wt = t % P.w_tiles;
@@ -337,6 +367,13 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int m = mt * kTileM + ml;
             const bool m_ok = m < P.N1;
             const int w0 = wt * kTileW;
+            float q4[4] = {0.25f * P.scale, 0.25f * P.scale, 0.25f * P.scale, 0.25f * P.scale};
+            if (P.f16) {
+                const float sa = 0.25f * P.scale * __ldg(P.inv_a + (b * P.m_tiles + mt) * 2 + (ml >> 6));
+                const float* sb = P.inv_b + (int64_t)(b * P.bands + band) * 4 * P.w_tiles + wt;
+#pragma unroll
+                for (int p = 0; p < 4; ++p) q4[p] = sa * __ldg(sb + p * P.w_tiles);
+            }
             mbar_wait(tfull_bar + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + lane_addr + acc * kTileN;
@@ -358,6 +395,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     tempty_arrive<PAIR_MMA>(tempty_bar + 8 * acc);
                 }
                 float l1[16];
+                const float q = q4[p];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) l1[j] = (ra[2 * j] + ra[2 * j + 1] + rb[2 * j] + rb[2 * j + 1]) * q;
                 const int h1 = band * 4 + p;
@@ -456,36 +494,47 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 }  // namespace
 
 int tc_feature_pitch(int D) { return (D + kBlockK - 1) / kBlockK * kBlockK; }
+int tc_feature_pitch_f16(int D) { return (D + 63) / 64 * 64; }
 
 // f1n/f2n: [B][H*W][Dp] fp32, TF32-rounded, zero-padded to Dp = tc_feature_pitch(D)
 int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, const raftcorr_pyramid_layout& lay,
                     int device, cudaStream_t s) {
+    return launch_build_tc_ex(f1n, f2n, D, pyramid, lay, device, s, false, nullptr, nullptr);
+}
+
+// f16: f1n/f2n are [B][H*W][Dp] fp16 (Dp = tc_feature_pitch_f16(D)), block-scaled by launch_f16_operands, whose
+// inverse scales are inv_a [B][2 ceil(N/128)] and inv_b [B][4 ceil(H/8)][ceil(W/32)]
+int launch_build_tc_ex(const void* f1n, const void* f2n, int D, float* pyramid, const raftcorr_pyramid_layout& lay,
+                       int device, cudaStream_t s, bool f16, const float* inv_a, const float* inv_b) {
     const int fusedL = lay.L < 4 ? lay.L : 4;  // levels 0..3 come out of the epilogue; deeper ones are pooled afterwards
     EncodeTiledFn fn;
     if (int rc = get_encode_fn(&fn)) return rc;
     const int B = lay.B, H = lay.H, W = lay.W, N1 = H * W;
-    const int Dp = tc_feature_pitch(D);
+    const int Dp = f16 ? tc_feature_pitch_f16(D) : tc_feature_pitch(D);
+    const int esz = f16 ? 2 : 4, k_elems = 128 / esz;   // a k-block is one 128-byte swizzle row
+    const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     // RAFTCORR_BUILD_CLUSTER: 1 = one CTA per tile, 2 = CTA pair with TMA multicast of B (measured slower),
     // 3 = CTA pair issuing tcgen05.mma.cta_group::2 (each CTA ingests only half of B)
     const char* ce = std::getenv("RAFTCORR_BUILD_CLUSTER");
     const int mode = (ce && ce[0] == '2') ? 1 : (ce && ce[0] == '3') ? 2 : kDefaultBuildMode;
     const int cl = mode == 0 ? 1 : 2;
+    RC_REQUIRE(!f16 || mode == 0, "f16 build: the CTA-pair experiments take TF32 operands only");
 
     CUtensorMap map_a, map_b, map_out;
     {
         cuuint64_t dims[3] = {(cuuint64_t)Dp, (cuuint64_t)N1, (cuuint64_t)B};
-        cuuint64_t strides[2] = {(cuuint64_t)Dp * 4, (cuuint64_t)N1 * Dp * 4};
-        cuuint32_t box[3] = {kBlockK, kTileM, 1};
-        if (int rc = encode_f32_map(fn, &map_a, (void*)f1n, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap1"))
+        cuuint64_t strides[2] = {(cuuint64_t)Dp * esz, (cuuint64_t)N1 * Dp * esz};
+        cuuint32_t box[3] = {(cuuint32_t)k_elems, kTileM, 1};
+        if (int rc = encode_map(fn, &map_a, dt, (void*)f1n, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap1"))
             return rc;
     }
     {
         cuuint64_t dims[4] = {(cuuint64_t)Dp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)Dp * 4, (cuuint64_t)W * Dp * 4, (cuuint64_t)N1 * Dp * 4};
-        cuuint32_t box[4] = {kBlockK, kTileW, (cuuint32_t)(kTileH / cl), 1};
-        if (int rc = encode_f32_map(fn, &map_b, (void*)f2n, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2"))
+        cuuint64_t strides[3] = {(cuuint64_t)Dp * esz, (cuuint64_t)W * Dp * esz, (cuuint64_t)N1 * Dp * esz};
+        cuuint32_t box[4] = {(cuuint32_t)k_elems, kTileW, (cuuint32_t)(kTileH / cl), 1};
+        if (int rc = encode_map(fn, &map_b, dt, (void*)f2n, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2"))
             return rc;
     }
     const bool il = lay.interleaved != 0;
@@ -522,7 +571,8 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
     P.m_groups = ceil_div(P.m_tiles, cl);
     P.bands = ceil_div(H, kTileH);
     P.w_tiles = ceil_div(W, kTileW);
-    P.k_blocks = Dp / kBlockK;
+    P.k_blocks = Dp / k_elems;
+    P.f16 = f16 ? 1 : 0; P.k_elems = k_elems; P.inv_a = inv_a; P.inv_b = inv_b;
     const int64_t total = (int64_t)B * P.m_groups * P.bands * P.w_tiles;  // tiles per cluster rank
     RC_REQUIRE(total < (1LL << 31), "tf32 build: too many tiles");
     P.total_tiles = (int)total;

@@ -2,11 +2,127 @@
 //   NCHW <-> NHWC transposes of the feature maps (the tcgen05 build and the on-the-fly path want
 //   the feature dim contiguous = K-major; the reference re-does this permute on every call,
 //   raft/core/corr.py:158-159), 2x2 average pooling (corr.py:42,138-139) and its adjoint.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace raftcorr {
 
 namespace {
+
+// ---- block-scaled fp16 operands for the kind::f16 build (RAFTCORR_BUILD_F16_TC) ----------------------------------
+// fp16 carries the same 11 significant bits as TF32 but only 5 exponent bits, so every operand BLOCK of 64 pixels (all
+// channels) gets its own power-of-two scale that puts the block's largest magnitude into [2^14, 2^15): anything down to
+// 2^-29 of the block maximum keeps full precision (below that it fades out through the subnormals, far below what 1e-3
+// of max|V| can see), nothing overflows, and powers of two make the scaling itself exact.  Blocks follow the build's
+// tiles -- fmap1: 64 consecutive source pixels (half an m-tile = one half of the TMEM lanes); fmap2: one ROW PAIR of an
+// 8 x 32 target tile (2 rows x 32 columns = one epilogue phase) -- so undoing the scales costs the epilogue one scalar
+// per thread and one per phase.  Both kinds of block are two segments of 32 contiguous pixels.
+struct F16PrepParams {
+    const float* f1;
+    const float* f2;
+    __half* o1;
+    __half* o2;
+    float* inv_a;   // [B][2 * m_tiles]
+    float* inv_b;   // [B][4 * bands][w_tiles]
+    int B, D, Dp, H, W, N, a_blocks, bands4, w_tiles;   // a_blocks = 2 * m_tiles per image
+};
+
+struct F16Block {
+    const float* src;   // image base [D][N]
+    __half* dst;        // image base [N][Dp]
+    float* inv;
+    int p0, p1, len0, len1;   // the two segments: first pixel, valid pixels (0..32)
+};
+
+__device__ __forceinline__ F16Block f16_block_of(const F16PrepParams& P, int id) {
+    F16Block k;
+    if (id < P.B * P.a_blocks) {
+        const int b = id / P.a_blocks, blk = id - b * P.a_blocks;
+        k.src = P.f1 + (int64_t)b * P.D * P.N;
+        k.dst = P.o1 + (int64_t)b * P.N * P.Dp;
+        k.inv = P.inv_a + id;
+        k.p0 = blk * 64;
+        k.p1 = k.p0 + 32;
+        k.len0 = max(0, min(32, P.N - k.p0));
+        k.len1 = max(0, min(32, P.N - k.p1));
+    } else {
+        id -= P.B * P.a_blocks;
+        const int per_b = P.bands4 * P.w_tiles;
+        const int b = id / per_b, r = id - b * per_b, hp = r / P.w_tiles, wt = r - hp * P.w_tiles;
+        k.src = P.f2 + (int64_t)b * P.D * P.N;
+        k.dst = P.o2 + (int64_t)b * P.N * P.Dp;
+        k.inv = P.inv_b + id;
+        const int cols = max(0, min(32, P.W - wt * 32));
+        k.p0 = (2 * hp) * P.W + wt * 32;
+        k.p1 = k.p0 + P.W;
+        k.len0 = 2 * hp < P.H ? cols : 0;
+        k.len1 = 2 * hp + 1 < P.H ? cols : 0;
+    }
+    return k;
+}
+
+// One CTA per block, ONE pass over HBM: the block (64 pixels x up to 256 channels) sits in registers (64 values per
+// thread, coalesced reads along the pixels) while its absmax is reduced, then it is scaled, rounded to fp16 and
+// transposed through shared memory; every pixel leaves as 128-byte runs of 64 channels.  Channels D..Dp are zeros.
+// NCH = ceil(Dp / 64) channel chunks of 64 (compile-time so that the register block stays in registers).
+template <int NCH>
+__global__ void __launch_bounds__(256, 2) f16_operand_kernel(const F16PrepParams P) {
+    __shared__ __half tile[64][NCH * 64 + 2];   // odd word stride: conflict-free both ways
+    __shared__ float red[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const F16Block k = f16_block_of(P, blockIdx.x);
+    float v[NCH][8][2];
+    float mx = 0.f;
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {              // warp: channel rows q*64 + warp*8 + c, lane = pixel of a segment
+            const int ch = q * 64 + warp * 8 + c;
+            const float* row = k.src + (int64_t)ch * P.N;
+            v[q][c][0] = (ch < P.D && lane < k.len0) ? __ldg(row + k.p0 + lane) : 0.f;
+            v[q][c][1] = (ch < P.D && lane < k.len1) ? __ldg(row + k.p1 + lane) : 0.f;
+        }
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mx = fmaxf(mx, fmaxf(fabsf(v[q][c][0]), fabsf(v[q][c][1])));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    float scale = 1.f, inv = 1.f;
+    if (mx > 0.f && mx < __int_as_float(0x7f800000)) {   // zero blocks and inf/NaN blocks keep scale 1 (inf/NaN propagate)
+        int e;
+        frexpf(mx, &e);                                  // mx = f * 2^e, f in [0.5, 1)
+        const int kk = max(-126, min(126, 15 - e));
+        scale = ldexpf(1.f, kk);
+        inv = ldexpf(1.f, -kk);
+    }
+    if (threadIdx.x == 0) *k.inv = inv;
+#pragma unroll
+    for (int q = 0; q < NCH; ++q)
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {
+            const int col = q * 64 + warp * 8 + c;
+            *reinterpret_cast<__half2*>(&tile[lane][col]) = __floats2half2_rn(v[q][c][0] * scale, v[q][c + 1][0] * scale);
+            *reinterpret_cast<__half2*>(&tile[32 + lane][col]) = __floats2half2_rn(v[q][c][1] * scale, v[q][c + 1][1] * scale);
+        }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                  // warp: 8 of the 64 pixels, lane = channel pair of every chunk
+        const int px = warp * 8 + i, seg = px >> 5, off = px & 31;
+        if (off < (seg ? k.len1 : k.len0)) {
+            __half* out = k.dst + (int64_t)((seg ? k.p1 : k.p0) + off) * P.Dp;
+#pragma unroll
+            for (int q = 0; q < NCH; ++q)
+                *reinterpret_cast<__half2*>(out + q * 64 + 2 * lane) = *reinterpret_cast<const __half2*>(&tile[px][q * 64 + 2 * lane]);
+        }
+    }
+}
 
 __device__ __forceinline__ float round_tf32(float x) {
     uint32_t u;
@@ -170,6 +286,28 @@ inline int grid_for(int64_t total, int threads) {
 }
 
 }  // namespace
+
+size_t f16_scale_floats(int B, int H, int W) {   // inv_a [B][2 m_tiles] followed by inv_b [B][4 bands][w_tiles]
+    return (size_t)B * (2 * ceil_div(H * W, 128) + 4 * ceil_div(H, 8) * ceil_div(W, 32));
+}
+
+int launch_f16_operands(const float* f1, const float* f2, int B, int D, int H, int W, void* f1h, void* f2h, float* inv_a,
+                        float* inv_b, cudaStream_t s) {
+    F16PrepParams P{};
+    P.f1 = f1; P.f2 = f2; P.o1 = (__half*)f1h; P.o2 = (__half*)f2h; P.inv_a = inv_a; P.inv_b = inv_b;
+    P.B = B; P.D = D; P.Dp = tc_feature_pitch_f16(D); P.H = H; P.W = W; P.N = H * W;
+    P.a_blocks = 2 * ceil_div(P.N, 128); P.bands4 = 4 * ceil_div(H, 8); P.w_tiles = ceil_div(W, 32);
+    const int blocks = B * (P.a_blocks + P.bands4 * P.w_tiles);
+    switch (P.Dp / 64) {
+        case 1: f16_operand_kernel<1><<<blocks, 256, 0, s>>>(P); break;
+        case 2: f16_operand_kernel<2><<<blocks, 256, 0, s>>>(P); break;
+        case 3: f16_operand_kernel<3><<<blocks, 256, 0, s>>>(P); break;
+        case 4: f16_operand_kernel<4><<<blocks, 256, 0, s>>>(P); break;
+        default: return fail("f16 build: feature dim %d > 256 is not supported (use the tf32 build)", D);
+    }
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
 
 int launch_nchw_to_nhwc_pair(const float* in1, float* out1, const float* in2, float* out2, int B, int D, int HW,
                              int Dout, bool round, cudaStream_t s) {

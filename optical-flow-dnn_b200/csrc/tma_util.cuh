@@ -24,14 +24,20 @@ inline int get_encode_fn(EncodeTiledFn* out) {
     return 0;
 }
 
+inline int encode_map(EncodeTiledFn fn, CUtensorMap* map, CUtensorMapDataType dtype, void* base, int rank,
+                      const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapSwizzle swizzle,
+                      CUtensorMapL2promotion promo, const char* what) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, dtype, (cuuint32_t)rank, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                    promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+    return 0;
+}
+
 inline int encode_f32_map(EncodeTiledFn fn, CUtensorMap* map, void* base, int rank, const cuuint64_t* dims,
                           const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapSwizzle swizzle,
                           CUtensorMapL2promotion promo, const char* what) {
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    RC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
-    return 0;
+    return encode_map(fn, map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides, box, swizzle, promo, what);
 }
 
 #ifdef __CUDACC__

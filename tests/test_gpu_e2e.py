@@ -20,7 +20,7 @@ def _epe(a, b):
     return float(np.sqrt(((a - b) ** 2).sum(1)).mean())
 
 
-@pytest.mark.parametrize("variant", ["corr_tf32", "corr_fp32", "alternate", "corr_tf32_fusedconvc1", "corr_fp32_fusedconvc1"])
+@pytest.mark.parametrize("variant", ["corr_f16", "corr_tf32", "corr_fp32", "alternate", "corr_f16_fusedconvc1", "corr_tf32_fusedconvc1", "corr_fp32_fusedconvc1"])
 def test_flow_after_12_iterations_matches_reference(variant):
     import optical_flow_dnn_b200 as rc
 
@@ -64,7 +64,8 @@ def test_training_step_gradients_flow_through_12_iterations():
         d, _ = O.lookup_grad(pyr, c, gw.astype(np.float64), r)
         acc = d if acc is None else [a + b for a, b in zip(acc, d)]
     e1, e2 = O.build_grad(acc, f1, f2)
-    for cls, kw in ((rc.CorrBlock, {"build_mode": "fp32"}), (rc.CorrBlock, {"build_mode": "tf32"}), (rc.AlternateCorrBlock, {})):
+    for cls, kw in ((rc.CorrBlock, {"build_mode": "fp32"}), (rc.CorrBlock, {"build_mode": "tf32"}), (rc.CorrBlock, {"build_mode": "f16"}),
+                    (rc.AlternateCorrBlock, {})):
         t1 = torch.from_numpy(f1).to(dev).requires_grad_()
         t2 = torch.from_numpy(f2).to(dev).requires_grad_()
         blk = cls(t1, t2, num_levels=L, radius=r, **kw)

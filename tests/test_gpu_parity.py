@@ -17,8 +17,8 @@ from oracle import corr_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 2e-5, "tf32": 1e-3}
-MODES = ["fp32", "tf32"]
+TOL = {"fp32": 2e-5, "tf32": 1e-3, "f16": 1e-3}   # f16 = block-scaled fp16 operands: TF32's 11 significant bits
+MODES = ["fp32", "tf32", "f16"]
 
 
 def dev():
@@ -80,7 +80,7 @@ def test_golden_gradients(pkg, golden, mode):
     assert rel_err(cs[1].grad, golden["dcoords1"]) <= TOL[mode] * 20
 
 
-ALT_TOL = {"fp32": 2e-5, "tf32": 1e-3}  # on-the-fly path: exact fp32 dots vs TF32 tensor-core tiles
+ALT_TOL = {"fp32": 2e-5, "tf32": 1e-3, "f16": 1e-3}  # on-the-fly path: exact fp32 dots vs TF32 tensor-core tiles
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -246,6 +246,36 @@ def test_full_size_properties(pkg, mode):
     assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs), 1.0)
 
 
+# ------------------------------------------------------------------ block-scaled fp16 operands: dynamic range
+def test_f16_block_scaling_dynamic_range(pkg):
+    """fp16 has 5 exponent bits; the per-tile power-of-two scales must make the f16 build as good as TF32 for feature
+    maps of any overall magnitude (1e-20 .. 1e+15), for magnitudes that differ by tile (x 2^+-20 per pixel block), and
+    for all-zero blocks; scaling by a power of two must give the same bits up to that factor."""
+    B, D, H, W, L, r = 2, 96, 24, 40, 3, 4   # D padded 96 -> 128 halves; 960 px = 7.5 m-tiles; 3 x 2 target tiles
+    N = H * W
+    g = torch.Generator(device=dev()).manual_seed(5)
+    f1 = torch.randn((B, D, H, W), generator=g, device=dev())
+    f2 = torch.randn((B, D, H, W), generator=g, device=dev())
+    # per-block magnitudes: every 128-pixel run of fmap1 and every 8x32 tile of fmap2 gets its own power of two
+    e1 = torch.randint(-20, 21, (B, 1, (N + 127) // 128), generator=g, device=dev()).float().repeat_interleave(128, 2)[..., :N]
+    f1 = f1 * torch.exp2(e1).reshape(B, 1, H, W)
+    e2 = torch.randint(-20, 21, (B, 1, (H + 7) // 8, (W + 31) // 32), generator=g, device=dev()).float()
+    f2 = f2 * torch.exp2(e2).repeat_interleave(8, 2).repeat_interleave(32, 3)[..., :H, :W]
+    f2[:, :, 8:16, 0:32] = 0.0   # an all-zero target tile
+    for mag in (1.0, 1e-20, 1e15):
+        a, b_ = f1 * mag, f2
+        ref = torch.einsum("bdm,bdn->bmn", a.reshape(B, D, N).double(), b_.reshape(B, D, N).double()) / np.sqrt(D)
+        for mode in ("tf32", "f16"):
+            v0 = pkg.CorrBlock(a, b_, L, r, build_mode=mode).corr_pyramid[0].reshape(B, N, N).double()
+            assert torch.isfinite(v0).all()
+            # per source-pixel row: the row's own scale (magnitudes differ by 2^40 between blocks)
+            err = (v0 - ref).abs().amax(dim=2) / ref.abs().amax(dim=2).clamp_min(1e-300)
+            assert float(err.max()) <= 1e-3, (mode, mag, float(err.max()))
+    v1 = pkg.CorrBlock(f1, f2, L, r, build_mode="f16").corr_pyramid[0]
+    v2 = pkg.CorrBlock(f1 * 1024.0, f2 * 0.125, L, r, build_mode="f16").corr_pyramid[0]
+    assert torch.equal(v1 * 128.0, v2)
+
+
 # ------------------------------------------------------------------ pyramids beyond 4 GiB (configs 4 and 5a)
 @pytest.mark.parametrize("shape", [(16, 256, 47, 156), (1, 256, 135, 240)], ids=["config4_B16_kitti", "config5a_B1_1080p"])
 def test_pyramid_larger_than_4GiB(pkg, shape):
@@ -360,7 +390,19 @@ def test_kernel_variants_agree(pkg, monkeypatch):
     coords = torch.from_numpy(O.coords_grid(B, H, W)).to(d) + 3.0 * torch.randn((B, 2, H, W), generator=g, device=d)
     coords[0, :, 0, :5] = torch.tensor([[-7.3, 0.0, 44.0, 100.5, 3.999], [2.0, -0.5, 29.0, 1.0, 29.999]], device=d)
 
-    # production: row-pair-interleaved pyramid, single-CTA build, TMA lookup
+    # the fp16-operand build: its pipeline shapes agree bit for bit, and with the TF32 build to rounding
+    v16 = pkg.CorrBlock(f1, f2, L, r, build_mode="f16").corr_pyramid
+    for pipe in ("322", "222", "242"):
+        monkeypatch.setenv("RAFTCORR_BUILD_PIPE", pipe)
+        for a, c in zip(v16, pkg.CorrBlock(f1, f2, L, r, build_mode="f16").corr_pyramid):
+            assert torch.equal(a, c), pipe
+    monkeypatch.delenv("RAFTCORR_BUILD_PIPE")
+    # everything below compares variants of the TF32 build (the CTA-pair experiments exist for it only)
+    import optical_flow_dnn_b200.corr as corr_mod
+    monkeypatch.setattr(corr_mod, "_default_mode", "tf32")
+    for a, c in zip(v16, pkg.CorrBlock(f1, f2, L, r).corr_pyramid):
+        assert float((a - c).abs().max()) <= 1e-3 * float(c.abs().max())
+    # production layout: row-pair-interleaved pyramid, single-CTA build, TMA lookup
     blk_il = pkg.CorrBlock(f1, f2, L, r)
     assert blk_il._layout.interleaved == 1
     o_il = blk_il(coords)
