@@ -224,6 +224,20 @@ int raftcorr_alt_lookup_fwd(const float* f1_nhwc, const float* f2_pyramid_nhwc, 
                             int D, int H, int W, int L, int radius, int mode, float* out, void* workspace,
                             size_t workspace_bytes, int device, raftcorr_stream_t stream);
 
+/* The tensor-core lookup on fp16 operands (TF32's 11 significant bits; half the operand bytes the kernel is bound by).
+ * raftcorr_alt_f16_prepare converts the NHWC tensors of raftcorr_alt_pyramid once per AlternateCorrBlock into a
+ * caller-owned buffer of raftcorr_alt_f16_bytes(): every (tensor, image) gets one power-of-two scale (its largest
+ * magnitude lands in [2^14, 2^15), so 2^29 of dynamic range inside an image stay at full precision; the lattice tiles
+ * of this kernel sit at arbitrary offsets, so there are no per-tile scales as in RAFTCORR_BUILD_F16_TC).
+ * raftcorr_alt_lookup_fwd_f16 == raftcorr_alt_lookup_fwd(mode RAFTCORR_BUILD_TF32_TC) on that buffer: same work space,
+ * same result to rounding.  D % 64 == 0.  The backward keeps reading the fp32 tensors. */
+size_t raftcorr_alt_f16_bytes(int B, int D, int H, int W, int L);
+int raftcorr_alt_f16_prepare(const float* f1_nhwc, const float* f2_pyramid_nhwc, int B, int D, int H, int W, int L,
+                             void* f16_operands, int device, raftcorr_stream_t stream);
+int raftcorr_alt_lookup_fwd_f16(const void* f16_operands, const float* coords, int B, int D, int H, int W, int L,
+                                int radius, float* out, void* workspace, size_t workspace_bytes, int device,
+                                raftcorr_stream_t stream);
+
 /* Gradient of raftcorr_alt_lookup_fwd w.r.t. the NHWC feature tensors (accumulated into
  * df1_nhwc [B,H,W,D] and df2_pyramid_nhwc, same layout as the forward pyramid; zero them first). */
 int raftcorr_alt_lookup_bwd(const float* f1_nhwc, const float* f2_pyramid_nhwc, const float* coords,

@@ -73,6 +73,10 @@ SIGNATURES = {
     "raftcorr_alt_lookup_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "raftcorr_alt_lookup_fwd": (_c_int, [_c_void_p] * 3 + [_c_int] * 7 + [_c_void_p, _c_void_p, _c_size_t, _c_int,
                                                                             _c_void_p]),
+    "raftcorr_alt_f16_bytes": (_c_size_t, [_c_int] * 5),
+    "raftcorr_alt_f16_prepare": (_c_int, [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p, _c_int, _c_void_p]),
+    "raftcorr_alt_lookup_fwd_f16": (_c_int, [_c_void_p, _c_void_p] + [_c_int] * 6 + [_c_void_p, _c_void_p, _c_size_t, _c_int,
+                                                                                      _c_void_p]),
     "raftcorr_alt_lookup_bwd": (_c_int, [_c_void_p] * 4 + [_c_int] * 6 + [_c_void_p, _c_void_p, _c_int, _c_void_p]),
     "raftcorr_alt_grad_finish": (_c_int, [_c_void_p, _c_void_p] + [_c_int] * 5 + [_c_void_p, _c_void_p, _c_int,
                                                                                   _c_void_p]),

@@ -641,11 +641,34 @@ class AlternateCorrBlock:
         self._ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         return f1n, f2p
 
+    def _ensure_f16(self, f1n, f2p):
+        """fp16 copies of the NHWC tensors (one power-of-two scale per image and tensor), made once per block: the
+        tensor-core lookup is bound by its operand bytes.  ``RAFTCORR_ALT_F16=0`` keeps TF32 operands (A/B)."""
+        if getattr(self, "_f16", None) is None:
+            use = (self._mode == _lib.BUILD_TF32_TC and self._D % 64 == 0 and
+                   os.environ.get("RAFTCORR_ALT_F16", "1") != "0" and os.environ.get("RAFTCORR_ALT_TC", "") != "resident")
+            if not use:
+                self._f16 = False
+            else:
+                B, D, H, W, L = self._B, self._D, self._H, self._W, self.num_levels
+                lib = _lib.lib()
+                buf = torch.empty(int(lib.raftcorr_alt_f16_bytes(B, D, H, W, L)), dtype=torch.uint8, device=self._device)
+                check(lib.raftcorr_alt_f16_prepare(_ptr(f1n), _ptr(f2p), B, D, H, W, L, _ptr(buf), self._device.index,
+                                                   _stream(self._device)), "raftcorr_alt_f16_prepare")
+                self._f16 = buf
+        return self._f16
+
     def _lookup(self, f1n, f2p, coords):
         B, D, H, W, L = self._B, self._D, self._H, self._W, self.num_levels
         dev = self._device
         K = 2 * self.radius + 1
         out = torch.empty((B, L * K * K, H, W), dtype=torch.float32, device=dev)
+        f16 = self._ensure_f16(f1n, f2p)
+        if f16 is not False:
+            check(_lib.lib().raftcorr_alt_lookup_fwd_f16(_ptr(f16), _ptr(coords), B, D, H, W, L, self.radius, _ptr(out),
+                                                         _ptr(self._ws), self._ws.numel(), dev.index, _stream(dev)),
+                  "raftcorr_alt_lookup_fwd_f16")
+            return out
         check(_lib.lib().raftcorr_alt_lookup_fwd(_ptr(f1n), _ptr(f2p), _ptr(coords), B, D, H, W, L, self.radius,
                                                  self._mode, _ptr(out), _ptr(self._ws), self._ws.numel(), dev.index,
                                                  _stream(dev)), "raftcorr_alt_lookup_fwd")

@@ -67,7 +67,21 @@ struct AltTcParams {
     int bb_w, bb_h;    // primary lattice tile shape the bounding boxes are cut into
     const float* f1;   // [B][H][W][C] (resident-A kernel reads it directly)
     int C;
+    // fp16 operands with one power-of-two scale per image and tensor (launch_alt_f16_operands): inv[b] for fmap1,
+    // inv[(1 + l) * B + b] for level l of the fmap2 pyramid; k_elems = operand elements per 128-byte k-block
+    int f16, k_elems;
+    const float* inv;
 };
+
+constexpr uint32_t kInstrDescF16 = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+__device__ __forceinline__ void tc_mma_f16_alt(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kInstrDescF16), "r"(accumulate)
+        : "memory");
+}
 
 constexpr int smem_bytes(int R) {
     return kStages * kStageBytes + 2 * kTileM * kRowPitch * 4 + (2 * R + 1) * (2 * R + 1) * kTileM * 4 + 1024 + 256;
@@ -219,8 +233,9 @@ __device__ __forceinline__ void alt_tc_epilogue(const AltTcParams& P, int ew, in
             if (valid) {
                 float* dst = P.out + ((((int64_t)b * P.L + l) * K * K + I0 * K) * P.H + y) * P.W + x;
                 const int64_t plane = (int64_t)P.H * P.W;
+                const float osc = P.f16 ? P.scale * __ldg(P.inv + b) * __ldg(P.inv + (1 + l) * P.B + b) : P.scale;
 #pragma unroll
-                for (int ch = 0; ch < IN * K; ++ch) dst[ch * plane] = my_acc[ch * kTileM] * P.scale;
+                for (int ch = 0; ch < IN * K; ++ch) dst[ch * plane] = my_acc[ch * kTileM] * osc;
             }
         }
     }
@@ -289,8 +304,8 @@ alt_fwd_tc_kernel(const __grid_constant__ AltTcMaps maps, const AltTcParams P) {
                                 mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                                 const uint32_t sa = stage_base + stage * kStageBytes;
                                 mbar_expect_tx(full_bar + 8 * stage, kStageBytes);
-                                tma_load_4d(sa, &maps.a, full_bar + 8 * stage, kb * kBlockK, tx * kSrcW, ty * kSrcH, b);
-                                tma_load_4d(sa + kABytes, mb, full_bar + 8 * stage, kb * kBlockK, bb.x + a * tw, bb.y + c * th, b);
+                                tma_load_4d(sa, &maps.a, full_bar + 8 * stage, kb * P.k_elems, tx * kSrcW, ty * kSrcH, b);
+                                tma_load_4d(sa + kABytes, mb, full_bar + 8 * stage, kb * P.k_elems, bb.x + a * tw, bb.y + c * th, b);
                                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
                 }
@@ -317,8 +332,11 @@ alt_fwd_tc_kernel(const __grid_constant__ AltTcMaps maps, const AltTcParams P) {
                             const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + kABytes);
 #pragma unroll
                             for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                                tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
-                                            (kb | k) != 0 ? 1u : 0u);
+                                if (P.f16)  // K = 16 halves: the same 32 bytes per instruction
+                                    tc_mma_f16_alt(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0 ? 1u : 0u);
+                                else
+                                    tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
+                                                (kb | k) != 0 ? 1u : 0u);
                             tc_commit(empty_bar + 8 * stage);
                             if (++stage == kStages) { stage = 0; phase ^= 1; }
                         }
@@ -533,9 +551,19 @@ size_t alt_tc_workspace_bytes(int B, int H, int W, int L) {
 int launch_alt_fwd_tc(const float* f1_nhwc, const AltLevels& lv, const CoordsView& cv, int B, int H, int W, int C,
                       int radius, float scale, float* out, void* workspace, size_t workspace_bytes, int device,
                       cudaStream_t s) {
+    return launch_alt_fwd_tc_ex(f1_nhwc, lv, cv, B, H, W, C, radius, scale, out, workspace, workspace_bytes, device, s, false,
+                                nullptr);
+}
+
+// f16: f1_nhwc / lv.f2[] point at fp16 NHWC copies (C % 64 == 0) scaled per image; inv: see AltTcParams
+int launch_alt_fwd_tc_ex(const void* f1_nhwc, const AltLevels& lv, const CoordsView& cv, int B, int H, int W, int C,
+                         int radius, float scale, float* out, void* workspace, size_t workspace_bytes, int device,
+                         cudaStream_t s, bool f16, const float* inv) {
+    const int esz = f16 ? 2 : 4, k_elems = 128 / esz;
+    const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    RC_REQUIRE(C % k_elems == 0, "alt tensor-core lookup: feature dim must be a multiple of %d (got %d)", k_elems, C);
     RC_REQUIRE(lv.L >= 1 && lv.L <= 4, "alt tf32: 1..4 levels supported (got %d)", lv.L);
     RC_REQUIRE(radius >= 1 && radius <= 4, "alt tf32: radius %d not supported (1..4)", radius);
-    RC_REQUIRE(C % kBlockK == 0 && C >= kBlockK, "alt tf32: feature dim must be a multiple of %d (got %d)", kBlockK, C);
     RC_REQUIRE(workspace && workspace_bytes >= alt_tc_workspace_bytes(B, H, W, lv.L), "alt tf32: workspace too small");
     RC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "alt tf32: workspace must be 16-byte aligned");
     EncodeTiledFn fn;
@@ -543,34 +571,35 @@ int launch_alt_fwd_tc(const float* f1_nhwc, const AltLevels& lv, const CoordsVie
     AltTcMaps maps;
     {
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-        cuuint32_t box[4] = {kBlockK, kSrcW, kSrcH, 1};
-        if (int rc = encode_f32_map(fn, &maps.a, (void*)f1_nhwc, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap1 (NHWC)"))
+        cuuint64_t strides[3] = {(cuuint64_t)C * esz, (cuuint64_t)W * C * esz, (cuuint64_t)H * W * C * esz};
+        cuuint32_t box[4] = {(cuuint32_t)k_elems, kSrcW, kSrcH, 1};
+        if (int rc = encode_map(fn, &maps.a, dt, (void*)f1_nhwc, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap1 (NHWC)"))
             return rc;
     }
     // RAFTCORR_ALT_TC=resident selects the kernel that keeps the fmap1 block in tensor memory (A/B switch, D <= 256;
     // measured slower: 3.2 us per 128-point tile vs 4.4 us per 256-point tile, see profiles/README.md)
     const char* ve = std::getenv("RAFTCORR_ALT_TC");
-    const bool resident = C <= 256 && ve && ve[0] == 'r';
+    const bool resident = !f16 && C <= 256 && ve && ve[0] == 'r';
     for (int l = 0; l < 4; ++l) {
         const int ll = l < lv.L ? l : 0;
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)lv.w[ll], (cuuint64_t)lv.h[ll], (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)lv.w[ll] * C * 4, (cuuint64_t)lv.h[ll] * lv.w[ll] * C * 4};
-        cuuint32_t box[4] = {kBlockK, (cuuint32_t)(resident ? kHalfW : kTgtW), (cuuint32_t)(resident ? kHalfH : kTgtH), 1};
-        if (int rc = encode_f32_map(fn, &maps.b[l], (void*)lv.f2[ll], 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2 level (NHWC)"))
+        cuuint64_t strides[3] = {(cuuint64_t)C * esz, (cuuint64_t)lv.w[ll] * C * esz, (cuuint64_t)lv.h[ll] * lv.w[ll] * C * esz};
+        cuuint32_t box[4] = {(cuuint32_t)k_elems, (cuuint32_t)(resident ? kHalfW : kTgtW), (cuuint32_t)(resident ? kHalfH : kTgtH), 1};
+        if (int rc = encode_map(fn, &maps.b[l], dt, (void*)lv.f2[ll], 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2 level (NHWC)"))
             return rc;
-        cuuint32_t box_sq[4] = {kBlockK, kSqW, kSqH, 1};
-        if (int rc = encode_f32_map(fn, &maps.bsq[l], (void*)lv.f2[ll], 4, dims, strides, box_sq, CU_TENSOR_MAP_SWIZZLE_128B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2 level (NHWC), square tiles"))
+        cuuint32_t box_sq[4] = {(cuuint32_t)k_elems, kSqW, kSqH, 1};
+        if (int rc = encode_map(fn, &maps.bsq[l], dt, (void*)lv.f2[ll], 4, dims, strides, box_sq, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2 level (NHWC), square tiles"))
             return rc;
     }
     AltTcParams P{};
     P.coords = cv.ptr; P.cb = cv.batch_stride; P.cc = cv.comp_stride; P.cp = cv.pix_stride;
     P.bbox = reinterpret_cast<int4*>(workspace);
     P.out = out;
-    P.B = B; P.H = H; P.W = W; P.L = lv.L; P.k_blocks = C / kBlockK;
+    P.B = B; P.H = H; P.W = W; P.L = lv.L; P.k_blocks = C / k_elems;
+    P.f16 = f16 ? 1 : 0; P.k_elems = k_elems; P.inv = inv;
     P.tiles_x = ceil_div(W, kSrcW); P.tiles_y = ceil_div(H, kSrcH);
     const int64_t total = (int64_t)B * P.tiles_x * P.tiles_y;
     RC_REQUIRE(total < (1LL << 31), "alt tf32: too many source blocks");
@@ -584,7 +613,7 @@ int launch_alt_fwd_tc(const float* f1_nhwc, const AltLevels& lv, const CoordsVie
     { const char* e = std::getenv("RAFTCORR_ALT_SQUARE"); P.allow_square = !resident && !(e && e[0] == '0'); }
     P.bb_w = resident ? kHalfW : kTgtW;
     P.bb_h = resident ? kHalfH : kTgtH;
-    P.f1 = f1_nhwc;
+    P.f1 = (const float*)f1_nhwc;
     P.C = C;
     int sms = 0;
     RC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));

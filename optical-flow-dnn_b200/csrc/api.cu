@@ -431,6 +431,67 @@ int raftcorr_alt_lookup_fwd(const float* f1_nhwc, const float* f2_pyr, const flo
     return launch_alt_fwd(f1_nhwc, lv, cv, B, 1, H, W, D, radius, scale, out, (cudaStream_t)stream);
 }
 
+// ---- fp16 operands for the tensor-core on-the-fly lookup ---------------------------------------------------------
+// layout of the caller's buffer: [fmap1 halves][pyramid halves (same element offsets as the fp32 pyramid)][inv][maxbits]
+namespace {
+struct AltF16Layout { size_t f1, f2, inv, bits, total; };
+AltF16Layout alt_f16_layout(int B, int D, int H, int W, int L) {
+    AltF16Layout a{};
+    a.f1 = 0;
+    a.f2 = align_up((size_t)B * H * W * D * 2, 1024);
+    a.inv = a.f2 + align_up((size_t)raftcorr_alt_level_offset(B, D, H, W, L) * 2, 1024);
+    a.bits = a.inv + align_up((size_t)(1 + L) * B * sizeof(float), 256);
+    a.total = a.bits + align_up((size_t)(1 + L) * B * sizeof(unsigned), 256);
+    return a;
+}
+}  // namespace
+
+size_t raftcorr_alt_f16_bytes(int B, int D, int H, int W, int L) {
+    if (B < 0 || D < 1 || H < 1 || W < 1 || L < 1 || L > 4) return 0;
+    return alt_f16_layout(B, D, H, W, L).total;
+}
+
+int raftcorr_alt_f16_prepare(const float* f1_nhwc, const float* f2_pyr, int B, int D, int H, int W, int L, void* f16_ops,
+                             int device, raftcorr_stream_t stream) {
+    RC_REQUIRE(B == 0 || (f1_nhwc && f2_pyr && f16_ops), "alt_f16_prepare: NULL tensor");
+    RC_REQUIRE(D % 64 == 0, "alt_f16_prepare: needs D %% 64 == 0 (got %d)", D);
+    AltLevels lv{};
+    if (int rc = alt_levels(f2_pyr, nullptr, B, D, H, W, L, &lv)) return rc;
+    if (B == 0) return 0;
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "alt_f16_prepare: cannot select device %d", device);
+    const AltF16Layout a = alt_f16_layout(B, D, H, W, L);
+    int64_t off[5] = {0}, per[5] = {0};
+    per[0] = (int64_t)H * W * D;
+    for (int l = 0; l < L; ++l) {
+        off[1 + l] = lv.f2[l] - f2_pyr;
+        per[1 + l] = (int64_t)lv.h[l] * lv.w[l] * D;
+    }
+    char* base = (char*)f16_ops;
+    return launch_alt_f16_operands(f1_nhwc, f2_pyr, base + a.f1, base + a.f2, off, per, 1 + L, B, (float*)(base + a.inv),
+                                   (unsigned*)(base + a.bits), (cudaStream_t)stream);
+}
+
+int raftcorr_alt_lookup_fwd_f16(const void* f16_ops, const float* coords, int B, int D, int H, int W, int L, int radius,
+                                float* out, void* workspace, size_t workspace_bytes, int device, raftcorr_stream_t stream) {
+    RC_REQUIRE(B == 0 || (f16_ops && coords && out), "alt_lookup_fwd_f16: NULL tensor");
+    RC_REQUIRE(D % 64 == 0, "alt_lookup_fwd_f16: needs D %% 64 == 0 (got %d)", D);
+    const AltF16Layout a = alt_f16_layout(B, D, H, W, L);
+    const char* base = (const char*)f16_ops;
+    AltLevels lv{};
+    if (int rc = alt_levels((const float*)(base + a.f2), nullptr, B, D, H, W, L, &lv)) return rc;
+    if (B == 0) return 0;
+    // alt_levels computed FLOAT offsets; the halves live at the same ELEMENT offsets
+    for (int l = 0; l < L; ++l)
+        lv.f2[l] = (const float*)(base + a.f2 + 2 * (size_t)raftcorr_alt_level_offset(B, D, H, W, l));
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "alt_lookup_fwd_f16: cannot select device %d", device);
+    const int64_t N1 = (int64_t)H * W;
+    CoordsView cv{coords, 2 * N1, N1, 1};  // [B,2,H,W]
+    return launch_alt_fwd_tc_ex(base + a.f1, lv, cv, B, H, W, D, radius, 1.0f / sqrtf((float)D), out, workspace, workspace_bytes,
+                                device, (cudaStream_t)stream, true, (const float*)(base + a.inv));
+}
+
 int raftcorr_alt_lookup_bwd(const float* f1_nhwc, const float* f2_pyr, const float* coords, const float* grad_out,
                             int B, int D, int H, int W, int L, int radius, float* df1_nhwc, float* df2_pyr,
                             int device, raftcorr_stream_t stream) {

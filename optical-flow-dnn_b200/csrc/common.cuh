@@ -145,6 +145,14 @@ size_t alt_tc_workspace_bytes(int B, int H, int W, int L);
 int launch_alt_fwd_tc(const float* f1_nhwc, const AltLevels& lv, const CoordsView& cv, int B, int H, int W, int C,
                       int radius, float scale, float* out, void* workspace, size_t workspace_bytes, int device,
                       cudaStream_t s);
+int launch_alt_fwd_tc_ex(const void* f1_nhwc, const AltLevels& lv, const CoordsView& cv, int B, int H, int W, int C,
+                         int radius, float scale, float* out, void* workspace, size_t workspace_bytes, int device,
+                         cudaStream_t s, bool f16, const float* inv);
+// fp32 NHWC tensors -> fp16 copies scaled by one power of two per image and tensor (prep.cu).  `count` tensors of
+// per_img[t] elements per image; src/dst element offsets off[t] (same numbers for both buffers);
+// inv [count][B] floats, maxbits [count][B] scratch.
+int launch_alt_f16_operands(const float* src_f1, const float* src_f2, void* dst_f1, void* dst_f2, const int64_t* off,
+                            const int64_t* per_img, int count, int B, float* inv, unsigned* maxbits, cudaStream_t s);
 int launch_alt_bwd(const float* f1_nhwc, const AltLevels& lv, const CoordsView& cv, const float* grad_out, int B,
                    int NC, int H1, int W1, int C, int radius, float scale, float* df1_nhwc, cudaStream_t s);
 

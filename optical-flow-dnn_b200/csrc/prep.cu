@@ -4,6 +4,8 @@
 //   raft/core/corr.py:158-159), 2x2 average pooling (corr.py:42,138-139) and its adjoint.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace raftcorr {
@@ -121,6 +123,58 @@ __global__ void __launch_bounds__(256, 2) f16_operand_kernel(const F16PrepParams
             for (int q = 0; q < NCH; ++q)
                 *reinterpret_cast<__half2*>(out + q * 64 + 2 * lane) = *reinterpret_cast<const __half2*>(&tile[px][q * 64 + 2 * lane]);
         }
+    }
+}
+
+// ---- fp16 operands for the on-the-fly tensor-core lookup: one power-of-two scale per image and tensor --------------
+// The lattice tiles of that kernel sit at arbitrary offsets (bounding boxes of the windows), so per-tile scales do not
+// exist; one scale per (tensor, image) leaves 2^29 of dynamic range inside an image at full 11-bit precision.
+struct AltF16Tensors {
+    const float* src[5];
+    __half* dst[5];
+    int64_t per_img[5];
+    int count, B;
+    float* inv;          // [count][B]
+    unsigned* maxbits;   // [count][B], zeroed before the first kernel
+};
+
+__global__ void __launch_bounds__(256) alt_f16_absmax_kernel(const AltF16Tensors T) {
+    const int t = blockIdx.z, b = blockIdx.y;
+    const int64_t n4 = T.per_img[t] >> 2;   // per-image sizes are multiples of 64 elements
+    const float4* src = reinterpret_cast<const float4*>(T.src[t] + (int64_t)b * T.per_img[t]);
+    float mx = 0.f;
+    for (int64_t i = blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+        const float4 v = __ldg(src + i);
+        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // non-negative floats order like their bit patterns (NaN compares above everything: the image keeps scale 1)
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(T.maxbits + t * T.B + b, __float_as_uint(mx));
+}
+
+__global__ void __launch_bounds__(256) alt_f16_convert_kernel(const AltF16Tensors T) {
+    const int t = blockIdx.z, b = blockIdx.y;
+    const float mx = __uint_as_float(T.maxbits[t * T.B + b]);
+    float scale = 1.f, inv = 1.f;
+    if (mx > 0.f && mx < __int_as_float(0x7f800000)) {
+        int e;
+        frexpf(mx, &e);
+        const int kk = max(-126, min(126, 15 - e));
+        scale = ldexpf(1.f, kk);
+        inv = ldexpf(1.f, -kk);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) T.inv[t * T.B + b] = inv;
+    const int64_t n4 = T.per_img[t] >> 2;
+    const float4* src = reinterpret_cast<const float4*>(T.src[t] + (int64_t)b * T.per_img[t]);
+    uint2* dst = reinterpret_cast<uint2*>(T.dst[t] + (int64_t)b * T.per_img[t]);
+    for (int64_t i = blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+        const float4 v = __ldg(src + i);
+        const __half2 lo = __floats2half2_rn(v.x * scale, v.y * scale), hi = __floats2half2_rn(v.z * scale, v.w * scale);
+        uint2 o;
+        o.x = *reinterpret_cast<const unsigned*>(&lo);
+        o.y = *reinterpret_cast<const unsigned*>(&hi);
+        dst[i] = o;
     }
 }
 
@@ -305,6 +359,28 @@ int launch_f16_operands(const float* f1, const float* f2, int B, int D, int H, i
         case 4: f16_operand_kernel<4><<<blocks, 256, 0, s>>>(P); break;
         default: return fail("f16 build: feature dim %d > 256 is not supported (use the tf32 build)", D);
     }
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_alt_f16_operands(const float* src_f1, const float* src_f2, void* dst_f1, void* dst_f2, const int64_t* off,
+                            const int64_t* per_img, int count, int B, float* inv, unsigned* maxbits, cudaStream_t s) {
+    RC_REQUIRE(count >= 2 && count <= 5, "alt f16 operands: 1..4 pyramid levels");
+    AltF16Tensors T{};
+    T.count = count; T.B = B; T.inv = inv; T.maxbits = maxbits;
+    int64_t biggest = 0;
+    for (int t = 0; t < count; ++t) {   // tensor 0 = fmap1, 1.. = fmap2 levels (off[] = element offset inside the pyramid)
+        T.src[t] = t == 0 ? src_f1 : src_f2 + off[t];
+        T.dst[t] = t == 0 ? (__half*)dst_f1 : (__half*)dst_f2 + off[t];
+        T.per_img[t] = per_img[t];
+        RC_REQUIRE(per_img[t] % 4 == 0, "alt f16 operands: per-image size must be a multiple of 4");
+        biggest = per_img[t] > biggest ? per_img[t] : biggest;
+    }
+    RC_CUDA(cudaMemsetAsync(maxbits, 0, sizeof(unsigned) * count * B, s));
+    const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div64(biggest / 4, 256 * 8), 148 * 4));
+    dim3 grid(chunks, B, count);
+    alt_f16_absmax_kernel<<<grid, 256, 0, s>>>(T);
+    alt_f16_convert_kernel<<<grid, 256, 0, s>>>(T);
     RC_CUDA(cudaGetLastError());
     return 0;
 }

@@ -276,6 +276,35 @@ def test_f16_block_scaling_dynamic_range(pkg):
     assert torch.equal(v1 * 128.0, v2)
 
 
+def test_alt_f16_operands_match_tf32_operands(pkg, monkeypatch):
+    """The on-the-fly tensor-core lookup reads fp16 copies of the feature tensors (one power-of-two scale per image and
+    tensor) by default; RAFTCORR_ALT_F16=0 keeps TF32 operands.  Same error against the exact-fp32 volume path, for any
+    overall magnitude and for images of very different magnitude inside one batch."""
+    B, D, H, W, L, r = 3, 128, 24, 40, 3, 4
+    g = torch.Generator(device=dev()).manual_seed(9)
+    f1 = torch.randn((B, D, H, W), generator=g, device=dev())
+    f2 = torch.randn((B, D, H, W), generator=g, device=dev())
+    f1 = f1 * torch.tensor([1.0, 2.0 ** 17, 2.0 ** -21], device=dev()).reshape(B, 1, 1, 1)   # per-image magnitudes
+    coords = torch.from_numpy(O.coords_grid(B, H, W)).to(dev()) + 3.0 * torch.randn((B, 2, H, W), generator=g, device=dev())
+    for mag in (1.0, 1e-18, 1e12):
+        a = f1 * mag
+        ref = pkg.CorrBlock(a, f2, L, r, build_mode="fp32")(coords).double()
+        scale = ref.abs().amax(dim=(1, 2, 3), keepdim=True)   # per image: their magnitudes differ by 2^38
+        outs = {}
+        for flag in ("1", "0"):
+            monkeypatch.setenv("RAFTCORR_ALT_F16", flag)
+            blk = pkg.AlternateCorrBlock(a, f2, L, r, build_mode="tf32")
+            outs[flag] = blk(coords).double()
+            assert (blk._f16 is not False) == (flag == "1")
+            assert float(((outs[flag] - ref).abs() / scale).max()) <= 1e-3, (flag, mag)
+        assert float(((outs["1"] - outs["0"]).abs() / scale).max()) <= 1e-3
+    monkeypatch.delenv("RAFTCORR_ALT_F16")
+    # D % 64 != 0: TF32 operands
+    blk = pkg.AlternateCorrBlock(f1[:, :96], f2[:, :96], L, r, build_mode="tf32")
+    blk(coords)
+    assert blk._f16 is False
+
+
 # ------------------------------------------------------------------ pyramids beyond 4 GiB (configs 4 and 5a)
 @pytest.mark.parametrize("shape", [(16, 256, 47, 156), (1, 256, 135, 240)], ids=["config4_B16_kitti", "config5a_B1_1080p"])
 def test_pyramid_larger_than_4GiB(pkg, shape):
