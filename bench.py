@@ -424,7 +424,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"tf32": "tf32", "f16": "f16 operands (block-scaled, 11-bit significands like tf32), f32 accumulate", "fp32": "f32"}[mode],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"tf32": "tf32", "f16": "f16xf16->f32", "fp32": "f32"}[mode],
             "data": "synthetic",
             "precision": ("volume and lookups within 1e-3 of max|ref| (north_star); measured 3.07e-4 for f16 and for tf32 alike "
                           "(profiles/r01_f16_parity_b8.json): block-scaled fp16 operands carry TF32's 11 significant bits, "
