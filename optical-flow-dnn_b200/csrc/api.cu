@@ -1,6 +1,7 @@
 // extern "C" surface of libraftcorr_b200.so -- see include/raftcorr.h for the contract and the
 // reference interfaces each entry point replaces.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "lookup_common.cuh"
@@ -154,7 +155,9 @@ int raftcorr_fnet_head_supported(int Cin, int D, int H, int W) {
 
 size_t raftcorr_fnet_head_build_workspace_bytes(int B, int Cin, int D, int H, int W) {
     if (B < 0 || Cin < 1 || D < 1 || H < 1 || W < 1) return 0;
-    return raftcorr_build_fwd_workspace_bytes(B, D, H, W, RAFTCORR_BUILD_TF32_TC) + fnet_head_weight_bytes(Cin, D);
+    // [TF32 operands the head writes][rounded weight][fp16 block-scaled operands + scales for the build (D <= 256)]
+    return raftcorr_build_fwd_workspace_bytes(B, D, H, W, RAFTCORR_BUILD_TF32_TC) + fnet_head_weight_bytes(Cin, D) +
+           (D <= 256 ? raftcorr_build_fwd_workspace_bytes(B, D, H, W, RAFTCORR_BUILD_F16_TC) : 0);
 }
 
 int raftcorr_fnet_head_build_fwd(const float* x, const float* weight, const float* bias, int Cin, int D, float* pyramid,
@@ -165,7 +168,7 @@ int raftcorr_fnet_head_build_fwd(const float* x, const float* weight, const floa
     RC_REQUIRE(x && weight && pyramid, "fnet_head_build_fwd: NULL tensor");
     RC_REQUIRE(Cin >= 1 && D >= 1, "fnet_head_build_fwd: bad sizes Cin=%d D=%d", Cin, D);
     const size_t ops = raftcorr_build_fwd_workspace_bytes(lay->B, D, lay->H, lay->W, RAFTCORR_BUILD_TF32_TC);
-    const size_t need = ops + fnet_head_weight_bytes(Cin, D);
+    const size_t need = raftcorr_fnet_head_build_workspace_bytes(lay->B, Cin, D, lay->H, lay->W);
     RC_REQUIRE(workspace && workspace_bytes >= need, "fnet_head_build_fwd: workspace too small (%zu < %zu)", workspace_bytes,
                need);
     DeviceGuard guard(device);
@@ -175,7 +178,20 @@ int raftcorr_fnet_head_build_fwd(const float* x, const float* weight, const floa
     float* f2n = (float*)((char*)workspace + ops / 2);
     float* wr = (float*)((char*)workspace + ops);
     if (int rc = launch_fnet_head(x, weight, bias, lay->B, Cin, D, lay->H * lay->W, f1n, f2n, wr, device, s)) return rc;
-    return launch_build_tc(f1n, f2n, D, pyramid, *lay, device, s);
+    // Measured (scripts/fnet_head_time.py): the extra conversion pays from about 64x64 feature maps on (55x128: 504 vs
+    // 556 us, 47x156 B=16: 1118 vs 1268 us) and costs ~5 us at 46x62.  RAFTCORR_HEAD_F16=0 / 1 force the choice.
+    const char* fe = std::getenv("RAFTCORR_HEAD_F16");
+    const bool want_f16 = fe ? fe[0] != '0' : lay->H * lay->W >= 4096;
+    if (D > 256 || !want_f16) return launch_build_tc(f1n, f2n, D, pyramid, *lay, device, s);
+    // the build runs on block-scaled fp16 operands (RAFTCORR_BUILD_F16_TC): convert the head's operands (still in L2)
+    char* h16 = (char*)workspace + ops + fnet_head_weight_bytes(Cin, D);
+    const size_t hops = align_up((size_t)lay->B * tc_feature_pitch_f16(D) * lay->H * lay->W * 2, 1024);
+    float* inv_a = (float*)(h16 + 2 * hops);
+    float* inv_b = inv_a + (size_t)lay->B * 2 * ((lay->H * lay->W + 127) / 128);
+    if (int rc = launch_f16_operands_from_nhwc(f1n, f2n, lay->B, D, tc_feature_pitch(D), lay->H, lay->W, h16, h16 + hops,
+                                               inv_a, inv_b, s))
+        return rc;
+    return launch_build_tc_ex(h16, h16 + hops, D, pyramid, *lay, device, s, true, inv_a, inv_b);
 }
 
 size_t raftcorr_fnet_head_alt_workspace_bytes(int Cin, int D) {

@@ -104,6 +104,8 @@ int launch_build_tc_ex(const void* f1_ops, const void* f2_ops, int D, float* pyr
 size_t f16_scale_floats(int B, int H, int W);   // floats in inv_a followed by inv_b
 int launch_f16_operands(const float* f1, const float* f2, int B, int D, int H, int W, void* f1h, void* f2h, float* inv_a,
                         float* inv_b, cudaStream_t s);
+int launch_f16_operands_from_nhwc(const float* f1n, const float* f2n, int B, int D, int Dp32, int H, int W, void* f1h,
+                                  void* f2h, float* inv_a, float* inv_b, cudaStream_t s);
 int launch_build_bwd_gemms(const PyramidView& dpv, const float* f1, const float* f2, int D, float* df1,
                            float* df2, cudaStream_t s);
 

@@ -126,6 +126,57 @@ __global__ void __launch_bounds__(256, 2) f16_operand_kernel(const F16PrepParams
     }
 }
 
+// The same blocks from PIXEL-MAJOR fp32 operands [B][N][Dp32] (what fnet_head_kernel writes, usually still in L2): a
+// block is one (fmap1) or two (fmap2) contiguous runs, so there is nothing to transpose -- registers, absmax, scale,
+// round, 8-byte stores.  Dp32 = pitch of the source rows, P.Dp = pitch of the fp16 rows (channels past Dp32 are zeros).
+template <int NCH>
+__global__ void __launch_bounds__(256, 2) f16_from_nhwc_kernel(const F16PrepParams P, int Dp32) {
+    __shared__ float red[8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    F16Block k = f16_block_of(P, blockIdx.x);
+    const float* src = k.src;                   // image base [N][Dp32] (P.D carries Dp32, see the launcher)
+    constexpr int Q = NCH * 16;                 // float4 per pixel row of NCH*64 channels
+    float4 v[NCH * 4];                          // 64 px * Q float4 / 256 threads
+    float mx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) {
+        const int idx = threadIdx.x + 256 * i, px = idx / Q, c4 = idx - px * Q;
+        const int seg = px >> 5, off = px & 31;
+        const bool ok = off < (seg ? k.len1 : k.len0) && 4 * c4 < Dp32;
+        v[i] = ok ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)((seg ? k.p1 : k.p0) + off) * Dp32) + c4)
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    float scale = 1.f, inv = 1.f;
+    if (mx > 0.f && mx < __int_as_float(0x7f800000)) {
+        int e;
+        frexpf(mx, &e);
+        const int kk = max(-126, min(126, 15 - e));
+        scale = ldexpf(1.f, kk);
+        inv = ldexpf(1.f, -kk);
+    }
+    if (threadIdx.x == 0) *k.inv = inv;
+#pragma unroll
+    for (int i = 0; i < NCH * 4; ++i) {
+        const int idx = threadIdx.x + 256 * i, px = idx / Q, c4 = idx - px * Q;
+        const int seg = px >> 5, off = px & 31;
+        if (off < (seg ? k.len1 : k.len0)) {
+            const __half2 lo = __floats2half2_rn(v[i].x * scale, v[i].y * scale), hi = __floats2half2_rn(v[i].z * scale, v[i].w * scale);
+            uint2 o;
+            o.x = *reinterpret_cast<const unsigned*>(&lo);
+            o.y = *reinterpret_cast<const unsigned*>(&hi);
+            *(reinterpret_cast<uint2*>(k.dst + (int64_t)((seg ? k.p1 : k.p0) + off) * P.Dp) + c4) = o;
+        }
+    }
+}
+
 // ---- fp16 operands for the on-the-fly tensor-core lookup: one power-of-two scale per image and tensor --------------
 // The lattice tiles of that kernel sit at arbitrary offsets (bounding boxes of the windows), so per-tile scales do not
 // exist; one scale per (tensor, image) leaves 2^29 of dynamic range inside an image at full 11-bit precision.
@@ -357,6 +408,26 @@ int launch_f16_operands(const float* f1, const float* f2, int B, int D, int H, i
         case 2: f16_operand_kernel<2><<<blocks, 256, 0, s>>>(P); break;
         case 3: f16_operand_kernel<3><<<blocks, 256, 0, s>>>(P); break;
         case 4: f16_operand_kernel<4><<<blocks, 256, 0, s>>>(P); break;
+        default: return fail("f16 build: feature dim %d > 256 is not supported (use the tf32 build)", D);
+    }
+    RC_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// f1n/f2n: [B][N][Dp32] fp32 (fnet_head_kernel's output) -> block-scaled fp16 operands, same blocks as launch_f16_operands
+int launch_f16_operands_from_nhwc(const float* f1n, const float* f2n, int B, int D, int Dp32, int H, int W, void* f1h,
+                                  void* f2h, float* inv_a, float* inv_b, cudaStream_t s) {
+    F16PrepParams P{};
+    P.f1 = f1n; P.f2 = f2n; P.o1 = (__half*)f1h; P.o2 = (__half*)f2h; P.inv_a = inv_a; P.inv_b = inv_b;
+    // f16_block_of strides images by D * N floats: the pixel-major source has Dp32 * N per image
+    P.B = B; P.D = Dp32; P.Dp = tc_feature_pitch_f16(D); P.H = H; P.W = W; P.N = H * W;
+    P.a_blocks = 2 * ceil_div(P.N, 128); P.bands4 = 4 * ceil_div(H, 8); P.w_tiles = ceil_div(W, 32);
+    const int blocks = B * (P.a_blocks + P.bands4 * P.w_tiles);
+    switch (P.Dp / 64) {
+        case 1: f16_from_nhwc_kernel<1><<<blocks, 256, 0, s>>>(P, Dp32); break;
+        case 2: f16_from_nhwc_kernel<2><<<blocks, 256, 0, s>>>(P, Dp32); break;
+        case 3: f16_from_nhwc_kernel<3><<<blocks, 256, 0, s>>>(P, Dp32); break;
+        case 4: f16_from_nhwc_kernel<4><<<blocks, 256, 0, s>>>(P, Dp32); break;
         default: return fail("f16 build: feature dim %d > 256 is not supported (use the tf32 build)", D);
     }
     RC_CUDA(cudaGetLastError());

@@ -98,15 +98,18 @@ def alt_config(name, B, D, H, W, L, r, reps=5, mode="tf32"):
 
 which = sys.argv[1:] or ["1", "2", "3", "4", "5a", "5b"]
 if "1" in which:
+    fwd_config("1 RAFT-small 368x496 B1 12it", 1, 128, 46, 62, 4, 3, 12, "f16")
     fwd_config("1 RAFT-small 368x496 B1 12it", 1, 128, 46, 62, 4, 3, 12, "tf32")
     fwd_config("1 RAFT-small 368x496 B1 12it", 1, 128, 46, 62, 4, 3, 12, "fp32")
 if "2" in which:
+    fwd_config("2 RAFT-basic 436x1024 B8 32it", 8, 256, 55, 128, 4, 4, 32, "f16")
     fwd_config("2 RAFT-basic 436x1024 B8 32it", 8, 256, 55, 128, 4, 4, 32, "tf32")
-    fwd_config("2 RAFT-basic 436x1024 B1 32it", 1, 256, 55, 128, 4, 4, 32, "tf32")
+    fwd_config("2 RAFT-basic 436x1024 B1 32it", 1, 256, 55, 128, 4, 4, 32, "f16")
 if "3" in which:
-    train_config("3 training 368x496 B10 12it fwd+bwd", 10, 256, 46, 62, 4, 4, 12, rc.CorrBlock, {"build_mode": "tf32"}, reps=20)
+    train_config("3 training 368x496 B10 12it fwd+bwd", 10, 256, 46, 62, 4, 4, 12, rc.CorrBlock, {"build_mode": "f16"}, reps=20)
     train_config("3 training (alternate) B2 2it fwd+bwd", 2, 256, 46, 62, 4, 4, 2, rc.AlternateCorrBlock, {}, reps=2)
 if "4" in which:
+    fwd_config("4 raft_uncertainty KITTI 375x1242 B16 24it", 16, 256, 47, 156, 4, 4, 24, "f16", reps=10)
     fwd_config("4 raft_uncertainty KITTI 375x1242 B16 24it", 16, 256, 47, 156, 4, 4, 24, "tf32", reps=10)
 if "5a" in which:
     alt_config("5a alt 1080x1920 B4", 4, 256, 135, 240, 4, 4, mode="tf32")

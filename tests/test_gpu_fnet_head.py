@@ -121,6 +121,22 @@ def test_operand_buffers_vs_oracle(pkg, shape):
         assert torch.equal(a, c)
 
 
+def test_head_build_operand_modes_agree(pkg, monkeypatch):
+    """After the head, the build runs on the head's TF32 operands (small maps) or on block-scaled fp16 copies of them
+    (from 64x64 maps on; RAFTCORR_HEAD_F16 forces either).  TF32-rounded values times a power of two are exact in fp16,
+    so the two volumes agree to the MMA's summation order."""
+    B, Cin, D, H, W, L = 2, 96, 128, 24, 40, 3
+    g = torch.Generator(device=dev()).manual_seed(51)
+    x = torch.randn((2 * B, Cin, H, W), generator=g, device=dev()) * 37.0
+    w = torch.randn((D, Cin), generator=g, device=dev()) / Cin ** 0.5
+    pyr = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("RAFTCORR_HEAD_F16", flag)
+        pyr[flag] = pkg.CorrBlock.from_encoder_head(x, w, None, num_levels=L, radius=3).corr_pyramid
+    for a, c in zip(pyr["0"], pyr["1"]):
+        assert float((a - c).abs().max()) <= 2e-6 * float(a.abs().max())
+
+
 def test_unsupported_shape_goes_through_conv2(pkg):
     """H*W % 4 != 0: the fused kernel's TMA strides do not exist; the constructor computes conv2 itself (still on the GPU)."""
     B, Cin, D, H, W = 1, 32, 64, 9, 11
