@@ -309,7 +309,7 @@ def run_ours(args):
 
             def unfused_head(x_):
                 f_ = torch.nn.functional.conv2d(x_, hw, hb)
-                return rc.CorrBlock(f_[:B], f_[B:], num_levels=L, radius=r, build_mode="tf32")
+                return rc.CorrBlock(f_[:B], f_[B:], num_levels=L, radius=r, build_mode=mode)
 
             head = {"ms_per_call": per_call(lambda x_: rc.CorrBlock.from_encoder_head(x_, hw, hb, num_levels=L, radius=r)),
                     "cudnn_conv2_plus_build_ms": per_call(unfused_head), "cin": 128,
