@@ -44,6 +44,12 @@ def _stream(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _raw_stream(index):
+    # the current stream of device `index` as an integer handle, without building a torch.cuda.Stream object
+    # (the lookup is called 12-32 times per volume; at batch 1 its kernel takes ~11 us, so host microseconds count)
+    return torch._C._cuda_getCurrentRawStream(index)
+
+
 def _check_fmaps(fmap1, fmap2, who):
     for name, t in (("fmap1", fmap1), ("fmap2", fmap2)):
         if not isinstance(t, torch.Tensor):
@@ -267,6 +273,11 @@ class CorrBlock:
         self._grad_acc = None
         self._plan = None
         self._plan_ptr = 0
+        K = 2 * self.radius + 1
+        self._out_shape = (B, self.num_levels * K * K, H, W)
+        self._coords_shape = (B, 2, H, W)
+        self._dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        self._lookup_fn = _lib.lib().raftcorr_lookup_fwd_planned
 
     @classmethod
     def from_encoder_head(cls, x, weight, bias=None, num_levels=4, radius=4):
@@ -334,19 +345,22 @@ class CorrBlock:
         return pyr
 
     def _lookup(self, pyr, coords):
-        lay, dev = self._layout, self._device
-        K = 2 * self.radius + 1
-        out = torch.empty((self._B, self.num_levels * K * K, self._H, self._W), dtype=torch.float32, device=dev)
-        L = _lib.lib()
-        # per-pyramid setup (tensor maps, launch geometry) once; every refinement iteration reuses it
-        check(L.raftcorr_lookup_fwd_planned(self._ensure_plan(pyr), _ptr(coords), _ptr(out), dev.index, _stream(dev)),
-              "raftcorr_lookup_fwd_planned")
+        dev = self._device
+        out = torch.empty(self._out_shape, dtype=torch.float32, device=dev)
+        # per-pyramid setup (tensor maps, launch geometry) once; every refinement iteration reuses it.  Plain integers
+        # go through ctypes' c_void_p argtypes as they are: no wrapper objects on the per-iteration path.
+        rc_ = self._lookup_fn(self._ensure_plan(pyr), coords.data_ptr(), out.data_ptr(), self._dev_index,
+                              _raw_stream(self._dev_index))
+        if rc_:
+            check(rc_, "raftcorr_lookup_fwd_planned")
         return out
 
     # -- reference surface ----------------------------------------------------------------------
     def __call__(self, coords):
-        _check_coords(coords, self._B, self._H, self._W, self._device, "CorrBlock.__call__")
-        coords = coords.contiguous()
+        if not (type(coords) is torch.Tensor and coords.shape == self._coords_shape and coords.dtype is torch.float32
+                and coords.device == self._device and coords.is_contiguous()):
+            _check_coords(coords, self._B, self._H, self._W, self._device, "CorrBlock.__call__")  # raises with the reason
+            coords = coords.contiguous()
         if torch.is_grad_enabled() and (self._pyr.requires_grad or coords.requires_grad):
             return _LookupFn.apply(self._pyr, coords, self)
         return self._lookup(self._pyr, coords)

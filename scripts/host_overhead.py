@@ -8,7 +8,7 @@ dev = torch.device("cuda:0")
 B, D, H, W = 1, 256, 16, 24   # tiny: the GPU is never the bottleneck, we time the enqueue path
 f1 = torch.randn(B, D, H, W, device=dev); f2 = torch.randn(B, D, H, W, device=dev)
 co = torch.rand(B, 2, H, W, device=dev) * 10
-for mode in ("tma", "cpasync"):
+for mode in ("tma",):
     os.environ["RAFTCORR_LOOKUP"] = mode
     blk = rc.CorrBlock(f1, f2, 2, 4)
     for _ in range(50): blk(co)
