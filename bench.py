@@ -403,6 +403,9 @@ def run_ours(args):
             "lookup": {"ms_per_launch": l_ms, "achieved_gbs": B * lb / (l_ms * 1e-3) / 1e9,
                        "share_of_step": 1.0 - build_share},
         }
+        # the step as a whole against the HBM roofline: algorithmic bytes of build + all lookups over the timed step
+        step_gbs = B * (bb + iters * lb) / (ms_total / args.steps * 1e-3) / 1e9
+        kern["step"] = {"algorithmic_bytes": B * (bb + iters * lb), "achieved_gbs": step_gbs, "frac_of_hbm_peak": step_gbs / hbm}
         if fused:
             kern["lookup_convc1"] = fused
         if head:

@@ -77,8 +77,8 @@ enum {
                                      of the block maximum at full precision and is undone by two scalars in the epilogue.
                                      fp32 accumulate; half the operand bytes, MMA instructions and accumulator
                                      updates of the TF32 build (which the 1 kW power cap turns into time).
-                                     raftcorr_build_fwd only; the backward and the on-the-fly entry points treat it
-                                     as RAFTCORR_BUILD_TF32_TC. */
+                                     raftcorr_build_fwd only, D <= 256; the backward and the on-the-fly entry points
+                                     treat it as RAFTCORR_BUILD_TF32_TC. */
 };
 
 int raftcorr_abi_version(void);
