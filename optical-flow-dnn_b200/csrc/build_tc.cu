@@ -633,7 +633,8 @@ int launch_build_tc_ex(const void* f1n, const void* f2n, int D, float* pyramid, 
         // nothing; at D<=128 the MMA side has slack and operand loads running far ahead only steal bandwidth
         // from the store pipeline, so two stages are faster (420 vs 462 us).
         const char* pe = std::getenv("RAFTCORR_BUILD_PIPE");
-        const int pipe = pe ? atoi(pe) : (P.k_blocks <= 4 ? 222 : 322);
+        // fp16 operands at D = 256 (4 k-blocks of 64): 322 measured 472 us vs 478 us for 222 and 242
+        const int pipe = pe ? atoi(pe) : (f16 ? (P.k_blocks >= 4 ? 322 : 222) : (P.k_blocks <= 4 ? 222 : 322));
 #define RAFTCORR_PIPE_CASE(NS, NB, RP, IL_)                                                                             \
     case NS * 100 + NB * 10 + RP: {                                                                                     \
         static_assert(smem_bytes(NS, NB, RP) <= 232448, "pipeline does not fit shared memory");                         \
