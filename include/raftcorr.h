@@ -71,7 +71,7 @@ enum {
     RAFTCORR_BUILD_FP32_SIMT = 0, /* exact fp32 FFMA accumulation (CUDA cores) */
     RAFTCORR_BUILD_TF32_TC = 1,   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM, TMA fed,
                                      pooling fused into the epilogue */
-    RAFTCORR_BUILD_F16_TC = 2     /* the same kernel on BLOCK-SCALED fp16 operands (kind::f16): fp16 has TF32's 11
+    RAFTCORR_BUILD_F16_TC = 2,    /* the same kernel on BLOCK-SCALED fp16 operands (kind::f16): fp16 has TF32's 11
                                      significant bits; one power-of-two scale per 64-pixel operand block (64 consecutive
                                      source pixels / one row pair of an 8x32 target tile) keeps everything down to 2^-29
                                      of the block maximum at full precision and is undone by two scalars in the epilogue.
@@ -79,6 +79,13 @@ enum {
                                      updates of the TF32 build (which the 1 kW power cap turns into time).
                                      raftcorr_build_fwd only, D <= 256; the backward and the on-the-fly entry points
                                      treat it as RAFTCORR_BUILD_TF32_TC. */
+    RAFTCORR_BUILD_F16X3_TC = 3   /* fp32-class accuracy on the tensor cores: every (block-scaled) feature is split
+                                     into hi = fp16(x) and lo = fp16(x - hi) and the K axis carries [hi|lo|hi] x
+                                     [hi|hi|lo], so one fp32 accumulation forms hi*hi + lo*hi + hi*lo -- the product
+                                     to ~2^-21 instead of 2^-11 (measured ~1e-6 of max|V|, the fp32 FFMA build's
+                                     class) at 3x the MMA work and operand bytes of RAFTCORR_BUILD_F16_TC, still
+                                     ~10x faster than RAFTCORR_BUILD_FP32_SIMT.  Forward only, D <= 256; the
+                                     backward runs as RAFTCORR_BUILD_TF32_TC. */
 };
 
 int raftcorr_abi_version(void);

@@ -14,6 +14,7 @@ MAX_LEVELS = 8
 BUILD_FP32_SIMT = 0
 BUILD_TF32_TC = 1
 BUILD_F16_TC = 2
+BUILD_F16X3_TC = 3
 LOOKUP_PLAN_BYTES = 4096
 
 

@@ -20,7 +20,7 @@ import torch
 from . import _lib
 from ._lib import RaftCorrError, check
 
-_MODES = {"fp32": _lib.BUILD_FP32_SIMT, "tf32": _lib.BUILD_TF32_TC, "f16": _lib.BUILD_F16_TC}
+_MODES = {"fp32": _lib.BUILD_FP32_SIMT, "tf32": _lib.BUILD_TF32_TC, "f16": _lib.BUILD_F16_TC, "f16x3": _lib.BUILD_F16X3_TC}
 _default_mode = os.environ.get("RAFTCORR_BUILD_MODE", "f16")
 
 
@@ -29,6 +29,7 @@ def set_default_build_mode(mode: str) -> None:
     ``"f16"``: the same kernel on block-scaled fp16 operands (TF32's 11 significant bits, one power-of-two scale per
     operand tile, fp32 accumulate; same error, half the operand traffic) -- volume build only, everything else
     (backward, on-the-fly class, fused encoder head) runs as ``"tf32"``.
+    ``"f16x3"``: fp32-class accuracy on the tensor cores (three-term fp16 split, ~1e-6 of max|V|; forward only).
     ``"fp32"``: exact fp32 FFMA build on CUDA cores."""
     global _default_mode
     if mode not in _MODES:
@@ -259,8 +260,8 @@ class CorrBlock:
         mode = build_mode or _default_mode
         if mode not in _MODES:
             raise ValueError(f"unknown build mode {mode!r}")
-        if mode == "f16" and D > 256:  # the fp16 operand pass keeps a 64-pixel x D block in registers: D <= 256
-            mode = "tf32"
+        if D > 256 and mode in ("f16", "f16x3"):  # the fp16 operand pass keeps a 64-pixel x D block in registers
+            mode = "tf32" if mode == "f16" else "fp32"
         self._mode = _MODES[mode]
         self._B, self._D, self._H, self._W = B, D, H, W
         self._device = device
@@ -268,7 +269,7 @@ class CorrBlock:
         # gradient pyramids are row-major inside the library whatever this says, and never larger
         # (RAFTCORR_PYRAMID_LAYOUT=rowmajor keeps the old layout: A/B switch, needed by the cp.async lookup and the
         # CTA-pair build experiments)
-        il = mode in ("tf32", "f16") and os.environ.get("RAFTCORR_PYRAMID_LAYOUT", "interleaved") != "rowmajor"
+        il = mode != "fp32" and os.environ.get("RAFTCORR_PYRAMID_LAYOUT", "interleaved") != "rowmajor"
         self._layout = _lib.make_layout(B, H, W, self.num_levels, interleaved=il)
         self._grad_acc = None
         self._plan = None
@@ -567,6 +568,8 @@ class AlternateCorrBlock:
             raise ValueError(f"unknown build mode {mode!r} (expected one of {sorted(_MODES)})")
         if mode == "f16":  # block-scaled fp16 operands exist for the volume build only
             mode = "tf32" if fmap1.shape[1] % 32 == 0 else "fp32"
+        if mode == "f16x3":  # the accurate on-the-fly path is the exact-fp32 kernel
+            mode = "fp32"
         if mode == "tf32" and fmap1.shape[1] % 32 != 0:
             raise RaftCorrError("AlternateCorrBlock: build_mode='tf32' needs a feature dim that is a multiple of 32")
         self._mode = _MODES[mode]

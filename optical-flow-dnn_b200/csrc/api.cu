@@ -104,9 +104,11 @@ int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* lay, int B, int H, int
 size_t raftcorr_build_fwd_workspace_bytes(int B, int D, int H, int W, int mode) {
     if (mode == RAFTCORR_BUILD_TF32_TC)  // two NHWC (K-major), TF32-rounded, K-padded copies of the feature maps
         return 2 * align_up((size_t)B * tc_feature_pitch(D) * H * W * sizeof(float), 1024);
-    if (mode == RAFTCORR_BUILD_F16_TC)   // two block-scaled fp16 copies + the inverse block scales
-        return 2 * align_up((size_t)B * tc_feature_pitch_f16(D) * H * W * 2, 1024) +
+    if (mode == RAFTCORR_BUILD_F16_TC || mode == RAFTCORR_BUILD_F16X3_TC) {  // two block-scaled fp16 copies + inverse scales
+        const size_t terms = mode == RAFTCORR_BUILD_F16X3_TC ? 3 : 1;
+        return 2 * align_up((size_t)B * terms * tc_feature_pitch_f16(D) * H * W * 2, 1024) +
                align_up(f16_scale_floats(B, H, W) * sizeof(float), 1024);
+    }
     return 0;
 }
 
@@ -135,16 +137,17 @@ int raftcorr_build_fwd(const float* fmap1, const float* fmap2, int D, float* pyr
         if (int rc = launch_nchw_to_nhwc_pair(fmap1, f1n, fmap2, f2n, lay->B, D, HW, Dp, true, s)) return rc;
         return launch_build_tc(f1n, f2n, D, pyramid, *lay, device, s);
     }
-    if (mode == RAFTCORR_BUILD_F16_TC) {
+    if (mode == RAFTCORR_BUILD_F16_TC || mode == RAFTCORR_BUILD_F16X3_TC) {
+        const bool split = mode == RAFTCORR_BUILD_F16X3_TC;
         const size_t need = raftcorr_build_fwd_workspace_bytes(lay->B, D, lay->H, lay->W, mode);
         RC_REQUIRE(workspace && workspace_bytes >= need, "build_fwd: workspace too small (%zu < %zu)", workspace_bytes, need);
-        const size_t ops = align_up((size_t)lay->B * tc_feature_pitch_f16(D) * lay->H * lay->W * 2, 1024);
+        const size_t ops = align_up((size_t)lay->B * (split ? 3 : 1) * tc_feature_pitch_f16(D) * lay->H * lay->W * 2, 1024);
         void* f1h = workspace;
         void* f2h = (char*)workspace + ops;
         float* inv_a = (float*)((char*)workspace + 2 * ops);
         float* inv_b = inv_a + (size_t)lay->B * 2 * ((lay->H * lay->W + 127) / 128);
-        if (int rc = launch_f16_operands(fmap1, fmap2, lay->B, D, lay->H, lay->W, f1h, f2h, inv_a, inv_b, s)) return rc;
-        return launch_build_tc_ex(f1h, f2h, D, pyramid, *lay, device, s, true, inv_a, inv_b);
+        if (int rc = launch_f16_operands(fmap1, fmap2, lay->B, D, lay->H, lay->W, f1h, f2h, inv_a, inv_b, s, split)) return rc;
+        return launch_build_tc_ex(f1h, f2h, D, pyramid, *lay, device, s, true, inv_a, inv_b, split);
     }
     return fail("build_fwd: unknown mode %d", mode);
 }
@@ -332,7 +335,7 @@ int raftcorr_lookup_bwd(const float* grad_out, const float* coords, const float*
 }
 
 size_t raftcorr_build_bwd_workspace_bytes(int B, int D, int H, int W, int mode) {
-    if ((mode == RAFTCORR_BUILD_TF32_TC || mode == RAFTCORR_BUILD_F16_TC) && build_bwd_tc_supported(D))
+    if (mode != RAFTCORR_BUILD_FP32_SIMT && build_bwd_tc_supported(D))
         return build_bwd_tc_workspace_bytes(B, D, H, W);
     return 0;
 }
@@ -343,8 +346,7 @@ int raftcorr_build_bwd(float* dpyramid, const raftcorr_pyramid_layout* lay, cons
     if (int rc = check_layout(lay)) return rc;
     if (lay->B == 0) return 0;
     RC_REQUIRE(dpyramid && fmap1 && fmap2 && dfmap1 && dfmap2, "build_bwd: NULL tensor");
-    RC_REQUIRE(mode == RAFTCORR_BUILD_FP32_SIMT || mode == RAFTCORR_BUILD_TF32_TC || mode == RAFTCORR_BUILD_F16_TC,
-               "build_bwd: unknown mode %d", mode);
+    RC_REQUIRE(mode >= RAFTCORR_BUILD_FP32_SIMT && mode <= RAFTCORR_BUILD_F16X3_TC, "build_bwd: unknown mode %d", mode);
     DeviceGuard guard(device);
     RC_REQUIRE(guard.ok, "build_bwd: cannot select device %d", device);
     cudaStream_t s = (cudaStream_t)stream;

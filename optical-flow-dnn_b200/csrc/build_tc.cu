@@ -504,13 +504,15 @@ int launch_build_tc(const float* f1n, const float* f2n, int D, float* pyramid, c
 
 // f16: f1n/f2n are [B][H*W][Dp] fp16 (Dp = tc_feature_pitch_f16(D)), block-scaled by launch_f16_operands, whose
 // inverse scales are inv_a [B][2 ceil(N/128)] and inv_b [B][4 ceil(H/8)][ceil(W/32)]
+// split: the K axis holds three fp16 terms per feature ([hi|lo|hi] x [hi|hi|lo], launch_f16_operands): 3 * Dp halves
 int launch_build_tc_ex(const void* f1n, const void* f2n, int D, float* pyramid, const raftcorr_pyramid_layout& lay,
-                       int device, cudaStream_t s, bool f16, const float* inv_a, const float* inv_b) {
+                       int device, cudaStream_t s, bool f16, const float* inv_a, const float* inv_b, bool split) {
     const int fusedL = lay.L < 4 ? lay.L : 4;  // levels 0..3 come out of the epilogue; deeper ones are pooled afterwards
     EncodeTiledFn fn;
     if (int rc = get_encode_fn(&fn)) return rc;
     const int B = lay.B, H = lay.H, W = lay.W, N1 = H * W;
-    const int Dp = f16 ? tc_feature_pitch_f16(D) : tc_feature_pitch(D);
+    RC_REQUIRE(!split || f16, "build: the three-term split exists for fp16 operands only");
+    const int Dp = f16 ? (split ? 3 : 1) * tc_feature_pitch_f16(D) : tc_feature_pitch(D);
     const int esz = f16 ? 2 : 4, k_elems = 128 / esz;   // a k-block is one 128-byte swizzle row
     const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     // RAFTCORR_BUILD_CLUSTER: 1 = one CTA per tile, 2 = CTA pair with TMA multicast of B (measured slower),

@@ -99,11 +99,11 @@ int launch_build_tc(const float* f1_nhwc, const float* f2_nhwc, int D, float* py
                     const raftcorr_pyramid_layout& lay, int device, cudaStream_t s);
 int tc_feature_pitch_f16(int D);  // K padding of the fp16 build (multiple of 64 halves)
 int launch_build_tc_ex(const void* f1_ops, const void* f2_ops, int D, float* pyramid, const raftcorr_pyramid_layout& lay,
-                       int device, cudaStream_t s, bool f16, const float* inv_a, const float* inv_b);
+                       int device, cudaStream_t s, bool f16, const float* inv_a, const float* inv_b, bool split = false);
 // NCHW fp32 maps -> block-scaled fp16 operand buffers [B][H*W][Dp] + inverse block scales (prep.cu)
 size_t f16_scale_floats(int B, int H, int W);   // floats in inv_a followed by inv_b
 int launch_f16_operands(const float* f1, const float* f2, int B, int D, int H, int W, void* f1h, void* f2h, float* inv_a,
-                        float* inv_b, cudaStream_t s);
+                        float* inv_b, cudaStream_t s, bool split = false);
 int launch_f16_operands_from_nhwc(const float* f1n, const float* f2n, int B, int D, int Dp32, int H, int W, void* f1h,
                                   void* f2h, float* inv_a, float* inv_b, cudaStream_t s);
 int launch_build_bwd_gemms(const PyramidView& dpv, const float* f1, const float* f2, int D, float* df1,

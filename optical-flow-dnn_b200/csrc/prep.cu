@@ -28,6 +28,10 @@ struct F16PrepParams {
     float* inv_a;   // [B][2 * m_tiles]
     float* inv_b;   // [B][4 * bands][w_tiles]
     int B, D, Dp, H, W, N, a_blocks, bands4, w_tiles;   // a_blocks = 2 * m_tiles per image
+    // split = 1 (RAFTCORR_BUILD_F16X3_TC): every value is written as hi = fp16(x s) and lo = fp16(x s - hi); the K axis
+    // of a pixel's row is [hi | lo | hi] for fmap1 and [hi | hi | lo] for fmap2 (3 * Dk halves, Dk = the single-term
+    // pitch), so that ONE accumulation computes hi*hi + lo*hi + hi*lo: the product to ~2^-21 instead of 2^-11.
+    int split, Dk;
 };
 
 struct F16Block {
@@ -35,6 +39,7 @@ struct F16Block {
     __half* dst;        // image base [N][Dp]
     float* inv;
     int p0, p1, len0, len1;   // the two segments: first pixel, valid pixels (0..32)
+    int is_b;                 // block of fmap2
 };
 
 __device__ __forceinline__ F16Block f16_block_of(const F16PrepParams& P, int id) {
@@ -48,6 +53,7 @@ __device__ __forceinline__ F16Block f16_block_of(const F16PrepParams& P, int id)
         k.p1 = k.p0 + 32;
         k.len0 = max(0, min(32, P.N - k.p0));
         k.len1 = max(0, min(32, P.N - k.p1));
+        k.is_b = 0;
     } else {
         id -= P.B * P.a_blocks;
         const int per_b = P.bands4 * P.w_tiles;
@@ -60,6 +66,7 @@ __device__ __forceinline__ F16Block f16_block_of(const F16PrepParams& P, int id)
         k.p1 = k.p0 + P.W;
         k.len0 = 2 * hp < P.H ? cols : 0;
         k.len1 = 2 * hp + 1 < P.H ? cols : 0;
+        k.is_b = 1;
     }
     return k;
 }
@@ -105,30 +112,42 @@ __global__ void __launch_bounds__(256, 2) f16_operand_kernel(const F16PrepParams
         inv = ldexpf(1.f, -kk);
     }
     if (threadIdx.x == 0) *k.inv = inv;
+    const int parts = P.split ? 2 : 1;
+    for (int part = 0; part < parts; ++part) {     // part 0: hi (or the only term), part 1: lo = x s - hi
 #pragma unroll
-    for (int q = 0; q < NCH; ++q)
+        for (int q = 0; q < NCH; ++q)
 #pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-            const int col = q * 64 + warp * 8 + c;
-            *reinterpret_cast<__half2*>(&tile[lane][col]) = __floats2half2_rn(v[q][c][0] * scale, v[q][c + 1][0] * scale);
-            *reinterpret_cast<__half2*>(&tile[32 + lane][col]) = __floats2half2_rn(v[q][c][1] * scale, v[q][c + 1][1] * scale);
+            for (int c = 0; c < 8; c += 2) {
+                const int col = q * 64 + warp * 8 + c;
+                float a0 = v[q][c][0] * scale, a1 = v[q][c + 1][0] * scale, b0 = v[q][c][1] * scale, b1 = v[q][c + 1][1] * scale;
+                if (part) {
+                    a0 -= __half2float(__float2half_rn(a0)); a1 -= __half2float(__float2half_rn(a1));
+                    b0 -= __half2float(__float2half_rn(b0)); b1 -= __half2float(__float2half_rn(b1));
+                }
+                *reinterpret_cast<__half2*>(&tile[lane][col]) = __floats2half2_rn(a0, a1);
+                *reinterpret_cast<__half2*>(&tile[32 + lane][col]) = __floats2half2_rn(b0, b1);
+            }
+        __syncthreads();
+        // K-axis slots this part goes to: single term: 0; split: hi -> 0 and (fmap1: 2, fmap2: 1), lo -> (fmap1: 1, fmap2: 2)
+        const int slot_a = !P.split ? 0 : (part == 0 ? 0 : (k.is_b ? 2 : 1));
+        const int slot_b = !P.split ? -1 : (part == 0 ? (k.is_b ? 1 : 2) : -1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {              // warp: 8 of the 64 pixels, lane = channel pair of every chunk
+            const int px = warp * 8 + i, seg = px >> 5, off = px & 31;
+            if (off < (seg ? k.len1 : k.len0)) {
+                __half* out = k.dst + (int64_t)((seg ? k.p1 : k.p0) + off) * P.Dp;
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) {
+                    const __half2 h = *reinterpret_cast<const __half2*>(&tile[px][q * 64 + 2 * lane]);
+                    *reinterpret_cast<__half2*>(out + slot_a * P.Dk + q * 64 + 2 * lane) = h;
+                    if (slot_b >= 0) *reinterpret_cast<__half2*>(out + slot_b * P.Dk + q * 64 + 2 * lane) = h;
+                }
+            }
         }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {                  // warp: 8 of the 64 pixels, lane = channel pair of every chunk
-        const int px = warp * 8 + i, seg = px >> 5, off = px & 31;
-        if (off < (seg ? k.len1 : k.len0)) {
-            __half* out = k.dst + (int64_t)((seg ? k.p1 : k.p0) + off) * P.Dp;
-#pragma unroll
-            for (int q = 0; q < NCH; ++q)
-                *reinterpret_cast<__half2*>(out + q * 64 + 2 * lane) = *reinterpret_cast<const __half2*>(&tile[px][q * 64 + 2 * lane]);
-        }
+        __syncthreads();
     }
 }
 
-// The same blocks from PIXEL-MAJOR fp32 operands [B][N][Dp32] (what fnet_head_kernel writes, usually still in L2): a
-// block is one (fmap1) or two (fmap2) contiguous runs, so there is nothing to transpose -- registers, absmax, scale,
-// round, 8-byte stores.  Dp32 = pitch of the source rows, P.Dp = pitch of the fp16 rows (channels past Dp32 are zeros).
 template <int NCH>
 __global__ void __launch_bounds__(256, 2) f16_from_nhwc_kernel(const F16PrepParams P, int Dp32) {
     __shared__ float red[8];
@@ -397,13 +416,14 @@ size_t f16_scale_floats(int B, int H, int W) {   // inv_a [B][2 m_tiles] followe
 }
 
 int launch_f16_operands(const float* f1, const float* f2, int B, int D, int H, int W, void* f1h, void* f2h, float* inv_a,
-                        float* inv_b, cudaStream_t s) {
+                        float* inv_b, cudaStream_t s, bool split) {
     F16PrepParams P{};
     P.f1 = f1; P.f2 = f2; P.o1 = (__half*)f1h; P.o2 = (__half*)f2h; P.inv_a = inv_a; P.inv_b = inv_b;
-    P.B = B; P.D = D; P.Dp = tc_feature_pitch_f16(D); P.H = H; P.W = W; P.N = H * W;
+    P.split = split ? 1 : 0; P.Dk = tc_feature_pitch_f16(D);
+    P.B = B; P.D = D; P.Dp = (split ? 3 : 1) * P.Dk; P.H = H; P.W = W; P.N = H * W;
     P.a_blocks = 2 * ceil_div(P.N, 128); P.bands4 = 4 * ceil_div(H, 8); P.w_tiles = ceil_div(W, 32);
     const int blocks = B * (P.a_blocks + P.bands4 * P.w_tiles);
-    switch (P.Dp / 64) {
+    switch (P.Dk / 64) {
         case 1: f16_operand_kernel<1><<<blocks, 256, 0, s>>>(P); break;
         case 2: f16_operand_kernel<2><<<blocks, 256, 0, s>>>(P); break;
         case 3: f16_operand_kernel<3><<<blocks, 256, 0, s>>>(P); break;

@@ -34,11 +34,11 @@ for case_i in range(n_cases):
         with torch.no_grad():
             ref_blk = rc.CorrBlock(f1, f2, L, r, build_mode="fp32")
             ref = ref_blk(coords)
-            for mode in ("f16", "tf32"):
+            for mode, tol in (("f16", 1e-3), ("tf32", 1e-3), ("f16x3", 2e-5)):
                 blk = rc.CorrBlock(f1, f2, L, r, build_mode=mode)
-                note(f"CorrBlock[{mode}] lookup", rel(blk(coords), ref), 1e-3, case)
+                note(f"CorrBlock[{mode}] lookup", rel(blk(coords), ref), tol, case)
                 for l, (a, c) in enumerate(zip(blk.corr_pyramid, ref_blk.corr_pyramid)):
-                    note(f"CorrBlock[{mode}] level", rel(a, c), 1e-3, case + (l,))
+                    note(f"CorrBlock[{mode}] level", rel(a, c), tol, case + (l,))
             if D % 4 == 0:
                 note("AlternateCorrBlock (default)", rel(rc.AlternateCorrBlock(f1, f2, L, r)(coords), ref), 1e-3, case)
             cout = int(rng.choice([16, 48, 96, 128, 256]))

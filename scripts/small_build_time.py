@@ -17,6 +17,6 @@ for (B, D, H, W, r) in [(1, 128, 46, 62, 3), (1, 256, 55, 128, 4), (2, 256, 55, 
     res = {}
     with torch.no_grad():
         for trial in range(3):
-            for mode in ("f16", "tf32"):
+            for mode in ("f16", "tf32", "f16x3"):
                 res.setdefault(mode, []).append(t(lambda: rc.CorrBlock(f1, f2, 4, r, build_mode=mode)))
     print(f"B={B} D={D} {H}x{W}: build us  " + "  ".join(f"{m}: {min(v):.1f} ({' '.join('%.0f' % x for x in v)})" for m, v in res.items()), flush=True)

@@ -276,6 +276,38 @@ def test_f16_block_scaling_dynamic_range(pkg):
     assert torch.equal(v1 * 128.0, v2)
 
 
+def test_f16x3_build_is_fp32_class(pkg, golden):
+    """build_mode="f16x3": three-term fp16 split on the tensor cores.  Same tolerance as the exact-fp32 FFMA build (2e-5
+    of max|ref|) on the reference goldens (every level, three coordinate sets) and, at the bench shape, against fp64."""
+    B, D, H, W, L, r = [int(v) for v in golden["meta"]]
+    blk = pkg.CorrBlock(torch.from_numpy(golden["fmap1"]).to(dev()), torch.from_numpy(golden["fmap2"]).to(dev()), L, r,
+                        build_mode="f16x3")
+    pyr = blk.corr_pyramid
+    for l in range(L):
+        ref = golden[f"pyr{l}"]
+        assert rel_err(pyr[l].reshape(ref.shape), ref) <= TOL["fp32"], f"level {l}"
+    for k in range(3):
+        assert rel_err(blk(torch.from_numpy(golden[f"coords{k}"]).to(dev())), golden[f"out64_{k}"]) <= TOL["fp32"], f"coords set {k}"
+
+
+def test_f16x3_full_size_and_range(pkg):
+    B, D, H, W, L, r = 1, 256, 55, 128, 4, 4
+    N = H * W
+    g = torch.Generator(device=dev()).manual_seed(21)
+    f1 = torch.randn((B, D, H, W), generator=g, device=dev())
+    f2 = torch.randn((B, D, H, W), generator=g, device=dev())
+    ref = torch.einsum("dm,dn->mn", f1[0].reshape(D, N).double(), f2[0].reshape(D, N).double()) / np.sqrt(D)
+    errs = {}
+    for mode in ("f16x3", "fp32", "f16"):
+        v0 = pkg.CorrBlock(f1, f2, L, r, build_mode=mode).corr_pyramid[0].reshape(N, N).double()
+        errs[mode] = float((v0 - ref).abs().max() / ref.abs().max())
+    print("max|dV|/max|V| at the bench shape:", errs)
+    assert errs["f16x3"] <= 5e-6 and errs["f16x3"] <= errs["f16"] / 50
+    for mag in (1e-20, 1e15):   # block scaling: any overall magnitude
+        v0 = pkg.CorrBlock(f1 * mag, f2, L, r, build_mode="f16x3").corr_pyramid[0].reshape(N, N).double()
+        assert float((v0 - ref * mag).abs().max() / (ref.abs().max() * mag)) <= 5e-6
+
+
 def test_alt_f16_operands_match_tf32_operands(pkg, monkeypatch):
     """The on-the-fly tensor-core lookup reads fp16 copies of the feature tensors (one power-of-two scale per image and
     tensor) by default; RAFTCORR_ALT_F16=0 keeps TF32 operands.  Same error against the exact-fp32 volume path, for any
