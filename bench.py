@@ -256,6 +256,22 @@ def run_ours(args):
             build_ms.append(kb0.elapsed_time(kb1))
             look_ms.append(kl0.elapsed_time(kl1) / iters)
             del blk
+        # beside the headline: the same build with the three-term fp16 split (fp32-class accuracy) and, for scale, what
+        # the exact-fp32 FFMA build costs
+        accurate = None
+        if rank == 0 and mode != "fp32" and not args.no_fused:
+            accurate = {}
+            for m_ in ("f16x3", "fp32"):
+                rc.CorrBlock(f1, f2, num_levels=L, radius=r, build_mode=m_)
+                torch.cuda.synchronize(dev)
+                kb0.record()
+                for _ in range(3):
+                    rc.CorrBlock(f1, f2, num_levels=L, radius=r, build_mode=m_)
+                kb1.record()
+                torch.cuda.synchronize(dev)
+                accurate[m_ + "_build_ms"] = kb0.elapsed_time(kb1) / 3
+            accurate["what"] = ("build_mode='f16x3': [hi|lo|hi] x [hi|hi|lo] fp16 split through the same tensor-core kernel, "
+                                "max|dV|/max|V| 2.5e-6; 'fp32': exact FFMA build on the CUDA cores (8.5e-7)")
         # SURVEY.md 8(f) rank 1, reported beside the headline (not part of it): the lookup fused with the motion
         # encoder's first 1x1 convolution + ReLU (update.py:158,170: 324 -> 256) against the unfused pair
         # (our lookup followed by cuDNN's convolution), per refinement iteration, same coordinates
@@ -406,6 +422,8 @@ def run_ours(args):
         # the step as a whole against the HBM roofline: algorithmic bytes of build + all lookups over the timed step
         step_gbs = B * (bb + iters * lb) / (ms_total / args.steps * 1e-3) / 1e9
         kern["step"] = {"algorithmic_bytes": B * (bb + iters * lb), "achieved_gbs": step_gbs, "frac_of_hbm_peak": step_gbs / hbm}
+        if accurate:
+            kern["accurate_build_modes"] = accurate
         if fused:
             kern["lookup_convc1"] = fused
         if head:

@@ -20,7 +20,7 @@ def _epe(a, b):
     return float(np.sqrt(((a - b) ** 2).sum(1)).mean())
 
 
-@pytest.mark.parametrize("variant", ["corr_f16", "corr_tf32", "corr_fp32", "alternate", "corr_f16_fusedconvc1", "corr_tf32_fusedconvc1", "corr_fp32_fusedconvc1"])
+@pytest.mark.parametrize("variant", ["corr_f16", "corr_f16x3", "corr_tf32", "corr_fp32", "alternate", "corr_f16_fusedconvc1", "corr_tf32_fusedconvc1", "corr_fp32_fusedconvc1"])
 def test_flow_after_12_iterations_matches_reference(variant):
     import optical_flow_dnn_b200 as rc
 
