@@ -27,6 +27,32 @@ __device__ __forceinline__ float ld_stream(const float* p) {
     return v;
 }
 
+// element `off` (32-bit) behind a 64-bit base: ONE IMAD.WIDE.U32 per address (the compiler's own code for
+// base + 64-bit index was 5-10 integer instructions per load)
+__device__ __forceinline__ float ld_stream_off(const float* base, unsigned off) {
+    float v;
+    asm volatile("{ .reg .u64 a; mad.wide.u32 a, %2, 4, %1; ld.global.nc.L1::no_allocate.f32 %0, [a]; }"
+                 : "=f"(v) : "l"(base), "r"(off));
+    return v;
+}
+__device__ __forceinline__ void st_off(float* base, unsigned off, float v) {
+    asm volatile("{ .reg .u64 a; mad.wide.u32 a, %1, 4, %0; st.global.f32 [a], %2; }" :: "l"(base), "r"(off), "f"(v) : "memory");
+}
+
+// exp2 / reciprocal on the SFU (one MUFU each).  ex2.approx is good to 2^-22 relative; the softmax argument is formed as
+// fma(m, log2e, -max * log2e), whose rounding of max * log2e is common to all nine terms and cancels in the normalisation.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+
 // flow neighbourhood of the CTA's pixels: rows h-1..h+1, columns w0-1..w0+32, times 8, zero outside the image
 template <int C>
 __device__ __forceinline__ void load_flow_tile(float (*fs)[3][kUpPix + 2], const float* __restrict__ flow, int b, int h, int w0,
@@ -54,10 +80,14 @@ upsample_fwd_kernel(const float* __restrict__ flow, const float* __restrict__ ma
     float mm[8][9];
     if (w < W) {
         const float* mp = mask + ((int64_t)b * 576 + i * 8) * HW + (int64_t)h * W + w;  // channel k*64 + i*8 + j
+        // channel offsets as 32-bit element counts (576 * H * W < 2^31 is checked by the launcher): one IMAD + one
+        // IMAD.WIDE (ld_stream_off) per load instead of a 64-bit multiply-add chain -- address arithmetic was 42 % of this kernel's
+        // instructions (ncu: issue slots 55 % busy at 25 % occupancy)
+        const unsigned hw = (unsigned)HW;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
 #pragma unroll
-            for (int k = 0; k < 9; ++k) mm[j][k] = ld_stream(mp + ((int64_t)k * 64 + j) * HW);
+            for (int k = 0; k < 9; ++k) mm[j][k] = ld_stream_off(mp, (unsigned)(k * 64 + j) * hw);
     }
     load_flow_tile<C>(fs, flow, b, h, w0, H, W);
     __syncthreads();
@@ -74,12 +104,13 @@ upsample_fwd_kernel(const float* __restrict__ flow, const float* __restrict__ ma
 #pragma unroll
             for (int k = 1; k < 9; ++k) mx = fmaxf(mx, m[k]);
             float den = 0.f;
+            const float mxl = mx * kLog2e;
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                m[k] = expf(m[k] - mx);
+                m[k] = ex2_approx(fmaf(m[k], kLog2e, -mxl));
                 den += m[k];
             }
-            const float inv = 1.0f / den;
+            const float inv = rcp_approx(den);
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 float acc = 0.f;
@@ -128,6 +159,9 @@ upsample_bwd_kernel(const float* __restrict__ flow, const float* __restrict__ ma
     __syncthreads();
     if (w < W) {
         const int64_t moff = ((int64_t)b * 576 + i * 8) * HW + (int64_t)h * W + w;
+        const float* mp = mask + moff;
+        float* dp = dmask + moff;
+        const unsigned hw = (unsigned)HW;  // 32-bit channel offsets, see the forward kernel
         float nb[C][9], dn[C][9];
 #pragma unroll
         for (int c = 0; c < C; ++c)
@@ -140,17 +174,18 @@ upsample_bwd_kernel(const float* __restrict__ flow, const float* __restrict__ ma
         for (int j = 0; j < 8; ++j) {
             float m[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) m[k] = ld_stream(mask + moff + ((int64_t)k * 64 + j) * HW);
+            for (int k = 0; k < 9; ++k) m[k] = ld_stream_off(mp, (unsigned)(k * 64 + j) * hw);
             float mx = m[0];
 #pragma unroll
             for (int k = 1; k < 9; ++k) mx = fmaxf(mx, m[k]);
             float den = 0.f;
+            const float mxl = mx * kLog2e;
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-                m[k] = expf(m[k] - mx);
+                m[k] = ex2_approx(fmaf(m[k], kLog2e, -mxl));
                 den += m[k];
             }
-            const float inv = 1.0f / den;
+            const float inv = rcp_approx(den);
             float g[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) g[c] = gs[c][i][8 * lane + j];
@@ -169,7 +204,7 @@ upsample_bwd_kernel(const float* __restrict__ flow, const float* __restrict__ ma
                 dot += m[k] * a;
             }
 #pragma unroll
-            for (int k = 0; k < 9; ++k) dmask[moff + ((int64_t)k * 64 + j) * HW] = m[k] * (s[k] - dot);
+            for (int k = 0; k < 9; ++k) st_off(dp, (unsigned)(k * 64 + j) * hw, m[k] * (s[k] - dot));
         }
 #pragma unroll
         for (int c = 0; c < C; ++c)
@@ -192,6 +227,7 @@ upsample_bwd_kernel(const float* __restrict__ flow, const float* __restrict__ ma
 int launch_upsample_fwd(const float* flow, const float* mask, int B, int C, int H, int W, float* out, cudaStream_t s) {
     RC_REQUIRE(C >= 1 && C <= kUpMaxC, "upsample_flow: 1..%d channels (got %d)", kUpMaxC, C);
     RC_REQUIRE(B <= 65535 && H <= 65535, "upsample_flow: batch / height too large for one launch");
+    RC_REQUIRE(576 * (int64_t)H * W < (1ll << 31), "upsample_flow: %d x %d map too large (576 * H * W must stay below 2^31)", H, W);
     dim3 grid(ceil_div(W, kUpPix), H, B);
 #define RAFTCORR_UP_CASE(C_) case C_: upsample_fwd_kernel<C_><<<grid, 256, 0, s>>>(flow, mask, out, H, W); break;
     switch (C) {
@@ -206,6 +242,7 @@ int launch_upsample_bwd(const float* flow, const float* mask, const float* gout,
                         float* dflow, cudaStream_t s) {
     RC_REQUIRE(C >= 1 && C <= 4, "upsample_flow backward: 1..4 channels (got %d)", C);
     RC_REQUIRE(B <= 65535 && H <= 65535, "upsample_flow: batch / height too large for one launch");
+    RC_REQUIRE(576 * (int64_t)H * W < (1ll << 31), "upsample_flow: %d x %d map too large (576 * H * W must stay below 2^31)", H, W);
     dim3 grid(ceil_div(W, kUpPix), H, B);
 #define RAFTCORR_UP_CASE(C_) case C_: upsample_bwd_kernel<C_><<<grid, 256, 0, s>>>(flow, mask, gout, dmask, dflow, H, W); break;
     switch (C) { RAFTCORR_UP_CASE(1) RAFTCORR_UP_CASE(2) RAFTCORR_UP_CASE(3) RAFTCORR_UP_CASE(4) }
