@@ -39,6 +39,17 @@ __device__ __forceinline__ void st_off(float* base, unsigned off, float v) {
     asm volatile("{ .reg .u64 a; mad.wide.u32 a, %1, 4, %0; st.global.f32 [a], %2; }" :: "l"(base), "r"(off), "f"(v) : "memory");
 }
 
+__device__ __forceinline__ void st_v4_off(float* base, unsigned off, float4 v) {
+    asm volatile("{ .reg .u64 a; mad.wide.u32 a, %1, 4, %0; st.global.v4.f32 [a], {%2, %3, %4, %5}; }"
+                 :: "l"(base), "r"(off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_v4_off(const float* base, unsigned off) {
+    float4 v;
+    asm volatile("{ .reg .u64 a; mad.wide.u32 a, %5, 4, %4; ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [a]; }"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(base), "r"(off));
+    return v;
+}
+
 // exp2 / reciprocal on the SFU (one MUFU each).  ex2.approx is good to 2^-22 relative; the softmax argument is formed as
 // fma(m, log2e, -max * log2e), whose rounding of max * log2e is common to all nine terms and cancels in the normalisation.
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -123,6 +134,19 @@ upsample_fwd_kernel(const float* __restrict__ flow, const float* __restrict__ ma
     __syncthreads();
     // eight output rows per channel, each 8 * (pixels of this CTA) contiguous floats
     const int npx = min(kUpPix, W - w0);
+    if (npx == kUpPix) {
+        // full tile: 64 float4 per output row, C * 8 rows; a thread keeps its column q and walks the rows in steps of 4
+        // (no runtime division, one 64-bit base + 32-bit row offsets)
+        const int q = threadIdx.x & 63, r0 = threadIdx.x >> 6;
+        float* ob = out + ((int64_t)b * C * 8 * H + 8 * h + r0) * (8 * (int64_t)W) + 8 * w0 + 4 * q;
+        const unsigned row = 8u * (unsigned)W;
+#pragma unroll
+        for (int it = 0; it < 2 * C; ++it) {  // row r0 + 4 * it = (c = it / 2, ii = 4 * (it & 1) + r0)
+            const float4 v = *reinterpret_cast<const float4*>(&os[it >> 1][4 * (it & 1) + r0][4 * q]);
+            st_v4_off(ob, ((unsigned)(it >> 1) * 8u * (unsigned)H + 4u * (it & 1)) * row, v);
+        }
+        return;
+    }
     const int row_len = 8 * npx;
     for (int idx = threadIdx.x; idx < C * 8 * (row_len / 4); idx += blockDim.x) {
         const int q = idx % (row_len / 4);
@@ -149,12 +173,22 @@ upsample_bwd_kernel(const float* __restrict__ flow, const float* __restrict__ ma
     for (int idx = threadIdx.x; idx < C * 3 * (kUpPix + 2); idx += blockDim.x) (&dfs[0][0][0])[idx] = 0.f;
     const int npx = min(kUpPix, W - w0);
     const int row_len = 8 * npx;
-    for (int idx = threadIdx.x; idx < C * 8 * (row_len / 4); idx += blockDim.x) {
-        const int q = idx % (row_len / 4);
-        const int ii = (idx / (row_len / 4)) % 8;
-        const int c = idx / ((row_len / 4) * 8);
-        *reinterpret_cast<float4*>(&gs[c][ii][4 * q]) =
-            *reinterpret_cast<const float4*>(gout + (((int64_t)b * C + c) * 8 * H + 8 * h + ii) * (8 * (int64_t)W) + 8 * w0 + 4 * q);
+    if (npx == kUpPix) {  // full tile: same walk as the forward kernel's write-out
+        const int q = threadIdx.x & 63, r0 = threadIdx.x >> 6;
+        const float* gb = gout + ((int64_t)b * C * 8 * H + 8 * h + r0) * (8 * (int64_t)W) + 8 * w0 + 4 * q;
+        const unsigned row = 8u * (unsigned)W;
+#pragma unroll
+        for (int it = 0; it < 2 * C; ++it)
+            *reinterpret_cast<float4*>(&gs[it >> 1][4 * (it & 1) + r0][4 * q]) =
+                ld_v4_off(gb, ((unsigned)(it >> 1) * 8u * (unsigned)H + 4u * (it & 1)) * row);
+    } else {
+        for (int idx = threadIdx.x; idx < C * 8 * (row_len / 4); idx += blockDim.x) {
+            const int q = idx % (row_len / 4);
+            const int ii = (idx / (row_len / 4)) % 8;
+            const int c = idx / ((row_len / 4) * 8);
+            *reinterpret_cast<float4*>(&gs[c][ii][4 * q]) =
+                *reinterpret_cast<const float4*>(gout + (((int64_t)b * C + c) * 8 * H + 8 * h + ii) * (8 * (int64_t)W) + 8 * w0 + 4 * q);
+        }
     }
     __syncthreads();
     if (w < W) {
