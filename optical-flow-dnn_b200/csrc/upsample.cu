@@ -12,6 +12,8 @@
 // leave as contiguous 1 KB runs.  Up to 4 channels share the pass (flow + variance of the uncertainty model).
 // The backward recomputes the softmax from the mask (one read) and writes d_mask once; d_flow is accumulated in
 // shared memory and leaves with one red.global.add per neighbourhood element.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace raftcorr {
@@ -158,8 +160,8 @@ upsample_fwd_kernel(const float* __restrict__ flow, const float* __restrict__ ma
 }
 
 // gout [B, C, 8H, 8W] -> dmask [B, 576, H, W] (overwritten), dflow [B, C, H, W] (ACCUMULATED into: zero it first)
-template <int C>
-__global__ void __launch_bounds__(256)
+template <int C, int U>
+__global__ void __launch_bounds__(256, 2)
 upsample_bwd_kernel(const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ gout,
                     float* __restrict__ dmask, float* __restrict__ dflow, int H, int W) {
     __shared__ float fs[C][3][kUpPix + 2];
@@ -204,11 +206,20 @@ upsample_bwd_kernel(const float* __restrict__ flow, const float* __restrict__ ma
                 nb[c][k] = fs[c][k / 3][lane + k % 3];
                 dn[c][k] = 0.f;
             }
-#pragma unroll 2
-        for (int j = 0; j < 8; ++j) {
-            float m[9];
+        // the mask rows of U sub-columns are requested together (9 * U loads in flight per thread); the asm loads and
+        // stores are volatile, i.e. kept in program order, so the batching has to be explicit
+#pragma unroll 1
+        for (int jb = 0; jb < 8; jb += U) {
+          float mblk[U][9];
+          const unsigned ob = (unsigned)jb * hw;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) m[k] = ld_stream_off(mp, (unsigned)(k * 64 + j) * hw);
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+              for (int k = 0; k < 9; ++k) mblk[u][k] = ld_stream_off(mp, (unsigned)(k * 64 + u) * hw + ob);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int j = jb + u;
+            float* m = mblk[u];
             float mx = m[0];
 #pragma unroll
             for (int k = 1; k < 9; ++k) mx = fmaxf(mx, m[k]);
@@ -238,7 +249,8 @@ upsample_bwd_kernel(const float* __restrict__ flow, const float* __restrict__ ma
                 dot += m[k] * a;
             }
 #pragma unroll
-            for (int k = 0; k < 9; ++k) st_off(dp, (unsigned)(k * 64 + j) * hw, m[k] * (s[k] - dot));
+            for (int k = 0; k < 9; ++k) st_off(dp, (unsigned)(k * 64 + u) * hw + ob, m[k] * (s[k] - dot));
+          }
         }
 #pragma unroll
         for (int c = 0; c < C; ++c)
@@ -278,7 +290,16 @@ int launch_upsample_bwd(const float* flow, const float* mask, const float* gout,
     RC_REQUIRE(B <= 65535 && H <= 65535, "upsample_flow: batch / height too large for one launch");
     RC_REQUIRE(576 * (int64_t)H * W < (1ll << 31), "upsample_flow: %d x %d map too large (576 * H * W must stay below 2^31)", H, W);
     dim3 grid(ceil_div(W, kUpPix), H, B);
-#define RAFTCORR_UP_CASE(C_) case C_: upsample_bwd_kernel<C_><<<grid, 256, 0, s>>>(flow, mask, gout, dmask, dflow, H, W); break;
+    static const int unroll = [] {  // RAFTCORR_UP_BWD_UNROLL=2|4|8: mask rows in flight per thread (A/B switch)
+        const char* e = std::getenv("RAFTCORR_UP_BWD_UNROLL");
+        return (e && e[0] == '4') ? 4 : (e && e[0] == '8') ? 8 : 2;
+    }();
+#define RAFTCORR_UP_CASE(C_)                                                                                            \
+    case C_:                                                                                                            \
+        if (unroll == 4) upsample_bwd_kernel<C_, 4><<<grid, 256, 0, s>>>(flow, mask, gout, dmask, dflow, H, W);          \
+        else if (unroll == 8) upsample_bwd_kernel<C_, 8><<<grid, 256, 0, s>>>(flow, mask, gout, dmask, dflow, H, W);     \
+        else upsample_bwd_kernel<C_, 2><<<grid, 256, 0, s>>>(flow, mask, gout, dmask, dflow, H, W);                      \
+        break;
     switch (C) { RAFTCORR_UP_CASE(1) RAFTCORR_UP_CASE(2) RAFTCORR_UP_CASE(3) RAFTCORR_UP_CASE(4) }
 #undef RAFTCORR_UP_CASE
     RC_CUDA(cudaGetLastError());
