@@ -375,31 +375,65 @@ __global__ void pool_level_kernel(const LevelView in, const LevelView out, int64
 // footprint.  One thread per 4 consecutive fine elements (rows are 32-byte aligned: pitch % 8 == 0), so
 // the pass streams float4s; values written into the row padding are harmless (nothing reads it).
 template <bool ROUND>
-__global__ void pool_adjoint_level_kernel(const LevelView coarse, const LevelView fine, int64_t total4) {
+__global__ void __launch_bounds__(256)
+pool_adjoint_level_kernel(const LevelView coarse, const LevelView fine, int64_t imgs) {
+    // One image per CTA step (grid-stride over the B*N images), threads laid out as (row, float4 column) ONCE: the first
+    // version split a flat 64-bit element index with three 64-bit divisions per float4 -- 123 instructions per element,
+    // 78 M warp instructions and issue slots 58 % busy for a pass that should only stream (ncu, fourth session).
     const int q4 = fine.pitch >> 2;  // float4 chunks per fine row
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total4;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int xq = (int)(idx % q4);
-        int64_t t = idx / q4;
-        const int y = (int)(t % fine.h);
-        const int64_t img = t / fine.h;
-        const int x = xq * 4;
-        if (x >= fine.w) continue;
-        float4* dst = reinterpret_cast<float4*>(fine.base + img * fine.img_stride + (int64_t)y * fine.pitch + x);
-        float4 v = *dst;
-        const int yc = y >> 1, xc = x >> 1;
-        if (yc < coarse.h) {
-            const float* c = coarse.base + img * coarse.img_stride + (int64_t)yc * coarse.pitch + xc;
-            const float c0 = xc < coarse.w ? 0.25f * c[0] : 0.f;
-            const float c1 = xc + 1 < coarse.w ? 0.25f * c[1] : 0.f;
-            v.x += c0; v.y += c0; v.z += c1; v.w += c1;
-        } else if (!ROUND) {
-            continue;
+    const int per = q4 * fine.h;     // float4 chunks per image
+    if (per <= 128) {
+        // small images (the coarse folds): several images per CTA step, one chunk per thread and step
+        const int ipp = 256 / per;
+        const int sub = (int)threadIdx.x / per, r = (int)threadIdx.x - sub * per;
+        const int y = r / q4, x = (r - y * q4) * 4, yc = y >> 1, xc = x >> 1;
+        if (sub >= ipp || x >= fine.w || (!ROUND && yc >= coarse.h)) return;
+        const int foff = y * fine.pitch + x, coff = yc * coarse.pitch + xc;
+        const bool has_c = yc < coarse.h, in0 = xc < coarse.w, in1 = xc + 1 < coarse.w;
+        for (int64_t img = (int64_t)blockIdx.x * ipp + sub; img < imgs; img += (int64_t)gridDim.x * ipp) {
+            float4* dst = reinterpret_cast<float4*>(fine.base + img * fine.img_stride + foff);
+            float4 v = *dst;
+            if (has_c) {
+                const float* c = coarse.base + img * coarse.img_stride + coff;
+                const float c0 = in0 ? 0.25f * c[0] : 0.f;
+                const float c1 = in1 ? 0.25f * c[1] : 0.f;
+                v.x += c0; v.y += c0; v.z += c1; v.w += c1;
+            }
+            if (ROUND) {
+                v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+            }
+            *dst = v;
         }
-        if (ROUND) {  // the folded level 0 feeds the tensor-core backward GEMMs
-            v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+        return;
+    }
+    const int tx = q4 >= 256 ? (int)threadIdx.x : (int)threadIdx.x % q4;
+    const int ty = q4 >= 256 ? 0 : (int)threadIdx.x / q4;
+    const int xstep = q4 >= 256 ? 256 : q4, ystep = q4 >= 256 ? 1 : 256 / q4;
+    if (ty >= ystep) return;
+    for (int64_t img = blockIdx.x; img < imgs; img += gridDim.x) {
+        float* fb = fine.base + img * fine.img_stride;
+        const float* cb = coarse.base + img * coarse.img_stride;
+        for (int y = ty; y < fine.h; y += ystep) {
+            const int yc = y >> 1;
+            if (!ROUND && yc >= coarse.h) continue;
+            for (int xq = tx; xq < q4; xq += xstep) {
+                const int x = xq * 4;
+                if (x >= fine.w) continue;
+                float4* dst = reinterpret_cast<float4*>(fb + y * fine.pitch + x);
+                float4 v = *dst;
+                if (yc < coarse.h) {
+                    const int xc = x >> 1;
+                    const float* c = cb + yc * coarse.pitch + xc;
+                    const float c0 = xc < coarse.w ? 0.25f * c[0] : 0.f;
+                    const float c1 = xc + 1 < coarse.w ? 0.25f * c[1] : 0.f;
+                    v.x += c0; v.y += c0; v.z += c1; v.w += c1;
+                }
+                if (ROUND) {  // the folded level 0 feeds the tensor-core backward GEMMs
+                    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+                }
+                *dst = v;
+            }
         }
-        *dst = v;
     }
 }
 
@@ -530,10 +564,13 @@ int launch_pool_adjoint_level(const LevelView& coarse, const LevelView& fine, in
                               cudaStream_t s) {
     const int64_t total = imgs * fine.h * (fine.pitch >> 2);
     if (total == 0) return 0;
+    const int per = (fine.pitch >> 2) * fine.h;
+    const int64_t steps = per <= 128 ? ceil_div64(imgs, 256 / per) : imgs;  // CTA steps (several small images per step)
+    const int grid = (int)(steps < 148 * 32 ? steps : 148 * 32);
     if (round_tf32_out)
-        pool_adjoint_level_kernel<true><<<grid_for(total, 256), 256, 0, s>>>(coarse, fine, total);
+        pool_adjoint_level_kernel<true><<<grid, 256, 0, s>>>(coarse, fine, imgs);
     else
-        pool_adjoint_level_kernel<false><<<grid_for(total, 256), 256, 0, s>>>(coarse, fine, total);
+        pool_adjoint_level_kernel<false><<<grid, 256, 0, s>>>(coarse, fine, imgs);
     RC_CUDA(cudaGetLastError());
     return 0;
 }
