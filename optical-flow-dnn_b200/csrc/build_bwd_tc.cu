@@ -190,11 +190,15 @@ __device__ __forceinline__ float round_tf32_dev(float x) {
 
 // dst[r][0..wp) = tf32(src[r][0..w)), zero padded
 __global__ void round_pad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int w, int wp) {
-    const int64_t total = rows * wp;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / wp;
-        const int c = (int)(i - r * wp);
-        dst[i] = c < w ? round_tf32_dev(__ldg(src + r * w + c)) : 0.f;
+    // (row, column) thread layout fixed once per thread -- the flat version paid a 64-bit division per ELEMENT (2.5 TB/s)
+    if (wp <= 256) {  // short rows: several rows per CTA step
+        const int rpp = 256 / wp, ty = (int)threadIdx.x / wp, tx = (int)threadIdx.x - ty * wp;
+        if (ty >= rpp) return;
+        for (int64_t r = (int64_t)blockIdx.x * rpp + ty; r < rows; r += (int64_t)gridDim.x * rpp)
+            dst[r * wp + tx] = tx < w ? round_tf32_dev(__ldg(src + r * w + tx)) : 0.f;
+    } else {
+        for (int64_t r = blockIdx.x; r < rows; r += gridDim.x)
+            for (int c = threadIdx.x; c < wp; c += 256) dst[r * wp + c] = c < w ? round_tf32_dev(__ldg(src + r * w + c)) : 0.f;
     }
 }
 
