@@ -91,12 +91,9 @@ class _BuildFn(torch.autograd.Function):
     def backward(ctx, dpyr):
         fmap1, fmap2 = ctx.saved_tensors
         block = ctx.block
-        acc = block._grad_acc
-        block._grad_acc = None  # a second backward pass (retain_graph) starts a fresh accumulator
+        dpyr = block._take_grad_acc(dpyr)
         if dpyr is None:
             return None, None, None
-        if acc is None or dpyr.data_ptr() != acc.data_ptr():
-            dpyr = dpyr.contiguous().clone()  # build_bwd folds levels in place: never clobber foreign grads
         lay = block._layout
         df1 = torch.empty_like(fmap1)
         df2 = torch.empty_like(fmap2)
@@ -125,12 +122,9 @@ class _HeadBuildFn(torch.autograd.Function):
     def backward(ctx, dpyr):
         x, w2, bias = ctx.saved_tensors
         block = ctx.block
-        acc = block._grad_acc
-        block._grad_acc = None
+        dpyr = block._take_grad_acc(dpyr)
         if dpyr is None:
             return None, None, None, None
-        if acc is None or dpyr.data_ptr() != acc.data_ptr():
-            dpyr = dpyr.contiguous().clone()  # build_bwd folds levels in place
         B, D = block._B, block._D
         dev = x.device
         with torch.enable_grad():
@@ -181,22 +175,47 @@ def _lookup_backward(block, gout, coords, pyr, want_pyr, want_dcoords):
         # backward runs) and the build backward -- which depends on every lookup -- only runs after
         # the last one has added its share.  The reference instead materialises iters x L dense,
         # zero-filled level-sized tensors (grid_sampler_2d_backward) and sums them.
-        first = block._grad_acc is None
+        acc, first = block._open_grad_acc()
         if first:
-            block._grad_acc = torch.zeros(lay.total_floats, dtype=torch.float32, device=dev)
-            dpyr_ret = block._grad_acc
-        acc = block._grad_acc
+            dpyr_ret = acc
     else:
         acc = None
     dcoords = torch.empty_like(coords) if want_dcoords else None
     if acc is None and dcoords is None:
         return None, None
     if acc is None:  # coords gradient only: scatter into a scratch pyramid
-        acc = torch.zeros(lay.total_floats, dtype=torch.float32, device=dev)
-    check(_lib.lib().raftcorr_lookup_bwd(_ptr(gout.contiguous()), _ptr(coords), _ptr(pyr), _ptr(acc),
+        acc = torch.zeros(block._grad_layout.total_floats, dtype=torch.float32, device=dev)
+    gout = gout.contiguous()  # bound to a local: the buffer must outlive the launch below
+    check(_lib.lib().raftcorr_lookup_bwd(_ptr(gout), _ptr(coords), _ptr(pyr), _ptr(acc),
                                          ctypes.byref(lay), block.radius, _ptr(dcoords), dev.index, _stream(dev)),
           "raftcorr_lookup_bwd")
     return dpyr_ret, dcoords
+
+
+class _PyramidLevelsFn(torch.autograd.Function):
+    """pyramid buffer -> the reference's ``corr_pyramid`` list (raft/core/corr.py:35-43) as independent tensors.  The
+    backward adds each level's gradient into the block's gradient pyramid (row-major gradient layout, whatever layout
+    the forward buffer has), under the same hand-over-once rule as the lookups."""
+
+    @staticmethod
+    def forward(ctx, pyr, block):
+        ctx.block = block
+        return tuple(t.clone() for t in block._levels(pyr))
+
+    @staticmethod
+    def backward(ctx, *glevels):
+        block = ctx.block
+        if all(g is None for g in glevels):
+            return None, None
+        acc, first = block._open_grad_acc()
+        glay = block._grad_layout
+        BN = block._B * block._H * block._W
+        for l, g in enumerate(glevels):
+            if g is None:
+                continue
+            h, w, p = glay.h[l], glay.w[l], glay.pitch[l]
+            acc[glay.offset[l]: glay.offset[l] + BN * h * p].view(BN, 1, h, p)[..., :w] += g
+        return (acc if first else None), None
 
 
 class _LookupConvFn(torch.autograd.Function):
@@ -271,7 +290,10 @@ class CorrBlock:
         # CTA-pair build experiments)
         il = mode != "fp32" and os.environ.get("RAFTCORR_PYRAMID_LAYOUT", "interleaved") != "rowmajor"
         self._layout = _lib.make_layout(B, H, W, self.num_levels, interleaved=il)
+        # gradient pyramids are GEMM operands of the build backward: always plain rows, own level offsets
+        self._grad_layout = _lib.make_layout(B, H, W, self.num_levels, interleaved=False) if il else self._layout
         self._grad_acc = None
+        self._grad_acc_pass = -1
         self._plan = None
         self._plan_ptr = 0
         K = 2 * self.radius + 1
@@ -290,7 +312,9 @@ class CorrBlock:
         ``layer3`` for the concatenated frames, frame-1 images first), ``weight``/``bias`` are ``conv2``'s parameters
         (``[D, Cin, 1, 1]`` or ``[D, Cin]``; ``[D]``).  The 1x1 convolution runs as a tcgen05 TF32 product (fp32
         accumulate -- the precision cuDNN uses for it by default) that writes the build's pixel-major operand buffers
-        directly; the NCHW feature maps are never materialised.  TF32 build only.  Differentiable w.r.t. ``x``,
+        directly; the NCHW feature maps are never materialised.  TF32 / block-scaled fp16 build; when the configured
+        default mode is ``"fp32"`` or ``"f16x3"`` the head runs as ``conv2`` in torch + the ordinary constructor in that
+        mode.  Differentiable w.r.t. ``x``,
         ``weight`` and ``bias`` (the backward recomputes ``conv2(x)`` and chains the volume's adjoint through it).
         Valid when the encoder's dropout is inactive (eval mode or ``dropout=0``, extractor.py:234-235).
         Shapes the fused kernel does not take (``Cin % 4``, ``H*W % 4``, ``D > 256``) go through ``conv2`` + the
@@ -310,6 +334,11 @@ class CorrBlock:
             raise RuntimeError("CorrBlock.from_encoder_head: bias must be a float32 CUDA tensor of shape [D]")
         x = x.float().contiguous()  # raft.py:114-115 casts after the head; the fused product wants fp32 input
         w2 = weight.reshape(D, Cin)
+        if _default_mode in ("fp32", "f16x3"):
+            # the user asked for fp32-class volume accuracy (set_default_build_mode / RAFTCORR_BUILD_MODE): the fused head
+            # is a TF32 product, so run conv2 in torch and the ordinary constructor in the configured mode
+            f = torch.nn.functional.conv2d(x, w2.reshape(D, Cin, 1, 1), bias)
+            return cls(f[: B2 // 2], f[B2 // 2:], num_levels=num_levels, radius=radius, build_mode=_default_mode)
         if not _lib.lib().raftcorr_fnet_head_supported(Cin, D, H, W):
             f = torch.nn.functional.conv2d(x, w2.reshape(D, Cin, 1, 1), bias)
             return cls(f[: B2 // 2], f[B2 // 2:], num_levels=num_levels, radius=radius, build_mode="tf32")
@@ -329,10 +358,41 @@ class CorrBlock:
         pyr = torch.empty(lay.total_floats, dtype=torch.float32, device=dev)
         ws_bytes = L.raftcorr_fnet_head_build_workspace_bytes(self._B, Cin, self._D, self._H, self._W)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        check(L.raftcorr_fnet_head_build_fwd(_ptr(x), _ptr(w2), _ptr(bias.contiguous() if bias is not None else None),
+        bias = bias.contiguous() if bias is not None else None  # local: must outlive the launch
+        check(L.raftcorr_fnet_head_build_fwd(_ptr(x), _ptr(w2), _ptr(bias),
                                              Cin, self._D, _ptr(pyr), ctypes.byref(lay), _ptr(ws), ws_bytes, dev.index,
                                              _stream(dev)), "raftcorr_fnet_head_build_fwd")
         return pyr
+
+    # -- the single gradient pyramid of a backward pass ---------------------------------------
+    def _open_grad_acc(self):
+        """The block's gradient pyramid (row-major gradient layout) and whether the caller is the FIRST contributor of
+        this backward pass.  The first contributor returns it to autograd as d(pyramid) -- exactly once; everybody else
+        adds into it in place and returns None.  The build backward depends on every contributor, so it runs last."""
+        # a pass that never reached the build backward (exception, interrupt) must not leak its partial sums into the
+        # next one: the accumulator is keyed to the autograd engine's graph-task id
+        this_pass = torch._C._current_graph_task_id()
+        first = self._grad_acc is None or self._grad_acc_pass != this_pass
+        if first:
+            self._grad_acc = torch.zeros(self._grad_layout.total_floats, dtype=torch.float32, device=self._device)
+            self._grad_acc_pass = this_pass
+        return self._grad_acc, first
+
+    def _take_grad_acc(self, dpyr):
+        """Called by the build backward with whatever autograd delivered for the pyramid buffer."""
+        acc = self._grad_acc
+        if acc is not None and self._grad_acc_pass != torch._C._current_graph_task_id():
+            acc = None  # left over from an aborted pass
+        self._grad_acc = None  # a second backward pass (retain_graph) starts a fresh accumulator
+        if dpyr is None:
+            return None
+        if acc is None or dpyr.data_ptr() != acc.data_ptr():
+            # every contributor in this module (lookups, corr_pyramid, CorrBlock.corr, lookup_convc1) adds into the
+            # accumulator and hands it to autograd once, so anything else is a gradient some foreign op attached to the
+            # PRIVATE flat buffer, whose layout (row pairs interleaved, padded rows) it cannot know
+            raise RaftCorrError("CorrBlock backward: unexpected gradient for the internal pyramid buffer; differentiate "
+                                "through corr_fn(coords), corr_fn.corr_pyramid or CorrBlock.corr instead")
+        return dpyr
 
     # -- kernels ------------------------------------------------------------------------------
     def _build(self, fmap1, fmap2):
@@ -436,6 +496,13 @@ class CorrBlock:
         views into the single pyramid buffer (rows are padded to a multiple of 8 floats).  tf32 build mode: the
         buffer stores row pairs interleaved, so the levels are de-interleaved copies (nothing in RAFT reads
         this attribute; the lookup works on the buffer)."""
+        if torch.is_grad_enabled() and self._pyr.requires_grad:
+            # differentiable like the reference's list (corr.py:35-43): the levels' gradients are written into the
+            # block's single row-major gradient pyramid, next to the lookups' contributions
+            return list(_PyramidLevelsFn.apply(self._pyr, self))
+        return self._levels(self._pyr.detach())
+
+    def _levels(self, pyr):
         lay = self._layout
         N = self._H * self._W
         out = []
@@ -443,11 +510,11 @@ class CorrBlock:
             h, w, p = lay.h[l], lay.w[l], lay.pitch[l]
             if lay.interleaved:
                 hp = (h + 1) // 2
-                flat = self._pyr[lay.offset[l]: lay.offset[l] + self._B * N * hp * 2 * p]
+                flat = pyr[lay.offset[l]: lay.offset[l] + self._B * N * hp * 2 * p]
                 lvl = flat.view(self._B * N, hp, p, 2).permute(0, 1, 3, 2).reshape(self._B * N, 1, 2 * hp, p)
                 out.append(lvl[:, :, :h, :w])
             else:
-                flat = self._pyr[lay.offset[l]: lay.offset[l] + self._B * N * h * p]
+                flat = pyr[lay.offset[l]: lay.offset[l] + self._B * N * h * p]
                 out.append(flat.view(self._B * N, 1, h, p)[..., :w])
         return out
 
@@ -456,7 +523,7 @@ class CorrBlock:
         """Level-0 volume ``[B, H, W, 1, H, W]`` = <f1, f2> / sqrt(D)  (raft/core/corr.py:93-116)."""
         blk = CorrBlock(fmap1, fmap2, num_levels=1, radius=1, build_mode=build_mode)
         B, H, W = blk._B, blk._H, blk._W
-        return blk.corr_pyramid[0].reshape(B, H, W, 1, H, W)
+        return blk.corr_pyramid[0].reshape(B, H, W, 1, H, W)  # differentiable (corr_pyramid)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -481,6 +548,8 @@ class _AltPrepFn(torch.autograd.Function):
         B, D, H, W, L = block._B, block._D, block._H, block._W, block.num_levels
         dev = block._device
         acc1, acc2 = block._grad_acc
+        if block._grad_acc_pass != torch._C._current_graph_task_id():
+            acc1 = acc2 = None  # left over from an aborted backward pass
         block._grad_acc = (None, None)
         if df1n is None:
             df1n = torch.zeros((B, H, W, D), dtype=torch.float32, device=dev)
@@ -490,7 +559,8 @@ class _AltPrepFn(torch.autograd.Function):
             df2p = df2p.contiguous().clone()  # grad_finish folds in place
         df1 = torch.empty((B, D, H, W), dtype=torch.float32, device=dev)
         df2 = torch.empty((B, D, H, W), dtype=torch.float32, device=dev)
-        check(_lib.lib().raftcorr_alt_grad_finish(_ptr(df1n.contiguous()), _ptr(df2p), B, D, H, W, L, _ptr(df1),
+        df1n = df1n.contiguous()  # bound to a local: must outlive the launch
+        check(_lib.lib().raftcorr_alt_grad_finish(_ptr(df1n), _ptr(df2p), B, D, H, W, L, _ptr(df1),
                                                   _ptr(df2), dev.index, _stream(dev)), "raftcorr_alt_grad_finish")
         return df1, df2, None
 
@@ -536,12 +606,15 @@ class _AltLookupFn(torch.autograd.Function):
         B, D, H, W, L = block._B, block._D, block._H, block._W, block.num_levels
         dev = block._device
         acc1, acc2 = block._grad_acc
-        first = acc1 is None
-        if first:  # same single-accumulator scheme as _LookupFn.backward
+        this_pass = torch._C._current_graph_task_id()
+        first = acc1 is None or block._grad_acc_pass != this_pass
+        if first:  # same single-accumulator scheme as _LookupFn.backward, keyed to the engine's graph task
             acc1 = torch.zeros((B, H, W, D), dtype=torch.float32, device=dev)
             acc2 = torch.zeros(_alt_sizes(B, D, H, W, L), dtype=torch.float32, device=dev)
             block._grad_acc = (acc1, acc2)
-        check(_lib.lib().raftcorr_alt_lookup_bwd(_ptr(f1n), _ptr(f2p), _ptr(coords), _ptr(gout.contiguous()), B, D, H,
+            block._grad_acc_pass = this_pass
+        gout = gout.contiguous()  # bound to a local: must outlive the launch
+        check(_lib.lib().raftcorr_alt_lookup_bwd(_ptr(f1n), _ptr(f2p), _ptr(coords), _ptr(gout), B, D, H,
                                                  W, L, block.radius, _ptr(acc1), _ptr(acc2), dev.index, _stream(dev)),
               "raftcorr_alt_lookup_bwd")
         # coords: no gradient, exactly like the reference kernel (correlation_kernel.cu:307 returns zeros
@@ -586,6 +659,7 @@ class AlternateCorrBlock:
         self._device = fmap1.device
         self._fmaps = (fmap1, fmap2)
         self._grad_acc = (None, None)
+        self._grad_acc_pass = -1
         fmap1 = fmap1.contiguous()
         fmap2 = fmap2.contiguous()
         if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
@@ -625,6 +699,7 @@ class AlternateCorrBlock:
         self._fmaps = None
         self._head = (x, w2, bias)
         self._grad_acc = (None, None)
+        self._grad_acc_pass = -1
         needs_grad = x.requires_grad or w2.requires_grad or (bias is not None and bias.requires_grad)
         if torch.is_grad_enabled() and needs_grad:
             self._f1n, self._f2p = _AltHeadPrepFn.apply(x, w2, bias, self)
@@ -640,7 +715,8 @@ class AlternateCorrBlock:
         f2p = torch.empty(_alt_sizes(B, D, H, W, L), dtype=torch.float32, device=dev)
         wsb = int(lib.raftcorr_fnet_head_alt_workspace_bytes(x.shape[1], D))
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        check(lib.raftcorr_fnet_head_alt_pyramid(_ptr(x), _ptr(w2), _ptr(bias.contiguous() if bias is not None else None), B,
+        bias = bias.contiguous() if bias is not None else None  # local: must outlive the launch
+        check(lib.raftcorr_fnet_head_alt_pyramid(_ptr(x), _ptr(w2), _ptr(bias), B,
                                                  x.shape[1], D, H, W, L, _ptr(f1n), _ptr(f2p), _ptr(ws), wsb, dev.index,
                                                  _stream(dev)), "raftcorr_fnet_head_alt_pyramid")
         ws_bytes = int(lib.raftcorr_alt_lookup_workspace_bytes(B, H, W, L, self._mode))

@@ -41,7 +41,8 @@ class _UpsampleFn(torch.autograd.Function):
         dev = flow.device
         dmask = torch.empty_like(mask)
         dflow = torch.empty_like(flow)
-        check(_lib.lib().raftcorr_upsample_flow_bwd(_ptr(flow), _ptr(mask), _ptr(gout.contiguous()), B, C, H, W, _ptr(dmask),
+        gout = gout.contiguous()  # bound to a local: must outlive the launch
+        check(_lib.lib().raftcorr_upsample_flow_bwd(_ptr(flow), _ptr(mask), _ptr(gout), B, C, H, W, _ptr(dmask),
                                                     _ptr(dflow), dev.index, _stream(dev)), "raftcorr_upsample_flow_bwd")
         return dflow, dmask
 

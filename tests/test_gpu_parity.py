@@ -77,7 +77,7 @@ def test_golden_gradients(pkg, golden, mode):
     assert rel_err(f1.grad, golden["df1"]) <= 1e-3
     assert rel_err(f2.grad, golden["df2"]) <= 1e-3
     # coordinates gradient (the reference CorrBlock provides it through grid_sample): generic coords only
-    assert rel_err(cs[1].grad, golden["dcoords1"]) <= TOL[mode] * 20
+    assert rel_err(cs[1].grad, golden["dcoords1"]) <= TOL[mode] * 2
 
 
 ALT_TOL = {"fp32": 2e-5, "tf32": 1e-3, "f16": 1e-3}  # on-the-fly path: exact fp32 dots vs TF32 tensor-core tiles
