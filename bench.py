@@ -84,6 +84,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """Index of the next sample: brackets a window of the run for :meth:`stats`."""
+        return len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -92,31 +96,61 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        return self.stats(0, len(self.lines))
+
+    def stats(self, lo, hi):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in self.lines[lo:hi]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
                 sm.append(float(f[1]))
                 smax.append(float(f[2]))
+                power.append(float(f[3]))
             except ValueError:
                 continue
             for n, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         sm.sort()
+        power.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w": power[len(power) // 2] if power else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ---------------------------------------------------------------------------------------------- CPU arm
+# ---------------------------------------------------------------------------------------------- reference arms
+def staged_reference_corr():
+    """The reference's own, unmodified ``raft/core/corr.py`` (+ ``core/utils/utils.py``) from the git-ignored
+    ``baseline/_ref/stock`` tree that ``build()`` stages and the snapshot carries to the GPU box
+    (scripts/vendor_reference.py); ``None`` when it is not there.  Baseline / checker only -- never on the product path."""
+    base = os.path.join(ROOT, "baseline", "_ref", "stock")
+    if not os.path.exists(os.path.join(base, "raft", "core", "corr.py")):
+        return None
+    import importlib
+
+    for p in (os.path.join(base, "raft"), base):  # `core.*`, and the reference's own compiled alt_cuda_corr*.so
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    mod = importlib.import_module("core.corr")
+    assert os.path.realpath(mod.__file__).startswith(os.path.realpath(base)), mod.__file__
+    return mod
+
+
 def cpu_port_run(steps, warmup, iters, shape, seed=1234):
-    """Times the oracle's torch-CPU port of the reference CorrBlock: one step = one frame pair (B=1)."""
+    """Times the reference CorrBlock on the host cores, one step = one frame pair (B=1): the reference's own file
+    from baseline/_ref (``kind: "reference"``) when staged, else the oracle's torch-CPU port of it (``"port"``)."""
     import torch
 
-    from oracle.torch_cpu_port import CpuCorrBlock
+    ref = staged_reference_corr()
+    if ref is not None:
+        CpuCorrBlock, kind = ref.CorrBlock, "reference"
+    else:
+        from oracle.torch_cpu_port import CpuCorrBlock
+        kind = "port"
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -141,8 +175,10 @@ def cpu_port_run(steps, warmup, iters, shape, seed=1234):
                 times.append(dt)
     _ = float(out.sum())
     total = sum(times)
-    return {"pairs_per_s": len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": torch.get_num_threads(),
-            "sample": f"B=1 frame pair x {len(times)} steps (build + {iters} lookups, D={D}, {H}x{W}, r={r}), torch {torch.__version__} CPU ops"}
+    what = ("the reference's unmodified raft/core/corr.py CorrBlock (baseline/_ref/stock)" if kind == "reference"
+            else "oracle/torch_cpu_port.py (same three ATen ops)")
+    return {"pairs_per_s": len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"B=1 frame pair x {len(times)} steps (build + {iters} lookups, D={D}, {H}x{W}, r={r}), {what}, torch {torch.__version__} CPU ops"}
 
 
 def run_reference(args):
@@ -156,7 +192,7 @@ def run_reference(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"RAFT-basic CorrBlock build + {args.iters} lookups, 436x1024 (fmap 55x128, D=256, r=4, L=4), "
                                "1 frame pair per step on host cores", "iters": args.iters},
-        "cpu_baseline": {"value": r["pairs_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "cpu_baseline": {"value": r["pairs_per_s"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["pairs_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -164,6 +200,67 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+def alt_1080p_side(rc, torch, dev, g, e0, e1, hbm, with_reference):
+    """north_star config 5a: AlternateCorrBlock (on-the-fly correlation) lookups at 1080x1920 -> 135x240, D=256, r=4,
+    L=4, B=4.  Algorithmic work per pair per lookup: bytes 4 D (N + sum H_l W_l) + 8 N + 4 N L K^2,
+    flops N L (K+1)^2 2 D."""
+    B, D, H, W, L, r, n_coords = 4, 256, 135, 240, 4, 4, 4
+    K = 2 * r + 1
+    N = H * W
+    sizes, h, w = [], H, W
+    for _ in range(L):
+        sizes.append(h * w)
+        h, w = h // 2, w // 2
+    alg_bytes = B * (4 * D * (N + sum(sizes)) + 8 * N + 4 * N * L * K * K)
+    flops = B * N * L * (K + 1) ** 2 * 2 * D
+    f1 = torch.randn((B, D, H, W), generator=g, device=dev)
+    f2 = torch.randn((B, D, H, W), generator=g, device=dev)
+    ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+    grid = torch.stack([xs, ys]).float()[None].expand(B, 2, H, W)
+    flow = 4.0 * torch.randn((B, 2, H, W), generator=g, device=dev)
+    flow = torch.nn.functional.avg_pool2d(flow, 5, stride=1, padding=2, count_include_pad=False) * 5.0
+    coords = [(grid + flow).contiguous()]
+    for _ in range(n_coords - 1):
+        coords.append((coords[-1] + 0.5 * torch.randn((B, 2, H, W), generator=g, device=dev)).contiguous())
+
+    def timed(fn, reps):
+        for c in coords:
+            fn(c)
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(reps):
+            e0.record()
+            for c in coords:
+                fn(c)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1) / len(coords))
+        return sorted(ts)[len(ts) // 2]
+
+    blk = rc.AlternateCorrBlock(f1, f2, num_levels=L, radius=r)
+    ms = timed(blk, 5)
+    res = {"ms_per_lookup": ms, "algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (ms * 1e-3) / 1e9,
+           "frac_of_hbm_peak": alg_bytes / (ms * 1e-3) / 1e9 / hbm, "useful_tflops": flops / (ms * 1e-3) / 1e12,
+           "pair_lookups_per_s": B / (ms * 1e-3),
+           "what": f"AlternateCorrBlock.__call__ at 1080p (fmap {H}x{W}, D={D}, r={r}, L={L}, B={B}), smooth sigma-4px flow, median of 5 x {n_coords} lookups; "
+                   "north_star config 5a, not part of the headline step"}
+    if with_reference:
+        ref_mod = staged_reference_corr()
+        try:
+            if ref_mod is None:
+                raise RuntimeError("baseline/_ref/stock is not staged")
+            import alt_cuda_corr  # noqa: F401  the reference's own extension, built from its sources for sm_100 by build()
+            rblk = ref_mod.AlternateCorrBlock(f1, f2, num_levels=L, radius=r)
+            res["reference_alt_cuda_corr_ms_per_lookup"] = timed(rblk, 2)
+            res["reference_max_abs_delta_over_max_abs"] = float((rblk(coords[0]) - blk(coords[0])).abs().max() / rblk(coords[0]).abs().max())
+            res["reference_what"] = ("the reference's unmodified AlternateCorrBlock (corr.py:119-167) over its own alt_cuda_corr kernel "
+                                     "(correlation_kernel.cu compiled for sm_100), same GPU and inputs")
+        except Exception as exc:  # the extension is a baseline only: report why it is absent, never fail the bench
+            res["reference_alt_cuda_corr_ms_per_lookup"] = None
+            res["reference_unavailable"] = f"{type(exc).__name__}: {exc}"[:200]
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -194,17 +291,27 @@ def run_ours(args):
     iters = args.iters
     K = 2 * r + 1
     mode = args.mode
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    f1 = torch.randn((B, D, H, W), generator=g, device=dev)
-    f2 = torch.randn((B, D, H, W), generator=g, device=dev)
+    # the job is world x B frame pairs, sharded by pair (optical_flow_dnn_b200/sharding.py: torch.chunk ranges, no
+    # collective); every pair is generated from its GLOBAL index, so a rank's data does not depend on the world size
+    from optical_flow_dnn_b200.sharding import shard_range
+    mine = shard_range(world * B, rank, world)
+    assert len(mine) == B
     ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
-    grid = torch.stack([xs, ys]).float()[None].expand(B, 2, H, W)
-    # "realistic" flow: sigma 4 px at 1/8 res smoothed by a 5x5 box filter, fresh coords per iteration
-    flow = 4.0 * torch.randn((B, 2, H, W), generator=g, device=dev)
-    flow = torch.nn.functional.avg_pool2d(flow, 5, stride=1, padding=2, count_include_pad=False) * 5.0
-    coords = [(grid + flow).contiguous()]
-    for _ in range(iters - 1):
-        coords.append((coords[-1] + 0.5 * torch.randn((B, 2, H, W), generator=g, device=dev)).contiguous())
+    grid = torch.stack([xs, ys]).float()
+    f1 = torch.empty((B, D, H, W), device=dev)
+    f2 = torch.empty((B, D, H, W), device=dev)
+    coords = [torch.empty((B, 2, H, W), device=dev) for _ in range(iters)]
+    for i, pair in enumerate(mine):
+        g = torch.Generator(device=dev).manual_seed(1234 + pair)
+        f1[i] = torch.randn((D, H, W), generator=g, device=dev)
+        f2[i] = torch.randn((D, H, W), generator=g, device=dev)
+        # "realistic" flow: sigma 4 px at 1/8 res smoothed by a 5x5 box filter, fresh coords per iteration
+        flow = 4.0 * torch.randn((1, 2, H, W), generator=g, device=dev)
+        flow = torch.nn.functional.avg_pool2d(flow, 5, stride=1, padding=2, count_include_pad=False)[0] * 5.0
+        coords[0][i] = grid + flow
+        for k in range(1, iters):
+            coords[k][i] = coords[k - 1][i] + 0.5 * torch.randn((2, H, W), generator=g, device=dev)
+    g = torch.Generator(device=dev).manual_seed(99 + rank)  # side measurements (weights etc.)
 
     def step():
         blk = rc.CorrBlock(f1, f2, num_levels=L, radius=r, build_mode=mode)
@@ -239,6 +346,30 @@ def run_ours(args):
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
+        # ---- sustained: the same step back to back for >= 2 s (the build runs into the board's power cap; the
+        # headline above is a short burst) with clocks and power sampled over exactly this window
+        sustained = None
+        if not args.no_sustained:
+            # the same number of steps on every rank (sized from the slowest rank's headline time)
+            n_t = torch.tensor([math.ceil(args.sustained_s * 1e3 / (ms_total / args.steps))], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(n_t, op=dist.ReduceOp.MIN)
+            n_sus = int(n_t[0])
+            m0 = sampler.mark() if rank == 0 else 0
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i_ in range(n_sus):
+                blk, out = step()
+                if i_ % 64 == 63:
+                    torch.cuda.synchronize(dev)  # keep the caching allocator's pending frees bounded
+            s1.record()
+            barrier()
+            sus_ms = s0.elapsed_time(s1)
+            sustained = {"steps": n_sus, "ms_per_step": sus_ms / n_sus, "seconds": sus_ms * 1e-3}
+            if rank == 0:
+                st = sampler.stats(m0, sampler.mark())
+                sustained.update({"sm_mhz": st["sm_mhz"], "power_w": st["power_w"], "reasons": st["reasons"], "clock_samples": st["samples"]})
         # per-kernel shares, measured live with events on the launch stream (same inputs)
         del blk, out
         kb0, kb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -256,6 +387,84 @@ def run_ours(args):
             build_ms.append(kb0.elapsed_time(kb1))
             look_ms.append(kl0.elapsed_time(kl1) / iters)
             del blk
+        # ---- the same step with TF32 operands (SURVEY K1's MMA kind), beside the f16 default
+        tf32_step = None
+        if rank == 0 and mode == "f16" and not args.no_fused:
+            def step_tf32():
+                b_ = rc.CorrBlock(f1, f2, num_levels=L, radius=r, build_mode="tf32")
+                for c in coords:
+                    o_ = b_(c)
+                return o_
+            for _ in range(3):
+                step_tf32()
+            torch.cuda.synchronize(dev)
+            kb0.record()
+            for _ in range(10):
+                step_tf32()
+            kb1.record()
+            torch.cuda.synchronize(dev)
+            tf32_step = {"ms_per_step": kb0.elapsed_time(kb1) / 10, "pairs_per_s": B * 10 / (kb0.elapsed_time(kb1) * 1e-3),
+                         "what": "build_mode='tf32' (kind::tf32 MMAs, TF32-rounded operands), same step, 10 steps after 3 warm-up"}
+        # ---- precision, measured in this run: 4096 random level-0 volume entries against fp64 dot products of the same
+        # features, and one full lookup against the exact-fp32 build mode's lookup
+        precision = None
+        if rank == 0:
+            blk = rc.CorrBlock(f1, f2, num_levels=L, radius=r, build_mode=mode)
+            lvl0 = blk.corr_pyramid[0].view(B, H * W, H * W)
+            gi = torch.Generator(device=dev).manual_seed(7)
+            bi = torch.randint(0, B, (4096,), generator=gi, device=dev)
+            mi = torch.randint(0, H * W, (4096,), generator=gi, device=dev)
+            ni = torch.randint(0, H * W, (4096,), generator=gi, device=dev)
+            got = lvl0[bi, mi, ni].double()
+            a_ = f1.view(B, D, H * W)[bi, :, mi].double()
+            b_ = f2.view(B, D, H * W)[bi, :, ni].double()
+            ref = (a_ * b_).sum(1) / math.sqrt(D)
+            vmax = float(lvl0.abs().max())
+            out_m = blk(coords[0])
+            del lvl0, blk
+            out_x = rc.CorrBlock(f1, f2, num_levels=L, radius=r, build_mode="fp32")(coords[0])
+            precision = {"measured": {"volume_max_abs_err_over_max_abs": float((got - ref).abs().max()) / vmax,
+                                      "volume_entries_checked": 4096, "volume_reference": "fp64 dot products of the same features / sqrt(D)",
+                                      "lookup_max_abs_err_over_max_abs_vs_fp32_mode": float((out_m - out_x).abs().max() / out_x.abs().max())},
+                         "tolerance": 1e-3, "build_mode": mode}
+            del out_m, out_x
+        # ---- like-for-like GPU baseline: the reference's own CorrBlock (stock PyTorch CUDA ops: cuBLAS SGEMM, avg_pool2d,
+        # grid_sample) on the same GPU and inputs -- baseline/_ref/stock/raft/core/corr.py, unmodified
+        gpu_baseline = None
+        if rank == 0 and not args.no_gpu_baseline:
+            ref_mod = staged_reference_corr()
+            if ref_mod is None:
+                gpu_baseline = {"unavailable": "baseline/_ref/stock is not staged (build() stages it where /root/reference exists)"}
+            else:
+                tf32_before = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = False  # the reference's default: fp32 SGEMM
+
+                def step_ref():
+                    b_ = ref_mod.CorrBlock(f1, f2, num_levels=L, radius=r)
+                    for c in coords:
+                        o_ = b_(c)
+                    return o_
+                o_ref = step_ref()
+                o_our = step()[1]
+                agree = float((o_our - o_ref).abs().max() / o_ref.abs().max())
+                del o_ref, o_our
+                step_ref()
+                torch.cuda.synchronize(dev)
+                kb0.record()
+                for _ in range(5):
+                    step_ref()
+                kb1.record()
+                torch.cuda.synchronize(dev)
+                torch.backends.cuda.matmul.allow_tf32 = tf32_before
+                ms_ref = kb0.elapsed_time(kb1) / 5
+                gpu_baseline = {"value": B * 1e3 / ms_ref, "unit": UNIT, "ms_per_step": ms_ref, "kind": "reference",
+                                "what": "the reference's unmodified raft/core/corr.py CorrBlock (baseline/_ref/stock) with stock PyTorch "
+                                        f"{torch.__version__} CUDA kernels, fp32 (allow_tf32 off), same GPU, same inputs, same step (B={B}), 5 steps after 2 warm-up",
+                                "last_lookup_max_abs_delta_over_max_abs_vs_this_library": agree}
+        # ---- the on-the-fly class (north_star config 5a): AlternateCorrBlock lookups at 1080p, B=4, beside the headline
+        alt = None
+        if rank == 0 and not args.no_fused:
+            alt = alt_1080p_side(rc, torch, dev, g, kl0, kl1, peaks()[0], not args.no_gpu_baseline)
         # beside the headline: the same build with the three-term fp16 split (fp32-class accuracy) and, for scale, what
         # the exact-fp32 FFMA build costs
         accurate = None
@@ -401,10 +610,10 @@ def run_ours(args):
             e2e_trials.append(x0.elapsed_time(x1))
         e2e_ms = sorted(e2e_trials)[1]
 
-    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_ms, sus_ms if sustained else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_total, e2e_ms, sus_ms_max = float(t[0]), float(t[1]), float(t[2])
 
     line = None
     if rank == 0:
@@ -422,6 +631,10 @@ def run_ours(args):
         # the step as a whole against the HBM roofline: algorithmic bytes of build + all lookups over the timed step
         step_gbs = B * (bb + iters * lb) / (ms_total / args.steps * 1e-3) / 1e9
         kern["step"] = {"algorithmic_bytes": B * (bb + iters * lb), "achieved_gbs": step_gbs, "frac_of_hbm_peak": step_gbs / hbm}
+        if tf32_step:
+            kern["step_tf32_mode"] = tf32_step
+        if alt:
+            kern["alt_1080p"] = alt
         if accurate:
             kern["accurate_build_modes"] = accurate
         if fused:
@@ -447,9 +660,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"tf32": "tf32", "f16": "f16xf16->f32", "fp32": "f32"}[mode],
             "data": "synthetic",
-            "precision": ("volume and lookups within 1e-3 of max|ref| (north_star); measured 3.07e-4 for f16 and for tf32 alike "
-                          "(profiles/r01_f16_parity_b8.json): block-scaled fp16 operands carry TF32's 11 significant bits, "
-                          "accumulation is fp32, the stored pyramid is fp32") if mode != "fp32" else "fp32 FFMA",
+            "precision": precision,
             "config": {"workload": f"RAFT-basic CorrBlock build + {iters} lookups @436x1024 (fmap {H}x{W}, D={D}, r={r}, L={L}), "
                                    f"B={B} frame pairs per GPU (BASELINE.json configs[1] shape)",
                        "pairs_per_gpu": B, "iters": iters, "build_mode": mode, "parallelism": f"pair-sharded x{world}, no collective",
@@ -458,16 +669,26 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                     "h2d_gbs_in_step": h2d / (e2e_ms / args.steps * 1e-3) / 1e9, "h2d_gbs_lone_pinned_copy": h2d_alone_gbs,
                     "trials_ms_per_step": [t_ / args.steps for t_ in e2e_trials], "reported": "median of 3 trials of K steps (rank 0's trials listed)",
+                    "d2h_covers": f"last of {iters} lookup outputs ({d2h} of {iters * d2h} bytes produced per step)",
                     "result": "last lookup's [B,324,H,W] features copied to pinned host memory each step; "
                               "steps pipelined over H2D | compute | D2H streams (2 buffer sets)"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                         "traffic": traffic, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+                         "traffic": traffic, "traffic_source": "static: profiles/ncu_traffic.json (ncu --set full capture of this "
+                         "kernel at this shape, committed; not measured in this run)" if traffic is not None else None,
+                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
             "kernels": kern,
         }
+        if sustained:
+            sustained["value"] = world * B * sustained["steps"] / (sus_ms_max * 1e-3)
+            sustained["unit"] = UNIT
+            sustained["what"] = f">= {args.sustained_s:g} s of back-to-back steps after the timed region; device-timed, max over ranks; clocks/power: rank 0's GPU, median over the window"
+            line["sustained"] = sustained
+        if gpu_baseline:
+            line["gpu_baseline"] = gpu_baseline
         if cpu:
-            line["cpu_baseline"] = {"value": cpu["pairs_per_s"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
+            line["cpu_baseline"] = {"value": cpu["pairs_per_s"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
                                     "sample": cpu["sample"]}
     if world > 1:
         dist.destroy_process_group()
@@ -500,7 +721,10 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("RAFTCORR_BUILD_MODE", "f16"), choices=["tf32", "f16", "fp32"])
     ap.add_argument("--batch", type=int, default=0, help="frame pairs per GPU (default 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fused", action="store_true", help="skip the lookup+convc1 side measurement")
+    ap.add_argument("--no-fused", action="store_true", help="skip the side measurements (lookup+convc1, encoder head, on-the-fly 1080p, tf32 step)")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch reference CorrBlock on the GPU")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the sustained loop (seconds)")
     ap.add_argument("--l2-fetch", type=int, default=0, help="set cudaLimitMaxL2FetchGranularity (32/64/128) first")
     args = ap.parse_args()
     line = None

@@ -184,7 +184,7 @@ def _lookup_backward(block, gout, coords, pyr, want_pyr, want_dcoords):
     if acc is None and dcoords is None:
         return None, None
     if acc is None:  # coords gradient only: scatter into a scratch pyramid
-        acc = torch.zeros(block._grad_layout.total_floats, dtype=torch.float32, device=dev)
+        acc = torch.zeros(lay.total_floats, dtype=torch.float32, device=dev)
     gout = gout.contiguous()  # bound to a local: the buffer must outlive the launch below
     check(_lib.lib().raftcorr_lookup_bwd(_ptr(gout), _ptr(coords), _ptr(pyr), _ptr(acc),
                                          ctypes.byref(lay), block.radius, _ptr(dcoords), dev.index, _stream(dev)),
@@ -374,7 +374,8 @@ class CorrBlock:
         this_pass = torch._C._current_graph_task_id()
         first = self._grad_acc is None or self._grad_acc_pass != this_pass
         if first:
-            self._grad_acc = torch.zeros(self._grad_layout.total_floats, dtype=torch.float32, device=self._device)
+            # sized like the forward buffer (autograd checks the shape); the row-major gradient layout is never larger
+            self._grad_acc = torch.zeros(self._layout.total_floats, dtype=torch.float32, device=self._device)
             self._grad_acc_pass = this_pass
         return self._grad_acc, first
 
