@@ -61,7 +61,12 @@ typedef struct raftcorr_pyramid_layout {
                             1: ROW PAIRS interleaved, element (y,x) at (y/2)*(2*pitch) + 2*x + (y%2), ceil(h/2) pair rows
                                per image (an odd last row is paired with zeros).  A (K+1)x(K+1) lookup window is then
                                ~(K+1)/2 runs of 2(K+1) floats instead of K+1 runs of K+1: fewer, longer DRAM bursts.
-                               The tensor-core build writes and the lookup reads either; gradient pyramids and the
+                            2: ROW QUADS interleaved, element (y,x) at (y/4)*(4*pitch) + 4*x + (y%4), ceil(h/4) groups per
+                               image (the last group is completed with rows of zeros).  One column of a group is 16
+                               bytes, so a window starts on TMA's 16-byte grid at ANY x: a (K+1)x(K+1) window is 3 or 4
+                               runs of exactly 4(K+1) floats (160 B at r=4), ~10.6 DRAM fills of 64 B instead of ~12.4
+                               (pairs) or ~17 (rows).  Default of the tensor-core builds.
+                               The tensor-core build writes and the lookup reads any of them; gradient pyramids and the
                                fp32 build use 0. */
     int32_t reserved_;
 } raftcorr_pyramid_layout;

@@ -110,7 +110,8 @@ def check(status: int, what: str):
         raise RaftCorrError(f"{what}: {msg.decode() if msg else 'unknown error'}")
 
 
-def make_layout(B: int, H: int, W: int, L: int, interleaved: bool = False) -> PyramidLayout:
+def make_layout(B: int, H: int, W: int, L: int, interleaved: int = 0) -> PyramidLayout:
+    """``interleaved``: 0 plain rows, 1 row pairs, 2 row quads (include/raftcorr.h)."""
     lay = PyramidLayout()
-    check(lib().raftcorr_pyramid_layout_init(ctypes.byref(lay), B, H, W, L, 1 if interleaved else 0), "pyramid layout")
+    check(lib().raftcorr_pyramid_layout_init(ctypes.byref(lay), B, H, W, L, int(interleaved)), "pyramid layout")
     return lay

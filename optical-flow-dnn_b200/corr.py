@@ -22,6 +22,7 @@ from ._lib import RaftCorrError, check
 
 _MODES = {"fp32": _lib.BUILD_FP32_SIMT, "tf32": _lib.BUILD_TF32_TC, "f16": _lib.BUILD_F16_TC, "f16x3": _lib.BUILD_F16X3_TC}
 _default_mode = os.environ.get("RAFTCORR_BUILD_MODE", "f16")
+_LAYOUTS = {"rowmajor": 0, "pairs": 1, "interleaved": 1, "quads": 2}  # raftcorr_pyramid_layout::interleaved
 
 
 def set_default_build_mode(mode: str) -> None:
@@ -284,14 +285,14 @@ class CorrBlock:
         self._mode = _MODES[mode]
         self._B, self._D, self._H, self._W = B, D, H, W
         self._device = device
-        # the tensor-core build writes row pairs interleaved (fewer, longer DRAM runs per lookup window);
-        # gradient pyramids are row-major inside the library whatever this says, and never larger
-        # (RAFTCORR_PYRAMID_LAYOUT=rowmajor keeps the old layout: A/B switch, needed by the cp.async lookup and the
-        # CTA-pair build experiments)
-        il = mode != "fp32" and os.environ.get("RAFTCORR_PYRAMID_LAYOUT", "interleaved") != "rowmajor"
+        # the tensor-core builds write row QUADS interleaved (a lookup window is 3-4 runs of 160 bytes at any x: fewest
+        # 64-byte DRAM fills, exact TMA boxes); gradient pyramids are row-major inside the library whatever this says, and
+        # never larger.  RAFTCORR_PYRAMID_LAYOUT = quads (default) | pairs (round-1 layout) | rowmajor: A/B switches
+        # (rowmajor is needed by the cp.async lookup and the CTA-pair build experiments)
+        il = 0 if mode == "fp32" else _LAYOUTS[os.environ.get("RAFTCORR_PYRAMID_LAYOUT", "quads")]
         self._layout = _lib.make_layout(B, H, W, self.num_levels, interleaved=il)
         # gradient pyramids are GEMM operands of the build backward: always plain rows, own level offsets
-        self._grad_layout = _lib.make_layout(B, H, W, self.num_levels, interleaved=False) if il else self._layout
+        self._grad_layout = _lib.make_layout(B, H, W, self.num_levels, interleaved=0) if il else self._layout
         self._grad_acc = None
         self._grad_acc_pass = -1
         self._plan = None
@@ -494,9 +495,9 @@ class CorrBlock:
     @property
     def corr_pyramid(self):
         """The reference's list of ``[B*H*W, 1, H_l, W_l]`` tensors (corr.py:35-43).  fp32 build mode: strided
-        views into the single pyramid buffer (rows are padded to a multiple of 8 floats).  tf32 build mode: the
-        buffer stores row pairs interleaved, so the levels are de-interleaved copies (nothing in RAFT reads
-        this attribute; the lookup works on the buffer)."""
+        views into the single pyramid buffer (rows are padded to a multiple of 8 floats).  Tensor-core build modes:
+        the buffer stores row quads interleaved, so the levels are de-interleaved copies (nothing in RAFT reads this
+        attribute; the lookup works on the buffer)."""
         if torch.is_grad_enabled() and self._pyr.requires_grad:
             # differentiable like the reference's list (corr.py:35-43): the levels' gradients are written into the
             # block's single row-major gradient pyramid, next to the lookups' contributions
@@ -510,9 +511,10 @@ class CorrBlock:
         for l in range(self.num_levels):
             h, w, p = lay.h[l], lay.w[l], lay.pitch[l]
             if lay.interleaved:
-                hp = (h + 1) // 2
-                flat = pyr[lay.offset[l]: lay.offset[l] + self._B * N * hp * 2 * p]
-                lvl = flat.view(self._B * N, hp, p, 2).permute(0, 1, 3, 2).reshape(self._B * N, 1, 2 * hp, p)
+                rg = 2 if lay.interleaved == 1 else 4  # rows per interleaved group
+                hp = (h + rg - 1) // rg
+                flat = pyr[lay.offset[l]: lay.offset[l] + self._B * N * hp * rg * p]
+                lvl = flat.view(self._B * N, hp, p, rg).permute(0, 1, 3, 2).reshape(self._B * N, 1, rg * hp, p)
                 out.append(lvl[:, :, :h, :w])
             else:
                 flat = pyr[lay.offset[l]: lay.offset[l] + self._B * N * h * p]

@@ -80,7 +80,9 @@ int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* lay, int B, int H, int
     RC_REQUIRE(B >= 0 && H >= 1 && W >= 1, "bad sizes B=%d H=%d W=%d", B, H, W);
     std::memset(lay, 0, sizeof(*lay));
     lay->B = B; lay->H = H; lay->W = W; lay->L = L;
-    lay->interleaved = interleaved ? 1 : 0;
+    RC_REQUIRE(interleaved >= 0 && interleaved <= 2, "pyramid layout: interleaved must be 0 (rows), 1 (row pairs) or 2 (row quads), got %d", interleaved);
+    lay->interleaved = interleaved;
+    const int rg = layout_group_rows(interleaved);
     int h = H, w = W;
     int64_t off = 0;
     const int64_t N = (int64_t)H * W;
@@ -92,7 +94,7 @@ int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* lay, int B, int H, int
         lay->w[l] = w;
         lay->pitch[l] = (w + 7) / 8 * 8;
         lay->offset[l] = off;
-        const int64_t rows = interleaved ? (h + 1) / 2 * 2 : h;  // an odd last row is paired with a row of zeros
+        const int64_t rows = (h + rg - 1) / rg * rg;  // the last group is completed with rows of zeros
         off += (int64_t)align_up((size_t)(B * N * rows * lay->pitch[l]), 64);
         h /= 2;
         w /= 2;

@@ -103,14 +103,20 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
-// IL: the pyramid is written with row pairs interleaved (raftcorr_pyramid_layout::interleaved); needs RP == 2.
-template <int MODE, int kStages = 3, int kNumStoreBufs = 2, int RP = 2, bool IL = false>
+// 8 bytes to global memory (two row slots of one column in the row-quad layout)
+__device__ __forceinline__ void st_global_v2(float* p, float a, float b) {
+    asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// IL: raftcorr_pyramid_layout::interleaved -- 0 plain rows, 1 row pairs, 2 row quads interleaved; 1 and 2 need RP == 2
+// (a store buffer then holds two [128 px][128 B] boxes: a row pair as columns 0..15 | 16..31, or 4 rows x 8 | 8 columns).
+template <int MODE, int kStages = 3, int kNumStoreBufs = 2, int RP = 2, int IL = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_out, const BuildParams P) {
     constexpr int CL = MODE == 0 ? 1 : 2;
     constexpr bool PAIR_MMA = MODE == 2;
-    static_assert(!IL || RP == 2, "the interleaved layout stores whole row pairs");
+    static_assert(!IL || RP == 2, "the interleaved layouts stage two boxes per phase");
     constexpr int kStoreBufBytes = RP * kRowTileBytes;
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment: required by the 128B swizzle atoms of TMA and UMMA
@@ -272,6 +278,49 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_wait(tfull_bar + 8 * acc, (it >> 1) & 1);
             tc_fence_after();
             const uint32_t t_acc = tmem_base + lane_addr + acc * kTileN;
+            if constexpr (IL == 2) {
+                // row quads: a phase is 4 target rows x 16 columns; column x of a quad is one 16-byte chunk (r0 r1 r2 r3),
+                // so the phase leaves as two [128 px][128 B] boxes of 8 columns each
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int rgp = p >> 1, chh = p & 1;
+                    float r0[16], r1[16], r2[16], r3[16];
+                    tmem_ld16(t_acc + (4 * rgp + 0) * kTileW + 16 * chh, r0);
+                    tmem_ld16(t_acc + (4 * rgp + 1) * kTileW + 16 * chh, r1);
+                    tmem_ld16(t_acc + (4 * rgp + 2) * kTileW + 16 * chh, r2);
+                    tmem_ld16(t_acc + (4 * rgp + 3) * kTileW + 16 * chh, r3);
+                    tmem_ld_wait();
+                    if (p == 3) {  // this warp has read all of the accumulator
+                        tc_fence_before();
+                        tempty_arrive<PAIR_MMA>(tempty_bar + 8 * acc);
+                    }
+                    const float s01 = sc4[2 * rgp], s23 = sc4[2 * rgp + 1];
+                    const uint32_t sa = store_base + buf * kStoreBufBytes + ml * 128;
+                    const uint32_t sb = sa + kRowTileBytes;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t off = ((uint32_t)j ^ swz) << 4;
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(r0[j] * s01), "f"(r1[j] * s01),
+                                     "f"(r2[j] * s23), "f"(r3[j] * s23)
+                                     : "memory");
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sb + off), "f"(r0[8 + j] * s01),
+                                     "f"(r1[8 + j] * s01), "f"(r2[8 + j] * s23), "f"(r3[8 + j] * s23)
+                                     : "memory");
+                    }
+                    fence_proxy_async();
+                    if (issuer) tma_store_wait_read_n<kNumStoreBufs - 2>();
+                    named_bar_sync(1, 128);
+                    if (issuer) {  // map_out: [4 * W interleaved floats][row quads][N1][B]
+                        const uint32_t s0 = store_base + buf * kStoreBufBytes;
+                        const int x4 = 4 * (wt * kTileW + 16 * chh);
+                        tma_store_4d(&map_out, s0, x4, band * 2 + rgp, mt * kTileM, b);
+                        tma_store_4d(&map_out, s0 + kRowTileBytes, x4 + 32, band * 2 + rgp, mt * kTileM, b);
+                        tma_store_commit();
+                    }
+                    if (++buf == kNumStoreBufs) buf = 0;
+                }
+                continue;
+            }
 #pragma unroll
             for (int p = 0; p < kTileH / RP; ++p) {
                 float ra[32], rb[32];
@@ -288,7 +337,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const uint32_t off = ((uint32_t)j ^ swz) << 4;
-                    if (IL) {
+                    if (IL == 1) {
                         // the two rows leave as ONE run (a0 b0 a1 b1 ...): first box = target columns 0..15, second = 16..31
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(ra[2 * j] * tsc),
                                      "f"(rb[2 * j] * tsc), "f"(ra[2 * j + 1] * tsc), "f"(rb[2 * j + 1] * tsc)
@@ -334,7 +383,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     if (issuer) {
                         const uint32_t s0 = store_base + buf * kStoreBufBytes;
                         const int h = band * kTileH + RP * p;
-                        if (IL) {  // map_out: [2 * W interleaved floats][pair rows][N1][B]
+                        if (IL == 1) {  // map_out: [2 * W interleaved floats][pair rows][N1][B]
                             tma_store_4d(&map_out, s0, wt * (2 * kTileW), h >> 1, mt * kTileM, b);
                             tma_store_4d(&map_out, s0 + kRowTileBytes, wt * (2 * kTileW) + kTileW, h >> 1, mt * kTileM, b);
                         } else {
@@ -383,6 +432,77 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 continue;
             }
             const int64_t pix = (int64_t)b * P.N1 + m;
+            if constexpr (IL == 2) {
+                // Row quads.  Level 1: the tile's 4 pooled rows are exactly one quad (group `band`), 16 columns, written
+                // as 32-byte sectors (2 columns x 4 rows).  Level 2: 2 rows = half a quad (8 bytes per column).  Level 3:
+                // 1 row = one slot per column.  Rows past a level's height inside its last quad are written as zeros
+                // (the lookup's tensor maps see whole quads).
+                const int hp1 = (P.lvl_h[1] + 3) & ~3, hp2 = (P.lvl_h[2] + 3) & ~3, hp3 = (P.lvl_h[3] + 3) & ~3;
+                float l2row[2][8];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float l1h[4][8];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        float ra[16], rb[16];
+                        tmem_ld16(t_acc + (2 * p) * kTileW + 16 * half, ra);
+                        tmem_ld16(t_acc + (2 * p + 1) * kTileW + 16 * half, rb);
+                        tmem_ld_wait();
+                        if (half == 1 && p == 3) {
+                            tc_fence_before();
+                            tempty_arrive<PAIR_MMA>(tempty_bar + 8 * acc);
+                        }
+                        const float q = (band * 4 + p < P.lvl_h[1]) ? q4[p] : 0.f;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) l1h[p][j] = (ra[2 * j] + ra[2 * j + 1] + rb[2 * j] + rb[2 * j + 1]) * q;
+                    }
+                    if (m_ok && band * 4 < hp1) {
+                        const int x1 = (w0 >> 1) + 8 * half;
+                        float* dst = P.lvl_base[1] + pix * P.lvl_img_stride[1] + (int64_t)band * (4 * P.lvl_pitch[1]) + 4 * x1;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            if (x1 + 2 * c + 2 <= P.lvl_pitch[1]) {
+                                const float v[8] = {l1h[0][2 * c], l1h[1][2 * c], l1h[2][2 * c], l1h[3][2 * c],
+                                                    l1h[0][2 * c + 1], l1h[1][2 * c + 1], l1h[2][2 * c + 1], l1h[3][2 * c + 1]};
+                                st_global_v8(dst + 8 * c, v);
+                            }
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            l2row[rr][4 * half + c] = (l1h[2 * rr][2 * c] + l1h[2 * rr][2 * c + 1] + l1h[2 * rr + 1][2 * c] +
+                                                       l1h[2 * rr + 1][2 * c + 1]) * 0.25f;
+                }
+                if (P.L > 2 && m_ok && band * 2 < hp2) {
+                    const int x2 = w0 >> 2;
+                    const bool ok0 = band * 2 < P.lvl_h[2], ok1 = band * 2 + 1 < P.lvl_h[2];
+                    // the last band also completes its quad with zeros when it ends half way
+                    const bool fill = band == P.bands - 1 && !(band & 1);
+                    float* dst = P.lvl_base[2] + pix * P.lvl_img_stride[2] + (int64_t)(band >> 1) * (4 * P.lvl_pitch[2]) + 4 * x2 +
+                                 2 * (band & 1);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        if (x2 + c < P.lvl_pitch[2]) {
+                            st_global_v2(dst + 4 * c, ok0 ? l2row[0][c] : 0.f, ok1 ? l2row[1][c] : 0.f);
+                            if (fill) st_global_v2(dst + 4 * c + 2, 0.f, 0.f);
+                        }
+                }
+                if (P.L > 3 && m_ok && band < hp3) {
+                    const int x3 = w0 >> 3;
+                    const bool ok = band < P.lvl_h[3];
+                    float* dst = P.lvl_base[3] + pix * P.lvl_img_stride[3] + (int64_t)(band >> 2) * (4 * P.lvl_pitch[3]) + 4 * x3 +
+                                 (band & 3);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (x3 + c < P.lvl_pitch[3]) {
+                            dst[4 * c] = ok ? (l2row[0][2 * c] + l2row[0][2 * c + 1] + l2row[1][2 * c] + l2row[1][2 * c + 1]) * 0.25f : 0.f;
+                            if (band == P.bands - 1)
+                                for (int sl = (band & 3) + 1; sl < 4; ++sl) dst[4 * c + sl - (band & 3)] = 0.f;
+                        }
+                }
+                continue;
+            }
             float l1prev[16], l2prev[8];
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
@@ -539,16 +659,18 @@ int launch_build_tc_ex(const void* f1n, const void* f2n, int D, float* pyramid, 
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2"))
             return rc;
     }
-    const bool il = lay.interleaved != 0;
+    const int il = lay.interleaved;
     RC_REQUIRE(!il || mode != 1, "tf32 build: the multicast-pair experiment writes the row-major layout only");
-    if (il) {  // level 0 as [2 * W interleaved floats][pair rows][N1][B]
-        const int hp = (lay.h[0] + 1) / 2;
-        const int64_t img = (int64_t)hp * 2 * lay.pitch[0];
-        cuuint64_t dims[4] = {(cuuint64_t)lay.w[0] * 2, (cuuint64_t)hp, (cuuint64_t)N1, (cuuint64_t)B};
-        cuuint64_t strides[3] = {(cuuint64_t)lay.pitch[0] * 8, (cuuint64_t)img * 4, (cuuint64_t)N1 * img * 4};
+    RC_REQUIRE(il != 2 || mode == 0, "tf32 build: the CTA-pair experiments write the row-major / row-pair layouts only");
+    if (il) {  // level 0 as [rg * W interleaved floats][row groups][N1][B], rg = 2 (pairs) or 4 (quads)
+        const int rg = layout_group_rows(il);
+        const int hp = (lay.h[0] + rg - 1) / rg;
+        const int64_t img = (int64_t)hp * rg * lay.pitch[0];
+        cuuint64_t dims[4] = {(cuuint64_t)lay.w[0] * rg, (cuuint64_t)hp, (cuuint64_t)N1, (cuuint64_t)B};
+        cuuint64_t strides[3] = {(cuuint64_t)lay.pitch[0] * 4 * rg, (cuuint64_t)img * 4, (cuuint64_t)N1 * img * 4};
         cuuint32_t box[4] = {kTileW, 1, kTileM, 1};
         if (int rc = encode_f32_map(fn, &map_out, (void*)(pyramid + lay.offset[0]), 4, dims, strides, box,
-                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, "volume (row pairs)"))
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, "volume (interleaved rows)"))
             return rc;
     } else {
         const int64_t img = (int64_t)lay.h[0] * lay.pitch[0];
@@ -566,7 +688,8 @@ int launch_build_tc_ex(const void* f1n, const void* f2n, int D, float* pyramid, 
         P.lvl_h[l] = lay.h[l];
         P.lvl_w[l] = lay.w[l];
         P.lvl_pitch[l] = lay.pitch[l];
-        P.lvl_img_stride[l] = (int64_t)(il ? (lay.h[l] + 1) / 2 * 2 : lay.h[l]) * lay.pitch[l];
+        const int rg = layout_group_rows(il);
+        P.lvl_img_stride[l] = (int64_t)((lay.h[l] + rg - 1) / rg * rg) * lay.pitch[l];
     }
     P.B = B; P.N1 = N1; P.H2 = H; P.W2 = W; P.L = fusedL;
     P.m_tiles = ceil_div(N1, kTileM);
@@ -609,13 +732,13 @@ int launch_build_tc_ex(const void* f1n, const void* f2n, int D, float* pyramid, 
         static_assert(smem2 <= 232448, "pair pipeline does not fit shared memory");                                 \
         cfg.dynamicSmemBytes = smem2;                                                                               \
         if (il) {                                                                                                   \
-            RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<2, NS, 2, 2, true>,                                        \
+            RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<2, NS, 2, 2, 1>,                                           \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));                      \
-            RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<2, NS, 2, 2, true>, map_a, map_b, map_out, P));        \
+            RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<2, NS, 2, 2, 1>, map_a, map_b, map_out, P));           \
         } else {                                                                                                    \
-            RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<2, NS, 2, 2, false>,                                       \
+            RC_CUDA(cudaFuncSetAttribute(build_tc_kernel<2, NS, 2, 2, 0>,                                           \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));                      \
-            RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<2, NS, 2, 2, false>, map_a, map_b, map_out, P));       \
+            RC_CUDA(cudaLaunchKernelEx(&cfg, build_tc_kernel<2, NS, 2, 2, 0>, map_a, map_b, map_out, P));           \
         }                                                                                                           \
         break;                                                                                                      \
     }
@@ -645,20 +768,27 @@ int launch_build_tc_ex(const void* f1n, const void* f2n, int D, float* pyramid, 
         build_tc_kernel<0, NS, NB, RP, IL_><<<clusters, kThreads, smem_bytes(NS, NB, RP), s>>>(map_a, map_b, map_out, P); \
         break;                                                                                                          \
     }
-        if (il) {
+        if (il == 2) {
             switch (pipe) {
-                RAFTCORR_PIPE_CASE(3, 2, 2, true)
-                RAFTCORR_PIPE_CASE(2, 2, 2, true)
-                RAFTCORR_PIPE_CASE(2, 4, 2, true)
+                RAFTCORR_PIPE_CASE(3, 2, 2, 2)
+                RAFTCORR_PIPE_CASE(2, 2, 2, 2)
+                RAFTCORR_PIPE_CASE(2, 4, 2, 2)
+                default: return fail("RAFTCORR_BUILD_PIPE=%d is not a compiled pipeline shape for the row-quad layout", pipe);
+            }
+        } else if (il) {
+            switch (pipe) {
+                RAFTCORR_PIPE_CASE(3, 2, 2, 1)
+                RAFTCORR_PIPE_CASE(2, 2, 2, 1)
+                RAFTCORR_PIPE_CASE(2, 4, 2, 1)
                 default: return fail("RAFTCORR_BUILD_PIPE=%d is not a compiled pipeline shape for the interleaved layout", pipe);
             }
         } else {
             switch (pipe) {
-                RAFTCORR_PIPE_CASE(3, 2, 2, false)
-                RAFTCORR_PIPE_CASE(2, 2, 2, false)
-                RAFTCORR_PIPE_CASE(2, 4, 2, false)
-                RAFTCORR_PIPE_CASE(3, 4, 1, false)
-                RAFTCORR_PIPE_CASE(4, 2, 1, false)
+                RAFTCORR_PIPE_CASE(3, 2, 2, 0)
+                RAFTCORR_PIPE_CASE(2, 2, 2, 0)
+                RAFTCORR_PIPE_CASE(2, 4, 2, 0)
+                RAFTCORR_PIPE_CASE(3, 4, 1, 0)
+                RAFTCORR_PIPE_CASE(4, 2, 1, 0)
                 default: return fail("RAFTCORR_BUILD_PIPE=%d is not a compiled pipeline shape", pipe);
             }
         }

@@ -48,13 +48,18 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 struct LevelView {
     float* base;          // level start
     int h, w, pitch;      // rows, valid cols, row pitch (floats)
-    int il;               // 1: row pairs interleaved (raftcorr_pyramid_layout::interleaved)
-    int64_t img_stride;   // floats between consecutive source pixels: h * pitch (il: 2 * ceil(h/2) * pitch)
+    int il;               // raftcorr_pyramid_layout::interleaved: 0 plain rows, 1 row pairs, 2 row quads interleaved
+    int64_t img_stride;   // floats between consecutive source pixels: round_up(h, rows per group) * pitch
     // offset of element (y, x) inside one image
     __host__ __device__ __forceinline__ int64_t at(int y, int x) const {
-        return il ? (int64_t)(y >> 1) * (2 * pitch) + 2 * x + (y & 1) : (int64_t)y * pitch + x;
+        return il == 2 ? (int64_t)(y >> 2) * (4 * pitch) + 4 * x + (y & 3)
+             : il ? (int64_t)(y >> 1) * (2 * pitch) + 2 * x + (y & 1) : (int64_t)y * pitch + x;
     }
+    __host__ __device__ __forceinline__ int group_rows() const { return il == 2 ? 4 : il ? 2 : 1; }
 };
+
+// rows interleaved per group for a layout code (0 / 1 / 2 -> 1 / 2 / 4)
+__host__ __device__ __forceinline__ int layout_group_rows(int interleaved) { return interleaved == 2 ? 4 : interleaved ? 2 : 1; }
 
 struct PyramidView {
     LevelView lvl[RAFTCORR_MAX_LEVELS];
@@ -72,7 +77,8 @@ inline PyramidView make_view(float* base, const raftcorr_pyramid_layout& lay) {
         v.lvl[l].w = lay.w[l];
         v.lvl[l].pitch = lay.pitch[l];
         v.lvl[l].il = lay.interleaved;
-        v.lvl[l].img_stride = (int64_t)(lay.interleaved ? (lay.h[l] + 1) / 2 * 2 : lay.h[l]) * lay.pitch[l];
+        const int rg = layout_group_rows(lay.interleaved);
+        v.lvl[l].img_stride = (int64_t)((lay.h[l] + rg - 1) / rg * rg) * lay.pitch[l];
     }
     return v;
 }

@@ -530,6 +530,7 @@ int launch_lookup_conv(const void* plan_blob, const float* coords, const float* 
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "packed convc1 weight"))
             return rc;
     }
+    RC_REQUIRE(g.lvl[0].il != 2, "lookup_convc1: the row-quad pyramid layout is not wired into the fused kernel yet");
     const bool il = g.lvl[0].il != 0;
     const LookupMaps& maps = plan.maps[0];
 #define RAFTCORR_LC_CASE(R_)                                                                    \

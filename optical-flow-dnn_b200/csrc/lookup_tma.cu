@@ -179,6 +179,153 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-quad layout (raftcorr_pyramid_layout::interleaved == 2): the default of the tensor-core builds.
+//
+// ncu on the row-pair kernel above (profiles/r02_ncu_lookup_pair_*.json) showed it bound by its own instruction stream,
+// not by DRAM (53 % DRAM cycles active, 121 warp instructions per (pixel, level) window, 16 warps per SM): per window
+// ~25 useful instructions and ~80 of addressing (per-tap row tables, alignment shifts, lane-0 box arithmetic).  Here
+//  * the box is exact (K+1 columns at any x, 3 or 4 quads): no alignment shift on either axis at evaluation time;
+//  * lane = window COLUMN, half-warp = pyramid level: a lane reads its column and the next as 16-byte quads
+//    (LDS.128, compile-time offsets), forms the horizontal lerps of all 4*GMAX quad rows and the vertical lerps of the
+//    K+3 quad-relative rows that can be an output; the window's start row inside its quad (sy) only moves the
+//    DESTINATION channel (one address subtraction) and predicates the stores -- no dynamic register indexing;
+//  * the LG boxes of a pixel are issued by LG lanes at once (each arrives on the pixel's mbarrier with its own byte
+//    count), so the coordinate / tensor-map arithmetic runs once per pixel instead of once per level.
+constexpr int kQPitch = 33;  // out tile row pitch (floats): conflict-free column writes and 4-channel x 8-quad reads
+
+template <int R, int LG, int kBufs>
+__global__ void __launch_bounds__(kWarps * 32, 2)
+lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView g, const float* __restrict__ coords,
+                       float* __restrict__ out) {
+    using Q = QuadGeo<R>;
+    constexpr int CH = LG * Q::KK;
+    constexpr int PIX_PER_WARP = kPix / kWarps;
+    constexpr int WARP_PATCH = kBufs * LG * Q::SLOT;  // bytes: this warp's ring of patch buffers
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+    // [kWarps][kBufs][LG][SLOT] patches | [kWarps][kBufs] mbarriers | out_s [CH][kQPitch]
+    const uint32_t bar_base = base + kWarps * WARP_PATCH;
+    float* out_s = reinterpret_cast<float*>(gen + kWarps * WARP_PATCH + kWarps * kBarBytes);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y, p0 = blockIdx.x * kPix;
+    const int N = g.N;
+    const uint32_t my_patch = base + warp * WARP_PATCH;
+    const float* my_patch_gen = reinterpret_cast<const float*>(gen + warp * WARP_PATCH);
+    const uint32_t my_bar = bar_base + warp * kBarBytes;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < kBufs; ++i) mbar_init(my_bar + 8 * i, LG);  // one arrival (+ its bytes) per level box
+        fence_mbar_init();
+        if (warp == 0) {
+#pragma unroll
+            for (int l = 0; l < LG; ++l) {
+                prefetch_tensormap(&maps.m[l]);
+                prefetch_tensormap(&maps.ms[l]);
+            }
+        }
+    }
+    __syncwarp();
+
+    const int half = lane >> 4, col = lane & 15;  // evaluation: half-warp = level of the pass, lane = window column
+
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: see lookup_fwd_tma_kernel
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    // lane n < PIX_PER_WARP holds the coordinates of the warp's pixel n (tile pixel q = warp + kWarps * n)
+    float cx = 0.f, cy = 0.f;
+    if (lane < PIX_PER_WARP) {
+        const int p = p0 + warp + kWarps * lane;
+        if (p < N) {
+            cx = clamp_coord(__ldg(coords + ((int64_t)b * 2 + 0) * N + p));
+            cy = clamp_coord(__ldg(coords + ((int64_t)b * 2 + 1) * N + p));
+        }
+    }
+    const float my_inv = g.inv_scale[lane < LG ? lane : 0];          // issue role: lane = level
+    const char* map_base = reinterpret_cast<const char*>(&maps);     // m[l] at 128 * l, ms[l] at 512 + 128 * l
+
+    auto issue = [&](int n, int buf) {  // whole warp; lanes < LG each issue one level's box
+        const float x = __shfl_sync(0xffffffffu, cx, n), y = __shfl_sync(0xffffffffu, cy, n);
+        if (lane < LG) {
+            const int x0 = __float2int_rd(x * my_inv) - R;
+            const int y0 = __float2int_rd(y * my_inv) - R;
+            const int nq = Q::quads(y0 & 3);
+            const uint32_t bar = my_bar + 8 * buf;
+            fence_proxy_async();  // the buffer was read through the generic proxy when it was last evaluated
+            mbar_expect_tx(bar, nq * Q::ROW_BYTES);
+            tma_load_3d(my_patch + (buf * LG + lane) * Q::SLOT,
+                        reinterpret_cast<const CUtensorMap*>(map_base + (nq == Q::GMAX ? 0 : 512) + 128 * lane), bar, 4 * x0,
+                        y0 >> 2, b * N + p0 + warp + kWarps * n);
+        }
+    };
+
+#pragma unroll
+    for (int n = 0; n < kBufs - 1 && n < PIX_PER_WARP; ++n)
+        if (p0 + warp + kWarps * n < N) issue(n, n);
+
+#pragma unroll
+    for (int n = 0; n < PIX_PER_WARP; ++n) {
+        const int q = warp + kWarps * n;
+        const int p = p0 + q;
+        if (p >= N) break;
+        const int buf = n % kBufs;
+        constexpr int kAhead = kBufs - 1;
+        if (n + kAhead < PIX_PER_WARP && p + kAhead * kWarps < N) issue(n + kAhead, (n + kAhead) % kBufs);
+        const float xq = __shfl_sync(0xffffffffu, cx, n), yq = __shfl_sync(0xffffffffu, cy, n);
+        mbar_wait(my_bar + 8 * buf, (n / kBufs) & 1);
+#pragma unroll
+        for (int pass = 0; pass < (LG + 1) / 2; ++pass) {
+            const int l = 2 * pass + half;
+            if (col < Q::K && l < LG) {
+                const float inv = g.inv_scale[l];
+                const float x = xq * inv, y = yq * inv;
+                const float xf = floorf(x), yf = floorf(y);
+                const float ax = x - xf, ay = y - yf;
+                const int sy = ((int)yf - R) & 3;
+                const float4* cp = reinterpret_cast<const float4*>(my_patch_gen + (buf * LG + l) * (Q::SLOT / 4)) + col;
+                float hh[4 * Q::GMAX];
+#pragma unroll
+                for (int gq = 0; gq < Q::GMAX; ++gq) {
+                    const float4 a = cp[gq * Q::K1], c = cp[gq * Q::K1 + 1];
+                    hh[4 * gq + 0] = a.x + ax * (c.x - a.x);
+                    hh[4 * gq + 1] = a.y + ax * (c.y - a.y);
+                    hh[4 * gq + 2] = a.z + ax * (c.z - a.z);
+                    hh[4 * gq + 3] = a.w + ax * (c.w - a.w);
+                }
+                // output row j = Y - sy of column `col` is channel col * K + j (x offset major, corr.py:66-78)
+                float* o = out_s + ((l * Q::KK + col * Q::K - sy) * kQPitch + q);
+#pragma unroll
+                for (int Y = 0; Y < Q::NV; ++Y) {
+                    const float v = hh[Y] + ay * (hh[Y + 1] - hh[Y]);
+                    const bool ok = Y < 3 ? (sy <= Y) : (Y >= Q::K ? (sy > Y - Q::K) : true);
+                    if (ok) o[Y * kQPitch] = v;
+                }
+            }
+        }
+        __syncwarp();  // all lanes are done with `buf` before it is refilled next iteration
+    }
+    __syncthreads();
+    if ((N & 3) == 0 && p0 + kPix <= N) {
+        // 8 lanes x 4 pixels per channel row: 128-byte lines leave as 128-bit stores
+        float* dst = out + ((int64_t)b * g.ctot + g.ch0) * N + p0;
+        for (int idx = threadIdx.x; idx < CH * 8; idx += kWarps * 32) {
+            const int ch = idx >> 3, qd = idx & 7;
+            const float* sp = out_s + ch * kQPitch + 4 * qd;
+            *reinterpret_cast<float4*>(dst + (int64_t)ch * N + 4 * qd) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+        }
+    } else {
+        const int p = p0 + lane;
+        if (p < N) {
+            float* dst = out + ((int64_t)b * g.ctot + g.ch0) * N + p;
+            for (int ch = warp; ch < CH; ch += kWarps) dst[(int64_t)ch * N] = out_s[ch * kQPitch + lane];
+        }
+    }
+}
+
 inline bool lookup_pdl() {  // RAFTCORR_LOOKUP_PDL=0 launches without programmatic stream serialization (A/B switch)
     static const bool on = [] {
         const char* e = std::getenv("RAFTCORR_LOOKUP_PDL");
@@ -214,6 +361,34 @@ int run_fwd_tma_bufs(const LookupMaps& maps, const GroupView& g, const float* co
     return 0;
 }
 
+
+template <int R, int LG>
+int run_fwd_quad(const LookupMaps& maps, const GroupView& g, const float* coords, float* out, cudaStream_t s) {
+    using Q = QuadGeo<R>;
+    constexpr int kBufs = 3;
+    const size_t smem = 128 + (size_t)kWarps * kBufs * LG * Q::SLOT + kWarps * kBarBytes + sizeof(float) * LG * Q::KK * kQPitch;
+    auto kern = lookup_fwd_quad_kernel<R, LG, kBufs>;
+    static bool attr_done[64] = {};
+    int dev = 0;
+    RC_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(ceil_div(g.N, kPix), g.B);
+    cfg.blockDim = dim3(kWarps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = lookup_pdl() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RC_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, g, coords, out));
+    return 0;
+}
+
 inline int lookup_ring_depth() {  // RAFTCORR_LOOKUP_BUFS=2|3 (A/B switch)
     static const int depth = [] {
         const char* e = std::getenv("RAFTCORR_LOOKUP_BUFS");
@@ -224,6 +399,7 @@ inline int lookup_ring_depth() {  // RAFTCORR_LOOKUP_BUFS=2|3 (A/B switch)
 
 template <int R, int LG>
 int run_fwd_tma(const LookupMaps& maps, const GroupView& g, const float* coords, float* out, cudaStream_t s) {
+    if (g.lvl[0].il == 2) return run_fwd_quad<R, LG>(maps, g, coords, out, s);
     if (g.lvl[0].il) return run_fwd_tma_bufs<R, LG, 3, true>(maps, g, coords, out, s);
     return lookup_ring_depth() == 2 ? run_fwd_tma_bufs<R, LG, 2, false>(maps, g, coords, out, s)
                                     : run_fwd_tma_bufs<R, LG, 3, false>(maps, g, coords, out, s);
@@ -253,8 +429,12 @@ int lookup_plan_init(void* plan_blob, const PyramidView& pv, int radius) {
     plan.magic = kPlanMagic;
     plan.radius = radius;
     const int K1 = 2 * radius + 2;
-    const bool il = pv.lvl[0].il != 0;
-    const int BC = il ? 2 * ((K1 + 1 + 1) / 2 * 2) : (K1 + 3 + 3) / 4 * 4, BR = il ? K1 / 2 + 1 : K1;  // == TmaGeo
+    const bool quad = pv.lvl[0].il == 2;
+    const bool il = pv.lvl[0].il == 1;
+    // == TmaGeo (rows / row pairs), QuadGeo (row quads)
+    const int BC = quad ? 4 * K1 : il ? 2 * ((K1 + 1 + 1) / 2 * 2) : (K1 + 3 + 3) / 4 * 4;
+    const int BR = quad ? (K1 + 2) / 4 + 1 : il ? K1 / 2 + 1 : K1;
+    const int rg = quad ? 4 : il ? 2 : 1;
     for (int l0 = 0; l0 < pv.L; l0 += 4) {
         const int gi = plan.groups++;
         const int lg = pv.L - l0 < 4 ? pv.L - l0 : 4;
@@ -264,14 +444,14 @@ int lookup_plan_init(void* plan_blob, const PyramidView& pv, int radius) {
             const LevelView& lv = pv.lvl[l0 + l];
             // logical width = W_l (not the pitch): columns in the row padding read as zeros, like everything outside
             // interleaved: [2 * W_l floats][ceil(H_l / 2) pair rows]; the odd partner of a last odd row holds zeros
-            cuuint64_t dims[3] = {(cuuint64_t)(il ? 2 * lv.w : lv.w), (cuuint64_t)(il ? (lv.h + 1) / 2 : lv.h),
-                                  (cuuint64_t)pv.B * pv.N};
-            cuuint64_t strides[2] = {(cuuint64_t)lv.pitch * (il ? 8 : 4), (cuuint64_t)lv.img_stride * 4};
+            // row groups: [rg * W_l floats][ceil(H_l / rg) groups]; the rows completing the last group hold zeros
+            cuuint64_t dims[3] = {(cuuint64_t)(rg * lv.w), (cuuint64_t)((lv.h + rg - 1) / rg), (cuuint64_t)pv.B * pv.N};
+            cuuint64_t strides[2] = {(cuuint64_t)lv.pitch * 4 * rg, (cuuint64_t)lv.img_stride * 4};
             cuuint32_t box[3] = {(cuuint32_t)BC, (cuuint32_t)BR, 1};
             if (int rc = encode_f32_map(fn, &plan.maps[gi].m[l], (void*)lv.base, 3, dims, strides, box,
                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, "pyramid level"))
                 return rc;
-            if (il) box[1] = (cuuint32_t)(BR - 1);
+            if (il || quad) box[1] = (cuuint32_t)(BR - 1);
             if (int rc = encode_f32_map(fn, &plan.maps[gi].ms[l], (void*)lv.base, 3, dims, strides, box,
                                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, "pyramid level"))
                 return rc;

@@ -24,9 +24,26 @@ struct TmaGeo {
     static constexpr int RPL = (K + GROUPS - 1) / GROUPS;
 };
 
+// Row-QUAD layout (raftcorr_pyramid_layout::interleaved == 2): one column of a quad is 16 bytes, so a box starts on
+// TMA's 16-byte grid at any x and is EXACTLY K+1 columns wide: GMAX or GMAX-1 quads of 4*(K+1) floats.
+template <int R>
+struct QuadGeo {
+    static constexpr int K = 2 * R + 1;
+    static constexpr int K1 = K + 1;
+    static constexpr int KK = K * K;
+    static constexpr int ROWF = 4 * K1;                     // floats per box row (one quad of the window)
+    static constexpr int ROW_BYTES = ROWF * 4;
+    static constexpr int GMAX = (K1 + 2) / 4 + 1;           // quads a window can span: ((3 + K1 - 1) >> 2) + 1
+    static constexpr int SLOT = (GMAX * ROW_BYTES + 127) / 128 * 128;
+    static constexpr int NV = K + 3;                        // quad-relative rows Y = 0 .. K+2 that can be an output row
+    static_assert(NV + 1 <= 4 * GMAX, "the horizontal pass reads rows 0 .. K+3");
+    // quads the window starting at row-in-quad sy spans
+    __host__ __device__ static constexpr int quads(int sy) { return ((sy + K1 - 1) >> 2) + 1; }
+};
+
 struct LookupMaps {
     CUtensorMap m[4];
-    CUtensorMap ms[4];  // interleaved layout: one pair row shorter, for windows that start on an even row
+    CUtensorMap ms[4];  // interleaved layouts: one row group shorter, for windows whose start row lets them fit
 };
 
 // plans: tensor maps + launch geometry encoded once per pyramid, reused by every refinement iteration

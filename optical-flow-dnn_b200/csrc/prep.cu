@@ -367,7 +367,8 @@ __global__ void pool_level_kernel(const LevelView in, const LevelView out, int64
         out.base[img * out.img_stride + out.at(y, x)] =
             (s[in.at(2 * y, 2 * x)] + s[in.at(2 * y, 2 * x + 1)] + s[in.at(2 * y + 1, 2 * x)] + s[in.at(2 * y + 1, 2 * x + 1)]) * 0.25f;
         // interleaved layout: the partner of an odd last row must read as zero
-        if (out.il && y == out.h - 1 && !(y & 1)) out.base[img * out.img_stride + out.at(y + 1, x)] = 0.f;
+        if (out.il && y == out.h - 1)  // the rows that complete the last group must read as zero
+            for (int yz = y + 1; yz % out.group_rows(); ++yz) out.base[img * out.img_stride + out.at(yz, x)] = 0.f;
     }
 }
 

@@ -46,18 +46,19 @@ def test_layout_matches_oracle_shapes(lib):
     from oracle.corr_oracle import level_shapes
 
     for (B, H, W, L) in [(8, 55, 128, 4), (1, 46, 62, 4), (16, 47, 156, 4), (2, 9, 12, 3)]:
-        for il in (False, True):  # row-major / row pairs interleaved (odd heights are padded to a full pair)
+        for il in (0, 1, 2):  # plain rows / row pairs / row quads interleaved (the last group is padded with zero rows)
             lay = lib.make_layout(B, H, W, L, interleaved=il)
-            assert lay.interleaved == int(il)
+            assert lay.interleaved == il
+            rg = (1, 2, 4)[il]
             assert [(lay.h[l], lay.w[l]) for l in range(L)] == level_shapes(H, W, L)
             off = 0
             for l in range(L):
                 assert lay.pitch[l] % 8 == 0 and lay.pitch[l] >= lay.w[l]
                 assert lay.offset[l] == off and off % 64 == 0
-                rows = (lay.h[l] + 1) // 2 * 2 if il else lay.h[l]
+                rows = (lay.h[l] + rg - 1) // rg * rg
                 off += -(-(B * H * W * rows * lay.pitch[l]) // 64) * 64
             assert lay.total_floats == off
-        assert lib.make_layout(B, H, W, L, True).total_floats >= lib.make_layout(B, H, W, L, False).total_floats
+        assert lib.make_layout(B, H, W, L, 2).total_floats >= lib.make_layout(B, H, W, L, 1).total_floats >= lib.make_layout(B, H, W, L, 0).total_floats
 
 
 def test_layout_rejects_collapsed_levels_and_bad_counts(lib):

@@ -66,7 +66,7 @@ def _operands(pkg, x, w, b, B, Cin, D, H, W, L=4):
     from optical_flow_dnn_b200 import _lib
 
     lib = _lib.lib()
-    lay = _lib.make_layout(B, H, W, L, interleaved=True)
+    lay = _lib.make_layout(B, H, W, L, interleaved=2)
     Dp = (D + 31) // 32 * 32
     ws_bytes = int(lib.raftcorr_fnet_head_build_workspace_bytes(B, Cin, D, H, W))
     ops_bytes = int(lib.raftcorr_build_fwd_workspace_bytes(B, D, H, W, _lib.BUILD_TF32_TC))

@@ -463,10 +463,18 @@ def test_kernel_variants_agree(pkg, monkeypatch):
     monkeypatch.setattr(corr_mod, "_default_mode", "tf32")
     for a, c in zip(v16, pkg.CorrBlock(f1, f2, L, r).corr_pyramid):
         assert float((a - c).abs().max()) <= 1e-3 * float(c.abs().max())
-    # production layout: row-pair-interleaved pyramid, single-CTA build, TMA lookup
+    # production layout: row-quad-interleaved pyramid, single-CTA build, TMA lookup
     blk_il = pkg.CorrBlock(f1, f2, L, r)
-    assert blk_il._layout.interleaved == 1
+    assert blk_il._layout.interleaved == 2
     o_il = blk_il(coords)
+    # round 1's row-pair layout: same arithmetic, different addresses -> bit-identical levels and lookups
+    monkeypatch.setenv("RAFTCORR_PYRAMID_LAYOUT", "pairs")
+    blk_p = pkg.CorrBlock(f1, f2, L, r)
+    assert blk_p._layout.interleaved == 1
+    for a, c in zip(blk_p.corr_pyramid, blk_il.corr_pyramid):
+        assert torch.equal(a, c)
+    assert torch.equal(blk_p(coords), o_il)
+    monkeypatch.delenv("RAFTCORR_PYRAMID_LAYOUT")
     for pipe in ("322", "222", "242"):  # operand stages / store buffers / rows per buffer
         monkeypatch.setenv("RAFTCORR_BUILD_PIPE", pipe)
         for a, c in zip(blk_il.corr_pyramid, pkg.CorrBlock(f1, f2, L, r).corr_pyramid):
