@@ -82,7 +82,6 @@ int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* lay, int B, int H, int
     lay->B = B; lay->H = H; lay->W = W; lay->L = L;
     RC_REQUIRE(interleaved >= 0 && interleaved <= 2, "pyramid layout: interleaved must be 0 (rows), 1 (row pairs) or 2 (row quads), got %d", interleaved);
     lay->interleaved = interleaved;
-    const int rg = layout_group_rows(interleaved);
     int h = H, w = W;
     int64_t off = 0;
     const int64_t N = (int64_t)H * W;
@@ -94,6 +93,7 @@ int raftcorr_pyramid_layout_init(raftcorr_pyramid_layout* lay, int B, int H, int
         lay->w[l] = w;
         lay->pitch[l] = (w + 7) / 8 * 8;
         lay->offset[l] = off;
+        const int rg = layout_group_rows(level_interleave(interleaved, l));
         const int64_t rows = (h + rg - 1) / rg * rg;  // the last group is completed with rows of zeros
         off += (int64_t)align_up((size_t)(B * N * rows * lay->pitch[l]), 64);
         h /= 2;

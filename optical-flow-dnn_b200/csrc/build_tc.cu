@@ -103,11 +103,6 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read_n() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
-// 8 bytes to global memory (two row slots of one column in the row-quad layout)
-__device__ __forceinline__ void st_global_v2(float* p, float a, float b) {
-    asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
-}
-
 // IL: raftcorr_pyramid_layout::interleaved -- 0 plain rows, 1 row pairs, 2 row quads interleaved; 1 and 2 need RP == 2
 // (a store buffer then holds two [128 px][128 B] boxes: a row pair as columns 0..15 | 16..31, or 4 rows x 8 | 8 columns).
 template <int MODE, int kStages = 3, int kNumStoreBufs = 2, int RP = 2, int IL = 0>
@@ -434,10 +429,9 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             const int64_t pix = (int64_t)b * P.N1 + m;
             if constexpr (IL == 2) {
                 // Row quads.  Level 1: the tile's 4 pooled rows are exactly one quad (group `band`), 16 columns, written
-                // as 32-byte sectors (2 columns x 4 rows).  Level 2: 2 rows = half a quad (8 bytes per column).  Level 3:
-                // 1 row = one slot per column.  Rows past a level's height inside its last quad are written as zeros
-                // (the lookup's tensor maps see whole quads).
-                const int hp1 = (P.lvl_h[1] + 3) & ~3, hp2 = (P.lvl_h[2] + 3) & ~3, hp3 = (P.lvl_h[3] + 3) & ~3;
+                // as 32-byte sectors (2 columns x 4 rows).  Rows past the level's height inside its last quad are written
+                // as zeros (the lookup's tensor maps see whole quads).
+                const int hp1 = (P.lvl_h[1] + 3) & ~3;
                 float l2row[2][8];
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -474,32 +468,30 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             l2row[rr][4 * half + c] = (l1h[2 * rr][2 * c] + l1h[2 * rr][2 * c + 1] + l1h[2 * rr + 1][2 * c] +
                                                        l1h[2 * rr + 1][2 * c + 1]) * 0.25f;
                 }
-                if (P.L > 2 && m_ok && band * 2 < hp2) {
-                    const int x2 = w0 >> 2;
-                    const bool ok0 = band * 2 < P.lvl_h[2], ok1 = band * 2 + 1 < P.lvl_h[2];
-                    // the last band also completes its quad with zeros when it ends half way
-                    const bool fill = band == P.bands - 1 && !(band & 1);
-                    float* dst = P.lvl_base[2] + pix * P.lvl_img_stride[2] + (int64_t)(band >> 1) * (4 * P.lvl_pitch[2]) + 4 * x2 +
-                                 2 * (band & 1);
+                // levels 2 and 3 are stored as row PAIRS (level_interleave): the tile's two level-2 rows are exactly pair
+                // `band` (64 bytes per thread), its level-3 row is one slot of pair band / 2
+                if (P.L > 2 && m_ok && band * 2 < P.lvl_h[2]) {
+                    const bool odd_ok = band * 2 + 1 < P.lvl_h[2];
+                    float* dst = P.lvl_base[2] + pix * P.lvl_img_stride[2] + (int64_t)band * (2 * P.lvl_pitch[2]) + (w0 >> 1);
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (x2 + c < P.lvl_pitch[2]) {
-                            st_global_v2(dst + 4 * c, ok0 ? l2row[0][c] : 0.f, ok1 ? l2row[1][c] : 0.f);
-                            if (fill) st_global_v2(dst + 4 * c + 2, 0.f, 0.f);
+                    for (int c = 0; c < 2; ++c)
+                        if ((w0 >> 2) + 4 * c + 4 <= P.lvl_pitch[2]) {
+                            float v[8];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                v[2 * e] = l2row[0][4 * c + e];
+                                v[2 * e + 1] = odd_ok ? l2row[1][4 * c + e] : 0.f;
+                            }
+                            st_global_v8(dst + 8 * c, v);
                         }
                 }
-                if (P.L > 3 && m_ok && band < hp3) {
-                    const int x3 = w0 >> 3;
-                    const bool ok = band < P.lvl_h[3];
-                    float* dst = P.lvl_base[3] + pix * P.lvl_img_stride[3] + (int64_t)(band >> 2) * (4 * P.lvl_pitch[3]) + 4 * x3 +
-                                 (band & 3);
+                if (P.L > 3 && m_ok && band < P.lvl_h[3] && (w0 >> 3) + 4 <= P.lvl_pitch[3]) {
+                    float* dst = P.lvl_base[3] + pix * P.lvl_img_stride[3] + (int64_t)(band >> 1) * (2 * P.lvl_pitch[3]) + (w0 >> 2) +
+                                 (band & 1);
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
-                        if (x3 + c < P.lvl_pitch[3]) {
-                            dst[4 * c] = ok ? (l2row[0][2 * c] + l2row[0][2 * c + 1] + l2row[1][2 * c] + l2row[1][2 * c + 1]) * 0.25f : 0.f;
-                            if (band == P.bands - 1)
-                                for (int sl = (band & 3) + 1; sl < 4; ++sl) dst[4 * c + sl - (band & 3)] = 0.f;
-                        }
+                        dst[2 * c] = (l2row[0][2 * c] + l2row[0][2 * c + 1] + l2row[1][2 * c] + l2row[1][2 * c + 1]) * 0.25f;
+                    if (!(band & 1) && band + 1 >= P.lvl_h[3]) dst[1] = dst[3] = dst[5] = dst[7] = 0.f;
                 }
                 continue;
             }
@@ -663,7 +655,7 @@ int launch_build_tc_ex(const void* f1n, const void* f2n, int D, float* pyramid, 
     RC_REQUIRE(!il || mode != 1, "tf32 build: the multicast-pair experiment writes the row-major layout only");
     RC_REQUIRE(il != 2 || mode == 0, "tf32 build: the CTA-pair experiments write the row-major / row-pair layouts only");
     if (il) {  // level 0 as [rg * W interleaved floats][row groups][N1][B], rg = 2 (pairs) or 4 (quads)
-        const int rg = layout_group_rows(il);
+        const int rg = layout_group_rows(level_interleave(il, 0));
         const int hp = (lay.h[0] + rg - 1) / rg;
         const int64_t img = (int64_t)hp * rg * lay.pitch[0];
         cuuint64_t dims[4] = {(cuuint64_t)lay.w[0] * rg, (cuuint64_t)hp, (cuuint64_t)N1, (cuuint64_t)B};
@@ -688,7 +680,7 @@ int launch_build_tc_ex(const void* f1n, const void* f2n, int D, float* pyramid, 
         P.lvl_h[l] = lay.h[l];
         P.lvl_w[l] = lay.w[l];
         P.lvl_pitch[l] = lay.pitch[l];
-        const int rg = layout_group_rows(il);
+        const int rg = layout_group_rows(level_interleave(il, l));
         P.lvl_img_stride[l] = (int64_t)((lay.h[l] + rg - 1) / rg * rg) * lay.pitch[l];
     }
     P.B = B; P.N1 = N1; P.H2 = H; P.W2 = W; P.L = fusedL;

@@ -58,8 +58,14 @@ struct LevelView {
     __host__ __device__ __forceinline__ int group_rows() const { return il == 2 ? 4 : il ? 2 : 1; }
 };
 
-// rows interleaved per group for a layout code (0 / 1 / 2 -> 1 / 2 / 4)
-__host__ __device__ __forceinline__ int layout_group_rows(int interleaved) { return interleaved == 2 ? 4 : interleaved ? 2 : 1; }
+// Per-level interleave code of a layout: `interleaved == 2` stores levels 0 and 1 as row quads and the deeper (small)
+// levels as row pairs -- the build's 8x32 target tile holds a whole quad of level 1 but only 2 rows of level 2 and 1 row
+// of level 3, and partial-sector stores cost as much as full ones on the SM's store path.
+__host__ __device__ __forceinline__ int level_interleave(int interleaved, int level) {
+    return interleaved == 2 ? (level < 2 ? 2 : 1) : interleaved;
+}
+// rows interleaved per group for a per-level code (0 / 1 / 2 -> 1 / 2 / 4)
+__host__ __device__ __forceinline__ int layout_group_rows(int il) { return il == 2 ? 4 : il ? 2 : 1; }
 
 struct PyramidView {
     LevelView lvl[RAFTCORR_MAX_LEVELS];
@@ -76,8 +82,8 @@ inline PyramidView make_view(float* base, const raftcorr_pyramid_layout& lay) {
         v.lvl[l].h = lay.h[l];
         v.lvl[l].w = lay.w[l];
         v.lvl[l].pitch = lay.pitch[l];
-        v.lvl[l].il = lay.interleaved;
-        const int rg = layout_group_rows(lay.interleaved);
+        v.lvl[l].il = level_interleave(lay.interleaved, l);
+        const int rg = layout_group_rows(v.lvl[l].il);
         v.lvl[l].img_stride = (int64_t)((lay.h[l] + rg - 1) / rg * rg) * lay.pitch[l];
     }
     return v;

@@ -181,7 +181,8 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Row-quad layout (raftcorr_pyramid_layout::interleaved == 2): the default of the tensor-core builds.
+// Layout 2 (raftcorr_pyramid_layout::interleaved == 2: levels 0 and 1 as row quads, deeper levels as row pairs): the
+// default of the tensor-core builds.
 //
 // ncu on the row-pair kernel above (profiles/r02_ncu_lookup_pair_*.json) showed it bound by its own instruction stream,
 // not by DRAM (53 % DRAM cycles active, 121 warp instructions per (pixel, level) window, 16 warps per SM): per window
@@ -200,6 +201,8 @@ __global__ void __launch_bounds__(kWarps * 32, 2)
 lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView g, const float* __restrict__ coords,
                        float* __restrict__ out) {
     using Q = QuadGeo<R>;
+    using PG = TmaGeo<R, true>;  // levels >= 2: row pairs
+    static_assert(PG::SLOT <= Q::SLOT, "patch slots are sized for the quad boxes");
     constexpr int CH = LG * Q::KK;
     constexpr int PIX_PER_WARP = kPix / kWarps;
     constexpr int WARP_PATCH = kBufs * LG * Q::SLOT;  // bytes: this warp's ring of patch buffers
@@ -253,13 +256,17 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
         if (lane < LG) {
             const int x0 = __float2int_rd(x * my_inv) - R;
             const int y0 = __float2int_rd(y * my_inv) - R;
+            const bool quad = lane < 2;
+            // quads: the window spans GMAX or GMAX-1 row quads; pairs: BR pair rows when it starts on an odd row, else BR-1
             const int nq = Q::quads(y0 & 3);
+            const bool big = quad ? nq == Q::GMAX : (y0 & 1);
+            const uint32_t bytes = quad ? nq * Q::ROW_BYTES : (big ? PG::BOX_BYTES : PG::BOX_BYTES - PG::BC * 4);
             const uint32_t bar = my_bar + 8 * buf;
             fence_proxy_async();  // the buffer was read through the generic proxy when it was last evaluated
-            mbar_expect_tx(bar, nq * Q::ROW_BYTES);
+            mbar_expect_tx(bar, bytes);
             tma_load_3d(my_patch + (buf * LG + lane) * Q::SLOT,
-                        reinterpret_cast<const CUtensorMap*>(map_base + (nq == Q::GMAX ? 0 : 512) + 128 * lane), bar, 4 * x0,
-                        y0 >> 2, b * N + p0 + warp + kWarps * n);
+                        reinterpret_cast<const CUtensorMap*>(map_base + (big ? 0 : 512) + 128 * lane), bar,
+                        quad ? 4 * x0 : 2 * (x0 & ~1), quad ? y0 >> 2 : y0 >> 1, b * N + p0 + warp + kWarps * n);
         }
     };
 
@@ -285,24 +292,46 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
                 const float x = xq * inv, y = yq * inv;
                 const float xf = floorf(x), yf = floorf(y);
                 const float ax = x - xf, ay = y - yf;
-                const int sy = ((int)yf - R) & 3;
-                const float4* cp = reinterpret_cast<const float4*>(my_patch_gen + (buf * LG + l) * (Q::SLOT / 4)) + col;
-                float hh[4 * Q::GMAX];
+                const float* pb = my_patch_gen + (buf * LG + l) * (Q::SLOT / 4);
+                if (pass == 0) {
+                    // ---- row quads: column chunk = 16 bytes (rows 4g .. 4g+3)
+                    const int sy = ((int)yf - R) & 3;
+                    const float4* cp = reinterpret_cast<const float4*>(pb) + col;
+                    float hh[4 * Q::GMAX];
 #pragma unroll
-                for (int gq = 0; gq < Q::GMAX; ++gq) {
-                    const float4 a = cp[gq * Q::K1], c = cp[gq * Q::K1 + 1];
-                    hh[4 * gq + 0] = a.x + ax * (c.x - a.x);
-                    hh[4 * gq + 1] = a.y + ax * (c.y - a.y);
-                    hh[4 * gq + 2] = a.z + ax * (c.z - a.z);
-                    hh[4 * gq + 3] = a.w + ax * (c.w - a.w);
-                }
-                // output row j = Y - sy of column `col` is channel col * K + j (x offset major, corr.py:66-78)
-                float* o = out_s + ((l * Q::KK + col * Q::K - sy) * kQPitch + q);
+                    for (int gq = 0; gq < Q::GMAX; ++gq) {
+                        const float4 a = cp[gq * Q::K1], c = cp[gq * Q::K1 + 1];
+                        hh[4 * gq + 0] = a.x + ax * (c.x - a.x);
+                        hh[4 * gq + 1] = a.y + ax * (c.y - a.y);
+                        hh[4 * gq + 2] = a.z + ax * (c.z - a.z);
+                        hh[4 * gq + 3] = a.w + ax * (c.w - a.w);
+                    }
+                    // output row j = Y - sy of column `col` is channel col * K + j (x offset major, corr.py:66-78)
+                    float* o = out_s + ((l * Q::KK + col * Q::K - sy) * kQPitch + q);
 #pragma unroll
-                for (int Y = 0; Y < Q::NV; ++Y) {
-                    const float v = hh[Y] + ay * (hh[Y + 1] - hh[Y]);
-                    const bool ok = Y < 3 ? (sy <= Y) : (Y >= Q::K ? (sy > Y - Q::K) : true);
-                    if (ok) o[Y * kQPitch] = v;
+                    for (int Y = 0; Y < Q::NV; ++Y) {
+                        const float v = hh[Y] + ay * (hh[Y + 1] - hh[Y]);
+                        const bool ok = Y < 3 ? (sy <= Y) : (Y >= Q::K ? (sy > Y - Q::K) : true);
+                        if (ok) o[Y * kQPitch] = v;
+                    }
+                } else {
+                    // ---- row pairs: column chunk = 8 bytes (rows 2g, 2g+1); the box starts at the even column <= x0
+                    const int sy = ((int)yf - R) & 1;
+                    const float2* cp = reinterpret_cast<const float2*>(pb) + (((int)xf - R) & 1) + col;
+                    float hh[2 * PG::BR];
+#pragma unroll
+                    for (int gp = 0; gp < PG::BR; ++gp) {
+                        const float2 a = cp[gp * (PG::BC / 2)], c = cp[gp * (PG::BC / 2) + 1];
+                        hh[2 * gp + 0] = a.x + ax * (c.x - a.x);
+                        hh[2 * gp + 1] = a.y + ax * (c.y - a.y);
+                    }
+                    float* o = out_s + ((l * Q::KK + col * Q::K - sy) * kQPitch + q);
+#pragma unroll
+                    for (int Y = 0; Y <= Q::K; ++Y) {
+                        const float v = hh[Y] + ay * (hh[Y + 1] - hh[Y]);
+                        const bool ok = Y == 0 ? (sy == 0) : (Y == Q::K ? (sy == 1) : true);
+                        if (ok) o[Y * kQPitch] = v;
+                    }
                 }
             }
         }
@@ -429,12 +458,6 @@ int lookup_plan_init(void* plan_blob, const PyramidView& pv, int radius) {
     plan.magic = kPlanMagic;
     plan.radius = radius;
     const int K1 = 2 * radius + 2;
-    const bool quad = pv.lvl[0].il == 2;
-    const bool il = pv.lvl[0].il == 1;
-    // == TmaGeo (rows / row pairs), QuadGeo (row quads)
-    const int BC = quad ? 4 * K1 : il ? 2 * ((K1 + 1 + 1) / 2 * 2) : (K1 + 3 + 3) / 4 * 4;
-    const int BR = quad ? (K1 + 2) / 4 + 1 : il ? K1 / 2 + 1 : K1;
-    const int rg = quad ? 4 : il ? 2 : 1;
     for (int l0 = 0; l0 < pv.L; l0 += 4) {
         const int gi = plan.groups++;
         const int lg = pv.L - l0 < 4 ? pv.L - l0 : 4;
@@ -442,8 +465,12 @@ int lookup_plan_init(void* plan_blob, const PyramidView& pv, int radius) {
         plan.g[gi] = make_group(pv, l0, lg, radius);
         for (int l = 0; l < lg; ++l) {
             const LevelView& lv = pv.lvl[l0 + l];
+            // box geometry of this level's layout == TmaGeo (rows / row pairs), QuadGeo (row quads)
+            const bool quad = lv.il == 2, il = lv.il == 1;
+            const int BC = quad ? 4 * K1 : il ? 2 * ((K1 + 1 + 1) / 2 * 2) : (K1 + 3 + 3) / 4 * 4;
+            const int BR = quad ? (K1 + 2) / 4 + 1 : il ? K1 / 2 + 1 : K1;
+            const int rg = lv.group_rows();
             // logical width = W_l (not the pitch): columns in the row padding read as zeros, like everything outside
-            // interleaved: [2 * W_l floats][ceil(H_l / 2) pair rows]; the odd partner of a last odd row holds zeros
             // row groups: [rg * W_l floats][ceil(H_l / rg) groups]; the rows completing the last group hold zeros
             cuuint64_t dims[3] = {(cuuint64_t)(rg * lv.w), (cuuint64_t)((lv.h + rg - 1) / rg), (cuuint64_t)pv.B * pv.N};
             cuuint64_t strides[2] = {(cuuint64_t)lv.pitch * 4 * rg, (cuuint64_t)lv.img_stride * 4};

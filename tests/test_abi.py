@@ -49,12 +49,12 @@ def test_layout_matches_oracle_shapes(lib):
         for il in (0, 1, 2):  # plain rows / row pairs / row quads interleaved (the last group is padded with zero rows)
             lay = lib.make_layout(B, H, W, L, interleaved=il)
             assert lay.interleaved == il
-            rg = (1, 2, 4)[il]
             assert [(lay.h[l], lay.w[l]) for l in range(L)] == level_shapes(H, W, L)
             off = 0
             for l in range(L):
                 assert lay.pitch[l] % 8 == 0 and lay.pitch[l] >= lay.w[l]
                 assert lay.offset[l] == off and off % 64 == 0
+                rg = (1, 2, 4 if l < 2 else 2)[il]  # layout 2: quads for levels 0-1, pairs deeper
                 rows = (lay.h[l] + rg - 1) // rg * rg
                 off += -(-(B * H * W * rows * lay.pitch[l]) // 64) * 64
             assert lay.total_floats == off
