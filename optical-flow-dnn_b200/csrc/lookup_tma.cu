@@ -202,10 +202,10 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
                        float* __restrict__ out) {
     using Q = QuadGeo<R>;
     using PG = TmaGeo<R, true>;  // levels >= 2: row pairs
-    static_assert(PG::SLOT <= Q::SLOT, "patch slots are sized for the quad boxes");
+    constexpr int SLOT = Q::SLOT > PG::SLOT ? Q::SLOT : PG::SLOT;  // a patch slot takes either kind of box
     constexpr int CH = LG * Q::KK;
     constexpr int PIX_PER_WARP = kPix / kWarps;
-    constexpr int WARP_PATCH = kBufs * LG * Q::SLOT;  // bytes: this warp's ring of patch buffers
+    constexpr int WARP_PATCH = kBufs * LG * SLOT;  // bytes: this warp's ring of patch buffers
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -264,7 +264,7 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
             const uint32_t bar = my_bar + 8 * buf;
             fence_proxy_async();  // the buffer was read through the generic proxy when it was last evaluated
             mbar_expect_tx(bar, bytes);
-            tma_load_3d(my_patch + (buf * LG + lane) * Q::SLOT,
+            tma_load_3d(my_patch + (buf * LG + lane) * SLOT,
                         reinterpret_cast<const CUtensorMap*>(map_base + (big ? 0 : 512) + 128 * lane), bar,
                         quad ? 4 * x0 : 2 * (x0 & ~1), quad ? y0 >> 2 : y0 >> 1, b * N + p0 + warp + kWarps * n);
         }
@@ -292,7 +292,7 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
                 const float x = xq * inv, y = yq * inv;
                 const float xf = floorf(x), yf = floorf(y);
                 const float ax = x - xf, ay = y - yf;
-                const float* pb = my_patch_gen + (buf * LG + l) * (Q::SLOT / 4);
+                const float* pb = my_patch_gen + (buf * LG + l) * (SLOT / 4);
                 if (pass == 0) {
                     // ---- row quads: column chunk = 16 bytes (rows 4g .. 4g+3)
                     const int sy = ((int)yf - R) & 3;
@@ -395,7 +395,8 @@ template <int R, int LG>
 int run_fwd_quad(const LookupMaps& maps, const GroupView& g, const float* coords, float* out, cudaStream_t s) {
     using Q = QuadGeo<R>;
     constexpr int kBufs = 3;
-    const size_t smem = 128 + (size_t)kWarps * kBufs * LG * Q::SLOT + kWarps * kBarBytes + sizeof(float) * LG * Q::KK * kQPitch;
+    constexpr int SLOT = Q::SLOT > TmaGeo<R, true>::SLOT ? Q::SLOT : TmaGeo<R, true>::SLOT;
+    const size_t smem = 128 + (size_t)kWarps * kBufs * LG * SLOT + kWarps * kBarBytes + sizeof(float) * LG * Q::KK * kQPitch;
     auto kern = lookup_fwd_quad_kernel<R, LG, kBufs>;
     static bool attr_done[64] = {};
     int dev = 0;
