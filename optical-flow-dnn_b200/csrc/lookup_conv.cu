@@ -92,11 +92,22 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, u
     }
 }
 
-template <int R, int LG, bool IL>
+// patch slot bytes per pyramid layout code (raftcorr_pyramid_layout::interleaved): layout 2 mixes quad and pair boxes
+template <int R, int LAY>
+struct ConvSlot {
+    static constexpr int value = LAY == 2 ? (QuadGeo<R>::SLOT > TmaGeo<R, true>::SLOT ? QuadGeo<R>::SLOT : TmaGeo<R, true>::SLOT)
+                                          : TmaGeo<R, LAY == 1>::SLOT;
+};
+
+// LAY = raftcorr_pyramid_layout::interleaved: 0 plain rows, 1 row pairs, 2 quads for levels 0-1 + pairs deeper
+template <int R, int LG, int LAY>
 __global__ void __launch_bounds__(kConvThreads, 1)
 lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constant__ CUtensorMap map_w, const ConvParams P) {
-    using G = TmaGeo<R, IL>;
+    constexpr bool IL = LAY == 1;
+    using G = TmaGeo<R, LAY != 0>;   // LAY 2: the pair geometry of its deeper levels
+    using Q = QuadGeo<R>;
     using C = ConvGeo<R>;
+    constexpr int SLOT = ConvSlot<R, LAY>::value;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -104,7 +115,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
     const uint32_t a_base = base;
     const uint32_t w_base = a_base + 2 * C::A_BYTES;
     const uint32_t patch_base = w_base + kWStages * kWStageBytes;
-    const uint32_t bar_base = patch_base + kGatherWarps * kSlots * G::SLOT;
+    const uint32_t bar_base = patch_base + kGatherWarps * kSlots * SLOT;
     const uint32_t patch_bar = bar_base;                                  // [kGatherWarps][kSlots]
     const uint32_t a_full = patch_bar + 8 * kGatherWarps * kSlots;        // [2]
     const uint32_t a_empty = a_full + 16;                                 // [2]
@@ -144,7 +155,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
 #pragma unroll
         for (int l = 0; l < LG; ++l) {
             prefetch_tensormap(&maps.m[l]);
-            if (IL) prefetch_tensormap(&maps.ms[l]);
+            if (LAY) prefetch_tensormap(&maps.ms[l]);
         }
     }
     // the channels a level does not have (K^2 .. 32 * KB) must read as zero, not as stale shared memory
@@ -165,7 +176,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
 
     if (warp < kGatherWarps) {
         // ===================== gather: patches -> bilinear samples -> A tile rows =====================
-        const uint32_t my_patch = patch_base + warp * (kSlots * G::SLOT);
+        const uint32_t my_patch = patch_base + warp * (kSlots * SLOT);
         const float* my_patch_gen = reinterpret_cast<const float*>(gen + (my_patch - base));
         const uint32_t my_bar = patch_bar + 8 * warp * kSlots;
         const int jg = lane / G::K, li = lane - jg * G::K;
@@ -190,6 +201,19 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
             const int ch = lane_ch + k;
             ch_off[k] = (uint32_t)(ch >> 5) * kKBlockBytes + (uint32_t)(ch & 3) * 4;
             ch_chunk[k] = (uint32_t)(ch & 31) >> 2;
+        }
+
+        // layout 2 evaluation (lookup_fwd_quad_kernel's scheme): half-warp = pixel of a pair, lane = window column;
+        // A tile address parts of the K outputs of this lane's column (channel col * K + j, x offset major)
+        const int half = lane >> 4, col = lane & 15;
+        uint32_t q_off[LAY == 2 ? G::K : 1], q_chunk[LAY == 2 ? G::K : 1];
+        if (LAY == 2) {
+#pragma unroll
+            for (int jj = 0; jj < G::K; ++jj) {
+                const int ch = (col < G::K ? col : 0) * G::K + jj;
+                q_off[jj] = (uint32_t)(ch >> 5) * kKBlockBytes + (uint32_t)(ch & 3) * 4;
+                q_chunk[jj] = (uint32_t)(ch & 31) >> 2;
+            }
         }
 
         // coordinates: lanes 0..7 hold the warp's pixels of the tile being consumed, lanes 16..23 those of the next tile
@@ -233,9 +257,15 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                 const int y0 = __float2int_rd(y * inv) - R;
                 const int slot = (i_n & 1) * kBatch + lane;
                 const uint32_t bar = my_bar + 8 * slot;
-                const uint32_t dst = my_patch + slot * G::SLOT;
+                const uint32_t dst = my_patch + slot * SLOT;
                 fence_proxy_async();  // the slot was read through the generic proxy two batches ago
-                if (IL) {
+                if (LAY == 2 && i_l < 2) {
+                    // row quads: exact box of K+1 columns at any x, GMAX or GMAX-1 quads
+                    const int nq = Q::quads(y0 & 3);
+                    mbar_expect_tx(bar, nq * Q::ROW_BYTES);
+                    tma_load_3d(dst, reinterpret_cast<const CUtensorMap*>(map_base + (nq == Q::GMAX ? 0 : 512) + 128 * i_l), bar,
+                                4 * x0, y0 >> 2, i_b * P.N + p);
+                } else if (LAY) {
                     const bool tall = y0 & 1;  // a window starting on an odd row spans one more pair row
                     mbar_expect_tx(bar, tall ? G::BOX_BYTES : G::BOX_BYTES - G::BC * 4);
                     tma_load_3d(dst, reinterpret_cast<const CUtensorMap*>(map_base + (tall ? 0 : 512) + 128 * i_l), bar,
@@ -278,6 +308,70 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
 #pragma unroll 1
                 for (int jb = 0; jb < kPixPerWarp; jb += kBatch, ++c_n) {
                     issue_batch(ti);
+                    if constexpr (LAY == 2) {
+#pragma unroll 1
+                        for (int k = 0; k < kBatch; k += 2) {
+                            if (p_base + jb + k >= P.N) break;                    // warp-uniform; pixels are consecutive
+                            const bool two = p_base + jb + k + 1 < P.N;          // the pair's second pixel exists
+                            const int slot0 = (c_n & 1) * kBatch + k;
+                            mbar_wait_spin(my_bar + 8 * slot0, (slot_phase >> slot0) & 1u);
+                            slot_phase ^= 1u << slot0;
+                            if (two) {
+                                mbar_wait_spin(my_bar + 8 * (slot0 + 1), (slot_phase >> (slot0 + 1)) & 1u);
+                                slot_phase ^= 1u << (slot0 + 1);
+                            }
+                            const int j = jb + k + half;                         // this half-warp's pixel (A tile row warp * 8 + j)
+                            const float x = __shfl_sync(0xffffffffu, cx, j) * inv, y = __shfl_sync(0xffffffffu, cy, j) * inv;
+                            if (col < G::K && (half == 0 || two)) {
+                                const float xf = floorf(x), yf = floorf(y);
+                                const float ax = x - xf, ay = y - yf;
+                                const float* pb = my_patch_gen + (slot0 + half) * (SLOT / 4);
+                                float hh[4 * Q::GMAX > 2 * G::BR ? 4 * Q::GMAX : 2 * G::BR];
+                                if (l < 2) {
+                                    // row quads: the lane's column and the next as 16-byte chunks (rows 4g .. 4g+3)
+                                    const float4* cp = reinterpret_cast<const float4*>(pb) + col;
+#pragma unroll
+                                    for (int gq = 0; gq < Q::GMAX; ++gq) {
+                                        const float4 a = cp[gq * Q::K1], c = cp[gq * Q::K1 + 1];
+                                        hh[4 * gq + 0] = a.x + ax * (c.x - a.x);
+                                        hh[4 * gq + 1] = a.y + ax * (c.y - a.y);
+                                        hh[4 * gq + 2] = a.z + ax * (c.z - a.z);
+                                        hh[4 * gq + 3] = a.w + ax * (c.w - a.w);
+                                    }
+                                    // the window starts at row sy of its first quad: rotate it to row 0 (two select stages)
+                                    const int sy = ((int)yf - R) & 3;
+                                    if (sy & 1) {
+#pragma unroll
+                                        for (int i = 0; i < Q::K1 + 2; ++i) hh[i] = hh[i + 1];
+                                    }
+                                    if (sy & 2) {
+#pragma unroll
+                                        for (int i = 0; i < Q::K1; ++i) hh[i] = hh[i + 2];
+                                    }
+                                } else {
+                                    // row pairs: 8-byte chunks (rows 2g, 2g+1); the box starts at the even column <= x0
+                                    const float2* cp = reinterpret_cast<const float2*>(pb) + (((int)xf - R) & 1) + col;
+#pragma unroll
+                                    for (int gp = 0; gp < G::BR; ++gp) {
+                                        const float2 a = cp[gp * (G::BC / 2)], c = cp[gp * (G::BC / 2) + 1];
+                                        hh[2 * gp + 0] = a.x + ax * (c.x - a.x);
+                                        hh[2 * gp + 1] = a.y + ax * (c.y - a.y);
+                                    }
+                                    if (((int)yf - R) & 1) {
+#pragma unroll
+                                        for (int i = 0; i < Q::K1; ++i) hh[i] = hh[i + 1];
+                                    }
+                                }
+                                const uint32_t row = abuf + (uint32_t)j * 128;  // A tile row warp * 8 + j, swizzled by j
+#pragma unroll
+                                for (int jj = 0; jj < G::K; ++jj) {
+                                    const float v = to_tf32(hh[jj] + ay * (hh[jj + 1] - hh[jj]));
+                                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + q_off[jj] + ((q_chunk[jj] ^ (uint32_t)j) << 4)), "f"(v)
+                                                 : "memory");
+                                }
+                            }
+                        }
+                    } else {
 #pragma unroll 1
                     for (int k = 0; k < kBatch; ++k) {
                         const int j = jb + k;
@@ -314,6 +408,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                                     }
                             }
                         }
+                    }
                     }
                     __syncwarp();  // all lanes are done with this half of the ring before it is refilled
                 }
@@ -438,14 +533,14 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, float* __re
     }
 }
 
-template <int R, int LG, bool IL>
+template <int R, int LG, int LAY>
 int run_lookup_conv(const LookupMaps& maps, const CUtensorMap& map_w, const ConvParams& P, int device, cudaStream_t s) {
-    using G = TmaGeo<R, IL>;
     using C = ConvGeo<R>;
-    constexpr size_t smem = 1024 + 2 * (size_t)C::A_BYTES + kWStages * kWStageBytes + (size_t)kGatherWarps * kSlots * G::SLOT +
+    constexpr size_t smem = 1024 + 2 * (size_t)C::A_BYTES + kWStages * kWStageBytes +
+                            (size_t)kGatherWarps * kSlots * ConvSlot<R, LAY>::value +
                             8 * (kGatherWarps * kSlots + 2 * kWStages + 8) + 16;
     static_assert(smem <= 232448, "lookup+conv pipeline does not fit shared memory");
-    auto kern = lookup_conv_kernel<R, LG, IL>;
+    auto kern = lookup_conv_kernel<R, LG, LAY>;
     static bool attr_done[64] = {};
     if (device < 0 || device >= 64 || !attr_done[device]) {
         RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -468,14 +563,14 @@ int run_lookup_conv(const LookupMaps& maps, const CUtensorMap& map_w, const Conv
     return 0;
 }
 
-template <int R, bool IL>
+template <int R, int LAY>
 int dispatch_lookup_conv(int lg, const LookupMaps& maps, const CUtensorMap& map_w, const ConvParams& P, int device,
                          cudaStream_t s) {
     switch (lg) {
-        case 1: return run_lookup_conv<R, 1, IL>(maps, map_w, P, device, s);
-        case 2: return run_lookup_conv<R, 2, IL>(maps, map_w, P, device, s);
-        case 3: return run_lookup_conv<R, 3, IL>(maps, map_w, P, device, s);
-        default: return run_lookup_conv<R, 4, IL>(maps, map_w, P, device, s);
+        case 1: return run_lookup_conv<R, 1, LAY>(maps, map_w, P, device, s);
+        case 2: return run_lookup_conv<R, 2, LAY>(maps, map_w, P, device, s);
+        case 3: return run_lookup_conv<R, 3, LAY>(maps, map_w, P, device, s);
+        default: return run_lookup_conv<R, 4, LAY>(maps, map_w, P, device, s);
     }
 }
 
@@ -530,13 +625,13 @@ int launch_lookup_conv(const void* plan_blob, const float* coords, const float* 
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "packed convc1 weight"))
             return rc;
     }
-    RC_REQUIRE(g.lvl[0].il != 2, "lookup_convc1: the row-quad pyramid layout is not wired into the fused kernel yet");
-    const bool il = g.lvl[0].il != 0;
+    const int lay = g.lvl[0].il;  // level 0's code identifies the layout: 0 rows, 1 pairs, 2 quads (+ pairs deeper)
     const LookupMaps& maps = plan.maps[0];
 #define RAFTCORR_LC_CASE(R_)                                                                    \
     case R_:                                                                                    \
-        return il ? dispatch_lookup_conv<R_, true>(lg, maps, map_w, P, device, s)               \
-                  : dispatch_lookup_conv<R_, false>(lg, maps, map_w, P, device, s);
+        return lay == 2 ? dispatch_lookup_conv<R_, 2>(lg, maps, map_w, P, device, s)            \
+             : lay      ? dispatch_lookup_conv<R_, 1>(lg, maps, map_w, P, device, s)            \
+                        : dispatch_lookup_conv<R_, 0>(lg, maps, map_w, P, device, s);
     switch (plan.radius) {
         RAFTCORR_LC_CASE(1)
         RAFTCORR_LC_CASE(2)

@@ -199,13 +199,14 @@ constexpr int kQPitch = 33;  // out tile row pitch (floats): conflict-free colum
 template <int R, int LG, int kBufs>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView g, const float* __restrict__ coords,
-                       float* __restrict__ out) {
+                       float* __restrict__ out, const int tiles_per_img, const int total_tiles) {
     using Q = QuadGeo<R>;
     using PG = TmaGeo<R, true>;  // levels >= 2: row pairs
     constexpr int SLOT = Q::SLOT > PG::SLOT ? Q::SLOT : PG::SLOT;  // a patch slot takes either kind of box
     constexpr int CH = LG * Q::KK;
     constexpr int PIX_PER_WARP = kPix / kWarps;
     constexpr int WARP_PATCH = kBufs * LG * SLOT;  // bytes: this warp's ring of patch buffers
+    static_assert(kBufs - 1 <= PIX_PER_WARP, "the issue cursor may run at most one tile ahead");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -214,11 +215,15 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
     float* out_s = reinterpret_cast<float*>(gen + kWarps * WARP_PATCH + kWarps * kBarBytes);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b = blockIdx.y, p0 = blockIdx.x * kPix;
     const int N = g.N;
     const uint32_t my_patch = base + warp * WARP_PATCH;
     const float* my_patch_gen = reinterpret_cast<const float*>(gen + warp * WARP_PATCH);
     const uint32_t my_bar = bar_base + warp * kBarBytes;
+    // PERSISTENT: the CTA walks tiles of kPix consecutive source pixels (first, first + stride, ...); a warp's ring of
+    // patch boxes runs ACROSS tiles, so only the very first pixels of a CTA pay the coordinates -> box -> data latency
+    // chain (ncu on the one-tile-per-CTA version: half of a CTA's life was that chain, DRAM 53 % busy)
+    const int first = blockIdx.x, stride = gridDim.x;
+    const int my_tiles = first < total_tiles ? (total_tiles - first + stride - 1) / stride : 0;
 
     if (lane == 0) {
 #pragma unroll
@@ -239,119 +244,158 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
     asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: see lookup_fwd_tma_kernel
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    // lane n < PIX_PER_WARP holds the coordinates of the warp's pixel n (tile pixel q = warp + kWarps * n)
-    float cx = 0.f, cy = 0.f;
-    if (lane < PIX_PER_WARP) {
-        const int p = p0 + warp + kWarps * lane;
-        if (p < N) {
-            cx = clamp_coord(__ldg(coords + ((int64_t)b * 2 + 0) * N + p));
-            cy = clamp_coord(__ldg(coords + ((int64_t)b * 2 + 1) * N + p));
+    auto tile_origin = [&](int it, int& b, int& p0) {
+        const int t = first + it * stride;
+        b = t / tiles_per_img;
+        p0 = (t - b * tiles_per_img) * kPix;
+    };
+    // lane n < PIX_PER_WARP: coordinates of the warp's pixel n (tile pixel q = warp + kWarps * n) of the tile being
+    // consumed; lanes PIX_PER_WARP .. 2 PIX_PER_WARP - 1: the same for the next tile; (nx, ny): the tile after that, on
+    // its way from memory (merged in at the next tile switch, a whole tile after the load was issued)
+    auto load_coords = [&](int it, float& x, float& y) {
+        x = y = 0.f;
+        if (it < my_tiles && lane < 2 * PIX_PER_WARP) {
+            int b, p0;
+            tile_origin(it, b, p0);
+            const int p = p0 + warp + kWarps * (lane & (PIX_PER_WARP - 1));
+            if (p < N) {
+                x = clamp_coord(__ldg(coords + ((int64_t)b * 2 + 0) * N + p));
+                y = clamp_coord(__ldg(coords + ((int64_t)b * 2 + 1) * N + p));
+            }
         }
-    }
+    };
+    float cx, cy, nx, ny;
+    load_coords(lane < PIX_PER_WARP ? 0 : 1, cx, cy);
+    load_coords(2, nx, ny);
     const float my_inv = g.inv_scale[lane < LG ? lane : 0];          // issue role: lane = level
     const char* map_base = reinterpret_cast<const char*>(&maps);     // m[l] at 128 * l, ms[l] at 512 + 128 * l
 
-    auto issue = [&](int n, int buf) {  // whole warp; lanes < LG each issue one level's box
-        const float x = __shfl_sync(0xffffffffu, cx, n), y = __shfl_sync(0xffffffffu, cy, n);
-        if (lane < LG) {
-            const int x0 = __float2int_rd(x * my_inv) - R;
-            const int y0 = __float2int_rd(y * my_inv) - R;
-            const bool quad = lane < 2;
-            // quads: the window spans GMAX or GMAX-1 row quads; pairs: BR pair rows when it starts on an odd row, else BR-1
-            const int nq = Q::quads(y0 & 3);
-            const bool big = quad ? nq == Q::GMAX : (y0 & 1);
-            const uint32_t bytes = quad ? nq * Q::ROW_BYTES : (big ? PG::BOX_BYTES : PG::BOX_BYTES - PG::BC * 4);
-            const uint32_t bar = my_bar + 8 * buf;
-            fence_proxy_async();  // the buffer was read through the generic proxy when it was last evaluated
-            mbar_expect_tx(bar, bytes);
-            tma_load_3d(my_patch + (buf * LG + lane) * SLOT,
-                        reinterpret_cast<const CUtensorMap*>(map_base + (big ? 0 : 512) + 128 * lane), bar,
-                        quad ? 4 * x0 : 2 * (x0 & ~1), quad ? y0 >> 2 : y0 >> 1, b * N + p0 + warp + kWarps * n);
+    // issue cursor: next (tile, pixel) whose boxes have not been requested; ring position of the next request
+    int i_it = 0, i_n = 0, i_buf = 0;
+    auto issue_next = [&](int c_it) {  // whole warp; lanes < LG each issue one level's box of the next valid pixel
+        // never more than one tile ahead of the tile being consumed (c_it): that is as far as the coordinates held in
+        // lanes PIX_PER_WARP.. reach (sparse last tiles of an image could otherwise let the cursor run further)
+        while (i_it < my_tiles && i_it <= c_it + 1) {
+            int b, p0;
+            tile_origin(i_it, b, p0);
+            const int p = p0 + warp + kWarps * i_n;
+            const int src = i_n + (i_it != c_it ? PIX_PER_WARP : 0);
+            if (++i_n == PIX_PER_WARP) { i_n = 0; ++i_it; }
+            if (p >= N) continue;  // past the end of an image (last tile only)
+            const float x = __shfl_sync(0xffffffffu, cx, src), y = __shfl_sync(0xffffffffu, cy, src);
+            if (lane < LG) {
+                const int x0 = __float2int_rd(x * my_inv) - R;
+                const int y0 = __float2int_rd(y * my_inv) - R;
+                const bool quad = lane < 2;
+                // quads: the window spans GMAX or GMAX-1 row quads; pairs: BR pair rows when it starts on an odd row, else BR-1
+                const int nq = Q::quads(y0 & 3);
+                const bool big = quad ? nq == Q::GMAX : (y0 & 1);
+                const uint32_t bytes = quad ? nq * Q::ROW_BYTES : (big ? PG::BOX_BYTES : PG::BOX_BYTES - PG::BC * 4);
+                const uint32_t bar = my_bar + 8 * i_buf;
+                fence_proxy_async();  // the buffer was read through the generic proxy when it was last evaluated
+                mbar_expect_tx(bar, bytes);
+                tma_load_3d(my_patch + (i_buf * LG + lane) * SLOT,
+                            reinterpret_cast<const CUtensorMap*>(map_base + (big ? 0 : 512) + 128 * lane), bar,
+                            quad ? 4 * x0 : 2 * (x0 & ~1), quad ? y0 >> 2 : y0 >> 1, b * N + p);
+            }
+            if (++i_buf == kBufs) i_buf = 0;
+            return;
         }
     };
+#pragma unroll
+    for (int i = 0; i < kBufs - 1; ++i) issue_next(0);
 
+    int c_buf = 0;
+    uint32_t c_par = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+        int b, p0;
+        tile_origin(it, b, p0);
 #pragma unroll
-    for (int n = 0; n < kBufs - 1 && n < PIX_PER_WARP; ++n)
-        if (p0 + warp + kWarps * n < N) issue(n, n);
-
+        for (int n = 0; n < PIX_PER_WARP; ++n) {
+            const int q = warp + kWarps * n;
+            if (p0 + q >= N) continue;  // warp-uniform
+            issue_next(it);
+            const float xq = __shfl_sync(0xffffffffu, cx, n), yq = __shfl_sync(0xffffffffu, cy, n);
+            mbar_wait(my_bar + 8 * c_buf, c_par);
 #pragma unroll
-    for (int n = 0; n < PIX_PER_WARP; ++n) {
-        const int q = warp + kWarps * n;
-        const int p = p0 + q;
-        if (p >= N) break;
-        const int buf = n % kBufs;
-        constexpr int kAhead = kBufs - 1;
-        if (n + kAhead < PIX_PER_WARP && p + kAhead * kWarps < N) issue(n + kAhead, (n + kAhead) % kBufs);
-        const float xq = __shfl_sync(0xffffffffu, cx, n), yq = __shfl_sync(0xffffffffu, cy, n);
-        mbar_wait(my_bar + 8 * buf, (n / kBufs) & 1);
+            for (int pass = 0; pass < (LG + 1) / 2; ++pass) {
+                const int l = 2 * pass + half;
+                if (col < Q::K && l < LG) {
+                    const float inv = g.inv_scale[l];
+                    const float x = xq * inv, y = yq * inv;
+                    const float xf = floorf(x), yf = floorf(y);
+                    const float ax = x - xf, ay = y - yf;
+                    const float* pb = my_patch_gen + (c_buf * LG + l) * (SLOT / 4);
+                    if (pass == 0) {
+                        // ---- row quads: column chunk = 16 bytes (rows 4g .. 4g+3)
+                        const int sy = ((int)yf - R) & 3;
+                        const float4* cp = reinterpret_cast<const float4*>(pb) + col;
+                        float hh[4 * Q::GMAX];
 #pragma unroll
-        for (int pass = 0; pass < (LG + 1) / 2; ++pass) {
-            const int l = 2 * pass + half;
-            if (col < Q::K && l < LG) {
-                const float inv = g.inv_scale[l];
-                const float x = xq * inv, y = yq * inv;
-                const float xf = floorf(x), yf = floorf(y);
-                const float ax = x - xf, ay = y - yf;
-                const float* pb = my_patch_gen + (buf * LG + l) * (SLOT / 4);
-                if (pass == 0) {
-                    // ---- row quads: column chunk = 16 bytes (rows 4g .. 4g+3)
-                    const int sy = ((int)yf - R) & 3;
-                    const float4* cp = reinterpret_cast<const float4*>(pb) + col;
-                    float hh[4 * Q::GMAX];
+                        for (int gq = 0; gq < Q::GMAX; ++gq) {
+                            const float4 a = cp[gq * Q::K1], c = cp[gq * Q::K1 + 1];
+                            hh[4 * gq + 0] = a.x + ax * (c.x - a.x);
+                            hh[4 * gq + 1] = a.y + ax * (c.y - a.y);
+                            hh[4 * gq + 2] = a.z + ax * (c.z - a.z);
+                            hh[4 * gq + 3] = a.w + ax * (c.w - a.w);
+                        }
+                        // output row j = Y - sy of column `col` is channel col * K + j (x offset major, corr.py:66-78)
+                        float* o = out_s + ((l * Q::KK + col * Q::K - sy) * kQPitch + q);
 #pragma unroll
-                    for (int gq = 0; gq < Q::GMAX; ++gq) {
-                        const float4 a = cp[gq * Q::K1], c = cp[gq * Q::K1 + 1];
-                        hh[4 * gq + 0] = a.x + ax * (c.x - a.x);
-                        hh[4 * gq + 1] = a.y + ax * (c.y - a.y);
-                        hh[4 * gq + 2] = a.z + ax * (c.z - a.z);
-                        hh[4 * gq + 3] = a.w + ax * (c.w - a.w);
-                    }
-                    // output row j = Y - sy of column `col` is channel col * K + j (x offset major, corr.py:66-78)
-                    float* o = out_s + ((l * Q::KK + col * Q::K - sy) * kQPitch + q);
+                        for (int Y = 0; Y < Q::NV; ++Y) {
+                            const float v = hh[Y] + ay * (hh[Y + 1] - hh[Y]);
+                            const bool ok = Y < 3 ? (sy <= Y) : (Y >= Q::K ? (sy > Y - Q::K) : true);
+                            if (ok) o[Y * kQPitch] = v;
+                        }
+                    } else {
+                        // ---- row pairs: column chunk = 8 bytes (rows 2g, 2g+1); the box starts at the even column <= x0
+                        const int sy = ((int)yf - R) & 1;
+                        const float2* cp = reinterpret_cast<const float2*>(pb) + (((int)xf - R) & 1) + col;
+                        float hh[2 * PG::BR];
 #pragma unroll
-                    for (int Y = 0; Y < Q::NV; ++Y) {
-                        const float v = hh[Y] + ay * (hh[Y + 1] - hh[Y]);
-                        const bool ok = Y < 3 ? (sy <= Y) : (Y >= Q::K ? (sy > Y - Q::K) : true);
-                        if (ok) o[Y * kQPitch] = v;
-                    }
-                } else {
-                    // ---- row pairs: column chunk = 8 bytes (rows 2g, 2g+1); the box starts at the even column <= x0
-                    const int sy = ((int)yf - R) & 1;
-                    const float2* cp = reinterpret_cast<const float2*>(pb) + (((int)xf - R) & 1) + col;
-                    float hh[2 * PG::BR];
+                        for (int gp = 0; gp < PG::BR; ++gp) {
+                            const float2 a = cp[gp * (PG::BC / 2)], c = cp[gp * (PG::BC / 2) + 1];
+                            hh[2 * gp + 0] = a.x + ax * (c.x - a.x);
+                            hh[2 * gp + 1] = a.y + ax * (c.y - a.y);
+                        }
+                        float* o = out_s + ((l * Q::KK + col * Q::K - sy) * kQPitch + q);
 #pragma unroll
-                    for (int gp = 0; gp < PG::BR; ++gp) {
-                        const float2 a = cp[gp * (PG::BC / 2)], c = cp[gp * (PG::BC / 2) + 1];
-                        hh[2 * gp + 0] = a.x + ax * (c.x - a.x);
-                        hh[2 * gp + 1] = a.y + ax * (c.y - a.y);
-                    }
-                    float* o = out_s + ((l * Q::KK + col * Q::K - sy) * kQPitch + q);
-#pragma unroll
-                    for (int Y = 0; Y <= Q::K; ++Y) {
-                        const float v = hh[Y] + ay * (hh[Y + 1] - hh[Y]);
-                        const bool ok = Y == 0 ? (sy == 0) : (Y == Q::K ? (sy == 1) : true);
-                        if (ok) o[Y * kQPitch] = v;
+                        for (int Y = 0; Y <= Q::K; ++Y) {
+                            const float v = hh[Y] + ay * (hh[Y + 1] - hh[Y]);
+                            const bool ok = Y == 0 ? (sy == 0) : (Y == Q::K ? (sy == 1) : true);
+                            if (ok) o[Y * kQPitch] = v;
+                        }
                     }
                 }
             }
+            if (++c_buf == kBufs) { c_buf = 0; c_par ^= 1u; }
+            __syncwarp();  // all lanes are done with the buffer before it is refilled
         }
-        __syncwarp();  // all lanes are done with `buf` before it is refilled next iteration
-    }
-    __syncthreads();
-    if ((N & 3) == 0 && p0 + kPix <= N) {
-        // 8 lanes x 4 pixels per channel row: 128-byte lines leave as 128-bit stores
-        float* dst = out + ((int64_t)b * g.ctot + g.ch0) * N + p0;
-        for (int idx = threadIdx.x; idx < CH * 8; idx += kWarps * 32) {
-            const int ch = idx >> 3, qd = idx & 7;
-            const float* sp = out_s + ch * kQPitch + 4 * qd;
-            *reinterpret_cast<float4*>(dst + (int64_t)ch * N + 4 * qd) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+        __syncthreads();
+        if ((N & 3) == 0 && p0 + kPix <= N) {
+            // 8 lanes x 4 pixels per channel row: 128-byte lines leave as 128-bit stores
+            float* dst = out + ((int64_t)b * g.ctot + g.ch0) * N + p0;
+            for (int idx = threadIdx.x; idx < CH * 8; idx += kWarps * 32) {
+                const int ch = idx >> 3, qd = idx & 7;
+                const float* sp = out_s + ch * kQPitch + 4 * qd;
+                *reinterpret_cast<float4*>(dst + (int64_t)ch * N + 4 * qd) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            }
+        } else {
+            const int p = p0 + lane;
+            if (p < N) {
+                float* dst = out + ((int64_t)b * g.ctot + g.ch0) * N + p;
+                for (int ch = warp; ch < CH; ch += kWarps) dst[(int64_t)ch * N] = out_s[ch * kQPitch + lane];
+            }
         }
-    } else {
-        const int p = p0 + lane;
-        if (p < N) {
-            float* dst = out + ((int64_t)b * g.ctot + g.ch0) * N + p;
-            for (int ch = warp; ch < CH; ch += kWarps) dst[(int64_t)ch * N] = out_s[ch * kQPitch + lane];
+        // tile switch: next tile's coordinates move to lanes 0 .. PIX_PER_WARP-1, the pending ones behind them
+        {
+            const float sx = __shfl_sync(0xffffffffu, cx, (lane & (PIX_PER_WARP - 1)) + PIX_PER_WARP);
+            const float sy2 = __shfl_sync(0xffffffffu, cy, (lane & (PIX_PER_WARP - 1)) + PIX_PER_WARP);
+            cx = lane < PIX_PER_WARP ? sx : nx;
+            cy = lane < PIX_PER_WARP ? sy2 : ny;
+            load_coords(it + 3, nx, ny);
         }
+        __syncthreads();  // out_s is free for the next tile
     }
 }
 
@@ -405,8 +449,18 @@ int run_fwd_quad(const LookupMaps& maps, const GroupView& g, const float* coords
         RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
+    static int sm_count[64] = {};
+    int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 0;
+    if (!sms) {
+        RC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        if (dev >= 0 && dev < 64) sm_count[dev] = sms;
+    }
+    const int tiles_per_img = ceil_div(g.N, kPix);
+    const int64_t total = (int64_t)tiles_per_img * g.B;
+    RC_REQUIRE(total < (1LL << 31), "lookup: too many tiles");
+    const int ctas = 2 * sms;  // two resident CTAs per SM (shared memory), each walking total / ctas tiles
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(ceil_div(g.N, kPix), g.B);
+    cfg.gridDim = dim3((unsigned)(total < ctas ? total : ctas));
     cfg.blockDim = dim3(kWarps * 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
@@ -415,7 +469,7 @@ int run_fwd_quad(const LookupMaps& maps, const GroupView& g, const float* coords
     attr[0].val.programmaticStreamSerializationAllowed = lookup_pdl() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RC_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, g, coords, out));
+    RC_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, g, coords, out, tiles_per_img, (int)total));
     return 0;
 }
 
