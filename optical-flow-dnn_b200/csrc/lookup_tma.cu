@@ -194,6 +194,23 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
 //    DESTINATION channel (one address subtraction) and predicates the stores -- no dynamic register indexing;
 //  * the LG boxes of a pixel are issued by LG lanes at once (each arrives on the pixel's mbarrier with its own byte
 //    count), so the coordinate / tensor-map arithmetic runs once per pixel instead of once per level.
+// Wait of the hot loop: no clock reads per poll (mbar_wait spends six instructions per poll on its time-out and waiting
+// warps take issue slots from evaluating ones); the suspend-time hint lets a poll sleep in hardware; a protocol bug
+// still becomes a trapped launch instead of a hang.
+__device__ __forceinline__ void mbar_wait_polls(uint32_t bar, uint32_t parity) {
+    uint32_t ok, polls = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity), "r"(4000u)
+            : "memory");
+        if (!ok && ++polls > (1u << 24)) __trap();
+    } while (!ok);
+}
+
 constexpr int kQPitch = 33;  // out tile row pitch (floats): conflict-free column writes and 4-channel x 8-quad reads
 
 template <int R, int LG, int kBufs>
@@ -244,19 +261,22 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
     asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: see lookup_fwd_tma_kernel
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    auto tile_origin = [&](int it, int& b, int& p0) {
+    auto tile_origin = [&](int it, int& b, int& p0) {  // integer division: only where a cursor is set up
         const int t = first + it * stride;
         b = t / tiles_per_img;
         p0 = (t - b * tiles_per_img) * kPix;
     };
+    const int img_span = tiles_per_img * kPix, step_span = stride * kPix;
+    auto tile_advance = [&](int& b, int& p0) {  // (b, p0) of the cursor's next tile without dividing
+        p0 += step_span;
+        while (p0 >= img_span) { p0 -= img_span; ++b; }
+    };
     // lane n < PIX_PER_WARP: coordinates of the warp's pixel n (tile pixel q = warp + kWarps * n) of the tile being
     // consumed; lanes PIX_PER_WARP .. 2 PIX_PER_WARP - 1: the same for the next tile; (nx, ny): the tile after that, on
     // its way from memory (merged in at the next tile switch, a whole tile after the load was issued)
-    auto load_coords = [&](int it, float& x, float& y) {
+    auto load_coords_at = [&](int it, int b, int p0, float& x, float& y) {
         x = y = 0.f;
         if (it < my_tiles && lane < 2 * PIX_PER_WARP) {
-            int b, p0;
-            tile_origin(it, b, p0);
             const int p = p0 + warp + kWarps * (lane & (PIX_PER_WARP - 1));
             if (p < N) {
                 x = clamp_coord(__ldg(coords + ((int64_t)b * 2 + 0) * N + p));
@@ -265,22 +285,35 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
         }
     };
     float cx, cy, nx, ny;
-    load_coords(lane < PIX_PER_WARP ? 0 : 1, cx, cy);
-    load_coords(2, nx, ny);
+    int l_b = 0, l_p0 = 0;  // coordinates cursor: tile it + 2 while tile it is consumed
+    {
+        int b0 = 0, p00 = 0, b1, p01;
+        if (my_tiles > 0) tile_origin(0, b0, p00);
+        b1 = b0; p01 = p00;
+        tile_advance(b1, p01);
+        load_coords_at(lane < PIX_PER_WARP ? 0 : 1, lane < PIX_PER_WARP ? b0 : b1, lane < PIX_PER_WARP ? p00 : p01, cx, cy);
+        l_b = b1; l_p0 = p01;
+        tile_advance(l_b, l_p0);
+        load_coords_at(2, l_b, l_p0, nx, ny);
+    }
     const float my_inv = g.inv_scale[lane < LG ? lane : 0];          // issue role: lane = level
     const char* map_base = reinterpret_cast<const char*>(&maps);     // m[l] at 128 * l, ms[l] at 512 + 128 * l
 
     // issue cursor: next (tile, pixel) whose boxes have not been requested; ring position of the next request
-    int i_it = 0, i_n = 0, i_buf = 0;
+    int i_it = 0, i_n = 0, i_buf = 0, i_b = 0, i_p0 = 0;
+    if (my_tiles > 0) tile_origin(0, i_b, i_p0);
     auto issue_next = [&](int c_it) {  // whole warp; lanes < LG each issue one level's box of the next valid pixel
         // never more than one tile ahead of the tile being consumed (c_it): that is as far as the coordinates held in
         // lanes PIX_PER_WARP.. reach (sparse last tiles of an image could otherwise let the cursor run further)
         while (i_it < my_tiles && i_it <= c_it + 1) {
-            int b, p0;
-            tile_origin(i_it, b, p0);
-            const int p = p0 + warp + kWarps * i_n;
+            const int b = i_b;
+            const int p = i_p0 + warp + kWarps * i_n;
             const int src = i_n + (i_it != c_it ? PIX_PER_WARP : 0);
-            if (++i_n == PIX_PER_WARP) { i_n = 0; ++i_it; }
+            if (++i_n == PIX_PER_WARP) {
+                i_n = 0;
+                ++i_it;
+                tile_advance(i_b, i_p0);
+            }
             if (p >= N) continue;  // past the end of an image (last tile only)
             const float x = __shfl_sync(0xffffffffu, cx, src), y = __shfl_sync(0xffffffffu, cy, src);
             if (lane < LG) {
@@ -307,16 +340,16 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
 
     int c_buf = 0;
     uint32_t c_par = 0;
+    int b = 0, p0 = 0;
+    if (my_tiles > 0) tile_origin(0, b, p0);
     for (int it = 0; it < my_tiles; ++it) {
-        int b, p0;
-        tile_origin(it, b, p0);
 #pragma unroll
         for (int n = 0; n < PIX_PER_WARP; ++n) {
             const int q = warp + kWarps * n;
             if (p0 + q >= N) continue;  // warp-uniform
             issue_next(it);
             const float xq = __shfl_sync(0xffffffffu, cx, n), yq = __shfl_sync(0xffffffffu, cy, n);
-            mbar_wait(my_bar + 8 * c_buf, c_par);
+            mbar_wait_polls(my_bar + 8 * c_buf, c_par);
 #pragma unroll
             for (int pass = 0; pass < (LG + 1) / 2; ++pass) {
                 const int l = 2 * pass + half;
@@ -393,7 +426,9 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
             const float sy2 = __shfl_sync(0xffffffffu, cy, (lane & (PIX_PER_WARP - 1)) + PIX_PER_WARP);
             cx = lane < PIX_PER_WARP ? sx : nx;
             cy = lane < PIX_PER_WARP ? sy2 : ny;
-            load_coords(it + 3, nx, ny);
+            tile_advance(l_b, l_p0);
+            load_coords_at(it + 3, l_b, l_p0, nx, ny);
+            tile_advance(b, p0);
         }
         __syncthreads();  // out_s is free for the next tile
     }
