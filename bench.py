@@ -641,7 +641,9 @@ def run_ours(args):
             kern["lookup_convc1"] = fused
         if head:
             kern["fnet_head_build"] = head
-        lookup_name = "lookup_fwd_kernel<4,4>" if os.environ.get("RAFTCORR_LOOKUP") == "cpasync" else "lookup_fwd_tma_kernel<4,4>"
+        lookup_name = ("lookup_fwd_kernel<4,4>" if os.environ.get("RAFTCORR_LOOKUP") == "cpasync" else
+                       "lookup_fwd_tma_kernel<4,4>" if mode == "fp32" or os.environ.get("RAFTCORR_PYRAMID_LAYOUT", "quads") != "quads"
+                       else "lookup_fwd_quad_kernel<4,4>")
         if build_share >= 0.5:
             dom, ach, alg = ("build_tc_kernel" if mode != "fp32" else "sgemm_kernel"), kern["build"]["achieved_gbs"], B * bb
         else:

@@ -213,7 +213,9 @@ __device__ __forceinline__ void mbar_wait_polls(uint32_t bar, uint32_t parity) {
 
 constexpr int kQPitch = 33;  // out tile row pitch (floats): conflict-free column writes and 4-channel x 8-quad reads
 
-template <int R, int LG, int kBufs>
+// EXP (measurement only, scripts/gather_roofline.py): 0 = the kernel; 1 = the gather alone (same boxes, same waits, no
+// evaluation, no output: what the memory system charges for this box list); 2 = evaluation + output alone (no boxes).
+template <int R, int LG, int kBufs, int EXP = 0>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView g, const float* __restrict__ coords,
                        float* __restrict__ out, const int tiles_per_img, const int total_tiles) {
@@ -326,10 +328,12 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
                 const uint32_t bytes = quad ? nq * Q::ROW_BYTES : (big ? PG::BOX_BYTES : PG::BOX_BYTES - PG::BC * 4);
                 const uint32_t bar = my_bar + 8 * i_buf;
                 fence_proxy_async();  // the buffer was read through the generic proxy when it was last evaluated
-                mbar_expect_tx(bar, bytes);
-                tma_load_3d(my_patch + (i_buf * LG + lane) * SLOT,
-                            reinterpret_cast<const CUtensorMap*>(map_base + (big ? 0 : 512) + 128 * lane), bar,
-                            quad ? 4 * x0 : 2 * (x0 & ~1), quad ? y0 >> 2 : y0 >> 1, b * N + p);
+                if (EXP != 2) {
+                    mbar_expect_tx(bar, bytes);
+                    tma_load_3d(my_patch + (i_buf * LG + lane) * SLOT,
+                                reinterpret_cast<const CUtensorMap*>(map_base + (big ? 0 : 512) + 128 * lane), bar,
+                                quad ? 4 * x0 : 2 * (x0 & ~1), quad ? y0 >> 2 : y0 >> 1, b * N + p);
+                }
             }
             if (++i_buf == kBufs) i_buf = 0;
             return;
@@ -349,11 +353,11 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
             if (p0 + q >= N) continue;  // warp-uniform
             issue_next(it);
             const float xq = __shfl_sync(0xffffffffu, cx, n), yq = __shfl_sync(0xffffffffu, cy, n);
-            mbar_wait_polls(my_bar + 8 * c_buf, c_par);
+            if (EXP != 2) mbar_wait_polls(my_bar + 8 * c_buf, c_par);
 #pragma unroll
             for (int pass = 0; pass < (LG + 1) / 2; ++pass) {
                 const int l = 2 * pass + half;
-                if (col < Q::K && l < LG) {
+                if (EXP != 1 && col < Q::K && l < LG) {
                     const float inv = g.inv_scale[l];
                     const float x = xq * inv, y = yq * inv;
                     const float xf = floorf(x), yf = floorf(y);
@@ -405,7 +409,9 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
             __syncwarp();  // all lanes are done with the buffer before it is refilled
         }
         __syncthreads();
-        if ((N & 3) == 0 && p0 + kPix <= N) {
+        if (EXP == 1) {
+            // gather alone: nothing was evaluated, nothing leaves
+        } else if ((N & 3) == 0 && p0 + kPix <= N) {
             // 8 lanes x 4 pixels per channel row: 128-byte lines leave as 128-bit stores
             float* dst = out + ((int64_t)b * g.ctot + g.ch0) * N + p0;
             for (int idx = threadIdx.x; idx < CH * 8; idx += kWarps * 32) {
@@ -483,6 +489,15 @@ int run_fwd_quad(const LookupMaps& maps, const GroupView& g, const float* coords
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    if (R == 4 && LG == 4) {
+        // RAFTCORR_LOOKUP_EXP=1|2: timing-only ablations of the bench shape (the results are NOT a lookup)
+        const char* e = std::getenv("RAFTCORR_LOOKUP_EXP");
+        if (e && (e[0] == '1' || e[0] == '2')) {
+            kern = e[0] == '1' ? lookup_fwd_quad_kernel<R, LG, kBufs, (R == 4 && LG == 4) ? 1 : 0>
+                               : lookup_fwd_quad_kernel<R, LG, kBufs, (R == 4 && LG == 4) ? 2 : 0>;
+            RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
     }
     static int sm_count[64] = {};
     int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 0;
