@@ -200,6 +200,39 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+def pin_to_gpu_cpus(gpu_index):
+    """Restrict this rank to the CPUs nvidia-smi lists as local to its GPU (same NUMA node / PCIe root), BEFORE the
+    pinned host buffers are allocated (first touch puts them on that node): with 8 ranks copying at once the default
+    placement sends most H2D traffic across the socket link.  Best effort: returns a description or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        head = None
+        for ln in out.splitlines():
+            cols = [c.strip() for c in ln.split("\t")]
+            if head is None and any("CPU Affinity" in c for c in cols):
+                head = [c for c in cols]
+                continue
+            if head is not None and cols and cols[0] == f"GPU{gpu_index}":
+                # the header has one leading empty cell per row label
+                idx = next(i for i, c in enumerate(head) if "CPU Affinity" in c)
+                spec = cols[idx] if idx < len(cols) else ""
+                cpus = set()
+                for part in spec.split(","):
+                    part = part.strip()
+                    if not part:
+                        continue
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+                cpus &= os.sched_getaffinity(0)
+                if cpus:
+                    os.sched_setaffinity(0, cpus)
+                    return f"{spec} ({len(cpus)} CPUs)"
+                return None
+    except Exception:
+        return None
+    return None
+
+
 def alt_1080p_side(rc, torch, dev, g, e0, e1, hbm, with_reference):
     """north_star config 5a: AlternateCorrBlock (on-the-fly correlation) lookups at 1080x1920 -> 135x240, D=256, r=4,
     L=4, B=4.  Algorithmic work per pair per lookup: bytes 4 D (N + sum H_l W_l) + 8 N + 4 N L K^2,
@@ -274,6 +307,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = None if args.no_affinity else pin_to_gpu_cpus(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -609,11 +643,39 @@ def run_ours(args):
             barrier()
             e2e_trials.append(x0.elapsed_time(x1))
         e2e_ms = sorted(e2e_trials)[1]
+        # ---- the platform's ceiling for this step's host traffic: the SAME copies (pinned H2D of both feature maps and
+        # the coordinates, D2H of the result) on the same streams with NO kernels, all ranks at once
+        def copies_only(n):
+            for i in range(n):
+                k = i & 1
+                d1, d2, dc = dbuf[k]
+                with torch.cuda.stream(s_in):
+                    d1.copy_(hf1, non_blocking=True)
+                    d2.copy_(hf2, non_blocking=True)
+                    dc.copy_(hco, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    houts[k].copy_(dout, non_blocking=True)
+        dout = torch.empty((B, L * K * K, H, W), dtype=torch.float32, device=dev)
+        copies_only(2)
+        for st in (s_in, s_out):
+            st.synchronize()
+        copy_trials = []
+        for _ in range(3):
+            barrier()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record(s_in)
+            copies_only(args.steps)
+            s_out.wait_stream(s_in)
+            x1.record(s_out)
+            barrier()
+            copy_trials.append(x0.elapsed_time(x1))
+        copy_ms = sorted(copy_trials)[1]
+        del dout
 
-    t = torch.tensor([ms_total, e2e_ms, sus_ms if sustained else 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_ms, sus_ms if sustained else 0.0, copy_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, sus_ms_max = float(t[0]), float(t[1]), float(t[2])
+    ms_total, e2e_ms, sus_ms_max, copy_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     line = None
     if rank == 0:
@@ -671,6 +733,13 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
                     "h2d_gbs_in_step": h2d / (e2e_ms / args.steps * 1e-3) / 1e9, "h2d_gbs_lone_pinned_copy": h2d_alone_gbs,
                     "trials_ms_per_step": [t_ / args.steps for t_ in e2e_trials], "reported": "median of 3 trials of K steps (rank 0's trials listed)",
+                    "copies_only": {"value": world * B * args.steps / (copy_ms * 1e-3), "unit": UNIT, "ms_per_step": copy_ms / args.steps,
+                                    "aggregate_h2d_gbs": world * h2d / (copy_ms / args.steps * 1e-3) / 1e9,
+                                    "aggregate_d2h_gbs": world * d2h / (copy_ms / args.steps * 1e-3) / 1e9,
+                                    "what": "the platform ceiling for this step: the same pinned H2D + D2H copies on the same streams "
+                                            "with no kernels, all ranks at once (median of 3, max over ranks)"},
+                    "frac_of_copies_only": (copy_ms / e2e_ms),
+                    "cpu_affinity": affinity,
                     "d2h_covers": f"last of {iters} lookup outputs ({d2h} of {iters * d2h} bytes produced per step)",
                     "result": "last lookup's [B,324,H,W] features copied to pinned host memory each step; "
                               "steps pipelined over H2D | compute | D2H streams (2 buffer sets)"},
@@ -726,6 +795,7 @@ def main():
     ap.add_argument("--no-fused", action="store_true", help="skip the side measurements (lookup+convc1, encoder head, on-the-fly 1080p, tf32 step)")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the stock-PyTorch reference CorrBlock on the GPU")
     ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-affinity", action="store_true", help="do not pin the rank to its GPU's local CPUs")
     ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the sustained loop (seconds)")
     ap.add_argument("--l2-fetch", type=int, default=0, help="set cudaLimitMaxL2FetchGranularity (32/64/128) first")
     args = ap.parse_args()

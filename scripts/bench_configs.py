@@ -1,11 +1,43 @@
 """Secondary measurements: the other BASELINE.json configs (parity-test shapes) timed with CUDA events.
-One JSON line per config -> profiles/. Not the headline bench (bench.py)."""
+One JSON line per config -> profiles/. Not the headline bench (bench.py).
+
+Single GPU: `python scripts/bench_configs.py [1 2 3 4 5a 5b]`.  N GPUs of one box (weak scaling: every rank runs the
+config on its own seeded pairs, no collective on the path; barrier + max-over-ranks device time, whole-job pairs/s):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 \
+        scripts/bench_configs.py 1 2 3 4 5a 5b
+"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+import torch.distributed as dist
 import optical_flow_dnn_b200 as rc
 
-dev = torch.device("cuda:0")
+WORLD = int(os.environ.get("WORLD_SIZE", "1")); RANK = int(os.environ.get("RANK", "0")); LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(LOCAL)
+dev = torch.device("cuda", LOCAL)
+if WORLD > 1:
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+_print = print
+
+
+def print(line):  # rank 0 reports; every line carries the GPU count
+    if RANK == 0:
+        d = json.loads(line)
+        d["n_gpus"] = WORLD
+        for k in ("pairs_per_s", "pair_iters_per_s"):
+            if k in d:
+                d[k] *= WORLD  # whole-job throughput (weak scaling: per-rank work is fixed)
+        _print(json.dumps(d), flush=True)
+
+
+def _max_over_ranks(ms):
+    if WORLD == 1:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
 HBM = 6547.2
 try:
     HBM = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -27,7 +59,7 @@ def alg_bytes(D, H, W, L, r):
 
 
 def inputs(B, D, H, W, iters, seed=1234):
-    g = torch.Generator(device=dev).manual_seed(seed)
+    g = torch.Generator(device=dev).manual_seed(seed + RANK)
     f1 = torch.randn((B, D, H, W), generator=g, device=dev); f2 = torch.randn((B, D, H, W), generator=g, device=dev)
     ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
     grid = torch.stack([xs, ys]).float()[None].expand(B, 2, H, W)
@@ -40,12 +72,15 @@ def inputs(B, D, H, W, iters, seed=1234):
 
 def timeit(fn, reps, warm=3):
     for _ in range(warm): fn()
+    if WORLD > 1: dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps): fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps
+    e1.record()
+    if WORLD > 1: dist.barrier()
+    torch.cuda.synchronize()
+    return _max_over_ranks(e0.elapsed_time(e1) / reps)
 
 
 def fwd_config(name, B, D, H, W, L, r, iters, mode="tf32", reps=20):
@@ -80,7 +115,7 @@ def train_config(name, B, D, H, W, L, r, iters, cls, kw, reps=5):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); step(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
-    ms = sorted(ts)[len(ts) // 2]
+    ms = _max_over_ranks(sorted(ts)[len(ts) // 2])
     print(json.dumps({"config": name, "shape": [B, D, H, W, L, r], "iters": iters, "class": cls.__name__, **kw, "ms_per_step_fwd_bwd": ms,
                       "pairs_per_s": B / (ms * 1e-3)}))
 
@@ -113,7 +148,11 @@ if "4" in which:
     fwd_config("4 raft_uncertainty KITTI 375x1242 B16 24it", 16, 256, 47, 156, 4, 4, 24, "tf32", reps=10)
 if "5a" in which:
     alt_config("5a alt 1080x1920 B4", 4, 256, 135, 240, 4, 4, mode="tf32")
-    alt_config("5a alt 1080x1920 B4", 4, 256, 135, 240, 4, 4, mode="fp32")
+    if WORLD == 1:
+        alt_config("5a alt 1080x1920 B4", 4, 256, 135, 240, 4, 4, mode="fp32")
 if "5b" in which:
     alt_config("5b alt 2160x3840 B4", 4, 256, 270, 480, 4, 4, reps=3, mode="tf32")
-    alt_config("5b alt 2160x3840 B4", 4, 256, 270, 480, 4, 4, reps=3, mode="fp32")
+    if WORLD == 1:
+        alt_config("5b alt 2160x3840 B4", 4, 256, 270, 480, 4, 4, reps=3, mode="fp32")
+if WORLD > 1:
+    dist.destroy_process_group()
