@@ -61,10 +61,8 @@ typedef struct raftcorr_pyramid_layout {
                             1: ROW PAIRS interleaved, element (y,x) at (y/2)*(2*pitch) + 2*x + (y%2), ceil(h/2) pair rows
                                per image (an odd last row is paired with zeros).  A (K+1)x(K+1) lookup window is then
                                ~(K+1)/2 runs of 2(K+1) floats instead of K+1 runs of K+1: fewer, longer DRAM bursts.
-                            2: levels 0 and 1 ROW QUADS interleaved, element (y,x) at (y/4)*(4*pitch) + 4*x + (y%4),
-                               ceil(h/4) groups per image (the last group is completed with rows of zeros); deeper
-                               levels as in 1 (the build's 8x32 target tile holds whole quads of levels 0 and 1 only, and
-                               partial-sector stores cost as much as full ones).  One column of a quad is 16
+                            2: ROW QUADS interleaved, element (y,x) at (y/4)*(4*pitch) + 4*x + (y%4), ceil(h/4) groups per
+                               image (the last group is completed with rows of zeros).  One column of a quad is 16
                                bytes, so a window starts on TMA's 16-byte grid at ANY x: a (K+1)x(K+1) window is 3 or 4
                                runs of exactly 4(K+1) floats (160 B at r=4), ~10.6 DRAM fills of 64 B instead of ~12.4
                                (pairs) or ~17 (rows).  Default of the tensor-core builds.

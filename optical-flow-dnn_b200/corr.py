@@ -285,8 +285,8 @@ class CorrBlock:
         self._mode = _MODES[mode]
         self._B, self._D, self._H, self._W = B, D, H, W
         self._device = device
-        # the tensor-core builds write levels 0-1 as row QUADS interleaved (a lookup window is 3-4 runs of 160 bytes at any
-        # x: fewest 64-byte DRAM fills, exact TMA boxes) and the deeper levels as row pairs; gradient pyramids are row-major inside the library whatever this says, and
+        # the tensor-core builds write row QUADS interleaved (a lookup window is 3-4 runs of 160 bytes at any x: fewest
+        # 64-byte DRAM fills, exact TMA boxes); gradient pyramids are row-major inside the library whatever this says, and
         # never larger.  RAFTCORR_PYRAMID_LAYOUT = quads (default) | pairs (round-1 layout) | rowmajor: A/B switches
         # (rowmajor is needed by the cp.async lookup and the CTA-pair build experiments)
         il = 0 if mode == "fp32" else _LAYOUTS[os.environ.get("RAFTCORR_PYRAMID_LAYOUT", "quads")]
@@ -511,8 +511,7 @@ class CorrBlock:
         for l in range(self.num_levels):
             h, w, p = lay.h[l], lay.w[l], lay.pitch[l]
             if lay.interleaved:
-                # rows per interleaved group: layout 1 = pairs; layout 2 = quads for levels 0-1, pairs deeper (raftcorr.h)
-                rg = 4 if (lay.interleaved == 2 and l < 2) else 2
+                rg = 4 if lay.interleaved == 2 else 2  # rows per interleaved group: layout 1 = pairs, 2 = quads (raftcorr.h)
                 hp = (h + rg - 1) // rg
                 flat = pyr[lay.offset[l]: lay.offset[l] + self._B * N * hp * rg * p]
                 lvl = flat.view(self._B * N, hp, p, rg).permute(0, 1, 3, 2).reshape(self._B * N, 1, rg * hp, p)

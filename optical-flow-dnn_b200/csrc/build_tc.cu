@@ -75,6 +75,10 @@ struct BuildParams {
     int B, N1, H2, W2, L;
     int m_tiles, m_groups, bands, w_tiles, k_blocks;  // m_groups = ceil(m_tiles / cluster size)
     int total_tiles;
+    // Work units: a CTA takes `unit_bands` vertically consecutive tiles (bands bg * unit_bands ...) of one (m-tile,
+    // w-tile) back to back.  1 for the row / row-pair layouts; 4 for the row-quad layout, where the epilogue of the
+    // pooled levels carries level-2 / level-3 rows from band to band until a whole quad can be stored.
+    int unit_bands, band_groups, total_units;
     int lsu_store;  // A/B: level-0 rows leave through LSU stores instead of TMA
     float scale;
     // RAFTCORR_BUILD_F16_TC: operands are fp16 with one power-of-two scale per 64-pixel operand BLOCK (fmap1: half an
@@ -165,18 +169,24 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int crank = CL > 1 ? (int)(blockIdx.x % CL) : 0;      // rank inside the cluster (cluster dims = (CL,1,1))
     const int first = (int)(blockIdx.x / CL), stride = (int)(gridDim.x / CL);
 
-    const int tiles_per_m = P.bands * P.w_tiles;
+    const int units_per_m = P.band_groups * P.w_tiles;
+// (w-tile, band group, m-tile, batch item) of work unit u; the unit's tiles are bands bg * unit_bands + bi
+#define RAFTCORR_DECODE_UNIT(u)                                      \
+    const int wt = (u) % P.w_tiles;                                  \
+    const int bg = ((u) / P.w_tiles) % P.band_groups;                \
+    const int mt = (((u) / units_per_m) % P.m_groups) * CL + crank;  \
+    const int b = (u) / (units_per_m * P.m_groups);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = first; t < P.total_tiles; t += stride) {
-                const int wt = t % P.w_tiles;
-                const int band = (t / P.w_tiles) % P.bands;
-                const int mt = ((t / tiles_per_m) % P.m_groups) * CL + crank;  // may be a dummy tile past the end
-                const int b = t / (tiles_per_m * P.m_groups);
+            for (int u = first; u < P.total_units; u += stride) {
+              RAFTCORR_DECODE_UNIT(u)  // mt may be a dummy tile past the end (pair modes)
+              for (int bi = 0; bi < P.unit_bands; ++bi) {
+                const int band = bg * P.unit_bands + bi;
+                if (band >= P.bands) break;
                 for (int kb = 0; kb < P.k_blocks; ++kb) {
                     mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                     const uint32_t sa = stage_base + stage * kStageStride;
@@ -202,6 +212,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+              }
             }
         }
     } else if (warp == 1) {
@@ -210,7 +221,9 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int t = first; t < P.total_tiles; t += stride, ++it) {
+            for (int u = first; u < P.total_units; u += stride) {
+              const int bg_ = (u / P.w_tiles) % P.band_groups;
+              for (int bi = 0; bi < P.unit_bands && bg_ * P.unit_bands + bi < P.bands; ++bi, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);  // epilogue has drained this accumulator
@@ -242,6 +255,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
                 if (PAIR_MMA) tc_commit_2sm_mcast(tfull_bar + 8 * acc, 3);  // accumulators complete in both CTAs
                 else tc_commit(tfull_bar + 8 * acc);                        // accumulator complete -> epilogue
+              }
             }
         }
     } else if (warp >= 4 && warp < 8) {
@@ -255,11 +269,10 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const uint32_t swz = (uint32_t)(ml & 7);
         int it = 0;
         int buf = 0;
-        for (int t = first; t < P.total_tiles; t += stride, ++it) {
-            const int wt = t % P.w_tiles;
-            const int band = (t / P.w_tiles) % P.bands;
-            const int mt = ((t / tiles_per_m) % P.m_groups) * CL + crank;
-            const int b = t / (tiles_per_m * P.m_groups);
+        for (int u = first; u < P.total_units; u += stride) {
+          RAFTCORR_DECODE_UNIT(u)
+          for (int bi = 0; bi < P.unit_bands && bg * P.unit_bands + bi < P.bands; ++bi, ++it) {
+            const int band = bg * P.unit_bands + bi;
             const int acc = it & 1;
             // block-scaled fp16 operands: undo the power-of-two block scales together with 1/sqrt(D); all five scalars
             // are fetched before the accumulator wait so that their latency never sits on the store chain
@@ -390,6 +403,7 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
                 if (++buf == kNumStoreBufs) buf = 0;
             }
+          }
         }
         if (issuer) tma_store_wait_all();  // global writes complete before the CTA exits
     } else if (warp >= 8) {
@@ -402,11 +416,13 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const int ml = ew * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
         int it = 0;
-        for (int t = first; t < P.total_tiles; t += stride, ++it) {
-            const int wt = t % P.w_tiles;
-            const int band = (t / P.w_tiles) % P.bands;
-            const int mt = ((t / tiles_per_m) % P.m_groups) * CL + crank;
-            const int b = t / (tiles_per_m * P.m_groups);
+        for (int u = first; u < P.total_units; u += stride) {
+          RAFTCORR_DECODE_UNIT(u)
+          // row-quad layout: level-2 rows of an even band wait for the odd band, level-3 rows for the end of the unit
+          float l2keep[2][8], l3keep[3][4];
+          for (int bi = 0; bi < P.unit_bands && bg * P.unit_bands + bi < P.bands; ++bi, ++it) {
+            const int band = bg * P.unit_bands + bi;
+            const bool last_band = bi == P.unit_bands - 1 || band == P.bands - 1;
             const int acc = it & 1;
             const int m = mt * kTileM + ml;
             const bool m_ok = m < P.N1;
@@ -468,30 +484,64 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             l2row[rr][4 * half + c] = (l1h[2 * rr][2 * c] + l1h[2 * rr][2 * c + 1] + l1h[2 * rr + 1][2 * c] +
                                                        l1h[2 * rr + 1][2 * c + 1]) * 0.25f;
                 }
-                // levels 2 and 3 are stored as row PAIRS (level_interleave): the tile's two level-2 rows are exactly pair
-                // `band` (64 bytes per thread), its level-3 row is one slot of pair band / 2
-                if (P.L > 2 && m_ok && band * 2 < P.lvl_h[2]) {
-                    const bool odd_ok = band * 2 + 1 < P.lvl_h[2];
-                    float* dst = P.lvl_base[2] + pix * P.lvl_img_stride[2] + (int64_t)band * (2 * P.lvl_pitch[2]) + (w0 >> 1);
+                // Level 2: the tile's two rows are half of quad band / 2 -- an even band keeps them, the odd band (or the
+                // end of the unit) stores the whole quad: 8 columns x 4 rows = 128 contiguous bytes per thread.
+                // Level 3: one row per band = one slot of quad bg (a unit is exactly 4 bands): stored at the unit's end.
+                // Rows past a level's height inside its last quad are zeros (the lookup's tensor maps see whole quads).
+                if (P.L > 2) {
+                    const bool ok0 = band * 2 < P.lvl_h[2], ok1 = band * 2 + 1 < P.lvl_h[2];
+                    if (!(bi & 1) && !last_band) {
 #pragma unroll
-                    for (int c = 0; c < 2; ++c)
-                        if ((w0 >> 2) + 4 * c + 4 <= P.lvl_pitch[2]) {
-                            float v[8];
+                        for (int c = 0; c < 8; ++c) { l2keep[0][c] = ok0 ? l2row[0][c] : 0.f; l2keep[1][c] = ok1 ? l2row[1][c] : 0.f; }
+                    } else if (m_ok && (band >> 1) * 4 < P.lvl_h[2]) {
+                        const bool odd = bi & 1;  // odd band: slots 2,3 of the quad are this band's rows; else they are zeros
+                        const int x2 = w0 >> 2;
+                        float* dst = P.lvl_base[2] + pix * P.lvl_img_stride[2] + (int64_t)(band >> 1) * (4 * P.lvl_pitch[2]) + 4 * x2;
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                v[2 * e] = l2row[0][4 * c + e];
-                                v[2 * e + 1] = odd_ok ? l2row[1][4 * c + e] : 0.f;
+                        for (int c = 0; c < 4; ++c)
+                            if (x2 + 2 * c + 2 <= P.lvl_pitch[2]) {
+                                float v[8];
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int cc = 2 * c + e;
+                                    v[4 * e + 0] = odd ? l2keep[0][cc] : (ok0 ? l2row[0][cc] : 0.f);
+                                    v[4 * e + 1] = odd ? l2keep[1][cc] : (ok1 ? l2row[1][cc] : 0.f);
+                                    v[4 * e + 2] = odd && ok0 ? l2row[0][cc] : 0.f;
+                                    v[4 * e + 3] = odd && ok1 ? l2row[1][cc] : 0.f;
+                                }
+                                st_global_v8(dst + 8 * c, v);
                             }
-                            st_global_v8(dst + 8 * c, v);
-                        }
+                    }
                 }
-                if (P.L > 3 && m_ok && band < P.lvl_h[3] && (w0 >> 3) + 4 <= P.lvl_pitch[3]) {
-                    float* dst = P.lvl_base[3] + pix * P.lvl_img_stride[3] + (int64_t)(band >> 1) * (2 * P.lvl_pitch[3]) + (w0 >> 2) +
-                                 (band & 1);
+                if (P.L > 3) {
+                    float l3[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
-                        dst[2 * c] = (l2row[0][2 * c] + l2row[0][2 * c + 1] + l2row[1][2 * c] + l2row[1][2 * c + 1]) * 0.25f;
-                    if (!(band & 1) && band + 1 >= P.lvl_h[3]) dst[1] = dst[3] = dst[5] = dst[7] = 0.f;
+                        l3[c] = band < P.lvl_h[3] ? (l2row[0][2 * c] + l2row[0][2 * c + 1] + l2row[1][2 * c] + l2row[1][2 * c + 1]) * 0.25f : 0.f;
+                    if (!last_band) {
+#pragma unroll
+                        for (int sl = 0; sl < 3; ++sl)
+                            if (sl == bi) {
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) l3keep[sl][c] = l3[c];
+                            }
+                    } else if (m_ok && bg * 4 < P.lvl_h[3]) {
+                        const int x3 = w0 >> 3;
+                        float* dst = P.lvl_base[3] + pix * P.lvl_img_stride[3] + (int64_t)bg * (4 * P.lvl_pitch[3]) + 4 * x3;
+#pragma unroll
+                        for (int c2 = 0; c2 < 2; ++c2)
+                            if (x3 + 2 * c2 + 2 <= P.lvl_pitch[3]) {
+                                float v[8];
+#pragma unroll
+                                for (int e = 0; e < 2; ++e) {
+                                    const int cc = 2 * c2 + e;
+#pragma unroll
+                                    for (int sl = 0; sl < 4; ++sl)
+                                        v[4 * e + sl] = sl < bi ? l3keep[sl < 3 ? sl : 0][cc] : (sl == bi ? l3[cc] : 0.f);
+                                }
+                                st_global_v8(dst + 8 * c2, v);
+                            }
+                    }
                 }
                 continue;
             }
@@ -587,8 +637,10 @@ build_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     }
                 }
             }
+          }
         }
     }
+#undef RAFTCORR_DECODE_UNIT
 
     tc_fence_before();
     if (CL > 1) cluster_sync_all();  // no CTA may exit while a peer can still multicast into / arrive on it
@@ -693,13 +745,16 @@ int launch_build_tc_ex(const void* f1n, const void* f2n, int D, float* pyramid, 
     const int64_t total = (int64_t)B * P.m_groups * P.bands * P.w_tiles;  // tiles per cluster rank
     RC_REQUIRE(total < (1LL << 31), "tf32 build: too many tiles");
     P.total_tiles = (int)total;
+    P.unit_bands = il == 2 ? 4 : 1;
+    P.band_groups = ceil_div(P.bands, P.unit_bands);
+    P.total_units = B * P.m_groups * P.band_groups * P.w_tiles;
     P.scale = 1.0f / sqrtf((float)D);  // corr.py:116
     { const char* e = std::getenv("RAFTCORR_BUILD_STORE"); P.lsu_store = (e && e[0] == 'l') ? 1 : 0; }
 
     int sms = 0;
     RC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const int max_clusters = sms / cl;
-    const int clusters = P.total_tiles < max_clusters ? P.total_tiles : max_clusters;
+    const int clusters = P.total_units < max_clusters ? P.total_units : max_clusters;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * cl);
     cfg.blockDim = dim3(kThreads);

@@ -58,11 +58,13 @@ struct LevelView {
     __host__ __device__ __forceinline__ int group_rows() const { return il == 2 ? 4 : il ? 2 : 1; }
 };
 
-// Per-level interleave code of a layout: `interleaved == 2` stores levels 0 and 1 as row quads and the deeper (small)
-// levels as row pairs -- the build's 8x32 target tile holds a whole quad of level 1 but only 2 rows of level 2 and 1 row
-// of level 3, and partial-sector stores cost as much as full ones on the SM's store path.
+// Per-level interleave code of a layout (one code for all levels today; kept as the single place that decides).
+// Layout 2 = row quads on every level: the build's 8x32 target tile holds a whole quad of level 1 but only 2 rows of
+// level 2 and 1 row of level 3, so its epilogue carries those rows across the 4 bands of a work unit and stores whole
+// quads (partial-sector stores cost as much as full ones on the SM's store path).
 __host__ __device__ __forceinline__ int level_interleave(int interleaved, int level) {
-    return interleaved == 2 ? (level < 2 ? 2 : 1) : interleaved;
+    (void)level;
+    return interleaved;
 }
 // rows interleaved per group for a per-level code (0 / 1 / 2 -> 1 / 2 / 4)
 __host__ __device__ __forceinline__ int layout_group_rows(int il) { return il == 2 ? 4 : il ? 2 : 1; }

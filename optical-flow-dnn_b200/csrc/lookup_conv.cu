@@ -259,7 +259,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                 const uint32_t bar = my_bar + 8 * slot;
                 const uint32_t dst = my_patch + slot * SLOT;
                 fence_proxy_async();  // the slot was read through the generic proxy two batches ago
-                if (LAY == 2 && i_l < 2) {
+                if (LAY == 2) {
                     // row quads: exact box of K+1 columns at any x, GMAX or GMAX-1 quads
                     const int nq = Q::quads(y0 & 3);
                     mbar_expect_tx(bar, nq * Q::ROW_BYTES);
@@ -327,7 +327,7 @@ lookup_conv_kernel(const __grid_constant__ LookupMaps maps, const __grid_constan
                                 const float ax = x - xf, ay = y - yf;
                                 const float* pb = my_patch_gen + (slot0 + half) * (SLOT / 4);
                                 float hh[4 * Q::GMAX > 2 * G::BR ? 4 * Q::GMAX : 2 * G::BR];
-                                if (l < 2) {
+                                if (true) {
                                     // row quads: the lane's column and the next as 16-byte chunks (rows 4g .. 4g+3)
                                     const float4* cp = reinterpret_cast<const float4*>(pb) + col;
 #pragma unroll

@@ -54,7 +54,7 @@ def test_layout_matches_oracle_shapes(lib):
             for l in range(L):
                 assert lay.pitch[l] % 8 == 0 and lay.pitch[l] >= lay.w[l]
                 assert lay.offset[l] == off and off % 64 == 0
-                rg = (1, 2, 4 if l < 2 else 2)[il]  # layout 2: quads for levels 0-1, pairs deeper
+                rg = (1, 2, 4)[il]
                 rows = (lay.h[l] + rg - 1) // rg * rg
                 off += -(-(B * H * W * rows * lay.pitch[l]) // 64) * 64
             assert lay.total_floats == off
