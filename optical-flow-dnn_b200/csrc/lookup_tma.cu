@@ -183,23 +183,16 @@ lookup_fwd_tma_kernel(const __grid_constant__ LookupMaps maps, const GroupView g
 // ---------------------------------------------------------------------------------------------------------------
 // Layout 2 (raftcorr_pyramid_layout::interleaved == 2: row quads on every level): the default of the tensor-core builds.
 //
-// ncu on the row-pair kernel above (profiles/r02_ncu_full_r2a_*.json) showed it bound by its own instruction stream, not
-// by DRAM (53 % DRAM cycles active, 121 warp instructions per (pixel, level) window, 16 warps per SM), and
-// scripts/gather_roofline.py measured the same for the first quad kernel: the gather alone 27 us, evaluation + output
-// alone 31 us.  Here
-//  * the box is exact (K+1 columns at any x, GMAX or GMAX-1 quads): no alignment shift on either axis at evaluation time;
-//  * a warp evaluates TWO pixels x four levels per pass: 4 lanes per (pixel, level) window, each lane owns 2-3 window
-//    COLUMNS, reads them as 16-byte quads (LDS.128, compile-time offsets), forms the horizontal lerps of the quad rows
-//    and the vertical lerps of the K+3 quad-relative rows that can be an output; the window's start row inside its
-//    quad (sy) only moves the DESTINATION channel (one address subtraction) and predicates the stores -- no dynamic
-//    register indexing, all 32 lanes busy, ~115 warp instructions per pixel instead of ~480;
-//  * the 8 boxes of a pixel pair are issued by 8 lanes at once (each arrives on the pair's mbarrier with its own byte
-//    count), so the coordinate / tensor-map arithmetic runs once per pair;
-//  * PERSISTENT: the CTA walks tiles of 16 consecutive source pixels (one pixel pair per warp and tile); the ring of
-//    patch boxes runs ACROSS tiles, so only the very first pair of a CTA pays the coordinates -> box -> data latency.
-constexpr int kQPix = 16;    // source pixels per tile: a 64-byte output segment per channel
-constexpr int kQPitch = 17;  // out tile row pitch (floats)
-
+// ncu on the row-pair kernel above (profiles/r02_ncu_lookup_pair_*.json) showed it bound by its own instruction stream,
+// not by DRAM (53 % DRAM cycles active, 121 warp instructions per (pixel, level) window, 16 warps per SM): per window
+// ~25 useful instructions and ~80 of addressing (per-tap row tables, alignment shifts, lane-0 box arithmetic).  Here
+//  * the box is exact (K+1 columns at any x, 3 or 4 quads): no alignment shift on either axis at evaluation time;
+//  * lane = window COLUMN, half-warp = pyramid level: a lane reads its column and the next as 16-byte quads
+//    (LDS.128, compile-time offsets), forms the horizontal lerps of all 4*GMAX quad rows and the vertical lerps of the
+//    K+3 quad-relative rows that can be an output; the window's start row inside its quad (sy) only moves the
+//    DESTINATION channel (one address subtraction) and predicates the stores -- no dynamic register indexing;
+//  * the LG boxes of a pixel are issued by LG lanes at once (each arrives on the pixel's mbarrier with its own byte
+//    count), so the coordinate / tensor-map arithmetic runs once per pixel instead of once per level.
 // Wait of the hot loop: no clock reads per poll (mbar_wait spends six instructions per poll on its time-out and waiting
 // warps take issue slots from evaluating ones); the suspend-time hint lets a poll sleep in hardware; a protocol bug
 // still becomes a trapped launch instead of a hang.
@@ -217,25 +210,24 @@ __device__ __forceinline__ void mbar_wait_polls(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 
+constexpr int kQPitch = 33;  // out tile row pitch (floats): conflict-free column writes and 4-channel x 8-quad reads
+
 // EXP (measurement only, scripts/gather_roofline.py): 0 = the kernel; 1 = the gather alone (same boxes, same waits, no
 // evaluation, no output: what the memory system charges for this box list); 2 = evaluation + output alone (no boxes).
-template <int R, int LG, int EXP = 0>
+template <int R, int LG, int kBufs, int EXP = 0>
 __global__ void __launch_bounds__(kWarps * 32, 2)
 lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView g, const float* __restrict__ coords,
                        float* __restrict__ out, const int tiles_per_img, const int total_tiles) {
     using Q = QuadGeo<R>;
+    constexpr int SLOT = Q::SLOT;
     constexpr int CH = LG * Q::KK;
-    constexpr int PPW = kQPix / kWarps;               // pixels per warp and tile: one pair
-    constexpr int kPairSlots = 2;                     // ring: the pair being evaluated + the pair in flight
-    constexpr int PAIR_BYTES = PPW * 4 * Q::SLOT;     // 2 pixels x 4 level slots
-    constexpr int WARP_PATCH = kPairSlots * PAIR_BYTES;
-    // window columns per lane: K columns over the 4 lanes of a window
-    constexpr int CBASE = Q::K / 4, CREM = Q::K % 4, CMAX = CBASE + (CREM ? 1 : 0);
-    static_assert(PPW == 2 && LG <= 4, "a pass is 2 pixels x 4 levels x 4 lanes");
+    constexpr int PIX_PER_WARP = kPix / kWarps;
+    constexpr int WARP_PATCH = kBufs * LG * SLOT;  // bytes: this warp's ring of patch buffers
+    static_assert(kBufs - 1 <= PIX_PER_WARP, "the issue cursor may run at most one tile ahead");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-    // [kWarps][2 pairs][2 px][4 levels][SLOT] patches | [kWarps][2] mbarriers | out_s [CH][kQPitch]
+    // [kWarps][kBufs][LG][SLOT] patches | [kWarps][kBufs] mbarriers | out_s [CH][kQPitch]
     const uint32_t bar_base = base + kWarps * WARP_PATCH;
     float* out_s = reinterpret_cast<float*>(gen + kWarps * WARP_PATCH + kWarps * kBarBytes);
 
@@ -244,12 +236,15 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
     const uint32_t my_patch = base + warp * WARP_PATCH;
     const float* my_patch_gen = reinterpret_cast<const float*>(gen + warp * WARP_PATCH);
     const uint32_t my_bar = bar_base + warp * kBarBytes;
+    // PERSISTENT: the CTA walks tiles of kPix consecutive source pixels (first, first + stride, ...); a warp's ring of
+    // patch boxes runs ACROSS tiles, so only the very first pixels of a CTA pay the coordinates -> box -> data latency
+    // chain (ncu on the one-tile-per-CTA version: half of a CTA's life was that chain, DRAM 53 % busy)
     const int first = blockIdx.x, stride = gridDim.x;
     const int my_tiles = first < total_tiles ? (total_tiles - first + stride - 1) / stride : 0;
 
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < kPairSlots; ++i) mbar_init(my_bar + 8 * i, PPW * 4);  // one arrival per (pixel, level slot)
+        for (int i = 0; i < kBufs; ++i) mbar_init(my_bar + 8 * i, LG);  // one arrival (+ its bytes) per level box
         fence_mbar_init();
         if (warp == 0) {
 #pragma unroll
@@ -261,11 +256,7 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
     }
     __syncwarp();
 
-    // roles of a lane.  Issue: lane i < 8 -> pixel i >> 2 of the pair, level i & 3.  Evaluation: window = lane >> 2
-    // (same numbering), sub = lane & 3 -> window columns [c0, c0 + cn).
-    const int w_px = (lane >> 4) & 1, w_lv = (lane >> 2) & 3, sub = lane & 3;
-    const int c0 = sub * CBASE + (sub < CREM ? sub : CREM), cn = CBASE + (sub < CREM ? 1 : 0);
-    const int i_px = (lane >> 2) & 1, i_lv = lane & 3;
+    const int half = lane >> 4, col = lane & 15;  // evaluation: half-warp = level of the pass, lane = window column
 
     asm volatile("griddepcontrol.wait;" ::: "memory");  // PDL: see lookup_fwd_tma_kernel
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -273,20 +264,20 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
     auto tile_origin = [&](int it, int& b, int& p0) {  // integer division: only where a cursor is set up
         const int t = first + it * stride;
         b = t / tiles_per_img;
-        p0 = (t - b * tiles_per_img) * kQPix;
+        p0 = (t - b * tiles_per_img) * kPix;
     };
-    const int img_span = tiles_per_img * kQPix, step_span = stride * kQPix;
+    const int img_span = tiles_per_img * kPix, step_span = stride * kPix;
     auto tile_advance = [&](int& b, int& p0) {  // (b, p0) of the cursor's next tile without dividing
         p0 += step_span;
         while (p0 >= img_span) { p0 -= img_span; ++b; }
     };
-    // lanes 0..1: coordinates of the warp's pixels (tile pixel q = warp + kWarps * n) of the tile being consumed; lanes
-    // 2..3: the same for the next tile; (nx, ny): the tile after that, on its way from memory (merged in at the next
-    // tile switch, a whole tile after the load was issued)
+    // lane n < PIX_PER_WARP: coordinates of the warp's pixel n (tile pixel q = warp + kWarps * n) of the tile being
+    // consumed; lanes PIX_PER_WARP .. 2 PIX_PER_WARP - 1: the same for the next tile; (nx, ny): the tile after that, on
+    // its way from memory (merged in at the next tile switch, a whole tile after the load was issued)
     auto load_coords_at = [&](int it, int b, int p0, float& x, float& y) {
         x = y = 0.f;
-        if (it < my_tiles && lane < 2 * PPW) {
-            const int p = p0 + warp + kWarps * (lane & (PPW - 1));
+        if (it < my_tiles && lane < 2 * PIX_PER_WARP) {
+            const int p = p0 + warp + kWarps * (lane & (PIX_PER_WARP - 1));
             if (p < N) {
                 x = clamp_coord(__ldg(coords + ((int64_t)b * 2 + 0) * N + p));
                 y = clamp_coord(__ldg(coords + ((int64_t)b * 2 + 1) * N + p));
@@ -294,115 +285,135 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
         }
     };
     float cx, cy, nx, ny;
-    int b = 0, p0 = 0;           // tile being consumed
-    int i_b = 0, i_p0 = 0;       // next tile (the one whose boxes are requested while this one is evaluated)
-    int l_b = 0, l_p0 = 0;       // coordinates cursor: tile it + 2
-    if (my_tiles > 0) tile_origin(0, b, p0);
-    i_b = b; i_p0 = p0;
-    tile_advance(i_b, i_p0);
-    load_coords_at(lane < PPW ? 0 : 1, lane < PPW ? b : i_b, lane < PPW ? p0 : i_p0, cx, cy);
-    l_b = i_b; l_p0 = i_p0;
-    tile_advance(l_b, l_p0);
-    load_coords_at(2, l_b, l_p0, nx, ny);
-    const float my_inv = g.inv_scale[i_lv < LG ? i_lv : 0];          // issue role
+    int l_b = 0, l_p0 = 0;  // coordinates cursor: tile it + 2 while tile it is consumed
+    {
+        int b0 = 0, p00 = 0, b1, p01;
+        if (my_tiles > 0) tile_origin(0, b0, p00);
+        b1 = b0; p01 = p00;
+        tile_advance(b1, p01);
+        load_coords_at(lane < PIX_PER_WARP ? 0 : 1, lane < PIX_PER_WARP ? b0 : b1, lane < PIX_PER_WARP ? p00 : p01, cx, cy);
+        l_b = b1; l_p0 = p01;
+        tile_advance(l_b, l_p0);
+        load_coords_at(2, l_b, l_p0, nx, ny);
+    }
+    const float my_inv = g.inv_scale[lane < LG ? lane : 0];          // issue role: lane = level
     const char* map_base = reinterpret_cast<const char*>(&maps);     // m[l] at 128 * l, ms[l] at 512 + 128 * l
 
-    // request the 8 boxes of a pixel pair: tile (tb, tp0), coordinates in lanes src0 / src0 + 1, ring slot `slot`
-    auto issue_pair = [&](int tb, int tp0, int src0, int slot) {
-        const float x = __shfl_sync(0xffffffffu, cx, src0 + i_px), y = __shfl_sync(0xffffffffu, cy, src0 + i_px);
-        if (lane < PPW * 4) {
-            const int p = tp0 + warp + kWarps * i_px;
-            const uint32_t bar = my_bar + 8 * slot;
-            if (EXP == 2 || i_lv >= LG || p >= N) {
-                mbar_arrive(bar);  // nothing to fetch for this slot: keep the arrival count
-            } else {
+    // issue cursor: next (tile, pixel) whose boxes have not been requested; ring position of the next request
+    int i_it = 0, i_n = 0, i_buf = 0, i_b = 0, i_p0 = 0;
+    if (my_tiles > 0) tile_origin(0, i_b, i_p0);
+    auto issue_next = [&](int c_it) {  // whole warp; lanes < LG each issue one level's box of the next valid pixel
+        // never more than one tile ahead of the tile being consumed (c_it): that is as far as the coordinates held in
+        // lanes PIX_PER_WARP.. reach (sparse last tiles of an image could otherwise let the cursor run further)
+        while (i_it < my_tiles && i_it <= c_it + 1) {
+            const int b = i_b;
+            const int p = i_p0 + warp + kWarps * i_n;
+            const int src = i_n + (i_it != c_it ? PIX_PER_WARP : 0);
+            if (++i_n == PIX_PER_WARP) {
+                i_n = 0;
+                ++i_it;
+                tile_advance(i_b, i_p0);
+            }
+            if (p >= N) continue;  // past the end of an image (last tile only)
+            const float x = __shfl_sync(0xffffffffu, cx, src), y = __shfl_sync(0xffffffffu, cy, src);
+            if (lane < LG) {
                 const int x0 = __float2int_rd(x * my_inv) - R;
                 const int y0 = __float2int_rd(y * my_inv) - R;
+                const bool quad = true;  // layout 2: every level is stored as row quads
                 const int nq = Q::quads(y0 & 3);  // the window spans GMAX or GMAX-1 row quads
-                fence_proxy_async();  // the slot was read through the generic proxy when it was last evaluated
-                mbar_expect_tx(bar, nq * Q::ROW_BYTES);
-                tma_load_3d(my_patch + slot * PAIR_BYTES + (i_px * 4 + i_lv) * Q::SLOT,
-                            reinterpret_cast<const CUtensorMap*>(map_base + (nq == Q::GMAX ? 0 : 512) + 128 * i_lv), bar, 4 * x0,
-                            y0 >> 2, tb * N + p);
-            }
-        }
-    };
-    if (my_tiles > 0) issue_pair(b, p0, 0, 0);
-
-    for (int it = 0; it < my_tiles; ++it) {
-        const int slot = it & 1;
-        if (it + 1 < my_tiles) issue_pair(i_b, i_p0, PPW, slot ^ 1);
-        const int q = warp + kWarps * w_px;        // this lane's pixel inside the tile
-        const float xq = __shfl_sync(0xffffffffu, cx, w_px), yq = __shfl_sync(0xffffffffu, cy, w_px);
-        mbar_wait_polls(my_bar + 8 * slot, (it >> 1) & 1);
-        if (EXP != 1 && w_lv < LG && p0 + q < N) {
-            const float inv = g.inv_scale[w_lv];
-            const float x = xq * inv, y = yq * inv;
-            const float xf = floorf(x), yf = floorf(y);
-            const float ax = x - xf, ay = y - yf;
-            const int sy = ((int)yf - R) & 3;
-            // column chunk = 16 bytes (rows 4g .. 4g+3); the lane's first column
-            const float4* cp = reinterpret_cast<const float4*>(my_patch_gen + (slot * PAIR_BYTES + (w_px * 4 + w_lv) * Q::SLOT) / 4) + c0;
-            // output row j = Y - sy of window column c is channel c * K + j (x offset major, corr.py:66-78)
-            float* o = out_s + ((w_lv * Q::KK + c0 * Q::K - sy) * kQPitch + q);
-            bool ok[Q::NV];
-#pragma unroll
-            for (int Y = 0; Y < Q::NV; ++Y) ok[Y] = Y < 3 ? (sy <= Y) : (Y >= Q::K ? (sy > Y - Q::K) : true);
-            float4 a[Q::GMAX];
-#pragma unroll
-            for (int gq = 0; gq < Q::GMAX; ++gq) a[gq] = cp[gq * Q::K1];
-#pragma unroll
-            for (int ci = 0; ci < CMAX; ++ci) {
-                if (ci < cn) {
-                    float4 c[Q::GMAX];
-#pragma unroll
-                    for (int gq = 0; gq < Q::GMAX; ++gq) c[gq] = cp[gq * Q::K1 + ci + 1];
-                    float hh[4 * Q::GMAX];
-#pragma unroll
-                    for (int gq = 0; gq < Q::GMAX; ++gq) {
-                        hh[4 * gq + 0] = a[gq].x + ax * (c[gq].x - a[gq].x);
-                        hh[4 * gq + 1] = a[gq].y + ax * (c[gq].y - a[gq].y);
-                        hh[4 * gq + 2] = a[gq].z + ax * (c[gq].z - a[gq].z);
-                        hh[4 * gq + 3] = a[gq].w + ax * (c[gq].w - a[gq].w);
-                    }
-#pragma unroll
-                    for (int Y = 0; Y < Q::NV; ++Y) {
-                        const float v = hh[Y] + ay * (hh[Y + 1] - hh[Y]);
-                        if (ok[Y]) o[(ci * Q::K + Y) * kQPitch] = v;
-                    }
-#pragma unroll
-                    for (int gq = 0; gq < Q::GMAX; ++gq) a[gq] = c[gq];
+                const bool big = nq == Q::GMAX;
+                const uint32_t bytes = nq * Q::ROW_BYTES;
+                const uint32_t bar = my_bar + 8 * i_buf;
+                fence_proxy_async();  // the buffer was read through the generic proxy when it was last evaluated
+                if (EXP != 2) {
+                    mbar_expect_tx(bar, bytes);
+                    tma_load_3d(my_patch + (i_buf * LG + lane) * SLOT,
+                                reinterpret_cast<const CUtensorMap*>(map_base + (big ? 0 : 512) + 128 * lane), bar,
+                                quad ? 4 * x0 : 2 * (x0 & ~1), quad ? y0 >> 2 : y0 >> 1, b * N + p);
                 }
             }
+            if (++i_buf == kBufs) i_buf = 0;
+            return;
         }
-        __syncthreads();  // (also: every lane of every warp is done with its patch slot)
+    };
+#pragma unroll
+    for (int i = 0; i < kBufs - 1; ++i) issue_next(0);
+
+    int c_buf = 0;
+    uint32_t c_par = 0;
+    int b = 0, p0 = 0;
+    if (my_tiles > 0) tile_origin(0, b, p0);
+    for (int it = 0; it < my_tiles; ++it) {
+#pragma unroll
+        for (int n = 0; n < PIX_PER_WARP; ++n) {
+            const int q = warp + kWarps * n;
+            if (p0 + q >= N) continue;  // warp-uniform
+            issue_next(it);
+            const float xq = __shfl_sync(0xffffffffu, cx, n), yq = __shfl_sync(0xffffffffu, cy, n);
+            if (EXP != 2) mbar_wait_polls(my_bar + 8 * c_buf, c_par);
+#pragma unroll
+            for (int pass = 0; pass < (LG + 1) / 2; ++pass) {
+                const int l = 2 * pass + half;
+                if (EXP != 1 && col < Q::K && l < LG) {
+                    const float inv = g.inv_scale[l];
+                    const float x = xq * inv, y = yq * inv;
+                    const float xf = floorf(x), yf = floorf(y);
+                    const float ax = x - xf, ay = y - yf;
+                    const float* pb = my_patch_gen + (c_buf * LG + l) * (SLOT / 4);
+                    {
+                        // ---- row quads: column chunk = 16 bytes (rows 4g .. 4g+3)
+                        const int sy = ((int)yf - R) & 3;
+                        const float4* cp = reinterpret_cast<const float4*>(pb) + col;
+                        float hh[4 * Q::GMAX];
+#pragma unroll
+                        for (int gq = 0; gq < Q::GMAX; ++gq) {
+                            const float4 a = cp[gq * Q::K1], c = cp[gq * Q::K1 + 1];
+                            hh[4 * gq + 0] = a.x + ax * (c.x - a.x);
+                            hh[4 * gq + 1] = a.y + ax * (c.y - a.y);
+                            hh[4 * gq + 2] = a.z + ax * (c.z - a.z);
+                            hh[4 * gq + 3] = a.w + ax * (c.w - a.w);
+                        }
+                        // output row j = Y - sy of column `col` is channel col * K + j (x offset major, corr.py:66-78)
+                        float* o = out_s + ((l * Q::KK + col * Q::K - sy) * kQPitch + q);
+#pragma unroll
+                        for (int Y = 0; Y < Q::NV; ++Y) {
+                            const float v = hh[Y] + ay * (hh[Y + 1] - hh[Y]);
+                            const bool ok = Y < 3 ? (sy <= Y) : (Y >= Q::K ? (sy > Y - Q::K) : true);
+                            if (ok) o[Y * kQPitch] = v;
+                        }
+                    }
+                }
+            }
+            if (++c_buf == kBufs) { c_buf = 0; c_par ^= 1u; }
+            __syncwarp();  // all lanes are done with the buffer before it is refilled
+        }
+        __syncthreads();
         if (EXP == 1) {
             // gather alone: nothing was evaluated, nothing leaves
-        } else if ((N & 3) == 0 && p0 + kQPix <= N) {
-            // 4 lanes x 4 pixels per channel row: 64-byte segments leave as 128-bit stores
+        } else if ((N & 3) == 0 && p0 + kPix <= N) {
+            // 8 lanes x 4 pixels per channel row: 128-byte lines leave as 128-bit stores
             float* dst = out + ((int64_t)b * g.ctot + g.ch0) * N + p0;
-            for (int idx = threadIdx.x; idx < CH * 4; idx += kWarps * 32) {
-                const int ch = idx >> 2, qd = idx & 3;
+            for (int idx = threadIdx.x; idx < CH * 8; idx += kWarps * 32) {
+                const int ch = idx >> 3, qd = idx & 7;
                 const float* sp = out_s + ch * kQPitch + 4 * qd;
                 *reinterpret_cast<float4*>(dst + (int64_t)ch * N + 4 * qd) = make_float4(sp[0], sp[1], sp[2], sp[3]);
             }
         } else {
-            const int px = threadIdx.x & (kQPix - 1), p = p0 + px;
+            const int p = p0 + lane;
             if (p < N) {
                 float* dst = out + ((int64_t)b * g.ctot + g.ch0) * N + p;
-                for (int ch = threadIdx.x / kQPix; ch < CH; ch += kWarps * 32 / kQPix) dst[(int64_t)ch * N] = out_s[ch * kQPitch + px];
+                for (int ch = warp; ch < CH; ch += kWarps) dst[(int64_t)ch * N] = out_s[ch * kQPitch + lane];
             }
         }
-        // tile switch: next tile's coordinates move to lanes 0..1, the pending ones behind them
+        // tile switch: next tile's coordinates move to lanes 0 .. PIX_PER_WARP-1, the pending ones behind them
         {
-            const float sx = __shfl_sync(0xffffffffu, cx, (lane & (PPW - 1)) + PPW);
-            const float sy2 = __shfl_sync(0xffffffffu, cy, (lane & (PPW - 1)) + PPW);
-            cx = lane < PPW ? sx : nx;
-            cy = lane < PPW ? sy2 : ny;
+            const float sx = __shfl_sync(0xffffffffu, cx, (lane & (PIX_PER_WARP - 1)) + PIX_PER_WARP);
+            const float sy2 = __shfl_sync(0xffffffffu, cy, (lane & (PIX_PER_WARP - 1)) + PIX_PER_WARP);
+            cx = lane < PIX_PER_WARP ? sx : nx;
+            cy = lane < PIX_PER_WARP ? sy2 : ny;
             tile_advance(l_b, l_p0);
             load_coords_at(it + 3, l_b, l_p0, nx, ny);
-            b = i_b; p0 = i_p0;
-            tile_advance(i_b, i_p0);
+            tile_advance(b, p0);
         }
         __syncthreads();  // out_s is free for the next tile
     }
@@ -447,8 +458,10 @@ int run_fwd_tma_bufs(const LookupMaps& maps, const GroupView& g, const float* co
 template <int R, int LG>
 int run_fwd_quad(const LookupMaps& maps, const GroupView& g, const float* coords, float* out, cudaStream_t s) {
     using Q = QuadGeo<R>;
-    const size_t smem = 128 + (size_t)kWarps * 2 * 2 * 4 * Q::SLOT + kWarps * kBarBytes + sizeof(float) * LG * Q::KK * kQPitch;
-    auto kern = lookup_fwd_quad_kernel<R, LG>;
+    constexpr int kBufs = 3;
+    constexpr int SLOT = Q::SLOT;
+    const size_t smem = 128 + (size_t)kWarps * kBufs * LG * SLOT + kWarps * kBarBytes + sizeof(float) * LG * Q::KK * kQPitch;
+    auto kern = lookup_fwd_quad_kernel<R, LG, kBufs>;
     static bool attr_done[64] = {};
     int dev = 0;
     RC_CUDA(cudaGetDevice(&dev));
@@ -460,8 +473,8 @@ int run_fwd_quad(const LookupMaps& maps, const GroupView& g, const float* coords
         // RAFTCORR_LOOKUP_EXP=1|2: timing-only ablations of the bench shape (the results are NOT a lookup)
         const char* e = std::getenv("RAFTCORR_LOOKUP_EXP");
         if (e && (e[0] == '1' || e[0] == '2')) {
-            kern = e[0] == '1' ? lookup_fwd_quad_kernel<R, LG, (R == 4 && LG == 4) ? 1 : 0>
-                               : lookup_fwd_quad_kernel<R, LG, (R == 4 && LG == 4) ? 2 : 0>;
+            kern = e[0] == '1' ? lookup_fwd_quad_kernel<R, LG, kBufs, (R == 4 && LG == 4) ? 1 : 0>
+                               : lookup_fwd_quad_kernel<R, LG, kBufs, (R == 4 && LG == 4) ? 2 : 0>;
             RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
     }
@@ -471,7 +484,7 @@ int run_fwd_quad(const LookupMaps& maps, const GroupView& g, const float* coords
         RC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (dev >= 0 && dev < 64) sm_count[dev] = sms;
     }
-    const int tiles_per_img = ceil_div(g.N, kQPix);
+    const int tiles_per_img = ceil_div(g.N, kPix);
     const int64_t total = (int64_t)tiles_per_img * g.B;
     RC_REQUIRE(total < (1LL << 31), "lookup: too many tiles");
     const int ctas = 2 * sms;  // two resident CTAs per SM (shared memory), each walking total / ctas tiles
