@@ -53,9 +53,12 @@ def step(allreduce):
         f1 = torch.einsum("oc,bchw->bohw", w2, x1) + head_b.view(1, D, 1, 1)
         f2 = torch.einsum("oc,bchw->bohw", w2, x2) + head_b.view(1, D, 1, 1)
         blk = rc.CorrBlock(f1, f2, L, r)
-    loss = 0
-    for c, w in zip(coords, ws): loss = loss + (blk(c) * w).sum()
-    loss.backward()          # accumulates straight into the bucket
+    if os.environ.get("TRAIN_LOSS_SUM") == "1":   # round-1 harness: 12 x (mul + sum) and their backward in torch
+        loss = 0
+        for c, w in zip(coords, ws): loss = loss + (blk(c) * w).sum()
+        loss.backward()          # accumulates straight into the bucket
+    else:                        # out.backward(randn) per iteration, accumulated
+        torch.autograd.backward([blk(c) for c in coords], ws)
     if allreduce:
         gb.all_reduce_async()   # side stream, averaged over ranks
         gb.wait()
