@@ -200,6 +200,32 @@ int raftcorr_build_bwd(float* dpyramid, const raftcorr_pyramid_layout* layout, c
                        const float* fmap2, int D, float* dfmap1, float* dfmap2, int mode, void* workspace,
                        size_t workspace_bytes, int device, raftcorr_stream_t stream);
 
+/* The adjoints of ALL lookups of one backward pass in one launch, with the adjoint of the pooling cascade folded in
+ * (autograd of corr.py:45-91 for every refinement iteration of raft.py:141-144 + avg_pool2d_backward of corr.py:41-43):
+ *   level 0 of dpyramid  <-  [accumulate ? level 0 : 0] + sum_i fold(scatter(grad_outs[i], coords[i]))
+ * where fold adds every pooled level's gradient into level 0 (dV0[y][x] += dV_l[y >> l][x >> l] / 4^l).  A source
+ * pixel's gradient image (all levels) is accumulated in shared memory and written once: no atomics, no zero-filled
+ * gradient pyramid, no fold passes.  grad_outs / coords: HOST arrays of `count` device pointers
+ * (count <= RAFTCORR_LOOKUP_BWD_MAX_BATCH; call again with accumulate = 1 for more).  Level 0 is written in the
+ * row-major gradient layout (raftcorr_pyramid_layout_init(.., interleaved = 0) of the same B, H, W, L) and is OVERWRITTEN
+ * unless accumulate != 0; the other levels of dpyramid are not touched.  round_tf32 != 0 rounds the stored values to
+ * TF32 (set it on the last call when raftcorr_build_bwd_folded runs in a tensor-core mode).  Feed the result to
+ * raftcorr_build_bwd_folded.  raftcorr_lookup_bwd_batched_supported() returns 1 when a pixel's gradient pyramid fits
+ * in shared memory (L <= 4; e.g. up to ~100x200 feature maps), else use raftcorr_lookup_bwd per iteration. */
+#define RAFTCORR_LOOKUP_BWD_MAX_BATCH 16
+int raftcorr_lookup_bwd_batched_supported(const raftcorr_pyramid_layout* layout, int radius);
+int raftcorr_lookup_bwd_batched(const float* const* grad_outs, const float* const* coords, int count, float* dpyramid,
+                                const raftcorr_pyramid_layout* layout, int radius, int accumulate, int round_tf32,
+                                int device, raftcorr_stream_t stream);
+/* raftcorr_build_bwd for a dpyramid whose level 0 already holds the FOLDED gradient (raftcorr_lookup_bwd_batched):
+ * only the two products run; the pooled levels of dpyramid are not read. */
+/* 1 when raftcorr_build_bwd(_folded) runs its products on the tensor cores for this (D, mode), i.e. when the last
+ * raftcorr_lookup_bwd_batched call of a pass should set round_tf32. */
+int raftcorr_build_bwd_wants_tf32(int D, int mode);
+int raftcorr_build_bwd_folded(float* dpyramid, const raftcorr_pyramid_layout* layout, const float* fmap1,
+                              const float* fmap2, int D, float* dfmap1, float* dfmap2, int mode, void* workspace,
+                              size_t workspace_bytes, int device, raftcorr_stream_t stream);
+
 /* alt_cuda_corr.forward (correlation.cpp:23-33, correlation_kernel.cu:260-286), same tensors:
  * fmap1 [B,H1,W1,C], fmap2 [B,H2,W2,C] (NHWC), coords [B,N,H1,W1,2] (x,y interleaved),
  * corr [B,N,(2r+1)^2,H1,W1] is OVERWRITTEN (the reference allocates zeros and accumulates). */

@@ -16,6 +16,7 @@ BUILD_TF32_TC = 1
 BUILD_F16_TC = 2
 BUILD_F16X3_TC = 3
 LOOKUP_PLAN_BYTES = 4096
+LOOKUP_BWD_MAX_BATCH = 16
 
 
 class RaftCorrError(RuntimeError):
@@ -67,6 +68,12 @@ SIGNATURES = {
     "raftcorr_build_bwd_workspace_bytes": (_c_size_t, [_c_int] * 5),
     "raftcorr_build_bwd": (_c_int, [_c_void_p, _LAYP, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int,
                                      _c_void_p, _c_size_t, _c_int, _c_void_p]),
+    "raftcorr_lookup_bwd_batched_supported": (_c_int, [_LAYP, _c_int]),
+    "raftcorr_lookup_bwd_batched": (_c_int, [_c_void_p, _c_void_p, _c_int, _c_void_p, _LAYP, _c_int, _c_int, _c_int, _c_int,
+                                              _c_void_p]),
+    "raftcorr_build_bwd_wants_tf32": (_c_int, [_c_int, _c_int]),
+    "raftcorr_build_bwd_folded": (_c_int, [_c_void_p, _LAYP, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_int,
+                                            _c_void_p, _c_size_t, _c_int, _c_void_p]),
     "raftcorr_alt_forward": (_c_int, [_c_void_p] * 3 + [_c_int] * 8 + [_c_void_p, _c_int, _c_void_p]),
     "raftcorr_alt_backward": (_c_int, [_c_void_p] * 4 + [_c_int] * 8 + [_c_void_p] * 3 + [_c_int, _c_void_p]),
     "raftcorr_alt_level_offset": (_c_i64, [_c_int] * 5),

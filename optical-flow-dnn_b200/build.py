@@ -18,7 +18,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB = os.path.join(PKG, "libraftcorr_b200.so")
-SOURCES = ["api.cu", "prep.cu", "lookup.cu", "lookup_tma.cu", "lookup_conv.cu", "upsample.cu", "build_simt.cu", "build_tc.cu", "build_bwd_tc.cu", "fnet_head.cu", "altcorr.cu",
+SOURCES = ["api.cu", "prep.cu", "lookup.cu", "lookup_tma.cu", "lookup_bwd_batched.cu", "lookup_conv.cu", "upsample.cu", "build_simt.cu", "build_tc.cu", "build_bwd_tc.cu", "fnet_head.cu", "altcorr.cu",
            "altcorr_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

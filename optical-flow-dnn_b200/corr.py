@@ -92,19 +92,12 @@ class _BuildFn(torch.autograd.Function):
     def backward(ctx, dpyr):
         fmap1, fmap2 = ctx.saved_tensors
         block = ctx.block
-        dpyr = block._take_grad_acc(dpyr)
+        dpyr, folded = block._take_grad_acc(dpyr)
         if dpyr is None:
             return None, None, None
-        lay = block._layout
         df1 = torch.empty_like(fmap1)
         df2 = torch.empty_like(fmap2)
-        dev = fmap1.device
-        L = _lib.lib()
-        ws_bytes = L.raftcorr_build_bwd_workspace_bytes(block._B, block._D, block._H, block._W, block._mode)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
-        check(L.raftcorr_build_bwd(_ptr(dpyr), ctypes.byref(lay), _ptr(fmap1), _ptr(fmap2), block._D, _ptr(df1),
-                                   _ptr(df2), block._mode, _ptr(ws), ws_bytes, dev.index, _stream(dev)),
-              "raftcorr_build_bwd")
+        block._build_bwd(dpyr, folded, fmap1, fmap2, df1, df2)
         return df1, df2, None
 
 
@@ -123,7 +116,7 @@ class _HeadBuildFn(torch.autograd.Function):
     def backward(ctx, dpyr):
         x, w2, bias = ctx.saved_tensors
         block = ctx.block
-        dpyr = block._take_grad_acc(dpyr)
+        dpyr, folded = block._take_grad_acc(dpyr)
         if dpyr is None:
             return None, None, None, None
         B, D = block._B, block._D
@@ -135,12 +128,7 @@ class _HeadBuildFn(torch.autograd.Function):
             f = torch.nn.functional.conv2d(xg, wg.reshape(D, -1, 1, 1), bg)
         fd = f.detach()
         df = torch.empty_like(fd)
-        L = _lib.lib()
-        ws_bytes = L.raftcorr_build_bwd_workspace_bytes(B, D, block._H, block._W, block._mode)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
-        check(L.raftcorr_build_bwd(_ptr(dpyr), ctypes.byref(block._layout), _ptr(fd[:B]), _ptr(fd[B:]), D, _ptr(df[:B]),
-                                   _ptr(df[B:]), block._mode, _ptr(ws), ws_bytes, dev.index, _stream(dev)),
-              "raftcorr_build_bwd")
+        block._build_bwd(dpyr, folded, fd[:B], fd[B:], df[:B], df[B:])
         wanted = [t for t in (xg, wg, bg) if t is not None and t.requires_grad]
         grads = list(torch.autograd.grad(f, wanted, df)) if wanted else []
         out = [grads.pop(0) if (t is not None and t.requires_grad) else None for t in (xg, wg, bg)]
@@ -170,7 +158,18 @@ def _lookup_backward(block, gout, coords, pyr, want_pyr, want_dcoords):
     lay = block._layout
     dev = coords.device
     dpyr_ret = None
-    if want_pyr:
+    if want_pyr and not want_dcoords and block._defer_ok:
+        # DEFERRED: the lookups of a backward pass only queue (grad_out, coords); the build backward -- which depends
+        # on every lookup, so it runs last -- scatters all of them in ONE launch that accumulates a source pixel's
+        # gradient image in shared memory, folds the pooled levels on chip and writes level 0 once
+        # (raftcorr_lookup_bwd_batched): no atomics, no zero-filled gradient pyramid, no fold passes.
+        acc, first = block._open_grad_acc(dense=False)
+        if not block._acc_dense:
+            block._queue_lookup_grad(gout.contiguous(), coords)
+            return (acc if first else None), None
+        if first:
+            dpyr_ret = acc
+    elif want_pyr:
         # One persistent gradient pyramid for ALL refinement iterations: every lookup backward
         # scatter-adds into it; it is handed to autograd exactly once (by the first lookup whose
         # backward runs) and the build backward -- which depends on every lookup -- only runs after
@@ -295,6 +294,13 @@ class CorrBlock:
         self._grad_layout = _lib.make_layout(B, H, W, self.num_levels, interleaved=0) if il else self._layout
         self._grad_acc = None
         self._grad_acc_pass = -1
+        self._acc_dense = True      # the accumulator is zero-filled and takes scatter-adds / dense level gradients
+        self._acc_folded = False    # its level 0 holds folded partial sums of already flushed lookups
+        self._pending = []          # (grad_out, coords) of lookups whose adjoint has not been launched yet
+        # batched lookup adjoint: needs a source pixel's gradient pyramid in shared memory (RAFTCORR_LOOKUP_BWD=
+        # immediate keeps the per-iteration red.global.add kernel: A/B switch)
+        self._defer_ok = (os.environ.get("RAFTCORR_LOOKUP_BWD", "batched") != "immediate" and
+                          bool(_lib.lib().raftcorr_lookup_bwd_batched_supported(ctypes.byref(self._layout), self.radius)))
         self._plan = None
         self._plan_ptr = 0
         K = 2 * self.radius + 1
@@ -366,35 +372,86 @@ class CorrBlock:
         return pyr
 
     # -- the single gradient pyramid of a backward pass ---------------------------------------
-    def _open_grad_acc(self):
+    def _open_grad_acc(self, dense=True):
         """The block's gradient pyramid (row-major gradient layout) and whether the caller is the FIRST contributor of
         this backward pass.  The first contributor returns it to autograd as d(pyramid) -- exactly once; everybody else
-        adds into it in place and returns None.  The build backward depends on every contributor, so it runs last."""
+        contributes in place and returns None.  The build backward depends on every contributor, so it runs last.
+        ``dense=False`` (queued lookups only): the buffer is not even zero-filled -- the batched adjoint overwrites level
+        0 and nothing reads the other levels.  A dense contributor (``corr_pyramid`` gradients, a lookup that also wants
+        d/dcoords) turns it into the zero-filled scatter-add accumulator, after flushing what was queued."""
         # a pass that never reached the build backward (exception, interrupt) must not leak its partial sums into the
         # next one: the accumulator is keyed to the autograd engine's graph-task id
         this_pass = torch._C._current_graph_task_id()
         first = self._grad_acc is None or self._grad_acc_pass != this_pass
         if first:
             # sized like the forward buffer (autograd checks the shape); the row-major gradient layout is never larger
-            self._grad_acc = torch.zeros(self._layout.total_floats, dtype=torch.float32, device=self._device)
+            alloc = torch.zeros if dense else torch.empty
+            self._grad_acc = alloc(self._layout.total_floats, dtype=torch.float32, device=self._device)
             self._grad_acc_pass = this_pass
+            self._acc_dense, self._acc_folded, self._pending = dense, False, []
+        elif dense and not self._acc_dense:
+            self._flush_lookup_grads(final=False)
+            if self._acc_folded:  # level 0 holds folded partial sums: keep them, zero the pooled levels
+                if self.num_levels > 1:
+                    self._grad_acc[self._grad_layout.offset[1]:].zero_()
+            else:
+                self._grad_acc.zero_()
+            self._acc_dense = True
         return self._grad_acc, first
 
+    def _queue_lookup_grad(self, gout, coords):
+        if len(self._pending) == _lib.LOOKUP_BWD_MAX_BATCH:  # bounds the memory held by queued grad_out tensors
+            self._flush_lookup_grads(final=False)
+        self._pending.append((gout, coords))
+
+    def _flush_lookup_grads(self, final):
+        """Launch the batched adjoint of the queued lookups into level 0 of the accumulator."""
+        if not self._pending:
+            return
+        n = len(self._pending)
+        L = _lib.lib()
+        gptr = (ctypes.c_void_p * n)(*[g.data_ptr() for g, _ in self._pending])
+        cptr = (ctypes.c_void_p * n)(*[c.data_ptr() for _, c in self._pending])
+        dev = self._device
+        rnd = 1 if (final and L.raftcorr_build_bwd_wants_tf32(self._D, self._mode)) else 0
+        check(L.raftcorr_lookup_bwd_batched(gptr, cptr, n, _ptr(self._grad_acc), ctypes.byref(self._layout), self.radius,
+                                            1 if self._acc_folded else 0, rnd, dev.index, _stream(dev)),
+              "raftcorr_lookup_bwd_batched")
+        self._acc_folded = True
+        self._pending = []  # the launch is stream-ordered: the caching allocator keeps the buffers valid for it
+
     def _take_grad_acc(self, dpyr):
-        """Called by the build backward with whatever autograd delivered for the pyramid buffer."""
+        """Called by the build backward with whatever autograd delivered for the pyramid buffer.  Returns the gradient
+        pyramid and whether its level 0 is already folded (batched lookup adjoint) or the pooled levels still have to be
+        folded into it (scatter-add accumulator)."""
         acc = self._grad_acc
         if acc is not None and self._grad_acc_pass != torch._C._current_graph_task_id():
             acc = None  # left over from an aborted pass
-        self._grad_acc = None  # a second backward pass (retain_graph) starts a fresh accumulator
         if dpyr is None:
-            return None
+            self._grad_acc, self._pending = None, []
+            return None, False
         if acc is None or dpyr.data_ptr() != acc.data_ptr():
+            self._grad_acc, self._pending = None, []
             # every contributor in this module (lookups, corr_pyramid, CorrBlock.corr, lookup_convc1) adds into the
             # accumulator and hands it to autograd once, so anything else is a gradient some foreign op attached to the
-            # PRIVATE flat buffer, whose layout (row pairs interleaved, padded rows) it cannot know
+            # PRIVATE flat buffer, whose layout (row quads interleaved, padded rows) it cannot know
             raise RaftCorrError("CorrBlock backward: unexpected gradient for the internal pyramid buffer; differentiate "
                                 "through corr_fn(coords), corr_fn.corr_pyramid or CorrBlock.corr instead")
-        return dpyr
+        folded = not self._acc_dense
+        if folded:
+            self._flush_lookup_grads(final=True)  # never empty here: a flush always leaves the newest lookup queued
+        self._grad_acc, self._pending = None, []  # a second backward pass (retain_graph) starts a fresh accumulator
+        return dpyr, folded
+
+    def _build_bwd(self, dpyr, folded, fmap1, fmap2, df1, df2):
+        L = _lib.lib()
+        dev = self._device
+        ws_bytes = L.raftcorr_build_bwd_workspace_bytes(self._B, self._D, self._H, self._W, self._mode)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+        fn = L.raftcorr_build_bwd_folded if folded else L.raftcorr_build_bwd
+        check(fn(_ptr(dpyr), ctypes.byref(self._layout), _ptr(fmap1), _ptr(fmap2), self._D, _ptr(df1), _ptr(df2),
+                 self._mode, _ptr(ws), ws_bytes, dev.index, _stream(dev)),
+              "raftcorr_build_bwd_folded" if folded else "raftcorr_build_bwd")
 
     # -- kernels ------------------------------------------------------------------------------
     def _build(self, fmap1, fmap2):

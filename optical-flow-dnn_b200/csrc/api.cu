@@ -336,15 +336,42 @@ int raftcorr_lookup_bwd(const float* grad_out, const float* coords, const float*
     return launch_lookup_bwd(grad_out, coords, dcoords ? &fpv : nullptr, dpv, radius, dcoords, s);
 }
 
+int raftcorr_lookup_bwd_batched_supported(const raftcorr_pyramid_layout* lay, int radius) {
+    if (check_layout(lay)) return 0;
+    raftcorr_pyramid_layout glay;
+    if (raftcorr_pyramid_layout_init(&glay, lay->B, lay->H, lay->W, lay->L, 0)) return 0;
+    PyramidView dpv = make_view(nullptr, glay);
+    return lookup_bwd_batched_supported(dpv, radius) ? 1 : 0;
+}
+
+int raftcorr_lookup_bwd_batched(const float* const* grad_outs, const float* const* coords, int count, float* dpyramid,
+                                const raftcorr_pyramid_layout* lay, int radius, int accumulate, int round_tf32,
+                                int device, raftcorr_stream_t stream) {
+    if (int rc = check_layout(lay)) return rc;
+    if (lay->B == 0) return 0;
+    RC_REQUIRE(grad_outs && coords && dpyramid, "lookup_bwd_batched: NULL argument");
+    DeviceGuard guard(device);
+    RC_REQUIRE(guard.ok, "lookup_bwd_batched: cannot select device %d", device);
+    raftcorr_pyramid_layout glay;  // gradient pyramids are always row-major
+    if (int rc = raftcorr_pyramid_layout_init(&glay, lay->B, lay->H, lay->W, lay->L, 0)) return rc;
+    PyramidView dpv = make_view(dpyramid, glay);
+    return launch_lookup_bwd_batched(grad_outs, coords, count, dpv, radius, accumulate != 0, round_tf32 != 0, device,
+                                     (cudaStream_t)stream);
+}
+
+int raftcorr_build_bwd_wants_tf32(int D, int mode) {
+    return (mode != RAFTCORR_BUILD_FP32_SIMT && build_bwd_tc_supported(D)) ? 1 : 0;
+}
+
 size_t raftcorr_build_bwd_workspace_bytes(int B, int D, int H, int W, int mode) {
     if (mode != RAFTCORR_BUILD_FP32_SIMT && build_bwd_tc_supported(D))
         return build_bwd_tc_workspace_bytes(B, D, H, W);
     return 0;
 }
 
-int raftcorr_build_bwd(float* dpyramid, const raftcorr_pyramid_layout* lay, const float* fmap1, const float* fmap2,
-                       int D, float* dfmap1, float* dfmap2, int mode, void* workspace, size_t workspace_bytes,
-                       int device, raftcorr_stream_t stream) {
+static int build_bwd_impl(float* dpyramid, const raftcorr_pyramid_layout* lay, const float* fmap1, const float* fmap2,
+                          int D, float* dfmap1, float* dfmap2, int mode, void* workspace, size_t workspace_bytes,
+                          int device, raftcorr_stream_t stream, bool folded) {
     if (int rc = check_layout(lay)) return rc;
     if (lay->B == 0) return 0;
     RC_REQUIRE(dpyramid && fmap1 && fmap2 && dfmap1 && dfmap2, "build_bwd: NULL tensor");
@@ -358,14 +385,30 @@ int raftcorr_build_bwd(float* dpyramid, const raftcorr_pyramid_layout* lay, cons
     const int64_t imgs = (int64_t)lay->B * lay->H * lay->W;
     // the fp16 forward mode shares the TF32 backward (gradient GEMMs read the fp32 maps); D > 256: CUDA-core GEMMs
     const bool tc = mode != RAFTCORR_BUILD_FP32_SIMT && build_bwd_tc_supported(D);
-    for (int l = lay->L - 1; l >= 1; --l)  // adjoint of corr.py:41-43, coarse to fine
-        if (int rc = launch_pool_adjoint_level(dpv.lvl[l], dpv.lvl[l - 1], imgs, tc && l == 1, s)) return rc;
+    if (!folded) {
+        for (int l = lay->L - 1; l >= 1; --l)  // adjoint of corr.py:41-43, coarse to fine
+            if (int rc = launch_pool_adjoint_level(dpv.lvl[l], dpv.lvl[l - 1], imgs, tc && l == 1, s)) return rc;
+    }
     if (!tc) return launch_build_bwd_gemms(dpv, fmap1, fmap2, D, dfmap1, dfmap2, s);
-    if (lay->L == 1)
+    if (lay->L == 1 && !folded)
         if (int rc = launch_round_level(dpv.lvl[0], imgs, s)) return rc;
     const size_t need = build_bwd_tc_workspace_bytes(lay->B, D, lay->H, lay->W);
     RC_REQUIRE(workspace && workspace_bytes >= need, "build_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
     return launch_build_bwd_tc(dpv, fmap1, fmap2, D, dfmap1, dfmap2, workspace, device, s);
+}
+
+int raftcorr_build_bwd(float* dpyramid, const raftcorr_pyramid_layout* lay, const float* fmap1, const float* fmap2,
+                       int D, float* dfmap1, float* dfmap2, int mode, void* workspace, size_t workspace_bytes,
+                       int device, raftcorr_stream_t stream) {
+    return build_bwd_impl(dpyramid, lay, fmap1, fmap2, D, dfmap1, dfmap2, mode, workspace, workspace_bytes, device,
+                          stream, false);
+}
+
+int raftcorr_build_bwd_folded(float* dpyramid, const raftcorr_pyramid_layout* lay, const float* fmap1,
+                              const float* fmap2, int D, float* dfmap1, float* dfmap2, int mode, void* workspace,
+                              size_t workspace_bytes, int device, raftcorr_stream_t stream) {
+    return build_bwd_impl(dpyramid, lay, fmap1, fmap2, D, dfmap1, dfmap2, mode, workspace, workspace_bytes, device,
+                          stream, true);
 }
 
 int raftcorr_alt_forward(const float* fmap1, const float* fmap2, const float* coords, int B, int N, int H1, int W1,

@@ -126,6 +126,10 @@ int launch_build_bwd_gemms(const PyramidView& dpv, const float* f1, const float*
 int launch_lookup_fwd(const PyramidView& pv, const float* coords, int radius, float* out, cudaStream_t s);
 int launch_lookup_bwd(const float* grad_out, const float* coords, const PyramidView* pv_fwd,
                       const PyramidView& dpv, int radius, float* dcoords, cudaStream_t s);
+// all lookups of a backward pass at once, pooled levels folded on chip (lookup_bwd_batched.cu); writes level 0 of dpv
+bool lookup_bwd_batched_supported(const PyramidView& dpv, int radius);
+int launch_lookup_bwd_batched(const float* const* gouts, const float* const* coords, int count, const PyramidView& dpv,
+                              int radius, bool accumulate, bool round_out, int device, cudaStream_t s);
 
 // lookup fused with the motion encoder's first 1x1 convolution (lookup_conv.cu)
 size_t conv_weight_bytes(int levels, int radius, int cout);

@@ -18,9 +18,12 @@ a = f1.clone().requires_grad_(); b = f2.clone().requires_grad_()
 def step():
     a.grad = None; b.grad = None
     blk = rc.CorrBlock(a, b, L, r)
-    loss = 0
-    for c, w in zip(coords, ws): loss = loss + (blk(c) * w).sum()
-    loss.backward()
+    if os.environ.get("TRAIN_LOSS_SUM") == "1":  # round-1 harness: 12 x (mul + sum) and their backward in torch
+        loss = 0
+        for c, w in zip(coords, ws): loss = loss + (blk(c) * w).sum()
+        loss.backward()
+    else:  # out.backward(randn) per iteration, accumulated -- only this library's kernels in the step
+        torch.autograd.backward([blk(c) for c in coords], ws)
 s = torch.cuda.Stream()
 with torch.cuda.stream(s):
     for _ in range(3): step()
@@ -36,4 +39,4 @@ for _ in range(20): gr.replay()
 e1.record(); torch.cuda.synchronize()
 assert torch.equal(ref1, a.grad)
 print(f"training step (B={B}, {H}x{W}, {iters} it, fwd+bwd) as a CUDA graph: {e0.elapsed_time(e1)/20:.3f} ms / step, "
-      f"{B/(e0.elapsed_time(e1)/20*1e-3):.0f} pairs/s  layout={os.environ.get('RAFTCORR_PYRAMID_LAYOUT','interleaved')}")
+      f"{B/(e0.elapsed_time(e1)/20*1e-3):.0f} pairs/s  lookup_bwd={os.environ.get('RAFTCORR_LOOKUP_BWD','batched')}")

@@ -13,8 +13,6 @@ ws = [torch.randn((B, L * 81, H, W), device=dev) for _ in range(iters)]
 for rep in range(3):
     a = f1.clone().requires_grad_(); b = f2.clone().requires_grad_()
     blk = rc.CorrBlock(a, b, L, r)
-    loss = 0
-    for c, w in zip(coords, ws): loss = loss + (blk(c) * w).sum()
-    loss.backward()
+    torch.autograd.backward([blk(c) for c in coords], ws)
 torch.cuda.synchronize()
 print("ok")
