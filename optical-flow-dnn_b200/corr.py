@@ -22,6 +22,7 @@ from ._lib import RaftCorrError, check
 
 _MODES = {"fp32": _lib.BUILD_FP32_SIMT, "tf32": _lib.BUILD_TF32_TC, "f16": _lib.BUILD_F16_TC, "f16x3": _lib.BUILD_F16X3_TC}
 _default_mode = os.environ.get("RAFTCORR_BUILD_MODE", "f16")
+_F16_MIN_PIXELS = 4096  # B*H*W below which the DEFAULT mode builds with TF32 operands instead of block-scaled fp16
 _LAYOUTS = {"rowmajor": 0, "pairs": 1, "interleaved": 1, "quads": 2}  # raftcorr_pyramid_layout::interleaved
 
 
@@ -279,6 +280,10 @@ class CorrBlock:
         mode = build_mode or _default_mode
         if mode not in _MODES:
             raise ValueError(f"unknown build mode {mode!r}")
+        if build_mode is None and mode == "f16" and B * H * W < _F16_MIN_PIXELS:
+            # small problems (batch-1 inference, evaluate.py:114-120) are launch-bound: the extra operand-scaling launch of
+            # the f16 build costs more than its MMAs save (config 1: 0.153 vs 0.195 ms per 12-iteration step, eager)
+            mode = "tf32"
         if D > 256 and mode in ("f16", "f16x3"):  # the fp16 operand pass keeps a 64-pixel x D block in registers
             mode = "tf32" if mode == "f16" else "fp32"
         self._mode = _MODES[mode]
