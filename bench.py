@@ -294,6 +294,95 @@ def alt_1080p_side(rc, torch, dev, g, e0, e1, hbm, with_reference):
     return res
 
 
+def lookup_ablation_side(torch, dev, blk, coords, e0, e1, l_ms):
+    """What the memory system charges for the lookup's box list, measured in this run: the production
+    kernel with its evaluation compiled out (RAFTCORR_LOOKUP_EXP=1: same TMA boxes, same waits, nothing evaluated or
+    written) and with its boxes compiled out (=2: evaluation + write-out from stale shared memory).  The switch is read
+    per launch; the outputs of these launches are NOT lookups and are discarded."""
+    res = {}
+    try:
+        for key, exp in (("gather_only_ms", "1"), ("evaluate_and_store_only_ms", "2")):
+            os.environ["RAFTCORR_LOOKUP_EXP"] = exp
+            for c in coords:
+                blk(c)
+            torch.cuda.synchronize(dev)
+            ts = []
+            for _ in range(5):
+                e0.record()
+                for c in coords:
+                    blk(c)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ts.append(e0.elapsed_time(e1) / len(coords))
+            res[key] = sorted(ts)[2]
+    finally:
+        os.environ.pop("RAFTCORR_LOOKUP_EXP", None)
+    res["frac_of_gather_peak"] = res["gather_only_ms"] / l_ms
+    res["what"] = ("timing-only ablations of the same kernel on the same coordinates: frac_of_gather_peak = time of the gather "
+                   "alone / time of the lookup (1.0 = the lookup costs what the memory system charges for its boxes)")
+    return res
+
+
+def train_step_side(rc, torch, dev, g):
+    """BASELINE.json configs[2] on one GPU: B=10 pairs at 368x496 (fmap 46x62, D=256, r=4, L=4), forward + backward
+    through 12 lookups and the volume (`out.backward(randn)` per iteration, accumulated: SURVEY 8d), replayed as ONE CUDA
+    graph -- only this library's kernels in the step.  Beside it the same step with the per-iteration lookup adjoint
+    (red.global.add + fold passes, round 1's path)."""
+    B, D, H, W, L, r, iters = 10, 256, 46, 62, 4, 4, 12
+    f1 = torch.randn((B, D, H, W), generator=g, device=dev)
+    f2 = torch.randn((B, D, H, W), generator=g, device=dev)
+    ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+    grid = torch.stack([xs, ys]).float()[None].expand(B, 2, H, W)
+    flow = torch.nn.functional.avg_pool2d(4.0 * torch.randn((B, 2, H, W), generator=g, device=dev), 5, 1, 2, count_include_pad=False) * 5
+    coords = [(grid + flow).contiguous()]
+    for _ in range(iters - 1):
+        coords.append((coords[-1] + 0.5 * torch.randn((B, 2, H, W), generator=g, device=dev)).contiguous())
+    ws = [torch.randn((B, L * (2 * r + 1) ** 2, H, W), generator=g, device=dev) for _ in range(iters)]
+    a, b = f1.clone().requires_grad_(), f2.clone().requires_grad_()
+
+    def step():
+        a.grad = None
+        b.grad = None
+        blk = rc.CorrBlock(a, b, L, r)
+        torch.autograd.backward([blk(c) for c in coords], ws)
+
+    def graph_ms():
+        side = torch.cuda.Stream(dev)
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, capture_error_mode="thread_local"):  # NCCL's watchdog thread may touch the device
+            step()
+        gr.replay()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            gr.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / 20
+
+    res = {"what": f"config 3: B={B}, fmap {H}x{W}, D={D}, r={r}, L={L}, {iters} iterations, forward + backward as one CUDA graph "
+                   "(autograd.backward(outs, randn weights)); not part of the headline step"}
+    old = os.environ.get("RAFTCORR_LOOKUP_BWD")
+    try:
+        os.environ["RAFTCORR_LOOKUP_BWD"] = "batched"
+        res["ms_per_step"] = graph_ms()
+        res["pairs_per_s"] = B / (res["ms_per_step"] * 1e-3)
+        os.environ["RAFTCORR_LOOKUP_BWD"] = "immediate"
+        res["ms_per_step_per_iteration_adjoint"] = graph_ms()
+    finally:
+        if old is None:
+            os.environ.pop("RAFTCORR_LOOKUP_BWD", None)
+        else:
+            os.environ["RAFTCORR_LOOKUP_BWD"] = old
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -397,6 +486,15 @@ def run_ours(args):
             build_ms.append(kb0.elapsed_time(kb1))
             look_ms.append(kl0.elapsed_time(kl1) / iters)
             del blk
+        l_ms_now = sorted(look_ms)[len(look_ms) // 2]
+        ablation = None
+        if rank == 0 and mode != "fp32" and not args.no_fused and os.environ.get("RAFTCORR_PYRAMID_LAYOUT", "quads") == "quads":
+            try:  # a side line must never take the headline down with it
+                blk = rc.CorrBlock(f1, f2, num_levels=L, radius=r, build_mode=mode)
+                ablation = lookup_ablation_side(torch, dev, blk, coords, kl0, kl1, l_ms_now)
+                del blk
+            except Exception as exc:
+                ablation = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
         # ---- sustained: the same step back to back for >= 2 s (the build runs into the board's power cap; the
         # headline above is a short burst) with clocks and power sampled over exactly this window
         sustained = None
@@ -499,6 +597,15 @@ def run_ours(args):
         alt = None
         if rank == 0 and not args.no_fused:
             alt = alt_1080p_side(rc, torch, dev, g, kl0, kl1, peaks()[0], not args.no_gpu_baseline)
+        # ---- north_star config 3 on this GPU: the training step (forward + backward) as one CUDA graph
+        train = None
+        if rank == 0 and not args.no_fused:
+            torch.cuda.empty_cache()
+            try:
+                with torch.enable_grad():
+                    train = train_step_side(rc, torch, dev, g)
+            except Exception as exc:
+                train = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
         # beside the headline: the same build with the three-term fp16 split (fp32-class accuracy) and, for scale, what
         # the exact-fp32 FFMA build costs
         accurate = None
@@ -697,6 +804,8 @@ def run_ours(args):
             kern["step_tf32_mode"] = tf32_step
         if alt:
             kern["alt_1080p"] = alt
+        if train:
+            kern["train_step_config3"] = train
         if accurate:
             kern["accurate_build_modes"] = accurate
         if fused:
@@ -751,6 +860,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
             "kernels": kern,
         }
+        if ablation:
+            line["roofline"]["lookup_ablation"] = ablation
         if sustained:
             sustained["value"] = world * B * sustained["steps"] / (sus_ms_max * 1e-3)
             sustained["unit"] = UNIT

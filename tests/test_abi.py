@@ -79,6 +79,22 @@ def test_null_pointers_are_rejected_without_a_gpu(lib):
     assert rc != 0
 
 
+def test_batched_lookup_adjoint_host_side_checks(lib):
+    """raftcorr_lookup_bwd_batched: the shared-memory fit query and the argument checks run without a GPU."""
+    L = lib.lib()
+    assert L.raftcorr_lookup_bwd_batched_supported(ctypes.byref(lib.make_layout(8, 55, 128, 4, 2)), 4) == 1   # config 2
+    assert L.raftcorr_lookup_bwd_batched_supported(ctypes.byref(lib.make_layout(10, 46, 62, 4, 2)), 4) == 1   # config 3
+    assert L.raftcorr_lookup_bwd_batched_supported(ctypes.byref(lib.make_layout(1, 135, 240, 4, 2)), 4) == 0  # 1080p: per-iteration path
+    assert L.raftcorr_lookup_bwd_batched_supported(ctypes.byref(lib.make_layout(1, 64, 64, 5, 0)), 4) == 0    # > 4 levels
+    assert L.raftcorr_lookup_bwd_batched_supported(ctypes.byref(lib.make_layout(1, 32, 32, 2, 0)), 5) == 0    # radius
+    lay = lib.make_layout(1, 16, 16, 2)
+    rc = L.raftcorr_lookup_bwd_batched(None, None, 1, None, ctypes.byref(lay), 4, 0, 0, 0, None)
+    assert rc != 0 and b"NULL" in L.raftcorr_last_error()
+    assert L.raftcorr_build_bwd_wants_tf32(256, lib.BUILD_F16_TC) == 1
+    assert L.raftcorr_build_bwd_wants_tf32(256, lib.BUILD_FP32_SIMT) == 0
+    assert L.raftcorr_build_bwd_wants_tf32(320, lib.BUILD_TF32_TC) == 0  # D > 256: CUDA-core products
+
+
 def test_cpu_tensors_fail_loudly(lib):
     import torch
 
