@@ -253,26 +253,15 @@ class _LookupConvFn(torch.autograd.Function):
         return dpyr_ret, None, dw, db, None, None
 
 
-class CorrBlock:
-    """All-pairs correlation volume + pyramid + lookup; drop-in for raft/core/corr.py:13-116.
+class _CorrCore:
+    """Everything of a :class:`CorrBlock` except the pyramid tensor: shapes, layouts, the lookup plan, the gradient
+    accumulator of a backward pass and the kernel calls (which take the pyramid as an argument).  The autograd nodes keep
+    THIS object alive, not the CorrBlock: a node that referenced the block would close a reference cycle
+    (block -> pyramid tensor -> grad_fn -> ctx -> block) and every training step's pyramid (0.4 - 2 GB) would live until
+    Python's cycle collector happened to run -- measured as two cudaMalloc calls per step and 4.5 ms of host time in an
+    eager config-3 step before this split (scripts/eager_profile.py)."""
 
-    ``build_mode`` (extension; RAFT never passes it): ``"f16"`` (default: block-scaled fp16 operands, TF32's 11
-    significant bits, fp32 accumulate) | ``"tf32"`` | ``"fp32"``; default from :func:`set_default_build_mode` /
-    ``RAFTCORR_BUILD_MODE``.
-    """
-
-    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, build_mode=None):
-        _check_fmaps(fmap1, fmap2, "CorrBlock")
-        B, D, H, W = fmap1.shape
-        self._setup(B, D, H, W, fmap1.device, num_levels, radius, build_mode)
-        fmap1 = fmap1.contiguous()
-        fmap2 = fmap2.contiguous()
-        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
-            self._pyr = _BuildFn.apply(fmap1, fmap2, self)
-        else:
-            self._pyr = self._build(fmap1, fmap2)
-
-    def _setup(self, B, D, H, W, device, num_levels, radius, build_mode):
+    def __init__(self, B, D, H, W, device, num_levels, radius, build_mode):
         self.num_levels = int(num_levels)
         self.radius = int(radius)
         if not 1 <= self.radius <= 4:
@@ -313,55 +302,6 @@ class CorrBlock:
         self._coords_shape = (B, 2, H, W)
         self._dev_index = device.index if device.index is not None else torch.cuda.current_device()
         self._lookup_fn = _lib.lib().raftcorr_lookup_fwd_planned
-
-    @classmethod
-    def from_encoder_head(cls, x, weight, bias=None, num_levels=4, radius=4):
-        """``CorrBlock(*split(conv2(x)))`` in one call -- the feature encoder's output head fused into the build.
-
-        Replaces the tail of the reference encoders, ``x = self.conv2(x)`` + ``torch.split`` (raft/core/extractor.py:
-        231,239 BasicEncoder; :341,349 SmallEncoder), the ``.float()`` casts and the ``CorrBlock(fmap1, fmap2)``
-        constructor (raft/core/raft.py:114-119): ``x`` is the head's INPUT ``[2B, Cin, H, W]`` (the output of
-        ``layer3`` for the concatenated frames, frame-1 images first), ``weight``/``bias`` are ``conv2``'s parameters
-        (``[D, Cin, 1, 1]`` or ``[D, Cin]``; ``[D]``).  The 1x1 convolution runs as a tcgen05 TF32 product (fp32
-        accumulate -- the precision cuDNN uses for it by default) that writes the build's pixel-major operand buffers
-        directly; the NCHW feature maps are never materialised.  TF32 / block-scaled fp16 build; when the configured
-        default mode is ``"fp32"`` or ``"f16x3"`` the head runs as ``conv2`` in torch + the ordinary constructor in that
-        mode.  Differentiable w.r.t. ``x``,
-        ``weight`` and ``bias`` (the backward recomputes ``conv2(x)`` and chains the volume's adjoint through it).
-        Valid when the encoder's dropout is inactive (eval mode or ``dropout=0``, extractor.py:234-235).
-        Shapes the fused kernel does not take (``Cin % 4``, ``H*W % 4``, ``D > 256``) go through ``conv2`` + the
-        ordinary constructor -- still this library's kernels, never a CPU path.
-        """
-        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4 and x.shape[0] % 2 == 0):
-            raise RuntimeError("CorrBlock.from_encoder_head: x must be a CUDA tensor [2B, Cin, H, W]")
-        if not (isinstance(weight, torch.Tensor) and weight.is_cuda and weight.dtype == torch.float32):
-            raise RuntimeError("CorrBlock.from_encoder_head: weight must be a float32 CUDA tensor")
-        if weight.dim() == 4 and tuple(weight.shape[2:]) != (1, 1):
-            raise RuntimeError("CorrBlock.from_encoder_head: weight must be a 1x1 convolution kernel")
-        B2, Cin, H, W = x.shape
-        if weight.dim() not in (2, 4) or weight.shape[1] != Cin:
-            raise RuntimeError(f"CorrBlock.from_encoder_head: weight must be [D, {Cin}(, 1, 1)], got {tuple(weight.shape)}")
-        D = int(weight.shape[0])
-        if bias is not None and not (bias.is_cuda and bias.dtype == torch.float32 and tuple(bias.shape) == (D,)):
-            raise RuntimeError("CorrBlock.from_encoder_head: bias must be a float32 CUDA tensor of shape [D]")
-        x = x.float().contiguous()  # raft.py:114-115 casts after the head; the fused product wants fp32 input
-        w2 = weight.reshape(D, Cin)
-        if _default_mode in ("fp32", "f16x3"):
-            # the user asked for fp32-class volume accuracy (set_default_build_mode / RAFTCORR_BUILD_MODE): the fused head
-            # is a TF32 product, so run conv2 in torch and the ordinary constructor in the configured mode
-            f = torch.nn.functional.conv2d(x, w2.reshape(D, Cin, 1, 1), bias)
-            return cls(f[: B2 // 2], f[B2 // 2:], num_levels=num_levels, radius=radius, build_mode=_default_mode)
-        if not _lib.lib().raftcorr_fnet_head_supported(Cin, D, H, W):
-            f = torch.nn.functional.conv2d(x, w2.reshape(D, Cin, 1, 1), bias)
-            return cls(f[: B2 // 2], f[B2 // 2:], num_levels=num_levels, radius=radius, build_mode="tf32")
-        self = cls.__new__(cls)
-        self._setup(B2 // 2, D, H, W, x.device, num_levels, radius, "tf32")
-        needs_grad = x.requires_grad or w2.requires_grad or (bias is not None and bias.requires_grad)
-        if torch.is_grad_enabled() and needs_grad:
-            self._pyr = _HeadBuildFn.apply(x, w2, bias, self)
-        else:
-            self._pyr = self._head_build(x, w2.contiguous(), bias)
-        return self
 
     def _head_build(self, x, w2, bias):
         lay, dev = self._layout, self._device
@@ -480,16 +420,6 @@ class CorrBlock:
             check(rc_, "raftcorr_lookup_fwd_planned")
         return out
 
-    # -- reference surface ----------------------------------------------------------------------
-    def __call__(self, coords):
-        if not (type(coords) is torch.Tensor and coords.shape == self._coords_shape and coords.dtype is torch.float32
-                and coords.device == self._device and coords.is_contiguous()):
-            _check_coords(coords, self._B, self._H, self._W, self._device, "CorrBlock.__call__")  # raises with the reason
-            coords = coords.contiguous()
-        if torch.is_grad_enabled() and (self._pyr.requires_grad or coords.requires_grad):
-            return _LookupFn.apply(self._pyr, coords, self)
-        return self._lookup(self._pyr, coords)
-
     def _ensure_plan(self, pyr):
         if self._plan is None or self._plan_ptr != pyr.data_ptr():
             self._plan = ctypes.create_string_buffer(_lib.LOOKUP_PLAN_BYTES)
@@ -497,6 +427,138 @@ class CorrBlock:
                                                        self._device.index), "raftcorr_lookup_plan_init")
             self._plan_ptr = pyr.data_ptr()
         return self._plan
+
+    def _lookup_convc1(self, pyr, coords, w2, bias, relu):
+        cout, cin = w2.shape
+        dev = self._device
+        L = _lib.lib()
+        if bias is not None:
+            bias = bias.contiguous()
+        # packed (TF32-rounded, k-blocked) copy of the weight, redone only when the parameter changes
+        key = (w2.data_ptr(), w2._version, cout)
+        if getattr(self, "_convw_key", None) != key:
+            nbytes = int(L.raftcorr_convc1_weight_bytes(self.num_levels, self.radius, cout))
+            packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            wc = w2.contiguous()
+            check(L.raftcorr_convc1_pack_weight(_ptr(wc), self.num_levels, self.radius, cout, _ptr(packed), dev.index,
+                                                _stream(dev)), "raftcorr_convc1_pack_weight")
+            self._convw_key, self._convw = key, packed
+        out = torch.empty((self._B, cout, self._H, self._W), dtype=torch.float32, device=dev)
+        check(L.raftcorr_lookup_convc1_fwd(self._ensure_plan(pyr), _ptr(coords), _ptr(self._convw), _ptr(bias), cout,
+                                           1 if relu else 0, _ptr(out), dev.index, _stream(dev)),
+              "raftcorr_lookup_convc1_fwd")
+        return out
+
+    def _levels(self, pyr):
+        lay = self._layout
+        N = self._H * self._W
+        out = []
+        for l in range(self.num_levels):
+            h, w, p = lay.h[l], lay.w[l], lay.pitch[l]
+            if lay.interleaved:
+                rg = 4 if lay.interleaved == 2 else 2  # rows per interleaved group: layout 1 = pairs, 2 = quads (raftcorr.h)
+                hp = (h + rg - 1) // rg
+                flat = pyr[lay.offset[l]: lay.offset[l] + self._B * N * hp * rg * p]
+                lvl = flat.view(self._B * N, hp, p, rg).permute(0, 1, 3, 2).reshape(self._B * N, 1, rg * hp, p)
+                out.append(lvl[:, :, :h, :w])
+            else:
+                flat = pyr[lay.offset[l]: lay.offset[l] + self._B * N * h * p]
+                out.append(flat.view(self._B * N, 1, h, p)[..., :w])
+        return out
+
+
+class CorrBlock:
+    """All-pairs correlation volume + pyramid + lookup; drop-in for raft/core/corr.py:13-116.
+
+    ``build_mode`` (extension; RAFT never passes it): ``"f16"`` (default: block-scaled fp16 operands, TF32's 11
+    significant bits, fp32 accumulate) | ``"tf32"`` | ``"fp32"``; default from :func:`set_default_build_mode` /
+    ``RAFTCORR_BUILD_MODE``.
+    """
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, build_mode=None):
+        _check_fmaps(fmap1, fmap2, "CorrBlock")
+        B, D, H, W = fmap1.shape
+        core = self._adopt(_CorrCore(B, D, H, W, fmap1.device, num_levels, radius, build_mode))
+        fmap1 = fmap1.contiguous()
+        fmap2 = fmap2.contiguous()
+        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+            self._pyr = _BuildFn.apply(fmap1, fmap2, core)
+        else:
+            self._pyr = core._build(fmap1, fmap2)
+
+    def _adopt(self, core):
+        """The block's immutable configuration is mirrored on the facade (``__call__`` runs 12-32 times per volume: no
+        delegation on that path); mutable state (plan, gradient accumulator) lives in the core only."""
+        self._core = core
+        for k in ("num_levels", "radius", "_mode", "_B", "_D", "_H", "_W", "_device", "_layout", "_grad_layout", "_defer_ok",
+                  "_out_shape", "_coords_shape", "_dev_index"):
+            setattr(self, k, getattr(core, k))
+        return core
+
+    def __getattr__(self, name):  # anything else private (plan, accumulator state, kernel wrappers) is the core's
+        core = self.__dict__.get("_core")
+        if core is None or name.startswith("__"):
+            raise AttributeError(name)
+        return getattr(core, name)
+
+    @classmethod
+    def from_encoder_head(cls, x, weight, bias=None, num_levels=4, radius=4):
+        """``CorrBlock(*split(conv2(x)))`` in one call -- the feature encoder's output head fused into the build.
+
+        Replaces the tail of the reference encoders, ``x = self.conv2(x)`` + ``torch.split`` (raft/core/extractor.py:
+        231,239 BasicEncoder; :341,349 SmallEncoder), the ``.float()`` casts and the ``CorrBlock(fmap1, fmap2)``
+        constructor (raft/core/raft.py:114-119): ``x`` is the head's INPUT ``[2B, Cin, H, W]`` (the output of
+        ``layer3`` for the concatenated frames, frame-1 images first), ``weight``/``bias`` are ``conv2``'s parameters
+        (``[D, Cin, 1, 1]`` or ``[D, Cin]``; ``[D]``).  The 1x1 convolution runs as a tcgen05 TF32 product (fp32
+        accumulate -- the precision cuDNN uses for it by default) that writes the build's pixel-major operand buffers
+        directly; the NCHW feature maps are never materialised.  TF32 / block-scaled fp16 build; when the configured
+        default mode is ``"fp32"`` or ``"f16x3"`` the head runs as ``conv2`` in torch + the ordinary constructor in that
+        mode.  Differentiable w.r.t. ``x``,
+        ``weight`` and ``bias`` (the backward recomputes ``conv2(x)`` and chains the volume's adjoint through it).
+        Valid when the encoder's dropout is inactive (eval mode or ``dropout=0``, extractor.py:234-235).
+        Shapes the fused kernel does not take (``Cin % 4``, ``H*W % 4``, ``D > 256``) go through ``conv2`` + the
+        ordinary constructor -- still this library's kernels, never a CPU path.
+        """
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4 and x.shape[0] % 2 == 0):
+            raise RuntimeError("CorrBlock.from_encoder_head: x must be a CUDA tensor [2B, Cin, H, W]")
+        if not (isinstance(weight, torch.Tensor) and weight.is_cuda and weight.dtype == torch.float32):
+            raise RuntimeError("CorrBlock.from_encoder_head: weight must be a float32 CUDA tensor")
+        if weight.dim() == 4 and tuple(weight.shape[2:]) != (1, 1):
+            raise RuntimeError("CorrBlock.from_encoder_head: weight must be a 1x1 convolution kernel")
+        B2, Cin, H, W = x.shape
+        if weight.dim() not in (2, 4) or weight.shape[1] != Cin:
+            raise RuntimeError(f"CorrBlock.from_encoder_head: weight must be [D, {Cin}(, 1, 1)], got {tuple(weight.shape)}")
+        D = int(weight.shape[0])
+        if bias is not None and not (bias.is_cuda and bias.dtype == torch.float32 and tuple(bias.shape) == (D,)):
+            raise RuntimeError("CorrBlock.from_encoder_head: bias must be a float32 CUDA tensor of shape [D]")
+        x = x.float().contiguous()  # raft.py:114-115 casts after the head; the fused product wants fp32 input
+        w2 = weight.reshape(D, Cin)
+        if _default_mode in ("fp32", "f16x3"):
+            # the user asked for fp32-class volume accuracy (set_default_build_mode / RAFTCORR_BUILD_MODE): the fused head
+            # is a TF32 product, so run conv2 in torch and the ordinary constructor in the configured mode
+            f = torch.nn.functional.conv2d(x, w2.reshape(D, Cin, 1, 1), bias)
+            return cls(f[: B2 // 2], f[B2 // 2:], num_levels=num_levels, radius=radius, build_mode=_default_mode)
+        if not _lib.lib().raftcorr_fnet_head_supported(Cin, D, H, W):
+            f = torch.nn.functional.conv2d(x, w2.reshape(D, Cin, 1, 1), bias)
+            return cls(f[: B2 // 2], f[B2 // 2:], num_levels=num_levels, radius=radius, build_mode="tf32")
+        self = cls.__new__(cls)
+        core = self._adopt(_CorrCore(B2 // 2, D, H, W, x.device, num_levels, radius, "tf32"))
+        needs_grad = x.requires_grad or w2.requires_grad or (bias is not None and bias.requires_grad)
+        if torch.is_grad_enabled() and needs_grad:
+            self._pyr = _HeadBuildFn.apply(x, w2, bias, core)
+        else:
+            self._pyr = core._head_build(x, w2.contiguous(), bias)
+        return self
+
+    # -- reference surface ----------------------------------------------------------------------
+    def __call__(self, coords):
+        if not (type(coords) is torch.Tensor and coords.shape == self._coords_shape and coords.dtype is torch.float32
+                and coords.device == self._device and coords.is_contiguous()):
+            _check_coords(coords, self._B, self._H, self._W, self._device, "CorrBlock.__call__")  # raises with the reason
+            coords = coords.contiguous()
+        if torch.is_grad_enabled() and (self._pyr.requires_grad or coords.requires_grad):
+            return _LookupFn.apply(self._pyr, coords, self._core)
+        return self._core._lookup(self._pyr, coords)
 
     def lookup_convc1(self, coords, weight, bias=None, relu=True):
         """``relu(conv1x1(self(coords), weight, bias))`` in one kernel -- the lookup fused with its only consumer,
@@ -530,29 +592,8 @@ class CorrBlock:
         w2 = weight.reshape(cout, cin)
         if torch.is_grad_enabled() and (weight.requires_grad or self._pyr.requires_grad or
                                         (bias is not None and bias.requires_grad)):
-            return _LookupConvFn.apply(self._pyr, coords, w2, bias, self, bool(relu))
-        return self._lookup_convc1(self._pyr.detach(), coords, w2.detach(), bias.detach() if bias is not None else None, relu)
-
-    def _lookup_convc1(self, pyr, coords, w2, bias, relu):
-        cout, cin = w2.shape
-        dev = self._device
-        L = _lib.lib()
-        if bias is not None:
-            bias = bias.contiguous()
-        # packed (TF32-rounded, k-blocked) copy of the weight, redone only when the parameter changes
-        key = (w2.data_ptr(), w2._version, cout)
-        if getattr(self, "_convw_key", None) != key:
-            nbytes = int(L.raftcorr_convc1_weight_bytes(self.num_levels, self.radius, cout))
-            packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-            wc = w2.contiguous()
-            check(L.raftcorr_convc1_pack_weight(_ptr(wc), self.num_levels, self.radius, cout, _ptr(packed), dev.index,
-                                                _stream(dev)), "raftcorr_convc1_pack_weight")
-            self._convw_key, self._convw = key, packed
-        out = torch.empty((self._B, cout, self._H, self._W), dtype=torch.float32, device=dev)
-        check(L.raftcorr_lookup_convc1_fwd(self._ensure_plan(pyr), _ptr(coords), _ptr(self._convw), _ptr(bias), cout,
-                                           1 if relu else 0, _ptr(out), dev.index, _stream(dev)),
-              "raftcorr_lookup_convc1_fwd")
-        return out
+            return _LookupConvFn.apply(self._pyr, coords, w2, bias, self._core, bool(relu))
+        return self._core._lookup_convc1(self._pyr.detach(), coords, w2.detach(), bias.detach() if bias is not None else None, relu)
 
     @property
     def corr_pyramid(self):
@@ -563,25 +604,8 @@ class CorrBlock:
         if torch.is_grad_enabled() and self._pyr.requires_grad:
             # differentiable like the reference's list (corr.py:35-43): the levels' gradients are written into the
             # block's single row-major gradient pyramid, next to the lookups' contributions
-            return list(_PyramidLevelsFn.apply(self._pyr, self))
-        return self._levels(self._pyr.detach())
-
-    def _levels(self, pyr):
-        lay = self._layout
-        N = self._H * self._W
-        out = []
-        for l in range(self.num_levels):
-            h, w, p = lay.h[l], lay.w[l], lay.pitch[l]
-            if lay.interleaved:
-                rg = 4 if lay.interleaved == 2 else 2  # rows per interleaved group: layout 1 = pairs, 2 = quads (raftcorr.h)
-                hp = (h + rg - 1) // rg
-                flat = pyr[lay.offset[l]: lay.offset[l] + self._B * N * hp * rg * p]
-                lvl = flat.view(self._B * N, hp, p, rg).permute(0, 1, 3, 2).reshape(self._B * N, 1, rg * hp, p)
-                out.append(lvl[:, :, :h, :w])
-            else:
-                flat = pyr[lay.offset[l]: lay.offset[l] + self._B * N * h * p]
-                out.append(flat.view(self._B * N, 1, h, p)[..., :w])
-        return out
+            return list(_PyramidLevelsFn.apply(self._pyr, self._core))
+        return self._core._levels(self._pyr.detach())
 
     @staticmethod
     def corr(fmap1, fmap2, build_mode=None):
@@ -589,7 +613,6 @@ class CorrBlock:
         blk = CorrBlock(fmap1, fmap2, num_levels=1, radius=1, build_mode=build_mode)
         B, H, W = blk._B, blk._H, blk._W
         return blk.corr_pyramid[0].reshape(B, H, W, 1, H, W)  # differentiable (corr_pyramid)
-
 
 # ----------------------------------------------------------------------------------------------
 # on-the-fly variant
@@ -599,12 +622,24 @@ def _alt_sizes(B, D, H, W, L):
     return int(total)
 
 
+class _AltState:
+    """What the autograd nodes of an :class:`AlternateCorrBlock` need in their backward: shapes and the gradient
+    accumulators of a pass -- no tensor with a grad_fn, so that keeping it in ``ctx`` closes no reference cycle through the
+    block's NHWC feature tensors (see :class:`_CorrCore`)."""
+
+    def __init__(self, B, D, H, W, num_levels, radius, device):
+        self._B, self._D, self._H, self._W = B, D, H, W
+        self.num_levels, self.radius, self._device = num_levels, radius, device
+        self._grad_acc = (None, None)
+        self._grad_acc_pass = -1
+
+
 class _AltPrepFn(torch.autograd.Function):
     """NCHW fmaps -> (fmap1 NHWC, pooled fmap2 pyramid NHWC)   (raft/core/corr.py:136-140,158-159)."""
 
     @staticmethod
     def forward(ctx, fmap1, fmap2, block):
-        ctx.block = block
+        ctx.block = block._state
         return block._prep(fmap1, fmap2)
 
     @staticmethod
@@ -637,7 +672,7 @@ class _AltHeadPrepFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w2, bias, block):
-        ctx.block = block
+        ctx.block = block._state
         ctx.save_for_backward(x, w2, bias)
         return block._head_prep(x, w2.contiguous(), bias)
 
@@ -660,7 +695,7 @@ class _AltHeadPrepFn(torch.autograd.Function):
 class _AltLookupFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, f1n, f2p, coords, block):
-        ctx.block = block
+        ctx.block = block._state
         ctx.save_for_backward(f1n, f2p, coords)
         return block._lookup(f1n, f2p, coords)
 
@@ -723,8 +758,7 @@ class AlternateCorrBlock:
         self._B, self._D, self._H, self._W = B, D, H, W
         self._device = fmap1.device
         self._fmaps = (fmap1, fmap2)
-        self._grad_acc = (None, None)
-        self._grad_acc_pass = -1
+        self._state = _AltState(B, D, H, W, self.num_levels, self.radius, fmap1.device)
         fmap1 = fmap1.contiguous()
         fmap2 = fmap2.contiguous()
         if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
@@ -763,8 +797,7 @@ class AlternateCorrBlock:
         self._device = x.device
         self._fmaps = None
         self._head = (x, w2, bias)
-        self._grad_acc = (None, None)
-        self._grad_acc_pass = -1
+        self._state = _AltState(B2 // 2, D, H, W, self.num_levels, self.radius, x.device)
         needs_grad = x.requires_grad or w2.requires_grad or (bias is not None and bias.requires_grad)
         if torch.is_grad_enabled() and needs_grad:
             self._f1n, self._f2p = _AltHeadPrepFn.apply(x, w2, bias, self)

@@ -210,24 +210,26 @@ __device__ __forceinline__ void mbar_wait_polls(uint32_t bar, uint32_t parity) {
     } while (!ok);
 }
 
-constexpr int kQPitch = 33;  // out tile row pitch (floats): conflict-free column writes and 4-channel x 8-quad reads
 
 // EXP (measurement only, scripts/gather_roofline.py): 0 = the kernel; 1 = the gather alone (same boxes, same waits, no
 // evaluation, no output: what the memory system charges for this box list); 2 = evaluation + output alone (no boxes).
-template <int R, int LG, int kBufs, int EXP = 0>
-__global__ void __launch_bounds__(kWarps * 32, 2)
+// TPX = source pixels per tile (32: one 128-byte line per channel; 16 with a 2-deep ring fits three CTAs per SM), MINB =
+// resident CTAs per SM the register allocation is sized for
+template <int R, int LG, int kBufs, int EXP = 0, int TPX = kPix, int MINB = 2>
+__global__ void __launch_bounds__(kWarps * 32, MINB)
 lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView g, const float* __restrict__ coords,
                        float* __restrict__ out, const int tiles_per_img, const int total_tiles) {
     using Q = QuadGeo<R>;
     constexpr int SLOT = Q::SLOT;
     constexpr int CH = LG * Q::KK;
-    constexpr int PIX_PER_WARP = kPix / kWarps;
+    constexpr int PIX_PER_WARP = TPX / kWarps;
+    constexpr int QP = TPX + 1;  // out tile row pitch (floats): conflict-free column writes
     constexpr int WARP_PATCH = kBufs * LG * SLOT;  // bytes: this warp's ring of patch buffers
     static_assert(kBufs - 1 <= PIX_PER_WARP, "the issue cursor may run at most one tile ahead");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
-    // [kWarps][kBufs][LG][SLOT] patches | [kWarps][kBufs] mbarriers | out_s [CH][kQPitch]
+    // [kWarps][kBufs][LG][SLOT] patches | [kWarps][kBufs] mbarriers | out_s [CH][QP]
     const uint32_t bar_base = base + kWarps * WARP_PATCH;
     float* out_s = reinterpret_cast<float*>(gen + kWarps * WARP_PATCH + kWarps * kBarBytes);
 
@@ -264,9 +266,9 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
     auto tile_origin = [&](int it, int& b, int& p0) {  // integer division: only where a cursor is set up
         const int t = first + it * stride;
         b = t / tiles_per_img;
-        p0 = (t - b * tiles_per_img) * kPix;
+        p0 = (t - b * tiles_per_img) * TPX;
     };
-    const int img_span = tiles_per_img * kPix, step_span = stride * kPix;
+    const int img_span = tiles_per_img * TPX, step_span = stride * TPX;
     auto tile_advance = [&](int& b, int& p0) {  // (b, p0) of the cursor's next tile without dividing
         p0 += step_span;
         while (p0 >= img_span) { p0 -= img_span; ++b; }
@@ -374,12 +376,12 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
                             hh[4 * gq + 3] = a.w + ax * (c.w - a.w);
                         }
                         // output row j = Y - sy of column `col` is channel col * K + j (x offset major, corr.py:66-78)
-                        float* o = out_s + ((l * Q::KK + col * Q::K - sy) * kQPitch + q);
+                        float* o = out_s + ((l * Q::KK + col * Q::K - sy) * QP + q);
 #pragma unroll
                         for (int Y = 0; Y < Q::NV; ++Y) {
                             const float v = hh[Y] + ay * (hh[Y + 1] - hh[Y]);
                             const bool ok = Y < 3 ? (sy <= Y) : (Y >= Q::K ? (sy > Y - Q::K) : true);
-                            if (ok) o[Y * kQPitch] = v;
+                            if (ok) o[Y * QP] = v;
                         }
                     }
                 }
@@ -390,19 +392,19 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
         __syncthreads();
         if (EXP == 1) {
             // gather alone: nothing was evaluated, nothing leaves
-        } else if ((N & 3) == 0 && p0 + kPix <= N) {
+        } else if ((N & 3) == 0 && p0 + TPX <= N) {
             // 8 lanes x 4 pixels per channel row: 128-byte lines leave as 128-bit stores
             float* dst = out + ((int64_t)b * g.ctot + g.ch0) * N + p0;
-            for (int idx = threadIdx.x; idx < CH * 8; idx += kWarps * 32) {
-                const int ch = idx >> 3, qd = idx & 7;
-                const float* sp = out_s + ch * kQPitch + 4 * qd;
+            for (int idx = threadIdx.x; idx < CH * (TPX / 4); idx += kWarps * 32) {
+                const int ch = idx / (TPX / 4), qd = idx - ch * (TPX / 4);
+                const float* sp = out_s + ch * QP + 4 * qd;
                 *reinterpret_cast<float4*>(dst + (int64_t)ch * N + 4 * qd) = make_float4(sp[0], sp[1], sp[2], sp[3]);
             }
         } else {
             const int p = p0 + lane;
-            if (p < N) {
+            if (lane < TPX && p < N) {
                 float* dst = out + ((int64_t)b * g.ctot + g.ch0) * N + p;
-                for (int ch = warp; ch < CH; ch += kWarps) dst[(int64_t)ch * N] = out_s[ch * kQPitch + lane];
+                for (int ch = warp; ch < CH; ch += kWarps) dst[(int64_t)ch * N] = out_s[ch * QP + lane];
             }
         }
         // tile switch: next tile's coordinates move to lanes 0 .. PIX_PER_WARP-1, the pending ones behind them
@@ -460,34 +462,46 @@ int run_fwd_quad(const LookupMaps& maps, const GroupView& g, const float* coords
     using Q = QuadGeo<R>;
     constexpr int kBufs = 3;
     constexpr int SLOT = Q::SLOT;
-    const size_t smem = 128 + (size_t)kWarps * kBufs * LG * SLOT + kWarps * kBarBytes + sizeof(float) * LG * Q::KK * kQPitch;
-    auto kern = lookup_fwd_quad_kernel<R, LG, kBufs>;
-    static bool attr_done[64] = {};
+    // Tile size.  32 pixels (one 128-byte output line per channel, 3-deep patch ring, two CTAs per SM) or 16 pixels with a
+    // 2-deep ring (63 KB per CTA: three CTAs = 24 warps per SM, twice as many tiles to balance).  Measured per launch,
+    // 16 vs 32 (profiles/README.md, round 2): config 1 B=1 4.5 / 5.4 us, config 2 B=1 7.1 / 8.1, B=4 23.1 / 21.6,
+    // B=8 43.1 / 41.8, config 3 23.3 / 27.3, config 4 91.3 / 103.5 -- small grids and ragged images (N not a multiple of
+    // 32) prefer 16, the large aligned ones 32.  RAFTCORR_LOOKUP_TILE=16|32 overrides.
+    static const int forced_tile = [] {
+        const char* e = std::getenv("RAFTCORR_LOOKUP_TILE");
+        return (e && e[0] == '1' && e[1] == '6') ? 16 : (e && e[0] == '3' && e[1] == '2') ? 32 : 0;
+    }();
     int dev = 0;
     RC_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (dev >= 0 && dev < 64) attr_done[dev] = true;
-    }
-    if (R == 4 && LG == 4) {
-        // RAFTCORR_LOOKUP_EXP=1|2: timing-only ablations of the bench shape (the results are NOT a lookup)
-        const char* e = std::getenv("RAFTCORR_LOOKUP_EXP");
-        if (e && (e[0] == '1' || e[0] == '2')) {
-            kern = e[0] == '1' ? lookup_fwd_quad_kernel<R, LG, kBufs, (R == 4 && LG == 4) ? 1 : 0>
-                               : lookup_fwd_quad_kernel<R, LG, kBufs, (R == 4 && LG == 4) ? 2 : 0>;
-            RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
-    }
     static int sm_count[64] = {};
     int sms = (dev >= 0 && dev < 64) ? sm_count[dev] : 0;
     if (!sms) {
         RC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         if (dev >= 0 && dev < 64) sm_count[dev] = sms;
     }
-    const int tiles_per_img = ceil_div(g.N, kPix);
+    // RAFTCORR_LOOKUP_EXP=1|2: timing-only ablations of the bench shape, 32-pixel tiles (the results are NOT a lookup)
+    const char* exp_env = (R == 4 && LG == 4) ? std::getenv("RAFTCORR_LOOKUP_EXP") : nullptr;
+    const int exp_mode = (exp_env && (exp_env[0] == '1' || exp_env[0] == '2')) ? exp_env[0] - '0' : 0;
+    const int64_t tiles32 = (int64_t)ceil_div(g.N, kPix) * g.B;
+    const bool small_tile = !exp_mode && (forced_tile ? forced_tile == 16 : ((g.N % kPix) != 0 || tiles32 <= 4 * (int64_t)sms));
+    const int bufs = small_tile ? 2 : kBufs, tile = small_tile ? 16 : kPix, per_sm = small_tile ? 3 : 2;
+    const size_t smem = 128 + (size_t)kWarps * bufs * LG * SLOT + kWarps * kBarBytes + sizeof(float) * LG * Q::KK * (tile + 1);
+    auto kern = small_tile ? lookup_fwd_quad_kernel<R, LG, 2, 0, 16, 3> : lookup_fwd_quad_kernel<R, LG, kBufs>;
+    // the shared-memory opt-in is per function AND per device (nn.DataParallel drives several devices from one process)
+    static bool attr_done[2][64] = {};
+    if (dev < 0 || dev >= 64 || !attr_done[small_tile][dev]) {
+        RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev >= 0 && dev < 64) attr_done[small_tile][dev] = true;
+    }
+    if (exp_mode) {
+        kern = exp_mode == 1 ? lookup_fwd_quad_kernel<R, LG, kBufs, (R == 4 && LG == 4) ? 1 : 0>
+                             : lookup_fwd_quad_kernel<R, LG, kBufs, (R == 4 && LG == 4) ? 2 : 0>;
+        RC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const int tiles_per_img = ceil_div(g.N, tile);
     const int64_t total = (int64_t)tiles_per_img * g.B;
     RC_REQUIRE(total < (1LL << 31), "lookup: too many tiles");
-    const int ctas = 2 * sms;  // two resident CTAs per SM (shared memory), each walking total / ctas tiles
+    const int ctas = per_sm * sms;  // resident CTAs per SM (shared memory), each walking total / ctas tiles
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)(total < ctas ? total : ctas));
     cfg.blockDim = dim3(kWarps * 32);

@@ -231,3 +231,44 @@ def test_large_maps_fall_back_to_the_per_iteration_path():
     assert _lib.lib().raftcorr_lookup_bwd_batched_supported(ctypes.byref(lay), 4) == 0
     lay = _lib.make_layout(8, 55, 128, 4, interleaved=2)
     assert _lib.lib().raftcorr_lookup_bwd_batched_supported(ctypes.byref(lay), 4) == 1
+
+
+@pytest.mark.parametrize("cls_name", ["CorrBlock", "AlternateCorrBlock", "CorrBlock.from_encoder_head"])
+def test_training_blocks_are_freed_by_refcount_not_by_the_cycle_collector(cls_name):
+    """The autograd nodes must not reference the block (block -> pyramid -> grad_fn -> ctx -> block would keep every
+    step's pyramid alive until Python's cycle collector runs: two cudaMalloc calls and 4.5 ms of host time per eager
+    config-3 step before the core/facade split, scripts/eager_profile.py)."""
+    import gc
+
+    import optical_flow_dnn_b200 as rc
+
+    B, D, H, W, L, r = 2, 64, 32, 48, 4, 4
+    f1, f2, coords, gouts = _inputs(B, D, H, W, L, r, 3, seed=2)
+    x = torch.randn((2 * B, 32, H, W), device=dev())
+    w = (torch.randn((D, 32), device=dev()) / 6).requires_grad_()
+
+    def step():
+        a, b = f1.clone().requires_grad_(), f2.clone().requires_grad_()
+        if cls_name == "CorrBlock":
+            blk = rc.CorrBlock(a, b, L, r)
+        elif cls_name == "AlternateCorrBlock":
+            blk = rc.AlternateCorrBlock(a, b, L, r)
+        else:
+            blk = rc.CorrBlock.from_encoder_head(x, w, None, num_levels=L, radius=r)
+        torch.autograd.backward([blk(c) for c in coords], gouts)
+        w.grad = None
+
+    step()
+    gc.collect()
+    torch.cuda.synchronize()
+    gc.disable()
+    try:
+        base = torch.cuda.memory_allocated()
+        for _ in range(4):
+            step()
+        torch.cuda.synchronize()
+        grown = torch.cuda.memory_allocated() - base
+    finally:
+        gc.enable()
+    pyramid_bytes = B * H * W * H * W * 4
+    assert grown < pyramid_bytes // 2, f"{grown} bytes still allocated after 4 steps without the cycle collector"
