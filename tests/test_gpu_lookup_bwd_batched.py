@@ -272,3 +272,35 @@ def test_training_blocks_are_freed_by_refcount_not_by_the_cycle_collector(cls_na
         gc.enable()
     pyramid_bytes = B * H * W * H * W * 4
     assert grown < pyramid_bytes // 2, f"{grown} bytes still allocated after 4 steps without the cycle collector"
+
+
+def test_second_backward_pass_over_a_retained_graph_and_an_aborted_pass():
+    """The accumulator and the queue of lookup gradients are keyed to the autograd engine's graph task: a second
+    backward over a retained graph starts fresh, and a pass that died half way leaks nothing into the next one."""
+    import optical_flow_dnn_b200 as rc
+
+    B, D, H, W, L, r, iters = 1, 32, 20, 28, 3, 3, 3
+    f1, f2, coords, gouts = _inputs(B, D, H, W, L, r, iters, seed=8)
+    t1, t2 = f1.clone().requires_grad_(), f2.clone().requires_grad_()
+    class Boom(torch.autograd.Function):  # kills a backward pass
+        @staticmethod
+        def forward(ctx, x):
+            return x.clone()
+
+        @staticmethod
+        def backward(ctx, g):
+            raise RuntimeError("boom")
+
+    blk = rc.CorrBlock(t1, t2, L, r, build_mode="fp32")
+    out0 = blk(coords[0])
+    bad = Boom.apply(out0)  # created BEFORE the other lookups: the engine runs it after their backward has queued gradients
+    outs = [out0, blk(coords[1]), blk(coords[2])]
+    torch.autograd.backward(outs, gouts, retain_graph=True)
+    g1, g2 = t1.grad.clone(), t2.grad.clone()
+    t1.grad = t2.grad = None
+    with pytest.raises(RuntimeError, match="boom"):
+        torch.autograd.backward([outs[2], outs[1], bad], [gouts[2], gouts[1], gouts[0]], retain_graph=True)
+    assert len(blk._core._pending) > 0  # the aborted pass left queued gradients behind ...
+    t1.grad = t2.grad = None
+    torch.autograd.backward(outs, gouts)  # ... which a clean pass afterwards must not see
+    assert _rel(t1.grad, g1) <= 1e-6 and _rel(t2.grad, g2) <= 1e-6
