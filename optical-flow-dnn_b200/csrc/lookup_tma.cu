@@ -467,10 +467,9 @@ int run_fwd_quad(const LookupMaps& maps, const GroupView& g, const float* coords
     // 16 vs 32 (profiles/README.md, round 2): config 1 B=1 4.5 / 5.4 us, config 2 B=1 7.1 / 8.1, B=4 23.1 / 21.6,
     // B=8 43.1 / 41.8, config 3 23.3 / 27.3, config 4 91.3 / 103.5 -- small grids and ragged images (N not a multiple of
     // 32) prefer 16, the large aligned ones 32.  RAFTCORR_LOOKUP_TILE=16|32 overrides.
-    static const int forced_tile = [] {
-        const char* e = std::getenv("RAFTCORR_LOOKUP_TILE");
-        return (e && e[0] == '1' && e[1] == '6') ? 16 : (e && e[0] == '3' && e[1] == '2') ? 32 : 0;
-    }();
+    const char* tile_env = std::getenv("RAFTCORR_LOOKUP_TILE");  // read per launch: the tests drive both variants
+    const int forced_tile = (tile_env && tile_env[0] == '1' && tile_env[1] == '6') ? 16
+                          : (tile_env && tile_env[0] == '3' && tile_env[1] == '2') ? 32 : 0;
     int dev = 0;
     RC_CUDA(cudaGetDevice(&dev));
     static int sm_count[64] = {};

@@ -663,3 +663,36 @@ def test_two_devices_from_one_process(pkg):
     ref = O.lookup(O.corr_pyramid(f1, f2, L, np.float64), coords, r)
     assert rel_err(o1[0][0], ref) <= TOL["tf32"]
     assert float((g0 - g1).abs().max()) <= 1e-5 * float(g0.abs().max())  # atomics: order differs between runs
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 55, 128, 4, 4), (3, 32, 23, 37, 4, 4), (1, 32, 46, 62, 4, 3), (2, 16, 17, 50, 3, 2)])
+def test_lookup_tile_variants_agree_bit_for_bit(pkg, shape):
+    """The quad-layout lookup runs with 32-pixel tiles (headline shape) or 16-pixel tiles (small / ragged problems), picked
+    by shape; RAFTCORR_LOOKUP_TILE forces either.  Same boxes, same arithmetic per window: identical bits, and both
+    within tolerance of the exact-fp32 build's lookup (corr.py:45-91)."""
+    import os
+
+    B, D, H, W, L, r = shape
+    g = torch.Generator(device=dev()).manual_seed(17)
+    f1 = torch.randn((B, D, H, W), generator=g, device=dev())
+    f2 = torch.randn((B, D, H, W), generator=g, device=dev())
+    ys, xs = torch.meshgrid(torch.arange(H, device=dev()), torch.arange(W, device=dev()), indexing="ij")
+    coords = torch.stack([xs, ys]).float()[None].repeat(B, 1, 1, 1) + 5.0 * torch.randn((B, 2, H, W), generator=g, device=dev())
+    coords[0, :, 0, 0] = torch.tensor([-20.0, 3.0], device=dev())   # a window entirely outside
+    coords[-1, :, -1, -1] = torch.tensor([W + 1.5, H - 0.25], device=dev())
+    blk = pkg.CorrBlock(f1, f2, L, r, build_mode="tf32")
+    outs = {}
+    old = os.environ.get("RAFTCORR_LOOKUP_TILE")
+    try:
+        for t in ("16", "32"):
+            os.environ["RAFTCORR_LOOKUP_TILE"] = t
+            outs[t] = blk(coords)
+    finally:
+        if old is None:
+            os.environ.pop("RAFTCORR_LOOKUP_TILE", None)
+        else:
+            os.environ["RAFTCORR_LOOKUP_TILE"] = old
+    assert torch.equal(outs["16"], outs["32"])
+    assert torch.equal(blk(coords), outs["16"])  # whatever the launcher picks by itself
+    ref = pkg.CorrBlock(f1, f2, L, r, build_mode="fp32")(coords)
+    assert rel_err(outs["32"], ref.cpu().numpy()) <= TOL["tf32"]
