@@ -9,6 +9,8 @@
  *   raft/core/extractor.py:231,239 + raft.py:114-119  conv2 head + CorrBlock  -> raftcorr_fnet_head_build_fwd
  *   autograd of corr.py:81       grid_sampler_2d_backward x L x iters        -> raftcorr_lookup_bwd
  *   autograd of corr.py:31-43    avg_pool2d_backward, mul, 2 x matmul bwd    -> raftcorr_build_bwd
+ *   the two rows above for ALL refinement iterations of a backward pass       -> raftcorr_lookup_bwd_batched
+ *                                (raft.py:141-144 x corr.py:81, then :41-43)     + raftcorr_build_bwd_folded
  *   raft/alt_cuda_corr/correlation.cpp:23-33  alt_cuda_corr.forward          -> raftcorr_alt_forward
  *   raft/alt_cuda_corr/correlation.cpp:36-49  alt_cuda_corr.backward         -> raftcorr_alt_backward
  *   raft/core/corr.py:124-140    AlternateCorrBlock.__init__ (feature pyramid)-> raftcorr_alt_pyramid

@@ -367,8 +367,17 @@ lookup_fwd_quad_kernel(const __grid_constant__ LookupMaps maps, const GroupView 
                         const int sy = ((int)yf - R) & 3;
                         const float4* cp = reinterpret_cast<const float4*>(pb) + col;
                         float hh[4 * Q::GMAX];
+                        // the last quad only belongs to windows that span GMAX quads (1 in 4 at r = 4: sy == 3); for the
+                        // others its slot holds stale bytes that no valid output reads.  Skipping it matters: only its first
+                        // row is ever used, so ptxas turns these loads into 4-byte LDS at a 16-byte lane stride -- 4-way bank
+                        // conflicts, 12 % of the kernel's shared-memory wavefronts (ncu source view, round 2)
+                        const bool last_quad = Q::quads(sy) == Q::GMAX;
 #pragma unroll
                         for (int gq = 0; gq < Q::GMAX; ++gq) {
+                            if (gq == Q::GMAX - 1 && !last_quad) {
+                                hh[4 * gq + 0] = hh[4 * gq + 1] = hh[4 * gq + 2] = hh[4 * gq + 3] = 0.f;
+                                continue;
+                            }
                             const float4 a = cp[gq * Q::K1], c = cp[gq * Q::K1 + 1];
                             hh[4 * gq + 0] = a.x + ax * (c.x - a.x);
                             hh[4 * gq + 1] = a.y + ax * (c.y - a.y);
