@@ -42,15 +42,23 @@ constexpr int kSqH = 16, kSqW = 16;    // shape 1: 16 x 16, n = ty * 16 + tx -- 
 constexpr int kTileM = kSrcH * kSrcW;
 constexpr int kTileN = kTgtH * kTgtW;
 constexpr int kBlockK = 32, kUmmaK = 8;
-constexpr int kStages = 3;
+// operand ring: 3 stages (measured at 1080p, r = 3 / r = 4: 4 stages 170 / 197 us, 3 stages 170 / 198, 2 stages 197 / 224 --
+// the ring is not what bounds the kernel)
+__host__ __device__ constexpr int ring_stages(int) { return 3; }
 constexpr int kABytes = kTileM * kBlockK * 4;  // 16 KB
 constexpr int kBBytes = kTileN * kBlockK * 4;  // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
 constexpr int kStagersPerQuarter = 2;         // stager warps per TMEM lane quarter (they split the chunks of a tile)
 constexpr int kStagerWarps = 4 * kStagersPerQuarter, kComputeWarps = 8;
 constexpr int kThreads = 32 * 20;              // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 + 16-19 stagers, 8-15 compute
-// window image of one pixel: (K+1)^2 floats + 3: an odd pitch (conflict-free reads with lane == pixel)
-__host__ __device__ constexpr int win_pitch(int R) { return (2 * R + 2) * (2 * R + 2) + 3; }
+// Window image of one pixel: K+1 rows of K+2 floats, pixel pitch rounded up to 3 (mod 4).  Lane = pixel in both roles; the
+// 32 lanes of a TMEM quarter are 2 source rows (sy) of 16 pixels (sx).  The stagers' store of tile column c goes to window
+// column c - c0 with c0 ~ c00 + sx and to window row wj ~ wj0 - sy, i.e. to bank (pitch - 1) * sx + (16 * pitch - row pitch)
+// * sy + const: pitch - 1 = 2 * odd keeps the 16 sx apart, the odd row pitch moves the second source row to the odd banks
+// (with K+1 floats per row and pitch (K+1)^2 + 3 ncu counted 35 % of the shared-memory wavefronts as conflicts: lane
+// (sx, 1) on lane (sx + 1, 0)).  The compute warps read one pixel per lane at an odd pitch: conflict-free.
+__host__ __device__ constexpr int win_row(int R) { return 2 * R + 3; }
+__host__ __device__ constexpr int win_pitch(int R) { return (((2 * R + 2) * win_row(R)) & ~3) + 3; }
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kInstrDesc = make_idesc_tf32(kTileM, kTileN, false, false);
 
@@ -78,6 +86,7 @@ struct AltTcParams {
     // inv[(1 + l) * B + b] for level l of the fmap2 pyramid; k_elems = operand elements per 128-byte k-block
     int f16, k_elems;
     const float* inv;
+    int stages;  // depth of the operand ring
 };
 
 constexpr uint32_t kInstrDescF16 = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
@@ -90,8 +99,8 @@ __device__ __forceinline__ void tc_mma_f16_alt(uint32_t tmem_d, uint64_t adesc, 
         : "memory");
 }
 
-constexpr int smem_bytes(int R) {
-    return kStages * kStageBytes + win_pitch(R) * kTileM * 4 + 1024 + 256;
+constexpr int smem_bytes(int R, int stages) {
+    return stages * kStageBytes + win_pitch(R) * kTileM * 4 + 1024 + 256;
 }
 
 // ---- pass 1: bounding box of the block's windows, per level ---------------------------------------------
@@ -147,7 +156,7 @@ struct AltWinBars {
 // c0 = first window column relative to the tile, jr = window row of the tile's first row.
 template <int R, bool SQ>
 __device__ __forceinline__ void alt_stage_tile(uint32_t t_acc, int sub, uint32_t win_s, int c0, int jr, bool valid) {
-    constexpr int K = 2 * R + 1, KP = K + 1;
+    constexpr int K = 2 * R + 1, KP = K + 1, WR = win_row(R);
     constexpr int TW = SQ ? kSqW : kTgtW, RPL = 32 / TW;  // rows of the tile per 32-column chunk
     uint32_t cm = 0;  // bit c: tile column c belongs to this lane's window
     if (valid && c0 + K >= 0 && c0 < TW) {
@@ -165,10 +174,10 @@ __device__ __forceinline__ void alt_stage_tile(uint32_t t_acc, int sub, uint32_t
         tmem_ld32(t_acc + q32 * 32, v);
         tmem_ld_wait();
         // element cc of the chunk = tile row q32 * RPL + cc / TW, column cc % TW -> window (wj + cc / TW, cc % TW - c0)
-        const uint32_t base = win_s + (uint32_t)((wj * KP - c0) * 4);
+        const uint32_t base = win_s + (uint32_t)((wj * WR - c0) * 4);
 #pragma unroll
         for (int cc = 0; cc < 32; ++cc) {
-            const int off = SQ ? ((cc >> 4) * KP + (cc & 15)) : cc;
+            const int off = SQ ? ((cc >> 4) * WR + (cc & 15)) : cc;
             if (mask & (1u << cc))
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + 4u * (uint32_t)off), "f"(v[cc]) : "memory");
         }
@@ -221,7 +230,7 @@ __device__ __forceinline__ void alt_tc_stager(const AltTcParams& P, int ew, int 
 template <int R, int J0, int JN, bool CHECK>
 __device__ __forceinline__ void alt_window_rows(const float* wp, float ax, float ay, float osc, int x0, int y0, int lw, int lh,
                                                 float* dst, int64_t plane) {
-    constexpr int K = 2 * R + 1, KP = K + 1;
+    constexpr int K = 2 * R + 1, KP = K + 1, WR = win_row(R);
     const float wt = 1.f - ay;
     float hp[K];
 #pragma unroll
@@ -229,7 +238,7 @@ __device__ __forceinline__ void alt_window_rows(const float* wp, float ax, float
         const int j = J0 + jj;
         float v[KP];
 #pragma unroll
-        for (int c = 0; c < KP; ++c) v[c] = wp[j * KP + c];
+        for (int c = 0; c < KP; ++c) v[c] = wp[j * WR + c];
         if (CHECK) {  // points outside the level are zero (grid_sample zero padding) and were never staged
             const bool row_ok = (unsigned)(y0 + j) < (unsigned)lh;
 #pragma unroll
@@ -289,6 +298,7 @@ template <int R>
 __global__ void __launch_bounds__(kThreads, 1)
 alt_fwd_tc_kernel(const __grid_constant__ AltTcMaps maps, const AltTcParams P) {
     constexpr int K = 2 * R + 1;
+    const int kStages = P.stages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B-swizzle atoms want 1024-byte alignment
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -415,11 +425,16 @@ alt_fwd_tc_kernel(const __grid_constant__ AltTcMaps maps, const AltTcParams P) {
 }
 
 template <int R>
-int run_alt_fwd_tc(const AltTcMaps& maps, const AltTcParams& P, int sms, cudaStream_t s) {
+int run_alt_fwd_tc(const AltTcMaps& maps, AltTcParams P, int sms, cudaStream_t s) {
     alt_bbox_kernel<R><<<P.total_tiles, kTileM, 0, s>>>(P);
     RC_CUDA(cudaGetLastError());
-    constexpr int smem = smem_bytes(R);
-    static_assert(smem <= 232448, "on-the-fly tensor-core kernel does not fit shared memory");
+    static_assert(smem_bytes(R, ring_stages(R)) <= 232448, "on-the-fly tensor-core kernel does not fit shared memory");
+    P.stages = ring_stages(R);
+    if (const char* e = std::getenv("RAFTCORR_ALT_STAGES")) {  // A/B: a shallower ring
+        const int v = std::atoi(e);
+        if (v >= 2 && v < P.stages) P.stages = v;
+    }
+    const int smem = smem_bytes(R, P.stages);
     RC_CUDA(cudaFuncSetAttribute(alt_fwd_tc_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = P.total_tiles < sms ? P.total_tiles : sms;
     alt_fwd_tc_kernel<R><<<grid, kThreads, smem, s>>>(maps, P);

@@ -40,6 +40,9 @@ for w in which:
         run("1080p noise s1  ", 4, 256, 135, 240, 4, 4, 1.0, False)
         run("1080p noise s4  ", 4, 256, 135, 240, 4, 4, 4.0, False)
         run("1080p D128 small", 4, 128, 135, 240, 4, 3, 4.0, True)
+    if w == "c":
+        run("1080p r3 smooth ", 4, 256, 135, 240, 4, 3, 4.0, True)
+        run("1080p r3 zero   ", 4, 256, 135, 240, 4, 3, 0.0, False)
     if w == "b":
         run("2160p smooth s4 ", 4, 256, 270, 480, 4, 4, 4.0, True, reps=3)
         run("2160p noise s4  ", 4, 256, 270, 480, 4, 4, 4.0, False, reps=2)
