@@ -71,7 +71,6 @@ template <int R, int ES>
 __global__ void __launch_bounds__(1024, 1)
 lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __restrict__ dv0) {
     constexpr int K = 2 * R + 1, KK = K * K;
-    constexpr int NT = (KK + 31) / 32;
     constexpr int EF = ES / 4;  // floats per staging chunk
     extern __shared__ float4 smem4[];
     float* smem = reinterpret_cast<float*>(smem4);
@@ -93,18 +92,33 @@ lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __res
     const int cpr = PX / EF;  // chunks per channel row
     const bool cpr1 = cpr == 1;
 
-    // lane -> window elements e = lane + 32 t: row j (y offset), column i (x offset); the gradient channel of (i, j) is
-    // i * K + j (x offset major, corr.py:66-78).  Rows of K consecutive lanes land on consecutive shared-memory words and
-    // the pitch is == K (mod 32), so the 32 lanes of a pass hit 32 different banks.
-    int eoff[NT], gch[NT];
+    // Lane -> (part, lattice column c) of the warp's window: the (K+1) x (K+1) lattice footprint of a window is split
+    // into NP groups of consecutive lattice rows, K+1 lanes per group (30 of 32 lanes at r = 4: rows 0-3 | 4-6 | 7-9).
+    // The bilinear adjoint is separable: a lane loads its column of the K x K gradient window for the rows it needs
+    // (channel of (x offset i, y offset j) = i * K + j, corr.py:66-78), takes the column to its left from the
+    // neighbouring lane (shuffle), forms h[j] = (1 - fx) g[j][c] + fx g[j][c - 1] and then each lattice row
+    // v[j'] = (1 - fy) h[j'] + fy h[j' - 1] -- ONE shared-memory read-modify-write per lattice point of the footprint
+    // (distinct lanes own distinct points: no phases, no __syncwarp), 100 per window instead of 4 x 81.  (The first
+    // version had lane = window element and four read-modify-write phases, one per bilinear tap: ~150 instructions per
+    // window, the kernel was bound by its instruction stream.)
+    constexpr int KP = K + 1;
+    constexpr int NP = (32 / KP) < KP ? (32 / KP) : KP;              // lane groups
+    constexpr int RB = KP / NP, RREM = KP % NP, MAXR = RB + (RREM ? 1 : 0);  // lattice rows per group
+    const int part = lane / KP, c = lane - part * KP;
+    const bool lane_on = part < NP;
+    const int r_cnt = lane_on ? RB + (part < RREM ? 1 : 0) : 0;       // this lane's lattice rows: r_start .. r_start + r_cnt - 1
+    const int r_start = part * RB + (part < RREM ? part : RREM);
+    // gradient rows j = r_start - 1 + k, k = 0 .. r_cnt (the rows above and inside the lane's lattice rows); rows outside
+    // 0 .. K-1 and the lattice column c = K (which has no gradient column of its own) read as zero
+    int goff[MAXR + 1];
+    bool gon[MAXR + 1];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        const int e = lane + 32 * t;
-        const int j = e / K, i = e - j * K;
-        eoff[t] = e < KK ? j * lsp + i : 0;
-        // lanes past the window (K*K is not a multiple of 32) read channel 0 and zero the value
-        gch[t] = (l * KK + (e < KK ? i * K + j : 0)) * PX + q;
+    for (int k = 0; k <= MAXR; ++k) {
+        const int j = r_start - 1 + k;
+        gon[k] = lane_on && k <= r_cnt && j >= 0 && j < K && c < K;
+        goff[k] = (l * KK + (gon[k] ? c * K + j : 0)) * PX + q;
     }
+    const int lat_off = r_start * lsp + c;  // the lane's first lattice point relative to the window origin
     // staging: the tile rows this thread copies (fixed for the whole launch) and their element offsets in the source
     constexpr int kRowsPerThread = 3;  // (K*K*L + 2) rows over PX*L*32 threads, PX >= 1
     int my_row[kRowsPerThread], my_src[kRowsPerThread];
@@ -114,8 +128,6 @@ lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __res
         my_row[r] = row < rows ? row : -1;
         my_src[r] = (row < geo.ctot ? row : row - geo.ctot) * N;  // ctot * N < 2^31 (checked by the launcher)
     }
-    const bool last_on = lane + 32 * (NT - 1) < KK;
-    const int scratch = geo.img_floats - 1 - geo.soff[l];  // the word behind the pixel's images, relative to simg
     const bool guarded = geo.gb[l] != 0;
     const int cx_off = geo.ctot * PX + q, cy_off = cx_off + PX;
 
@@ -164,10 +176,9 @@ lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __res
             asm volatile("cp.async.commit_group;" ::: "memory");
             if (p >= N) continue;
             const float* tile = stage + (it % kStages) * tile_floats;
-            float g[NT];
+            float g[MAXR + 1];
 #pragma unroll
-            for (int t = 0; t < NT; ++t) g[t] = tile[gch[t]];
-            if (NT * 32 > KK && !last_on) g[NT - 1] = 0.f;
+            for (int k = 0; k <= MAXR; ++k) g[k] = tile[goff[k]];
             const float cx = tile[cx_off], cy = tile[cy_off];
             const float x = cx * inv, y = cy * inv;
             const float xf = floorf(x), yf = floorf(y);
@@ -176,60 +187,27 @@ lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __res
             // warp-uniform: windows entirely outside the level contribute nothing (zero padding)
             if (x0 + K < 0 || x0 >= lw || y0 + K < 0 || y0 >= lh) continue;
             const float gx1 = 1.f - fx, gy1 = 1.f - fy;
-            const float w00 = gx1 * gy1, w01 = fx * gy1, w10 = gx1 * fy, w11 = fx * fy;
-            const int o = y0 * lsp + x0;
-            // four phases, one per tap of the bilinear footprint: inside a phase distinct lanes / passes own distinct
-            // elements, so a plain read-modify-write is exact; __syncwarp orders the phases
-            if (guarded || (x0 >= 0 && y0 >= 0 && x0 + K < lw && y0 + K < lh)) {
-                // the whole (K+1) x (K+1) lattice is inside the level (or its guard band): no bounds predicates.  The lanes of the last
-                // pass that lie past the window (K*K is not a multiple of 32) add their zeros to the scratch word.
-                int a[NT];
+            float h[MAXR + 1];
 #pragma unroll
-                for (int t = 0; t < NT; ++t) a[t] = o + eoff[t];
-                if (NT * 32 > KK) a[NT - 1] = last_on ? a[NT - 1] : scratch - lsp - 1;
-#pragma unroll
-                for (int t = 0; t < NT; ++t) simg[a[t]] += w00 * g[t];
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < NT; ++t) simg[a[t] + 1] += w01 * g[t];
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < NT; ++t) simg[a[t] + lsp] += w10 * g[t];
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < NT; ++t) simg[a[t] + lsp + 1] += w11 * g[t];
-                __syncwarp();
-            } else {
-                // taps outside the level go to the scratch word behind the pixel's images instead (never read; several
-                // lanes may collide there, which only matters for a value nobody uses)
-                int a00[NT], a01[NT], a10[NT], a11[NT];
-#pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    // (row, column) of the lane's element, recomputed here: kept in registers they cost the common path
-                    const int e = lane + 32 * t;
-                    const int j = e < KK ? e / K : (1 << 20), i = e < KK ? e - (e / K) * K : 0;  // "row 2^20": off-level
-                    const unsigned yy = (unsigned)(y0 + j), xx = (unsigned)(x0 + i);
-                    const bool r0 = yy < (unsigned)lh, r1 = yy + 1u < (unsigned)lh;
-                    const bool c0 = xx < (unsigned)lw, c1 = xx + 1u < (unsigned)lw;
-                    const int e0 = o + eoff[t];
-                    a00[t] = (r0 && c0) ? e0 : scratch;
-                    a01[t] = (r0 && c1) ? e0 + 1 : scratch;
-                    a10[t] = (r1 && c0) ? e0 + lsp : scratch;
-                    a11[t] = (r1 && c1) ? e0 + lsp + 1 : scratch;
-                }
-#pragma unroll
-                for (int t = 0; t < NT; ++t) simg[a00[t]] += w00 * g[t];
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < NT; ++t) simg[a01[t]] += w01 * g[t];
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < NT; ++t) simg[a10[t]] += w10 * g[t];
-                __syncwarp();
-#pragma unroll
-                for (int t = 0; t < NT; ++t) simg[a11[t]] += w11 * g[t];
-                __syncwarp();
+            for (int k = 0; k <= MAXR; ++k) {
+                const float gc = gon[k] ? g[k] : 0.f;
+                float gl = __shfl_up_sync(0xffffffffu, gc, 1);  // column c - 1 of the same rows (same lane group for c >= 1)
+                gl = c > 0 ? gl : 0.f;
+                h[k] = gx1 * gc + fx * gl;
             }
+            float* wp = simg + (y0 * lsp + x0 + lat_off);
+            if (guarded || (x0 >= 0 && y0 >= 0 && x0 + K < lw && y0 + K < lh)) {
+                // the whole (K+1) x (K+1) lattice is inside the level (or its guard band): no bounds predicates
+#pragma unroll
+                for (int k = 0; k < MAXR; ++k)
+                    if (k < r_cnt) wp[k * lsp] += gy1 * h[k + 1] + fy * h[k];
+            } else {
+                const bool col_ok = (unsigned)(x0 + c) < (unsigned)lw;
+#pragma unroll
+                for (int k = 0; k < MAXR; ++k)
+                    if (k < r_cnt && col_ok && (unsigned)(y0 + r_start + k) < (unsigned)lh) wp[k * lsp] += gy1 * h[k + 1] + fy * h[k];
+            }
+            __syncwarp();  // the next iteration's window overlaps this one: its lanes own different points of it
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
@@ -287,11 +265,13 @@ lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __res
     }
 }
 
-// shared-memory pitch of a level image: >= w and == K (mod m).  m = 32 makes the 32 lanes of a pass hit 32 different
-// banks (see the lane mapping in the kernel); the small guarded levels take m = 16 (at most 2-way conflicts) to save space
-inline int smem_pitch(int w, int K, int m) {
+// shared-memory pitch of a level image: >= w and == s (mod 32), s chosen so that the lane groups of a window (lattice
+// rows r_start(part) + k, K+1 consecutive words each; see the lane mapping in the kernel) land on disjoint banks in
+// every step k: r = 4: rows 0 | 4 | 7 -> 0, 12, 21; r = 3: rows 0 | 2 | 4 | 6 -> 0, 8, 16, 24; r = 2: 0, 12, 18, 24, 30
+inline int smem_pitch(int w, int K) {
+    const int want = K == 9 ? 3 : K == 7 ? 4 : K == 5 ? 6 : 4;
     int sp = w;
-    while (((sp - K) & (m - 1)) != 0) ++sp;
+    while (((sp - want) & 31) != 0) ++sp;
     return sp;
 }
 
@@ -302,14 +282,12 @@ void layout_images(BatchGeo& g, const PyramidView& dpv, int K, bool guards) {
         g.h[l] = dpv.lvl[l].h;
         g.w[l] = dpv.lvl[l].w;
         g.gb[l] = (guards && l >= 2) ? K : 0;
-        g.sp[l] = smem_pitch(g.w[l] + 2 * g.gb[l], K, g.gb[l] ? 16 : 32);
+        g.sp[l] = smem_pitch(g.w[l] + 2 * g.gb[l], K);
         g.soff[l] = off + g.gb[l] * (g.sp[l] + 1);
         g.inv_scale[l] = 1.0f / (float)(1 << l);
         off += (g.h[l] + 2 * g.gb[l]) * g.sp[l];
     }
-    // + a scratch area behind the images: out-of-level taps are redirected to its last word; the predicate-free path
-    // points idle lanes sp + 1 words before that, so all four of their taps stay inside the scratch area
-    off += g.sp[0] + 2;
+    off += 4;  // slack behind the images
     g.img_floats = (off + 3) & ~3;
 }
 
