@@ -837,7 +837,7 @@ class AlternateCorrBlock:
         tensor-core lookup is bound by its operand bytes.  ``RAFTCORR_ALT_F16=0`` keeps TF32 operands (A/B)."""
         if getattr(self, "_f16", None) is None:
             use = (self._mode == _lib.BUILD_TF32_TC and self._D % 64 == 0 and
-                   os.environ.get("RAFTCORR_ALT_F16", "1") != "0" and os.environ.get("RAFTCORR_ALT_TC", "") != "resident")
+                   os.environ.get("RAFTCORR_ALT_F16", "1") != "0")
             if not use:
                 self._f16 = False
             else:

@@ -28,7 +28,7 @@ def run(tag, B, D, H, W, L, r, sigma, smooth, reps=5):
     nblk = bb.shape[0]
     K = 2 * r + 1
     useful = B * H * W * L * (K + 1) ** 2
-    tile_n = 128 if (D <= 256 and os.environ.get("RAFTCORR_ALT_TC", "")[:1] == "r") else 256  # resident-A kernel: 8x16 tiles
+    tile_n = 256
     done = sum(tiles) * 128 * tile_n
     print(f"{tag}: {ms*1e3:8.1f} us  blocks={nblk} lattice tiles/level={tiles} (16x16: {square}) (x{tile_n} pts) per block={sum(tiles)/nblk:.1f} "
           f"redundancy={done/useful:.2f}x  MMA TFLOP/s={done*2*D/ms/1e9:.0f}  us/tile={ms*1e3*148/max(sum(tiles),1):.2f}")
