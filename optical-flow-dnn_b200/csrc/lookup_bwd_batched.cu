@@ -67,17 +67,21 @@ __device__ __forceinline__ float round_tf32_b(float x) {
     return __uint_as_float(r);
 }
 
-template <int R, int ES>
+// PXT: pixels per CTA step as a compile-time constant (4: the config-3 / RAFT-small shapes), or 0 = geo.PX.  With PX known
+// the offsets inside a staged tile are immediates: the ncu source view of the runtime-PX kernel charged 24 instructions
+// per window to rematerialised offset arithmetic.
+template <int R, int ES, int PXT = 0>
 __global__ void __launch_bounds__(1024, 1)
 lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __restrict__ dv0) {
     constexpr int K = 2 * R + 1, KK = K * K;
     constexpr int EF = ES / 4;  // floats per staging chunk
+    static_assert(PXT == 0 || (PXT * 4) % ES == 0, "a row of PX pixels is a whole number of staging chunks");
     extern __shared__ float4 smem4[];
     float* smem = reinterpret_cast<float*>(smem4);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
-    const int L = geo.L, N = geo.N, PX = geo.PX;
+    const int L = geo.L, N = geo.N, PX = PXT ? PXT : geo.PX;
     const int q = warp / L, l = warp - q * L;  // this warp's source pixel of the CTA step and its pyramid level
     const int lh = geo.h[l], lw = geo.w[l], lsp = geo.sp[l];
     const float inv = geo.inv_scale[l];
@@ -110,14 +114,15 @@ lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __res
     const int r_start = part * RB + (part < RREM ? part : RREM);
     // gradient rows j = r_start - 1 + k, k = 0 .. r_cnt (the rows above and inside the lane's lattice rows); rows outside
     // 0 .. K-1 and the lattice column c = K (which has no gradient column of its own) read as zero
-    int goff[MAXR + 1];
     bool gon[MAXR + 1];
 #pragma unroll
     for (int k = 0; k <= MAXR; ++k) {
         const int j = r_start - 1 + k;
         gon[k] = lane_on && k <= r_cnt && j >= 0 && j < K && c < K;
-        goff[k] = (l * KK + (gon[k] ? c * K + j : 0)) * PX + q;
     }
+    // element offset inside a staged tile of gradient row r_start - 1 of this lane's column (lanes without a column of
+    // their own read column 0; rows outside 0 .. K-1 are the neighbouring channels' values: loaded, then discarded)
+    const int gbase = (l * KK + ((lane_on && c < K) ? c * K : 0) + r_start - 1) * PX + q;
     const int lat_off = r_start * lsp + c;  // the lane's first lattice point relative to the window origin
     // staging: the tile rows this thread copies (fixed for the whole launch) and their element offsets in the source
     constexpr int kRowsPerThread = 3;  // (K*K*L + 2) rows over PX*L*32 threads, PX >= 1
@@ -129,7 +134,7 @@ lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __res
         my_src[r] = (row < geo.ctot ? row : row - geo.ctot) * N;  // ctot * N < 2^31 (checked by the launcher)
     }
     const bool guarded = geo.gb[l] != 0;
-    const int cx_off = geo.ctot * PX + q, cy_off = cx_off + PX;
+    const int cx_off = geo.ctot * PX + q;
 
     // zero this CTA's images once; every step leaves them zeroed again
     for (int i = threadIdx.x; i < geo.PX * geo.img_floats / 4; i += blockDim.x) smem4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -144,17 +149,20 @@ lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __res
         // instructions per window (a branch around every predicated read-modify-write), 120 per written row, a
         // division per staged chunk.  Hence: a predicate-free path for windows inside the level, a branch-free one
         // (out-of-level taps redirected to a scratch word) otherwise, division-free loops everywhere.
-        const int64_t g_off = (int64_t)b * geo.ctot * N + p0, c_off = (int64_t)b * 2 * N + p0;
-        auto issue = [&](int it) {  // all threads: stage iteration `it` of this group
-            const uint32_t tile_u32 = stage_u32 + (uint32_t)((it % kStages) * tile_floats) * 4u;
-            const float* gsrc = ptrs.gout[it] + g_off;
-            const float* csrc = ptrs.coords[it] + c_off;
+        // source of a staged row: (grad_out or coords of the iteration) + element offset of (batch item, channel row, first
+        // pixel) -- 32-bit (B * ctot * N < 2^31, checked by the launcher) and fixed per (thread, group)
+        const int g_row0 = b * (geo.ctot * N) + p0, c_row0 = b * (2 * N) + p0;
+        auto issue = [&](int it, int st) {  // all threads: stage iteration `it` of this group into ring slot `st`
+            const uint32_t tile_u32 = stage_u32 + (uint32_t)(st * tile_floats) * 4u;
+            const float* gsrc = ptrs.gout[it];
+            const float* csrc = ptrs.coords[it];
 #pragma unroll
             for (int r = 0; r < kRowsPerThread; ++r) {
                 if (my_row[r] < 0) break;
-                const float* src = (my_row[r] < geo.ctot ? gsrc : csrc) + my_src[r];
+                const bool is_g = my_row[r] < geo.ctot;
+                const float* src = (is_g ? gsrc : csrc) + ((is_g ? g_row0 : c_row0) + my_src[r]);
                 const uint32_t dst = tile_u32 + (uint32_t)(my_row[r] * PX) * 4u;
-                if (ES == 16 && cpr1) {
+                if (ES == 16 && (PXT == 4 || cpr1)) {
                     cp_async_chunk<ES>(dst, src, true);  // PX == 4 and p0 < N: the one chunk of the row is inside
                 } else {
                     for (int k = 0; k < cpr; ++k) {
@@ -166,20 +174,24 @@ lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __res
         };
 #pragma unroll
         for (int i = 0; i < kStages - 1; ++i) {
-            if (i < geo.count) issue(i);
+            if (i < geo.count) issue(i, i);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
+        int cur_stage = kStages - 1, nxt_stage = kStages - 2;  // ring slots of iteration it / it + kStages - 1 (advanced at the loop top)
         for (int it = 0; it < geo.count; ++it) {
+            cur_stage = cur_stage == kStages - 1 ? 0 : cur_stage + 1;
+            nxt_stage = nxt_stage == kStages - 1 ? 0 : nxt_stage + 1;
             asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 2) : "memory");
             __syncthreads();  // iteration `it` is staged for everybody; everybody is done with the tile of it - 1
-            if (it + kStages - 1 < geo.count) issue(it + kStages - 1);
+            if (it + kStages - 1 < geo.count) issue(it + kStages - 1, nxt_stage);
             asm volatile("cp.async.commit_group;" ::: "memory");
             if (p >= N) continue;
-            const float* tile = stage + (it % kStages) * tile_floats;
+            const float* tile = stage + cur_stage * tile_floats;
+            const float* tg = tile + gbase;
             float g[MAXR + 1];
 #pragma unroll
-            for (int k = 0; k <= MAXR; ++k) g[k] = tile[goff[k]];
-            const float cx = tile[cx_off], cy = tile[cy_off];
+            for (int k = 0; k <= MAXR; ++k) g[k] = tg[k * PX];
+            const float cx = tile[cx_off], cy = tile[cx_off + PX];
             const float x = cx * inv, y = cy * inv;
             const float xf = floorf(x), yf = floorf(y);
             const float fx = x - xf, fy = y - yf;
@@ -363,6 +375,7 @@ int make_geo(const PyramidView& dpv, int radius, BatchGeo* out, size_t* smem_byt
 
 bool lookup_bwd_batched_supported(const PyramidView& dpv, int radius) {
     if (radius < 1 || radius > 4) return false;
+    if ((int64_t)dpv.B * dpv.L * 81 * dpv.N >= (1LL << 31)) return false;  // 32-bit element offsets into grad_out
     BatchGeo g;
     size_t smem;
     int threads, per_sm;
@@ -372,7 +385,7 @@ bool lookup_bwd_batched_supported(const PyramidView& dpv, int radius) {
 int launch_lookup_bwd_batched(const float* const* gouts, const float* const* coords, int count, const PyramidView& dpv,
                               int radius, bool accumulate, bool round_out, int device, cudaStream_t s) {
     RC_REQUIRE(count >= 1 && count <= kMaxBatch, "lookup_bwd_batched: count %d outside 1..%d", count, kMaxBatch);
-    RC_REQUIRE((int64_t)dpv.L * 81 * dpv.N < (1LL << 31), "lookup_bwd_batched: feature map too large");
+    RC_REQUIRE((int64_t)dpv.B * dpv.L * 81 * dpv.N < (1LL << 31), "lookup_bwd_batched: grad_out tensors of 2^31 elements or more");
     BatchGeo g;
     size_t smem;
     int threads, per_sm;
@@ -399,6 +412,7 @@ int launch_lookup_bwd_batched(const float* const* gouts, const float* const* coo
     };
     auto by_chunk = [&](auto r_tag) -> int {
         constexpr int R = decltype(r_tag)::value;
+        if (g.es == 16 && g.PX == 4) return launch(lookup_bwd_batched_kernel<R, 16, 4>);
         if (g.es == 16) return launch(lookup_bwd_batched_kernel<R, 16>);
         if (g.es == 8) return launch(lookup_bwd_batched_kernel<R, 8>);
         return launch(lookup_bwd_batched_kernel<R, 4>);
