@@ -126,13 +126,16 @@ lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __res
     const int lat_off = r_start * lsp + c;  // the lane's first lattice point relative to the window origin
     // staging: the tile rows this thread copies (fixed for the whole launch) and their element offsets in the source
     constexpr int kRowsPerThread = 3;  // (K*K*L + 2) rows over PX*L*32 threads, PX >= 1
-    int my_row[kRowsPerThread], my_src[kRowsPerThread];
+    int my_row[kRowsPerThread], my_src[kRowsPerThread], my_sel[kRowsPerThread];
 #pragma unroll
     for (int r = 0; r < kRowsPerThread; ++r) {
         const int row = threadIdx.x + r * blockDim.x;
         my_row[r] = row < rows ? row : -1;
         my_src[r] = (row < geo.ctot ? row : row - geo.ctot) * N;  // ctot * N < 2^31 (checked by the launcher)
+        my_sel[r] = row < geo.ctot ? 0 : kMaxBatch;               // BatchPtrs = gout[kMaxBatch] | coords[kMaxBatch]
     }
+    static_assert(sizeof(BatchPtrs) == 2 * kMaxBatch * sizeof(const float*), "BatchPtrs is indexed as one pointer array");
+    const float* const* psrc = reinterpret_cast<const float* const*>(&ptrs);
     const bool guarded = geo.gb[l] != 0;
     const int cx_off = geo.ctot * PX + q;
 
@@ -152,15 +155,15 @@ lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __res
         // source of a staged row: (grad_out or coords of the iteration) + element offset of (batch item, channel row, first
         // pixel) -- 32-bit (B * ctot * N < 2^31, checked by the launcher) and fixed per (thread, group)
         const int g_row0 = b * (geo.ctot * N) + p0, c_row0 = b * (2 * N) + p0;
+        int my_off[kRowsPerThread];
+#pragma unroll
+        for (int r = 0; r < kRowsPerThread; ++r) my_off[r] = (my_sel[r] ? c_row0 : g_row0) + my_src[r];
         auto issue = [&](int it, int st) {  // all threads: stage iteration `it` of this group into ring slot `st`
             const uint32_t tile_u32 = stage_u32 + (uint32_t)(st * tile_floats) * 4u;
-            const float* gsrc = ptrs.gout[it];
-            const float* csrc = ptrs.coords[it];
 #pragma unroll
             for (int r = 0; r < kRowsPerThread; ++r) {
                 if (my_row[r] < 0) break;
-                const bool is_g = my_row[r] < geo.ctot;
-                const float* src = (is_g ? gsrc : csrc) + ((is_g ? g_row0 : c_row0) + my_src[r]);
+                const float* src = psrc[it + my_sel[r]] + my_off[r];
                 const uint32_t dst = tile_u32 + (uint32_t)(my_row[r] * PX) * 4u;
                 if (ES == 16 && (PXT == 4 || cpr1)) {
                     cp_async_chunk<ES>(dst, src, true);  // PX == 4 and p0 < N: the one chunk of the row is inside
@@ -259,6 +262,29 @@ lookup_bwd_batched_kernel(const BatchPtrs ptrs, const BatchGeo geo, float* __res
                     const float* r0 = b0 + warp * sp0;
                     float* dd = d + warp * P0;
                     const int s0step = nwarps * sp0, dstep = nwarps * P0;
+                    if ((nwarps & 1) == 0) {
+                        // an even warp count keeps a warp on rows of one parity: the level-1 parent row advances by
+                        // nwarps / 2 per step (a running pointer instead of shift + select + multiply), and only the rows
+                        // below 2 * h1 have a parent at all (ncu source view of the generic loop: 24 instructions per
+                        // 32 floats written, 15 % of the kernel)
+                        const int hpar = min(h0, 2 * h1);
+                        const float* p1 = b1 + (warp >> 1) * sp1;
+                        const int s1step = (nwarps >> 1) * sp1;
+                        int yy = warp;
+                        for (; yy < hpar; yy += nwarps, r0 += s0step, p1 += s1step, dd += dstep) {
+                            float v = fmaf(kx, *p1, in0 ? *r0 : 0.f);
+                            if (acc) v += *dd;
+                            if (rnd) v = round_tf32_b(v);
+                            *dd = v;
+                        }
+                        for (; yy < h0; yy += nwarps, r0 += s0step, dd += dstep) {  // h0 odd: the last row has no parent
+                            float v = in0 ? *r0 : 0.f;
+                            if (acc) v += *dd;
+                            if (rnd) v = round_tf32_b(v);
+                            *dd = v;
+                        }
+                        continue;
+                    }
                     for (int yy = warp; yy < h0; yy += nwarps, r0 += s0step, dd += dstep) {
                         const int y1 = yy >> 1;
                         const bool par = y1 < h1;  // rows without a parent read row 0 with weight 0
