@@ -39,6 +39,10 @@ namespace {
 constexpr int kSrcH = 8, kSrcW = 16;   // source block: 128 pixels = TMEM lanes, m = sy * 16 + sx
 constexpr int kTgtH = 8, kTgtW = 32;   // lattice tile: 256 points = UMMA N, n = ty * 32 + tx  (shape 0: 8 rows x 32 cols)
 constexpr int kSqH = 16, kSqW = 16;    // shape 1: 16 x 16, n = ty * 16 + tx -- covers the small boxes of the coarse levels in one tile
+constexpr int kShortH = 12;            // shape 2: 16 wide x 12 high = UMMA N 192 -- boxes of at most 12 rows (levels 2-3 at r = 4:
+                                       // 14 x 12 and 12 x 11 points) pay three quarters of the fmap2 bytes and MMA cycles
+__host__ __device__ constexpr int shape_w(int s) { return s ? kSqW : kTgtW; }
+__host__ __device__ constexpr int shape_h(int s) { return s == 0 ? kTgtH : s == 1 ? kSqH : kShortH; }
 constexpr int kTileM = kSrcH * kSrcW;
 constexpr int kTileN = kTgtH * kTgtW;
 constexpr int kBlockK = 32, kUmmaK = 8;
@@ -60,7 +64,6 @@ constexpr int kThreads = 32 * 20;              // warp 0 TMA, 1 MMA, 2 TMEM allo
 __host__ __device__ constexpr int win_row(int R) { return 2 * R + 3; }
 __host__ __device__ constexpr int win_pitch(int R) { return (((2 * R + 2) * win_row(R)) & ~3) + 3; }
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kInstrDesc = make_idesc_tf32(kTileM, kTileN, false, false);
 
 __device__ __forceinline__ float clamp_coord(float v) { return fminf(fmaxf(v, -1048576.f), 1048576.f); }
 
@@ -68,6 +71,7 @@ struct AltTcMaps {
     CUtensorMap a;
     CUtensorMap b[4];    // 8 x 32 lattice tiles
     CUtensorMap bsq[4];  // 16 x 16 lattice tiles
+    CUtensorMap bs12[4]; // 16 x 12 lattice tiles
 };
 
 struct AltTcParams {
@@ -81,6 +85,7 @@ struct AltTcParams {
     float inv_scale[4];
     float scale;
     int allow_square;  // pick 16 x 16 lattice tiles where they cover a box with fewer tiles than 8 x 32
+    int allow_short;   // pick 16 x 12 lattice tiles (N = 192) where they cover a box with fewer lattice points
     int bb_w, bb_h;    // primary lattice tile shape the bounding boxes are cut into
     // fp16 operands with one power-of-two scale per image and tensor (launch_alt_f16_operands): inv[b] for fmap1,
     // inv[(1 + l) * B + b] for level l of the fmap2 pyramid; k_elems = operand elements per 128-byte k-block
@@ -89,13 +94,13 @@ struct AltTcParams {
     int stages;  // depth of the operand ring
 };
 
-constexpr uint32_t kInstrDescF16 = (1u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-__device__ __forceinline__ void tc_mma_f16_alt(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__host__ __device__ constexpr uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24); }
+__device__ __forceinline__ void tc_mma_f16_alt(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kInstrDescF16), "r"(accumulate)
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 
@@ -140,6 +145,8 @@ __global__ void __launch_bounds__(kTileM) alt_bbox_kernel(const AltTcParams P) {
                 const int nx1 = (x1 - x0) / kSqW + 1, ny1 = (y1 - y0) / kSqH + 1;    // 16 x 16 tiling
                 bb = (P.allow_square && nx1 * ny1 < nx0 * ny0) ? make_int4(x0, y0, nx1 | (1 << 16), ny1)
                                                                : make_int4(x0, y0, nx0, ny0);
+                const int ny2 = (y1 - y0) / kShortH + 1;                             // 16 x 12 tiling: 192 points per tile
+                if (P.allow_short && nx1 * ny2 * 3 < (bb.z & 0xffff) * bb.w * 4) bb = make_int4(x0, y0, nx1 | (2 << 16), ny2);
             }
             P.bbox[(int64_t)t * P.L + l] = bb;
         }
@@ -155,7 +162,7 @@ struct AltWinBars {
 // One lattice tile: copy the window points of this lane's pixel out of the accumulator chunks q32 = sub, sub + S, ...
 // c0 = first window column relative to the tile, jr = window row of the tile's first row.
 template <int R, bool SQ>
-__device__ __forceinline__ void alt_stage_tile(uint32_t t_acc, int sub, uint32_t win_s, int c0, int jr, bool valid) {
+__device__ __forceinline__ void alt_stage_tile(uint32_t t_acc, int sub, int nchunks, uint32_t win_s, int c0, int jr, bool valid) {
     constexpr int K = 2 * R + 1, KP = K + 1, WR = win_row(R);
     constexpr int TW = SQ ? kSqW : kTgtW, RPL = 32 / TW;  // rows of the tile per 32-column chunk
     uint32_t cm = 0;  // bit c: tile column c belongs to this lane's window
@@ -165,7 +172,7 @@ __device__ __forceinline__ void alt_stage_tile(uint32_t t_acc, int sub, uint32_t
         if (SQ) cm &= 0xffffu;
     }
 #pragma unroll 1
-    for (int q32 = sub; q32 < kTileN / 32; q32 += kStagersPerQuarter) {
+    for (int q32 = sub; q32 < nchunks; q32 += kStagersPerQuarter) {  // a 16 x 12 tile ends after 6 chunks (columns 192.. are stale)
         const int wj = jr + q32 * RPL;  // window row of the chunk's first tile row
         uint32_t mask = (unsigned)wj <= (unsigned)K ? cm : 0u;
         if (SQ) mask |= (unsigned)(wj + 1) <= (unsigned)K ? (cm << 16) : 0u;
@@ -203,8 +210,9 @@ __device__ __forceinline__ void alt_tc_stager(const AltTcParams& P, int ew, int 
         for (int l = 0; l < P.L; ++l, ++n) {
             const int4 bb = P.bbox[(int64_t)t * P.L + l];
             const int x0 = __float2int_rd(cx * P.inv_scale[l]) - R, y0 = __float2int_rd(cy * P.inv_scale[l]) - R;
-            const bool sq = bb.z >> 16;
-            const int ntx = bb.z & 0xffff, tw = sq ? kSqW : kTgtW, th = sq ? kSqH : kTgtH;
+            const int shape = bb.z >> 16;
+            const bool sq = shape != 0;
+            const int ntx = bb.z & 0xffff, tw = shape_w(shape), th = shape_h(shape), nchunks = th * tw / 32;
             mbar_wait(wb.empty, (n & 1u) ^ 1u);  // the compute warps have read the previous level's window images
             for (int c = 0; c < bb.w; ++c)
                 for (int a = 0; a < ntx; ++a, ++it) {
@@ -214,9 +222,9 @@ __device__ __forceinline__ void alt_tc_stager(const AltTcParams& P, int ew, int 
                     const uint32_t t_acc = tmem_base + lane_addr + as * kTileN;
                     const int c0 = x0 - (bb.x + a * tw), jr = (bb.y + c * th) - y0;
                     if (sq)
-                        alt_stage_tile<R, true>(t_acc, sub, win_s, c0, jr, valid);
+                        alt_stage_tile<R, true>(t_acc, sub, nchunks, win_s, c0, jr, valid);
                     else
-                        alt_stage_tile<R, false>(t_acc, sub, win_s, c0, jr, valid);
+                        alt_stage_tile<R, false>(t_acc, sub, nchunks, win_s, c0, jr, valid);
                     tc_fence_before();
                     mbar_arrive(tempty_bar + 8 * as);  // every tcgen05.ld of this thread on the stage has completed
                 }
@@ -316,6 +324,7 @@ alt_fwd_tc_kernel(const __grid_constant__ AltTcMaps maps, const AltTcParams P) {
         for (int l = 0; l < P.L; ++l) {
             prefetch_tensormap(&maps.b[l]);
             prefetch_tensormap(&maps.bsq[l]);
+            prefetch_tensormap(&maps.bs12[l]);
         }
     }
     if (warp == 1 && lane == 0) {
@@ -351,15 +360,16 @@ alt_fwd_tc_kernel(const __grid_constant__ AltTcMaps maps, const AltTcParams P) {
                 const int tx = t % P.tiles_x, ty = (t / P.tiles_x) % P.tiles_y, b = t / tiles_per_b;
                 for (int l = 0; l < P.L; ++l) {
                     const int4 bb = P.bbox[(int64_t)t * P.L + l];
-                    const bool sq = bb.z >> 16;
-                    const int ntx = bb.z & 0xffff, tw = sq ? kSqW : kTgtW, th = sq ? kSqH : kTgtH;
-                    const CUtensorMap* mb = sq ? &maps.bsq[l] : &maps.b[l];
+                    const int shape = bb.z >> 16;
+                    const int ntx = bb.z & 0xffff, tw = shape_w(shape), th = shape_h(shape);
+                    const CUtensorMap* mb = shape == 0 ? &maps.b[l] : shape == 1 ? &maps.bsq[l] : &maps.bs12[l];
+                    const uint32_t stage_tx = kABytes + (uint32_t)(tw * th) * 128u;  // fmap1 block + the tile's lattice points x 128 B
                     for (int c = 0; c < bb.w; ++c)
                         for (int a = 0; a < ntx; ++a)
                             for (int kb = 0; kb < P.k_blocks; ++kb) {
                                 mbar_wait(empty_bar + 8 * stage, phase ^ 1);
                                 const uint32_t sa = stage_base + stage * kStageBytes;
-                                mbar_expect_tx(full_bar + 8 * stage, kStageBytes);
+                                mbar_expect_tx(full_bar + 8 * stage, stage_tx);
                                 tma_load_4d(sa, &maps.a, full_bar + 8 * stage, kb * P.k_elems, tx * kSrcW, ty * kSrcH, b);
                                 tma_load_4d(sa + kABytes, mb, full_bar + 8 * stage, kb * P.k_elems, bb.x + a * tw, bb.y + c * th, b);
                                 if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -376,6 +386,8 @@ alt_fwd_tc_kernel(const __grid_constant__ AltTcMaps maps, const AltTcParams P) {
                 for (int l = 0; l < P.L; ++l) {
                     const int4 bb = P.bbox[(int64_t)t * P.L + l];
                     const int ntiles = (bb.z & 0xffff) * bb.w;
+                    const int tile_n = shape_w(bb.z >> 16) * shape_h(bb.z >> 16);  // UMMA N: 256, or 192 for 16 x 12 tiles
+                    const uint32_t idesc = P.f16 ? idesc_f16(tile_n) : make_idesc_tf32(kTileM, tile_n, false, false);
                     for (int n = 0; n < ntiles; ++n, ++it) {
                         const int as = it & 1;
                         mbar_wait(tempty_bar + 8 * as, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
@@ -389,10 +401,9 @@ alt_fwd_tc_kernel(const __grid_constant__ AltTcMaps maps, const AltTcParams P) {
 #pragma unroll
                             for (int k = 0; k < kBlockK / kUmmaK; ++k)
                                 if (P.f16)  // K = 16 halves: the same 32 bytes per instruction
-                                    tc_mma_f16_alt(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (kb | k) != 0 ? 1u : 0u);
+                                    tc_mma_f16_alt(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
                                 else
-                                    tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kInstrDesc,
-                                                (kb | k) != 0 ? 1u : 0u);
+                                    tc_mma_tf32(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
                             tc_commit(empty_bar + 8 * stage);
                             if (++stage == kStages) { stage = 0; phase ^= 1; }
                         }
@@ -490,6 +501,10 @@ int launch_alt_fwd_tc_ex(const void* f1_nhwc, const AltLevels& lv, const CoordsV
         if (int rc = encode_map(fn, &maps.bsq[l], dt, (void*)lv.f2[ll], 4, dims, strides, box_sq, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2 level (NHWC), square tiles"))
             return rc;
+        cuuint32_t box_12[4] = {(cuuint32_t)k_elems, kSqW, kShortH, 1};
+        if (int rc = encode_map(fn, &maps.bs12[l], dt, (void*)lv.f2[ll], 4, dims, strides, box_12, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2 level (NHWC), 16 x 12 tiles"))
+            return rc;
     }
     AltTcParams P{};
     P.coords = cv.ptr; P.cb = cv.batch_stride; P.cc = cv.comp_stride; P.cp = cv.pix_stride;
@@ -508,6 +523,7 @@ int launch_alt_fwd_tc_ex(const void* f1_nhwc, const AltLevels& lv, const CoordsV
     }
     P.scale = scale;
     { const char* e = std::getenv("RAFTCORR_ALT_SQUARE"); P.allow_square = !(e && e[0] == '0'); }
+    { const char* e = std::getenv("RAFTCORR_ALT_SHORT"); P.allow_short = P.allow_square && !(e && e[0] == '0'); }
     P.bb_w = kTgtW;
     P.bb_h = kTgtH;
     int sms = 0;
