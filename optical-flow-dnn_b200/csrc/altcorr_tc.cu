@@ -5,7 +5,8 @@
 // it needs -- 102 k FMAs per pixel at D=256, r=4, L=4, on the CUDA cores.  Neighbouring source pixels look at
 // overlapping windows, so here a CTA takes a block of 8x16 source pixels, finds the bounding box of all
 // their windows on a level (alt_bbox_kernel), and computes the dot products of the 128 pixels with EVERY
-// lattice point of that box as a 128 x 256 x D TF32 GEMM per 8x32 lattice tile on tcgen05: fmap1 block and
+// lattice point of that box as 128 x N x D GEMMs (fp16 or TF32 operands, N <= 256 lattice points per tile, shapes
+// below) on tcgen05: fmap1 block and
 // fmap2 tile arrive by TMA as 128B-swizzled K-major operands straight from the NHWC feature tensors (4-D
 // boxes; rows/columns outside the level are zero-filled by the TMA unit = grid_sample's zero padding),
 // accumulators live in TMEM (two 256-column stages).  For smooth flow the box is (16+K+1) x (8+K+1) points,
@@ -37,12 +38,15 @@ namespace raftcorr {
 namespace {
 
 constexpr int kSrcH = 8, kSrcW = 16;   // source block: 128 pixels = TMEM lanes, m = sy * 16 + sx
-constexpr int kTgtH = 8, kTgtW = 32;   // lattice tile: 256 points = UMMA N, n = ty * 32 + tx  (shape 0: 8 rows x 32 cols)
-constexpr int kSqH = 16, kSqW = 16;    // shape 1: 16 x 16, n = ty * 16 + tx -- covers the small boxes of the coarse levels in one tile
-constexpr int kShortH = 12;            // shape 2: 16 wide x 12 high = UMMA N 192 -- boxes of at most 12 rows (levels 2-3 at r = 4:
-                                       // 14 x 12 and 12 x 11 points) pay three quarters of the fmap2 bytes and MMA cycles
-__host__ __device__ constexpr int shape_w(int s) { return s ? kSqW : kTgtW; }
-__host__ __device__ constexpr int shape_h(int s) { return s == 0 ? kTgtH : s == 1 ? kSqH : kShortH; }
+constexpr int kTgtH = 8, kTgtW = 32;   // largest lattice tile: 256 points = UMMA N (8 rows x 32 columns, n = ty * 32 + tx)
+// Lattice tile shapes: 32, 16 or 8 points wide (so that a 32-column accumulator chunk is 1, 2 or 4 whole tile rows) and
+// th = 4 .. 256 / width rows high in steps of 4 (the fmap2 tile arrives as th / 4 TMA boxes of [width][4 rows]): UMMA
+// N = width * th, a multiple of 32.  alt_bbox_kernel picks, per (source block, level), the width and height that cover
+// the box with the fewest operand bytes (fmap1 block + lattice points); bbox.z = tiles in x | width code << 16 | th << 20.
+// Default: widths 32 and 16 (8-point-wide tiles cut the redundancy further but not the time: profiles/README.md).
+constexpr int kBoxRows = 4;
+__host__ __device__ constexpr int shape_w(int z) { return 32 >> ((z >> 16) & 3); }
+__host__ __device__ constexpr int shape_h(int z) { return (z >> 20) & 63; }
 constexpr int kTileM = kSrcH * kSrcW;
 constexpr int kTileN = kTgtH * kTgtW;
 constexpr int kBlockK = 32, kUmmaK = 8;
@@ -69,9 +73,7 @@ __device__ __forceinline__ float clamp_coord(float v) { return fminf(fmaxf(v, -1
 
 struct AltTcMaps {
     CUtensorMap a;
-    CUtensorMap b[4];    // 8 x 32 lattice tiles
-    CUtensorMap bsq[4];  // 16 x 16 lattice tiles
-    CUtensorMap bs12[4]; // 16 x 12 lattice tiles
+    CUtensorMap b[3][4];  // [width code: 32 / 16 / 8 points][level]: boxes of [width][4 rows] lattice points x one k-block
 };
 
 struct AltTcParams {
@@ -84,9 +86,8 @@ struct AltTcParams {
     int lvl_h[4], lvl_w[4];
     float inv_scale[4];
     float scale;
-    int allow_square;  // pick 16 x 16 lattice tiles where they cover a box with fewer tiles than 8 x 32
-    int allow_short;   // pick 16 x 12 lattice tiles (N = 192) where they cover a box with fewer lattice points
-    int bb_w, bb_h;    // primary lattice tile shape the bounding boxes are cut into
+    int allow_square;  // number of lattice tile widths to choose from: 1 = 32 points only, 2 = + 16, 3 = + 8
+    int allow_short;   // tile heights fitted to the box (N < 256) instead of always 256 points per tile
     // fp16 operands with one power-of-two scale per image and tensor (launch_alt_f16_operands): inv[b] for fmap1,
     // inv[(1 + l) * B + b] for level l of the fmap2 pyramid; k_elems = operand elements per 128-byte k-block
     int f16, k_elems;
@@ -141,12 +142,21 @@ __global__ void __launch_bounds__(kTileM) alt_bbox_kernel(const AltTcParams P) {
             y0 = max(y0, 0); y1 = min(y1, P.lvl_h[l] - 1);
             int4 bb = make_int4(0, 0, 0, 0);
             if (x1 >= x0 && y1 >= y0) {
-                const int nx0 = (x1 - x0) / P.bb_w + 1, ny0 = (y1 - y0) / P.bb_h + 1;  // 8 x 32 (8 x 16) tiling
-                const int nx1 = (x1 - x0) / kSqW + 1, ny1 = (y1 - y0) / kSqH + 1;    // 16 x 16 tiling
-                bb = (P.allow_square && nx1 * ny1 < nx0 * ny0) ? make_int4(x0, y0, nx1 | (1 << 16), ny1)
-                                                               : make_int4(x0, y0, nx0, ny0);
-                const int ny2 = (y1 - y0) / kShortH + 1;                             // 16 x 12 tiling: 192 points per tile
-                if (P.allow_short && nx1 * ny2 * 3 < (bb.z & 0xffff) * bb.w * 4) bb = make_int4(x0, y0, nx1 | (2 << 16), ny2);
+                const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
+                int best = INT_MAX;
+                for (int wc = 0; wc < P.allow_square; ++wc) {
+                    const int tw = 32 >> wc, th_max = kTileN / tw;
+                    const int nx = (bw + tw - 1) / tw, ny = (bh + th_max - 1) / th_max;
+                    // rows spread evenly over the ny tiles, rounded up to whole TMA boxes
+                    const int th = P.allow_short ? min(th_max, (((bh + ny - 1) / ny) + kBoxRows - 1) / kBoxRows * kBoxRows) : th_max;
+                    // operand bytes per tile and k-block: 128 fmap1 rows + tw * th fmap2 rows of 128 B; + a constant for
+                    // the per-tile hand-overs, so that ties go to fewer, larger tiles
+                    const int cost = nx * ny * (kTileM + 32 + tw * th);
+                    if (cost < best) {
+                        best = cost;
+                        bb = make_int4(x0, y0, nx | (wc << 16) | (th << 20), ny);
+                    }
+                }
             }
             P.bbox[(int64_t)t * P.L + l] = bb;
         }
@@ -161,21 +171,22 @@ struct AltWinBars {
 
 // One lattice tile: copy the window points of this lane's pixel out of the accumulator chunks q32 = sub, sub + S, ...
 // c0 = first window column relative to the tile, jr = window row of the tile's first row.
-template <int R, bool SQ>
+template <int R, int TW>
 __device__ __forceinline__ void alt_stage_tile(uint32_t t_acc, int sub, int nchunks, uint32_t win_s, int c0, int jr, bool valid) {
     constexpr int K = 2 * R + 1, KP = K + 1, WR = win_row(R);
-    constexpr int TW = SQ ? kSqW : kTgtW, RPL = 32 / TW;  // rows of the tile per 32-column chunk
+    constexpr int RPL = 32 / TW;  // rows of the tile per 32-column chunk
     uint32_t cm = 0;  // bit c: tile column c belongs to this lane's window
     if (valid && c0 + K >= 0 && c0 < TW) {
         const uint32_t w = (1u << KP) - 1u;
         cm = c0 >= 0 ? (w << c0) : (w >> (-c0));
-        if (SQ) cm &= 0xffffu;
+        if (TW < 32) cm &= (1u << (TW & 31)) - 1u;
     }
 #pragma unroll 1
-    for (int q32 = sub; q32 < nchunks; q32 += kStagersPerQuarter) {  // a 16 x 12 tile ends after 6 chunks (columns 192.. are stale)
+    for (int q32 = sub; q32 < nchunks; q32 += kStagersPerQuarter) {  // a tile of N < 256 points ends early (later columns are stale)
         const int wj = jr + q32 * RPL;  // window row of the chunk's first tile row
-        uint32_t mask = (unsigned)wj <= (unsigned)K ? cm : 0u;
-        if (SQ) mask |= (unsigned)(wj + 1) <= (unsigned)K ? (cm << 16) : 0u;
+        uint32_t mask = 0u;
+#pragma unroll
+        for (int r = 0; r < RPL; ++r) mask |= (unsigned)(wj + r) <= (unsigned)K ? (cm << ((r * TW) & 31)) : 0u;
         if (!__any_sync(0xffffffffu, mask != 0u)) continue;
         float v[32];
         tmem_ld32(t_acc + q32 * 32, v);
@@ -184,7 +195,7 @@ __device__ __forceinline__ void alt_stage_tile(uint32_t t_acc, int sub, int nchu
         const uint32_t base = win_s + (uint32_t)((wj * WR - c0) * 4);
 #pragma unroll
         for (int cc = 0; cc < 32; ++cc) {
-            const int off = SQ ? ((cc >> 4) * WR + (cc & 15)) : cc;
+            const int off = (cc / TW) * WR + (cc % TW);
             if (mask & (1u << cc))
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(base + 4u * (uint32_t)off), "f"(v[cc]) : "memory");
         }
@@ -210,9 +221,7 @@ __device__ __forceinline__ void alt_tc_stager(const AltTcParams& P, int ew, int 
         for (int l = 0; l < P.L; ++l, ++n) {
             const int4 bb = P.bbox[(int64_t)t * P.L + l];
             const int x0 = __float2int_rd(cx * P.inv_scale[l]) - R, y0 = __float2int_rd(cy * P.inv_scale[l]) - R;
-            const int shape = bb.z >> 16;
-            const bool sq = shape != 0;
-            const int ntx = bb.z & 0xffff, tw = shape_w(shape), th = shape_h(shape), nchunks = th * tw / 32;
+            const int ntx = bb.z & 0xffff, tw = shape_w(bb.z), th = shape_h(bb.z), nchunks = th * tw / 32;
             mbar_wait(wb.empty, (n & 1u) ^ 1u);  // the compute warps have read the previous level's window images
             for (int c = 0; c < bb.w; ++c)
                 for (int a = 0; a < ntx; ++a, ++it) {
@@ -221,10 +230,12 @@ __device__ __forceinline__ void alt_tc_stager(const AltTcParams& P, int ew, int 
                     tc_fence_after();
                     const uint32_t t_acc = tmem_base + lane_addr + as * kTileN;
                     const int c0 = x0 - (bb.x + a * tw), jr = (bb.y + c * th) - y0;
-                    if (sq)
-                        alt_stage_tile<R, true>(t_acc, sub, nchunks, win_s, c0, jr, valid);
+                    if (tw == 32)
+                        alt_stage_tile<R, 32>(t_acc, sub, nchunks, win_s, c0, jr, valid);
+                    else if (tw == 16)
+                        alt_stage_tile<R, 16>(t_acc, sub, nchunks, win_s, c0, jr, valid);
                     else
-                        alt_stage_tile<R, false>(t_acc, sub, nchunks, win_s, c0, jr, valid);
+                        alt_stage_tile<R, 8>(t_acc, sub, nchunks, win_s, c0, jr, valid);
                     tc_fence_before();
                     mbar_arrive(tempty_bar + 8 * as);  // every tcgen05.ld of this thread on the stage has completed
                 }
@@ -322,9 +333,7 @@ alt_fwd_tc_kernel(const __grid_constant__ AltTcMaps maps, const AltTcParams P) {
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&maps.a);
         for (int l = 0; l < P.L; ++l) {
-            prefetch_tensormap(&maps.b[l]);
-            prefetch_tensormap(&maps.bsq[l]);
-            prefetch_tensormap(&maps.bs12[l]);
+            for (int wc = 0; wc < 3; ++wc) prefetch_tensormap(&maps.b[wc][l]);
         }
     }
     if (warp == 1 && lane == 0) {
@@ -360,10 +369,10 @@ alt_fwd_tc_kernel(const __grid_constant__ AltTcMaps maps, const AltTcParams P) {
                 const int tx = t % P.tiles_x, ty = (t / P.tiles_x) % P.tiles_y, b = t / tiles_per_b;
                 for (int l = 0; l < P.L; ++l) {
                     const int4 bb = P.bbox[(int64_t)t * P.L + l];
-                    const int shape = bb.z >> 16;
-                    const int ntx = bb.z & 0xffff, tw = shape_w(shape), th = shape_h(shape);
-                    const CUtensorMap* mb = shape == 0 ? &maps.b[l] : shape == 1 ? &maps.bsq[l] : &maps.bs12[l];
+                    const int ntx = bb.z & 0xffff, tw = shape_w(bb.z), th = shape_h(bb.z);
+                    const CUtensorMap* mb = &maps.b[(bb.z >> 16) & 3][l];
                     const uint32_t stage_tx = kABytes + (uint32_t)(tw * th) * 128u;  // fmap1 block + the tile's lattice points x 128 B
+                    const uint32_t box_bytes = (uint32_t)(tw * kBoxRows) * 128u;
                     for (int c = 0; c < bb.w; ++c)
                         for (int a = 0; a < ntx; ++a)
                             for (int kb = 0; kb < P.k_blocks; ++kb) {
@@ -371,7 +380,9 @@ alt_fwd_tc_kernel(const __grid_constant__ AltTcMaps maps, const AltTcParams P) {
                                 const uint32_t sa = stage_base + stage * kStageBytes;
                                 mbar_expect_tx(full_bar + 8 * stage, stage_tx);
                                 tma_load_4d(sa, &maps.a, full_bar + 8 * stage, kb * P.k_elems, tx * kSrcW, ty * kSrcH, b);
-                                tma_load_4d(sa + kABytes, mb, full_bar + 8 * stage, kb * P.k_elems, bb.x + a * tw, bb.y + c * th, b);
+                                for (int r4 = 0; r4 * kBoxRows < th; ++r4)  // the tile's rows, one box of 4 at a time
+                                    tma_load_4d(sa + kABytes + r4 * box_bytes, mb, full_bar + 8 * stage, kb * P.k_elems, bb.x + a * tw,
+                                                bb.y + c * th + r4 * kBoxRows, b);
                                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
                 }
@@ -386,7 +397,7 @@ alt_fwd_tc_kernel(const __grid_constant__ AltTcMaps maps, const AltTcParams P) {
                 for (int l = 0; l < P.L; ++l) {
                     const int4 bb = P.bbox[(int64_t)t * P.L + l];
                     const int ntiles = (bb.z & 0xffff) * bb.w;
-                    const int tile_n = shape_w(bb.z >> 16) * shape_h(bb.z >> 16);  // UMMA N: 256, or 192 for 16 x 12 tiles
+                    const int tile_n = shape_w(bb.z) * shape_h(bb.z);  // UMMA N = the tile's lattice points (32 .. 256)
                     const uint32_t idesc = P.f16 ? idesc_f16(tile_n) : make_idesc_tf32(kTileM, tile_n, false, false);
                     for (int n = 0; n < ntiles; ++n, ++it) {
                         const int as = it & 1;
@@ -493,18 +504,12 @@ int launch_alt_fwd_tc_ex(const void* f1_nhwc, const AltLevels& lv, const CoordsV
         const int ll = l < lv.L ? l : 0;
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)lv.w[ll], (cuuint64_t)lv.h[ll], (cuuint64_t)B};
         cuuint64_t strides[3] = {(cuuint64_t)C * esz, (cuuint64_t)lv.w[ll] * C * esz, (cuuint64_t)lv.h[ll] * lv.w[ll] * C * esz};
-        cuuint32_t box[4] = {(cuuint32_t)k_elems, kTgtW, kTgtH, 1};
-        if (int rc = encode_map(fn, &maps.b[l], dt, (void*)lv.f2[ll], 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
-                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2 level (NHWC)"))
-            return rc;
-        cuuint32_t box_sq[4] = {(cuuint32_t)k_elems, kSqW, kSqH, 1};
-        if (int rc = encode_map(fn, &maps.bsq[l], dt, (void*)lv.f2[ll], 4, dims, strides, box_sq, CU_TENSOR_MAP_SWIZZLE_128B,
-                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2 level (NHWC), square tiles"))
-            return rc;
-        cuuint32_t box_12[4] = {(cuuint32_t)k_elems, kSqW, kShortH, 1};
-        if (int rc = encode_map(fn, &maps.bs12[l], dt, (void*)lv.f2[ll], 4, dims, strides, box_12, CU_TENSOR_MAP_SWIZZLE_128B,
-                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2 level (NHWC), 16 x 12 tiles"))
-            return rc;
+        for (int wc = 0; wc < 3; ++wc) {
+            cuuint32_t box[4] = {(cuuint32_t)k_elems, (cuuint32_t)(32 >> wc), kBoxRows, 1};
+            if (int rc = encode_map(fn, &maps.b[wc][l], dt, (void*)lv.f2[ll], 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, "fmap2 level (NHWC)"))
+                return rc;
+        }
     }
     AltTcParams P{};
     P.coords = cv.ptr; P.cb = cv.batch_stride; P.cc = cv.comp_stride; P.cp = cv.pix_stride;
@@ -522,10 +527,8 @@ int launch_alt_fwd_tc_ex(const void* f1_nhwc, const AltLevels& lv, const CoordsV
         P.inv_scale[l] = 1.0f / (float)(1 << l);
     }
     P.scale = scale;
-    { const char* e = std::getenv("RAFTCORR_ALT_SQUARE"); P.allow_square = !(e && e[0] == '0'); }
-    { const char* e = std::getenv("RAFTCORR_ALT_SHORT"); P.allow_short = P.allow_square && !(e && e[0] == '0'); }
-    P.bb_w = kTgtW;
-    P.bb_h = kTgtH;
+    { const char* e = std::getenv("RAFTCORR_ALT_SQUARE"); P.allow_square = (e && e[0] == '0') ? 1 : (e && e[0] == '3') ? 3 : 2; }
+    { const char* e = std::getenv("RAFTCORR_ALT_SHORT"); P.allow_short = !(e && e[0] == '0'); }
     int sms = 0;
     RC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     switch (radius) {

@@ -23,17 +23,18 @@ def run(tag, B, D, H, W, L, r, sigma, smooth, reps=5):
         e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     bb = blk._ws.view(torch.int32).view(-1, L, 4)
-    cnt = (bb[..., 2] & 0xffff) * bb[..., 3]
-    shape = bb[..., 2] >> 16  # 0: 8 x 32, 1: 16 x 16, 2: 16 x 12 (192 points)
+    z = bb[..., 2]
+    cnt = (z & 0xffff) * bb[..., 3]
+    tw, th = 32 >> ((z >> 16) & 3), (z >> 20) & 63   # lattice tile width / height (bbox.z encoding of altcorr_tc.cu)
     tiles = cnt.sum(0).tolist()
-    square = (cnt * (shape == 1)).sum(0).tolist()
-    short = (cnt * (shape == 2)).sum(0).tolist()
+    by_w = {w: int((cnt * (tw == w)).sum()) for w in (32, 16, 8)}
+    pts = cnt * tw * th
     nblk = bb.shape[0]
     K = 2 * r + 1
     useful = B * H * W * L * (K + 1) ** 2
     tile_n = 256
-    done = int((cnt * torch.where(shape == 2, 192, 256)).sum()) * 128
-    print(f"{tag}: {ms*1e3:8.1f} us  blocks={nblk} lattice tiles/level={tiles} (16x16: {square}, 16x12: {short}) per block={sum(tiles)/nblk:.1f} "
+    done = int(pts.sum()) * 128
+    print(f"{tag}: {ms*1e3:8.1f} us  blocks={nblk} lattice tiles/level={tiles} (tiles by width: {by_w}, mean N {int(pts.sum()) / max(sum(tiles), 1):.0f}) per block={sum(tiles)/nblk:.1f} "
           f"redundancy={done/useful:.2f}x  MMA TFLOP/s={done*2*D/ms/1e9:.0f}  us/tile={ms*1e3*148/max(sum(tiles),1):.2f}")
 which = sys.argv[1:] or ["a"]
 for w in which:

@@ -533,9 +533,9 @@ def test_kernel_variants_agree(pkg, monkeypatch):
     alt_t = pkg.AlternateCorrBlock(f1, f2, L, r, build_mode="tf32")
     a_t = alt_t(coords)
     assert float((a_t - a_s).abs().max()) <= 1e-3 * float(a_s.abs().max())
-    # ... whose variants (8x32-only lattice tiles, no 16x12 tiles: other tilings of the same boxes; a 2-stage operand
-    # ring: the same arithmetic) differ by nothing but the order in which a window's points arrive
-    for var, val in (("RAFTCORR_ALT_SQUARE", "0"), ("RAFTCORR_ALT_SHORT", "0"), ("RAFTCORR_ALT_STAGES", "2")):
+    # ... whose variants (32-point-wide lattice tiles only; 32, 16 and 8; always 256 points per tile: other tilings of the
+    # same boxes; a 2-stage operand ring: the same arithmetic) differ by nothing but the order in which a window's points arrive
+    for var, val in (("RAFTCORR_ALT_SQUARE", "0"), ("RAFTCORR_ALT_SQUARE", "3"), ("RAFTCORR_ALT_SHORT", "0"), ("RAFTCORR_ALT_STAGES", "2")):
         monkeypatch.setenv(var, val)
         a_v = alt_t(coords)
         monkeypatch.delenv(var)
