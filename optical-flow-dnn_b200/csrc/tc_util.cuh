@@ -113,6 +113,13 @@ __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
                  "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
                  : "memory");
 }
+// ... with an L2 cache policy (createpolicy) when `hint` is set
+__device__ __forceinline__ void st_global_v8(float* p, const float* v, uint64_t policy, bool hint) {
+    if (!hint) return st_global_v8(p, v);
+    asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(p), "f"(v[0]), "f"(v[1]),
+                 "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "l"(policy)
+                 : "memory");
+}
 // 16 consecutive fp32 columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);

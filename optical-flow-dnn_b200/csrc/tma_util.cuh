@@ -92,6 +92,17 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
                  "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                  : "memory");
 }
+// the same store with an L2 eviction-priority hint (createpolicy) for streaming outputs that nobody re-reads soon
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_store_4d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;" ::"l"(map),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
                  "r"(c0), "r"(c1), "r"(c2)
